@@ -1,0 +1,541 @@
+"""CPU oracle: NumPy restatement of the reference hot path (TEST INFRASTRUCTURE ONLY).
+
+This file restates, in vectorised NumPy, the algorithm of the reference's
+analysis classes (``/root/reference/JacketAnalysisGUI_v2.py``, cited below as
+``GUI.py:LINE``).  It is the checker for the CUDA path: only ``tests/``,
+``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may
+import it.  Nothing in the product package imports it and there is no CPU
+fallback in the product.
+
+Parity status
+-------------
+* Airy (closed form, the reference's fallback branch GUI.py:187-195, 265,
+  277-280): PINNED.  ``tests/golden/*.npz`` were produced by executing the
+  reference's own classes (``tests/golden/make_golden.py`` via
+  ``oracle/ref_loader.py``) and ``tests/test_oracle_golden.py`` checks this
+  file against them; in the build container
+  ``tests/test_oracle_vs_reference.py`` additionally compares against the live
+  reference.  Operation order follows the reference statement by statement
+  (including sequential accumulation order over Gauss points, members and the
+  interleaved node-1/node-2 scatter) so agreement is at the 1e-15 level.
+* Fourier-series kinematics (Stokes / Fenton through the third-party
+  ``raschii>=1.0.0`` package, requirements.txt:7, not vendored and not
+  installable here): PARITY UNPINNED.  ``fourier_*`` below restates the
+  reference's wrapper semantics (GUI.py:259-281) around a cosine/cosh series;
+  it is checked only for self-consistency.
+
+Everything is FP64.  Inputs are plain arrays (structure-of-arrays), so the
+oracle is independent of the product package:
+
+    xyz[Nn,3]  node coordinates in m, z = 0 at mean water level
+    conn[M,2]  member end-node indices (int)
+    sec_id[M]  index into ``sections``
+    sections   list of (D_outer_mm, t_mm, rho_steel)
+    fixed      fixed node indices (all 6 DOF removed, GUI.py:473-479)
+    top        interface node indices (GUI.py:1959-1977)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+G_ACC = 9.81  # GUI.py:105
+
+
+# --------------------------------------------------------------------------
+# a1  TubularSection.__post_init__  (GUI.py:122-137)
+# --------------------------------------------------------------------------
+def section_props(D_outer, t, rho_steel=7850.0):
+    D_inner = D_outer - 2 * t
+    R_outer = D_outer / 2.0
+    Ax = np.pi / 4.0 * (D_outer**2 - D_inner**2)
+    Iy = np.pi / 64.0 * (D_outer**4 - D_inner**4)
+    Ix = np.pi / 32.0 * (D_outer**4 - D_inner**4)
+    return dict(D_outer=float(D_outer), t=float(t), R_outer=R_outer, Ax=Ax, Ax_m2=Ax / 1e6,
+                Iy=Iy, Iz=Iy, Ix=Ix, Ay=0.5 * Ax, Az=0.5 * Ax,
+                mass_per_m=Ax / 1e6 * rho_steel)
+
+
+# --------------------------------------------------------------------------
+# a2  RaschiiWave.__init__ / _solve_dispersion, fallback branch (GUI.py:171-206)
+# --------------------------------------------------------------------------
+@dataclass
+class AiryWave:
+    H: float
+    T: float
+    d: float
+    U_c: float = 0.0
+    dt: float = 0.001
+    a: float = field(init=False)
+    omega: float = field(init=False)
+    k: float = field(init=False)
+    L: float = field(init=False)
+    c: float = field(init=False)
+    steepness: float = field(init=False)
+
+    def __post_init__(self):
+        self.a = self.H / 2.0
+        self.omega = 2.0 * np.pi / self.T
+        self.k = float(solve_dispersion(self.omega, self.d))
+        self.L = 2.0 * np.pi / self.k
+        self.c = self.L / self.T
+        self.steepness = self.H / self.L
+
+
+def solve_dispersion(omega, d):
+    """Newton on omega^2 = g k tanh(k d)  (GUI.py:197-206)."""
+    k = omega**2 / G_ACC
+    for _ in range(50):
+        f = omega**2 - G_ACC * k * np.tanh(k * d)
+        df = -G_ACC * (np.tanh(k * d) + k * d / np.cosh(k * d)**2)
+        k_new = k - f / df
+        if abs(k_new - k) < 1e-10:
+            break
+        k = k_new
+    return k
+
+
+# --------------------------------------------------------------------------
+# model container
+# --------------------------------------------------------------------------
+@dataclass
+class Model:
+    xyz: np.ndarray
+    conn: np.ndarray
+    sec_id: np.ndarray
+    sections: list
+    fixed: np.ndarray
+    top: np.ndarray
+
+    def __post_init__(self):
+        self.xyz = np.ascontiguousarray(self.xyz, dtype=np.float64)
+        self.conn = np.ascontiguousarray(self.conn, dtype=np.int64)
+        self.sec_id = np.ascontiguousarray(self.sec_id, dtype=np.int64)
+        self.fixed = np.asarray(self.fixed, dtype=np.int64)
+        self.top = np.asarray(self.top, dtype=np.int64)
+        self.props = [section_props(*s) for s in self.sections]
+        self.n_nodes = self.xyz.shape[0]
+        self.n_members = self.conn.shape[0]
+        self.n_dof = 6 * self.n_nodes
+
+    def prop(self, key):
+        return np.array([p[key] for p in self.props], dtype=np.float64)[self.sec_id]
+
+
+# --------------------------------------------------------------------------
+# a4-a11  Morison load integration over phases
+# --------------------------------------------------------------------------
+def morison_angles(wave_direction, current_direction):
+    """Compass -> math angles (GUI.py:555-556)."""
+    return np.deg2rad(90.0 - wave_direction), np.deg2rad(90.0 - current_direction)
+
+
+def phase_times(T, n_steps):
+    """t_i = i*T/n_steps (GUI.py:696), evaluated exactly as the reference does."""
+    return np.array([i * T / n_steps for i in range(n_steps)], dtype=np.float64)
+
+
+def _airy_velocity(wave, xw, z, t):
+    """RaschiiWave.velocity, fallback branch (GUI.py:267-281). Returns (u+U_c, w, wet)."""
+    phase = wave.k * xw - wave.omega * t
+    eta = wave.a * np.cos(phase)                       # GUI.py:265
+    dry = z > eta                                      # GUI.py:269
+    kd = wave.k * wave.d
+    kz = wave.k * (z + wave.d)
+    u = wave.a * wave.omega * np.cosh(kz) / np.sinh(kd) * np.cos(phase)
+    w = wave.a * wave.omega * np.sinh(kz) / np.sinh(kd) * np.sin(phase)
+    u = np.where(dry, 0.0, u + wave.U_c)               # dry -> (0, 0), not (U_c, 0)
+    w = np.where(dry, 0.0, w)
+    return u, w, ~dry
+
+
+def morison_phases(model, wave, t, wave_direction=0.0, current_direction=0.0,
+                   Cd=0.7, Cm=2.0, rho_water=1025.0, n_gauss=15, velocity_fn=None,
+                   want_details=False, chunk=None):
+    """MorisonCalculator.compute_all_morison_forces for every t in ``t``.
+
+    Follows GUI.py:591-682 (+ get_kinematics_3d 559-589, get_kinematics 290-296,
+    acceleration 283-288).  Returns a dict of arrays with a leading phase axis:
+      nodal_forces[P,Nn,3], total_drag[P,3], total_inertia[P,3], total_morison[P,3]
+      and, if want_details, member_details[P,M,4] = drag_kN, inertia_kN, total_kN,
+      submerged_length (GUI.py:668-674).
+    """
+    t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+    P = t.shape[0]
+    M, Nn = model.n_members, model.n_nodes
+    vel = velocity_fn if velocity_fn is not None else _airy_velocity
+    theta_w, theta_c = morison_angles(wave_direction, current_direction)
+    cos_w, sin_w = np.cos(theta_w), np.sin(theta_w)
+    cos_c, sin_c = np.cos(theta_c), np.sin(theta_c)
+
+    c1 = model.xyz[model.conn[:, 0]]
+    c2 = model.xyz[model.conn[:, 1]]
+    D = model.prop("D_outer") / 1000.0                  # GUI.py:610
+    dL = c2 - c1
+    L = np.sqrt(dL[:, 0]**2 + dL[:, 1]**2 + dL[:, 2]**2)  # np.linalg.norm, GUI.py:612
+    e = dL / L[:, None]
+    xi, weights = np.polynomial.legendre.leggauss(n_gauss)  # GUI.py:615-617
+    s_values = (xi + 1.0) / 2.0
+    w_scaled = weights / 2.0
+    A_cross = np.pi * D**2 / 4.0                        # GUI.py:645
+
+    out = dict(nodal_forces=np.zeros((P, Nn, 3)), total_drag=np.zeros((P, 3)),
+               total_inertia=np.zeros((P, 3)), total_morison=np.zeros((P, 3)))
+    if want_details:
+        out["member_details"] = np.zeros((P, M, 4))
+    if chunk is None:
+        chunk = max(1, int(4e6 // max(1, M)))
+    # interleaved scatter order: node1 of member 0, node2 of member 0, node1 of member 1, ...
+    scat_idx = model.conn.reshape(-1)
+
+    for p0 in range(0, P, chunk):
+        tt = t[p0:p0 + chunk][:, None]                  # [Pc,1]
+        Pc = tt.shape[0]
+        F1 = np.zeros((Pc, M, 3)); F2 = np.zeros((Pc, M, 3))
+        mdrag = np.zeros((Pc, M, 3)); minert = np.zeros((Pc, M, 3))
+        sub_len = np.zeros((Pc, M))
+        for s, w in zip(s_values, w_scaled):            # GUI.py:624, sequential accumulation
+            pos = c1 + s * dL                            # GUI.py:625  [M,3]
+            x, y, z = pos[:, 0][None, :], pos[:, 1][None, :], pos[:, 2][None, :]
+            xw = x * cos_w + y * sin_w                   # GUI.py:562
+            u0, w0, wet = vel(wave, xw, z, tt)           # GUI.py:291-294
+            u1, w1, _ = vel(wave, xw, z, tt + wave.dt)   # GUI.py:287
+            du = (u1 - u0) / wave.dt                     # GUI.py:288
+            dw = (w1 - w0) / wave.dt
+            u_wave_only = u0 - wave.U_c                  # GUI.py:573
+            U0 = u_wave_only * cos_w + wave.U_c * cos_c  # GUI.py:633-637
+            U1 = u_wave_only * sin_w + wave.U_c * sin_c
+            U2 = w0
+            A0, A1, A2 = du * cos_w, du * sin_w, dw      # GUI.py:584-586
+            Ue = U0 * e[:, 0] + U1 * e[:, 1] + U2 * e[:, 2]
+            Ae = A0 * e[:, 0] + A1 * e[:, 1] + A2 * e[:, 2]
+            Up = np.stack([U0 - Ue * e[:, 0], U1 - Ue * e[:, 1], U2 - Ue * e[:, 2]], axis=-1)
+            Ap = np.stack([A0 - Ae * e[:, 0], A1 - Ae * e[:, 1], A2 - Ae * e[:, 2]], axis=-1)
+            mag = np.sqrt(Up[..., 0]**2 + Up[..., 1]**2 + Up[..., 2]**2)
+            fd = (0.5 * rho_water * Cd * D * mag)[..., None] * Up * L[None, :, None] * w   # GUI.py:649
+            fd = np.where((mag > 1e-10)[..., None], fd, 0.0)
+            fi = (rho_water * Cm * A_cross)[None, :, None] * Ap * L[None, :, None] * w     # GUI.py:652
+            wetm = wet[..., None]
+            fd = np.where(wetm, fd, 0.0)                 # GUI.py:627-628 (continue)
+            fi = np.where(wetm, fi, 0.0)
+            ft = fd + fi
+            sub_len += np.where(wet, w * L[None, :], 0.0)  # GUI.py:630
+            mdrag += fd; minert += fi                    # GUI.py:656-657
+            F1 += (1.0 - s) * ft                         # GUI.py:658-659
+            F2 += s * ft
+        nf = out["nodal_forces"][p0:p0 + Pc]
+        vals = np.stack([F1, F2], axis=2).reshape(Pc, 2 * M, 3)
+        nf_t = np.zeros((Nn, Pc, 3))
+        np.add.at(nf_t, scat_idx, np.moveaxis(vals, 1, 0))   # GUI.py:661-662, member order
+        nf[...] = np.moveaxis(nf_t, 0, 1)
+        # sequential member-order totals (GUI.py:664-666)
+        out["total_drag"][p0:p0 + Pc] = np.cumsum(mdrag, axis=1)[:, -1]
+        out["total_inertia"][p0:p0 + Pc] = np.cumsum(minert, axis=1)[:, -1]
+        out["total_morison"][p0:p0 + Pc] = np.cumsum(mdrag + minert, axis=1)[:, -1]
+        if want_details:
+            mt = mdrag + minert
+            nrm = lambda v: np.sqrt(v[..., 0]**2 + v[..., 1]**2 + v[..., 2]**2)
+            det = out["member_details"][p0:p0 + Pc]
+            det[..., 0] = nrm(mdrag) / 1000
+            det[..., 1] = nrm(minert) / 1000
+            det[..., 2] = nrm(mt) / 1000
+            det[..., 3] = sub_len
+    return out
+
+
+def phase_table(morison_out, t, omega):
+    """The 8 columns of find_critical_phase rows (GUI.py:705-714) + critical index (717)."""
+    nrm = lambda v: np.sqrt(v[:, 0]**2 + v[:, 1]**2 + v[:, 2]**2)
+    tm = morison_out["total_morison"]
+    tab = np.stack([t, np.degrees(omega * t) % 360,
+                    nrm(tm) / 1000, nrm(morison_out["total_drag"]) / 1000,
+                    nrm(morison_out["total_inertia"]) / 1000,
+                    tm[:, 0] / 1000, tm[:, 1] / 1000, tm[:, 2] / 1000], axis=1)
+    crit = int(np.argmax(tab[:, 2]))                    # first maximum, like max(key=...)
+    return tab, crit
+
+
+# --------------------------------------------------------------------------
+# a12-a15  elements and assembly
+# --------------------------------------------------------------------------
+def element_frames(model):
+    """BeamElement3D._compute_transformation_matrix (GUI.py:371-387) -> R[M,3,3], L[M] (m)."""
+    c1 = model.xyz[model.conn[:, 0]]
+    c2 = model.xyz[model.conn[:, 1]]
+    dL = c2 - c1
+    L = np.sqrt(dL[:, 0]**2 + dL[:, 1]**2 + dL[:, 2]**2)
+    lx = dL / L[:, None]
+    gz = np.array([0.0, 0.0, 1.0])
+    R = np.zeros((model.n_members, 3, 3))
+    for m in range(model.n_members):
+        if abs(lx[m, 2]) > 0.999:
+            ly = np.cross(gz, lx[m])
+            n = np.linalg.norm(ly)
+            ly = ly / n if n > 1e-10 else np.array([0.0, 1.0, 0.0])
+            lz = np.cross(lx[m], ly)
+        else:
+            lz = np.cross(lx[m], gz)
+            lz = lz / np.linalg.norm(lz)
+            ly = np.cross(lz, lx[m])
+        R[m] = np.array([lx[m], ly, lz])
+    return R, L
+
+
+def element_frames_vec(model):
+    """Vectorised form of element_frames (same formulas, used at 10k members)."""
+    c1 = model.xyz[model.conn[:, 0]]
+    c2 = model.xyz[model.conn[:, 1]]
+    dL = c2 - c1
+    L = np.sqrt(dL[:, 0]**2 + dL[:, 1]**2 + dL[:, 2]**2)
+    lx = dL / L[:, None]
+    vert = np.abs(lx[:, 2]) > 0.999
+    gz = np.array([0.0, 0.0, 1.0])
+    # vertical branch
+    ly_v = np.cross(gz, lx)
+    n_v = np.sqrt((ly_v**2).sum(1))
+    ok = n_v > 1e-10
+    ly_v = np.where(ok[:, None], ly_v / np.where(ok, n_v, 1.0)[:, None], np.array([0.0, 1.0, 0.0]))
+    lz_v = np.cross(lx, ly_v)
+    # general branch
+    lz_g = np.cross(lx, gz)
+    n_g = np.sqrt((lz_g**2).sum(1))
+    lz_g = lz_g / np.where(n_g > 0, n_g, 1.0)[:, None]
+    ly_g = np.cross(lz_g, lx)
+    ly = np.where(vert[:, None], ly_v, ly_g)
+    lz = np.where(vert[:, None], lz_v, lz_g)
+    return np.stack([lx, ly, lz], axis=1), L
+
+
+def element_local_stiffness(model, L_m, E, G):
+    """BeamElement3D._compute_local_stiffness (GUI.py:389-422) -> K_local[M,12,12]."""
+    L = L_m * 1000.0
+    Ax, Iy, Iz, Ix = model.prop("Ax"), model.prop("Iy"), model.prop("Iz"), model.prop("Ix")
+    Ay, Az = model.prop("Ay"), model.prop("Az")
+    Phi_y = 12.0 * E * Iz / (G * Az * L**2)
+    Phi_z = 12.0 * E * Iy / (G * Ay * L**2)
+    alpha = E * Ax / L
+    bz = E * Iz / ((1.0 + Phi_y) * L**3)
+    by = E * Iy / ((1.0 + Phi_z) * L**3)
+    tt = G * Ix / L
+    K = np.zeros((model.n_members, 12, 12))
+    K[:, 0, 0] = K[:, 6, 6] = alpha
+    K[:, 0, 6] = K[:, 6, 0] = -alpha
+    K[:, 1, 1] = K[:, 7, 7] = 12.0 * bz
+    K[:, 1, 7] = K[:, 7, 1] = -12.0 * bz
+    K[:, 1, 5] = K[:, 5, 1] = K[:, 1, 11] = K[:, 11, 1] = 6.0 * bz * L
+    K[:, 7, 5] = K[:, 5, 7] = K[:, 7, 11] = K[:, 11, 7] = -6.0 * bz * L
+    K[:, 5, 5] = K[:, 11, 11] = (4.0 + Phi_y) * bz * L**2
+    K[:, 5, 11] = K[:, 11, 5] = (2.0 - Phi_y) * bz * L**2
+    K[:, 2, 2] = K[:, 8, 8] = 12.0 * by
+    K[:, 2, 8] = K[:, 8, 2] = -12.0 * by
+    K[:, 2, 4] = K[:, 4, 2] = K[:, 2, 10] = K[:, 10, 2] = -6.0 * by * L
+    K[:, 8, 4] = K[:, 4, 8] = K[:, 8, 10] = K[:, 10, 8] = 6.0 * by * L
+    K[:, 4, 4] = K[:, 10, 10] = (4.0 + Phi_z) * by * L**2
+    K[:, 4, 10] = K[:, 10, 4] = (2.0 - Phi_z) * by * L**2
+    K[:, 3, 3] = K[:, 9, 9] = tt
+    K[:, 3, 9] = K[:, 9, 3] = -tt
+    return K
+
+
+def element_T(R):
+    M = R.shape[0]
+    T = np.zeros((M, 12, 12))
+    for i in range(4):
+        T[:, 3 * i:3 * i + 3, 3 * i:3 * i + 3] = R
+    return T
+
+
+@dataclass
+class FEM:
+    """FEMSolver restated (GUI.py:438-533)."""
+    model: Model
+    E: float = 210000.0
+    nu: float = 0.3
+
+    def __post_init__(self):
+        m = self.model
+        self.G = self.E / (2 * (1 + self.nu))           # GUI.py:443
+        self.R, self.L = element_frames_vec(m) if m.n_members > 512 else element_frames(m)
+        self.K_local = element_local_stiffness(m, self.L, self.E, self.G)
+        self.T = element_T(self.R)
+        self.K_elem = np.matmul(np.matmul(np.transpose(self.T, (0, 2, 1)), self.K_local), self.T)  # GUI.py:369
+        self.dofs = np.concatenate([6 * m.conn[:, 0:1] + np.arange(6), 6 * m.conn[:, 1:2] + np.arange(6)], axis=1)
+        self.fixed_dofs = (6 * m.fixed[:, None] + np.arange(6)).reshape(-1)       # GUI.py:474-478
+        self.free_dofs = np.setdiff1d(np.arange(m.n_dof), self.fixed_dofs)          # GUI.py:479
+        self._K = None
+
+    @property
+    def K_global(self):
+        """Dense assembly in member order (GUI.py:457-467)."""
+        if self._K is None:
+            n = self.model.n_dof
+            K = np.zeros((n, n))
+            rows = np.repeat(self.dofs, 12, axis=1).reshape(-1)
+            cols = np.tile(self.dofs, (1, 12)).reshape(-1)
+            np.add.at(K, (rows, cols), self.K_elem.reshape(-1))
+            self._K = K
+        return self._K
+
+    # a16 -----------------------------------------------------------------
+    def static_loads(self, wave_direction=0.0, F_axial_kN=0.0, F_shear_kN=0.0, M_moment_kNm=0.0,
+                     M_torsion_kNm=0.0, self_weight="calculated", custom_sw_tonnes=0.0):
+        """Interface loads + self-weight exactly as run_analysis builds them (GUI.py:1962-2015)."""
+        m = self.model
+        F = np.zeros(m.n_dof)
+        n_legs = len(m.top)
+        theta = np.deg2rad(90.0 - wave_direction)
+        force = np.array([F_shear_kN * 1000.0 * np.cos(theta) / n_legs,
+                          F_shear_kN * 1000.0 * np.sin(theta) / n_legs,
+                          -(F_axial_kN * 1000.0) / n_legs,
+                          M_torsion_kNm * 1e6 / n_legs,
+                          M_moment_kNm * 1e6 / n_legs,
+                          0.0])
+        for idx in m.top:
+            F[6 * idx:6 * idx + 6] += force
+        return F, self._self_weight(self_weight, custom_sw_tonnes)
+
+    def _self_weight(self, mode, custom_sw_tonnes):
+        m = self.model
+        F = np.zeros(m.n_dof)
+        if mode == "calculated":                        # GUI.py:1995-2006
+            w = m.prop("mass_per_m") * G_ACC
+            Fw = (w * self.L) / 2.0
+            idx = np.stack([6 * m.conn[:, 0] + 2, 6 * m.conn[:, 1] + 2], axis=1).reshape(-1)
+            np.subtract.at(F, idx, np.repeat(Fw, 2))
+        elif mode == "custom":                          # GUI.py:2008-2012
+            custom = custom_sw_tonnes * 1000 * G_ACC
+            F[2::6] -= custom / m.n_nodes
+        return F
+
+    def load_matrix(self, nodal_forces, interface, self_weight):
+        """F_global per phase in the reference's accumulation order:
+        interface (1968-1977) -> Morison (1986-1989) -> self-weight (1994-2012)."""
+        P = nodal_forces.shape[0]
+        F = np.tile(interface, (P, 1))
+        F3 = F.reshape(P, self.model.n_nodes, 6)
+        F3[:, :, :3] += nodal_forces
+        # the reference subtracts each member's half weight one at a time; _self_weight keeps that order
+        # but here the accumulated vector is added once: identical up to the 1e-16 level.
+        F = F3.reshape(P, -1) + self_weight
+        return F
+
+    # a18 -----------------------------------------------------------------
+    def solve(self, F):
+        """np.linalg.solve on the free-free partition, all right-hand sides at once (GUI.py:481-490)."""
+        F = np.atleast_2d(F)
+        K = self.K_global
+        K_ff = K[np.ix_(self.free_dofs, self.free_dofs)]
+        U_f = np.linalg.solve(K_ff, F[:, self.free_dofs].T).T
+        U = np.zeros_like(F)
+        U[:, self.free_dofs] = U_f
+        return U
+
+    # a19 -----------------------------------------------------------------
+    def reactions(self, U, F):
+        """R = K U - F at the fixed DOFs (GUI.py:492-502) -> [P, n_fixed_nodes, 6]."""
+        K = self.K_global
+        R = U @ K[self.fixed_dofs, :].T - F[:, self.fixed_dofs]
+        return R.reshape(U.shape[0], len(self.model.fixed), 6)
+
+    # a20-a22 -------------------------------------------------------------
+    def member_forces(self, U, fy=355.0):
+        """get_member_internal_forces (GUI.py:504-533) for every phase.
+
+        Returns dict of arrays [P, M]: Fx_max_kN, Fy_max_kN, Fz_max_kN, My_max_kNm, Mz_max_kNm,
+        von_mises_max_MPa, utilization; plus end_forces[P, M, 12] (node-1 sign-flipped as in 428-431).
+        """
+        m = self.model
+        U = np.atleast_2d(U)
+        u_e = U[:, self.dofs]                            # [P,M,12]
+        u_l = np.einsum("mij,pmj->pmi", self.T, u_e)     # GUI.py:425
+        F_l = np.einsum("mij,pmj->pmi", self.K_local, u_l)  # GUI.py:426
+        n1 = -F_l[..., 0:6]
+        n2 = F_l[..., 6:12]
+        Ax, Iy, Iz, Ix = m.prop("Ax"), m.prop("Iy"), m.prop("Iz"), m.prop("Ix")
+        Ay, Az, Ro = m.prop("Ay"), m.prop("Az"), m.prop("R_outer")
+        Fx, Fy, Fz, Mx, My, Mz = (n1[..., i] for i in range(6))
+        max_vm = np.zeros(Fx.shape)
+        for angle in [0, 45, 90, 135, 180, 225, 270, 315]:   # GUI.py:139-145
+            rad = np.radians(angle)
+            y = Ro * np.cos(rad)
+            z = Ro * np.sin(rad)
+            sigma = Fx / Ax + My * z / Iy + Mz * y / Iz      # GUI.py:150-153
+            Rr = np.sqrt(y**2 + z**2)
+            tau = np.sqrt((Mx * Rr / Ix)**2 + (Fy / Ay)**2 + (Fz / Az)**2)  # GUI.py:154-158
+            vm = np.sqrt(sigma**2 + 3.0 * tau**2)
+            max_vm = np.maximum(max_vm, vm)
+        mx = lambda i: np.maximum(np.abs(n1[..., i]), np.abs(n2[..., i]))
+        return dict(Fx_max_kN=mx(0) / 1000, Fy_max_kN=mx(1) / 1000, Fz_max_kN=mx(2) / 1000,
+                    My_max_kNm=mx(4) / 1e6, Mz_max_kNm=mx(5) / 1e6,
+                    von_mises_max_MPa=max_vm, utilization=max_vm / fy,
+                    end_forces=np.concatenate([n1, n2], axis=-1), length_m=self.L)
+
+
+# --------------------------------------------------------------------------
+# full per-phase analysis = run_analysis replayed with t_analysis = t_i
+# --------------------------------------------------------------------------
+def phase_scan(model, wave, t, *, wave_direction=0.0, current_direction=0.0, Cd=0.7, Cm=2.0,
+               rho_water=1025.0, E=210000.0, nu=0.3, fy=355.0, F_axial_kN=0.0, F_shear_kN=0.0,
+               M_moment_kNm=0.0, M_torsion_kNm=0.0, self_weight="calculated", custom_sw_tonnes=0.0,
+               n_gauss=15, fem=None, velocity_fn=None):
+    t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+    mor = morison_phases(model, wave, t, wave_direction, current_direction, Cd, Cm, rho_water,
+                         n_gauss, velocity_fn=velocity_fn)
+    table, crit = phase_table(mor, t, wave.omega)
+    fem = fem if fem is not None else FEM(model, E, nu)
+    interface, sw = fem.static_loads(wave_direction, F_axial_kN, F_shear_kN, M_moment_kNm,
+                                     M_torsion_kNm, self_weight, custom_sw_tonnes)
+    F = fem.load_matrix(mor["nodal_forces"], interface, sw)
+    U = fem.solve(F)
+    R = fem.reactions(U, F)
+    mf = fem.member_forces(U, fy)
+    return dict(t=t, morison=mor, table=table, critical=crit, F=F, U=U, reactions=R, members=mf, fem=fem)
+
+
+# --------------------------------------------------------------------------
+# Fourier-series kinematics (Stokes / Fenton form) -- PARITY UNPINNED
+# --------------------------------------------------------------------------
+@dataclass
+class FourierWave:
+    """A periodic wave given by host-fitted series, wrapped with the reference's
+    raschii-branch semantics (GUI.py:259-264, 271-275, 281):
+
+        eta(x,t)  = sum_j E[j] cos(j (k x - omega t))            (elevation about MWL)
+        u(x,z,t)  = sum_j B[j] cosh(j k zb)/cosh(j k d) cos(j phi) + U_c
+        w(x,z,t)  = sum_j B[j] sinh(j k zb)/cosh(j k d) sin(j phi)
+        zb        = max(0.01, min(z + d, d + eta - 0.01))
+    with j = 1..N; B[j] already contains the j*k factor and the frame shift.
+    """
+    H: float
+    T: float
+    d: float
+    k: float
+    E: np.ndarray
+    B: np.ndarray
+    U_c: float = 0.0
+    dt: float = 0.001
+
+    def __post_init__(self):
+        self.omega = 2.0 * np.pi / self.T
+        self.a = self.H / 2.0
+        self.E = np.asarray(self.E, dtype=np.float64)
+        self.B = np.asarray(self.B, dtype=np.float64)
+
+
+def fourier_velocity(wave, xw, z, t):
+    phase = wave.k * xw - wave.omega * t
+    j = np.arange(1, len(wave.E) + 1, dtype=np.float64)
+    eta = np.zeros(np.broadcast(phase, z).shape)
+    for jj, Ej in zip(j, wave.E):
+        eta = eta + Ej * np.cos(jj * phase)
+    dry = z > eta
+    zb = np.maximum(0.01, np.minimum(z + wave.d, wave.d + eta - 0.01))
+    u = np.zeros_like(eta); w = np.zeros_like(eta)
+    for jj, Bj in zip(j, wave.B):
+        den = np.cosh(jj * wave.k * wave.d)
+        u = u + Bj * np.cosh(jj * wave.k * zb) / den * np.cos(jj * phase)
+        w = w + Bj * np.sinh(jj * wave.k * zb) / den * np.sin(jj * phase)
+    u = np.where(dry, 0.0, u + wave.U_c)
+    w = np.where(dry, 0.0, w)
+    return u, w, ~dry
