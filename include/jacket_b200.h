@@ -1,0 +1,192 @@
+/* jacket_b200.h -- C ABI of libjacket_b200.so (B200 / sm_100a only).
+ *
+ * The reference (JK-hqy/Small-FEM-Solver-based-on-a-lot-of-assumption,
+ * JacketAnalysisGUI_v2.py, cited as GUI.py:LINE) has no FFI: its "operator
+ * interface" for the hot path is the Python class surface
+ *   MorisonCalculator.compute_all_morison_forces / find_critical_phase  (GUI.py:591-724)
+ *   FEMSolver.__init__ / apply_boundary_conditions / solve /
+ *             get_reactions / get_member_internal_forces                (GUI.py:438-533)
+ * called from JacketAnalysisGUI.run_analysis (GUI.py:1827-2082).  The Python
+ * package in this repo keeps that surface and forwards to the entry points
+ * below through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is caller-owned HOST memory
+ *     unless the name ends in _dev;
+ *   - every function returns 0 on success, a negative JK_E* code on failure;
+ *     jk_last_error(h) (or jk_last_error(NULL) for jk_create failures) gives
+ *     the message;
+ *   - one opaque handle per (structure, GPU); a handle owns one CUDA stream
+ *     (or borrows the one passed to jk_create) and all its device buffers;
+ *   - calls are blocking unless stated; there is NO CPU fallback: without a
+ *     CUDA device jk_create fails with JK_ENODEVICE.
+ *   - units follow the reference: coordinates m, section properties mm,
+ *     forces N, moments N*mm, displacements mm / rad, stresses MPa.
+ */
+#ifndef JACKET_B200_H
+#define JACKET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jk_handle_s* jk_handle_t;
+
+#define JK_OK            0
+#define JK_EINVAL       -1
+#define JK_ECUDA        -2
+#define JK_ENODEVICE    -3
+#define JK_ENOTSPD      -4   /* Cholesky met a non-positive pivot (the reference would fall to lstsq, GUI.py:486-487) */
+#define JK_ESTATE       -5   /* call order violated (e.g. scan before factor) */
+
+/* per-section property row passed to jk_create (mm units, GUI.py:122-137) */
+#define JK_SEC_NPROP     8
+#define JK_SEC_D_OUTER   0
+#define JK_SEC_AX        1
+#define JK_SEC_IY        2
+#define JK_SEC_IZ        3
+#define JK_SEC_IX        4
+#define JK_SEC_AY        5
+#define JK_SEC_AZ        6
+#define JK_SEC_R_OUTER   7
+
+/* columns of the per-phase result table written by jk_phase_scan / jk_morison_scan.
+ * 0..7 are the reference's find_critical_phase row (GUI.py:705-714); column 1
+ * (phase_deg) is left 0 by the library and filled by the host wrapper with
+ * numpy.degrees(omega*t) % 360 so it is bit-identical to the reference.
+ * 8..15 are the per-phase FEM summary (run_analysis replayed at t_i). */
+#define JK_TABLE_NCOL       16
+#define JK_COL_T             0
+#define JK_COL_PHASE_DEG     1
+#define JK_COL_TOTAL_KN      2
+#define JK_COL_DRAG_KN       3
+#define JK_COL_INERTIA_KN    4
+#define JK_COL_FX_KN         5
+#define JK_COL_FY_KN         6
+#define JK_COL_FZ_KN         7
+#define JK_COL_MAX_DISP_MM   8   /* max nodal |translation|, GUI.py:2035-2040 */
+#define JK_COL_MAX_DISP_NODE 9   /* node index of that maximum (first maximum) */
+#define JK_COL_MAX_UTIL     10   /* max member utilisation, GUI.py:2054 */
+#define JK_COL_MAX_UTIL_MEM 11   /* member index of that maximum (first maximum) */
+#define JK_COL_MAX_VM_MPA   12
+#define JK_COL_SUM_RX       13   /* sum of support reactions, N (GUI.py:2027-2033) */
+#define JK_COL_SUM_RY       14
+#define JK_COL_SUM_RZ       15
+
+/* member result row (GUI.py:521-532 numeric fields, in this order) */
+#define JK_MEMBER_NCOL       7   /* Fx_max_kN Fy_max_kN Fz_max_kN My_max_kNm Mz_max_kNm von_mises_max_MPa utilization */
+/* Morison member detail row (GUI.py:668-674) */
+#define JK_DETAIL_NCOL       4   /* drag_kN inertia_kN total_kN submerged_length */
+
+/* node ordering of the free-free system */
+#define JK_ORDER_NATURAL     0   /* reference order (node_list order) */
+#define JK_ORDER_RCM         1   /* reverse Cuthill-McKee on the member graph (minimises the tile band) */
+/* solver storage */
+#define JK_SOLVER_BANDED     0   /* tile band derived from the ordering */
+#define JK_SOLVER_DENSE      1   /* full lower triangle (the reference's dense K_ff, GUI.py:482) */
+
+/* stage timers returned by jk_get_timings (milliseconds, CUDA events on the handle's stream) */
+#define JK_NTIMERS          12
+#define JK_T_ASSEMBLE        0
+#define JK_T_FACTOR          1
+#define JK_T_WAVE_SETUP      2
+#define JK_T_MORISON         3
+#define JK_T_RHS             4
+#define JK_T_SOLVE_FWD       5
+#define JK_T_SOLVE_BWD       6
+#define JK_T_POST            7
+#define JK_T_REDUCE          8
+#define JK_T_SCAN_TOTAL      9
+#define JK_T_H2D            10
+#define JK_T_D2H            11
+
+int         jk_version(void);
+const char* jk_last_error(jk_handle_t h);
+
+/* Replaces CustomJacketStructure (GUI.py:302-354) as the geometry carrier:
+ * xyz[n_nodes*3] (m, z = 0 at MWL), conn[n_members*2] node indices,
+ * sec_id[n_members] rows of sec_props[n_sec*JK_SEC_NPROP].
+ * stream: a cudaStream_t to borrow, or NULL to create one. */
+int jk_create(int device, void* stream,
+              int n_nodes, const double* xyz,
+              int n_members, const int32_t* conn, const int32_t* sec_id,
+              int n_sec, const double* sec_props,
+              jk_handle_t* out);
+int jk_destroy(jk_handle_t h);
+
+/* FEMSolver.apply_boundary_conditions (GUI.py:473-479): all 6 DOF of each
+ * fixed node are removed.  Chooses the ordering / storage of K_ff. */
+int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_nodes, int ordering, int solver);
+
+/* FEMSolver.__init__ (GUI.py:439-467): element stiffness (BeamElement3D,
+ * GUI.py:361-422), transform, deterministic assembly of K_ff into tile storage. */
+int jk_assemble(jk_handle_t h, double E, double G);
+/* factor half of np.linalg.solve (GUI.py:485): blocked Cholesky, once per structure */
+int jk_factor(jk_handle_t h);
+
+/* F_global contributions that do not depend on the phase (interface loads
+ * GUI.py:1962-1977 and self-weight GUI.py:1994-2012), built by the host. */
+int jk_set_static_load(jk_handle_t h, const double* F_static /* [6*n_nodes] */);
+
+/* RaschiiWave closed-form branch (GUI.py:265, 277-281) */
+int jk_set_wave_airy(jk_handle_t h, double a, double k, double omega, double d, double U_c, double dt);
+/* Fourier-series kinematics (Stokes / Fenton form, wrapper semantics GUI.py:259-281):
+ * eta = sum E[j] cos(j phi) ; u = sum B[j] cosh(j k zb)/cosh(j k d) cos(j phi) + U_c ; j = 1..n_harm */
+int jk_set_wave_fourier(jk_handle_t h, double k, double omega, double d, double U_c, double dt,
+                        int n_harm, const double* E, const double* B);
+/* MorisonCalculator.__init__ (GUI.py:544-557) + the Gauss rule of GUI.py:615-617
+ * (nodes s in [0,1] and weights w, computed by the host with numpy.leggauss). */
+int jk_set_morison(jk_handle_t h, double theta_wave, double theta_current,
+                   double rho, double Cd, double Cm,
+                   int n_gauss, const double* gauss_s, const double* gauss_w);
+
+/* MorisonCalculator.find_critical_phase (GUI.py:684-724): Morison only.
+ * table[P*JK_TABLE_NCOL] (columns 8.. are 0), *critical = first index of max total_kN. */
+int jk_morison_scan(jk_handle_t h, int P, const double* t, double* table, int64_t* critical);
+
+/* MorisonCalculator.compute_all_morison_forces at one t (GUI.py:591-682):
+ * nodal_forces[n_nodes*3], totals[9] = drag xyz, inertia xyz, morison xyz (N),
+ * details[n_members*JK_DETAIL_NCOL]; any output may be NULL. */
+int jk_morison_single(jk_handle_t h, double t, double* nodal_forces, double* totals, double* details);
+
+/* The whole hot path for P phases: Morison -> RHS -> two triangular sweeps ->
+ * reactions / member forces / utilisation -> per-phase table -> critical phase.
+ * Full per-phase results stay in HBM; fetch rows with jk_fetch_phase. */
+int jk_phase_scan(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical);
+/* Same, but nothing is copied: t_dev[P] is already in HBM and the table stays
+ * there (jk_read_table copies it out).  Asynchronous on the handle's stream. */
+int jk_phase_scan_dev(jk_handle_t h, int P, const double* t_dev, double fy);
+int jk_read_table(jk_handle_t h, int P, double* table, int64_t* critical);
+
+/* FEMSolver.solve with caller-built right-hand sides (GUI.py:481-490):
+ * F[nrhs*6*n_nodes] (row = load case) -> same pipeline as jk_phase_scan minus Morison. */
+int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy);
+
+/* Full rows of one phase / load case of the last scan or solve:
+ * U[6*n_nodes] (GUI.py:488-490), reactions[6*n_fixed] (GUI.py:492-502),
+ * member_rows[n_members*JK_MEMBER_NCOL] (GUI.py:521-532),
+ * end_forces[n_members*12] (GUI.py:427-432, node-1 sign already flipped),
+ * nodal_forces[n_nodes*3] Morison nodal loads (NULL-able, zeros after jk_solve). */
+int jk_fetch_phase(jk_handle_t h, int phase, double* U, double* reactions,
+                   double* member_rows, double* end_forces, double* nodal_forces);
+/* One member-result column for all phases of the last scan: out[P] */
+int jk_fetch_member_column(jk_handle_t h, int member, int column, int P, double* out);
+
+/* Introspection used by the FEMSolver facade and the parity tests */
+int jk_get_dims(jk_handle_t h, int32_t* out /* n_nodes n_members n_fixed n_free_dof n_pad tile band_tiles n_tiles */);
+int jk_get_order(jk_handle_t h, int32_t* free_nodes /* [n_nodes-n_fixed] solver order */);
+int jk_get_K(jk_handle_t h, double* K /* [n_dof*n_dof] dense, reference DOF order */);
+int jk_get_elements(jk_handle_t h, double* Ke /* [M*144] */, double* Kl /* [M*144] */, double* R /* [M*9] */, double* L /* [M] */);
+int jk_get_timings(jk_handle_t h, double* ms /* [JK_NTIMERS] */);
+/* max_i |K u - F|_i / max_i |F|_i over the free DOFs of every phase of the last scan (diagnostic) */
+int jk_residual(jk_handle_t h, double* rel_residual);
+/* kernels launched by this handle since creation (bench "gpu_launches") */
+int64_t jk_launch_count(jk_handle_t h);
+void* jk_stream(jk_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,14 @@
+"""Import shim: ``import jacket_b200`` loads the package that lives in
+``small-fem-solver-based-on-a-lot-of-assumption_b200/`` (a directory name Python
+cannot import directly because of the hyphens)."""
+import importlib.util
+import os
+import sys
+
+_PKG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                        "small-fem-solver-based-on-a-lot-of-assumption_b200")
+_spec = importlib.util.spec_from_file_location(
+    "jacket_b200", os.path.join(_PKG_DIR, "__init__.py"), submodule_search_locations=[_PKG_DIR])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["jacket_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,905 @@
+// jk_api.cu -- C ABI of libjacket_b200.so (see include/jacket_b200.h).
+// Host-side orchestration only: SoA upload, ordering (reverse Cuthill-McKee), CSR builds for the
+// deterministic gathers, buffer management, kernel launches and CUDA-event stage timers.
+// There is no CPU compute path: every jk_* numeric entry point launches kernels or fails.
+#include "../../include/jacket_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "jk_chol.cuh"
+#include "jk_common.cuh"
+#include "jk_fem.cuh"
+#include "jk_morison.cuh"
+
+using namespace jk;
+
+static thread_local std::string g_err;
+
+struct jk_handle_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+
+    // geometry
+    int Nn = 0, M = 0, nsec = 0;
+    std::vector<double> h_xyz;
+    std::vector<int> h_conn, h_sec;
+    double *d_xyz = nullptr, *d_secp = nullptr, *d_mc = nullptr, *d_Ke = nullptr, *d_Kl = nullptr;
+    int *d_conn = nullptr, *d_sec = nullptr, *d_adj_ptr = nullptr, *d_adj = nullptr;
+    std::vector<int> h_adj_ptr, h_adj;
+
+    // supports / ordering / storage
+    bool have_supports = false;
+    int n_fixed = 0, n_free_nodes = 0, n_free = 0, n_pad = 0, NT = 0, bw = 0, solver = 0;
+    std::vector<int> h_node2slot, h_free_nodes, h_fixed;
+    int *d_node2slot = nullptr, *d_fixed_nodes = nullptr, *d_free_nodes = nullptr;
+    KBlock* d_blocks = nullptr;
+    int2* d_contrib = nullptr;
+    int nblocks = 0;
+    double *d_tiles = nullptr, *d_Linv = nullptr;
+    size_t tiles_elems = 0;
+    int* d_info = nullptr;
+    bool assembled = false, factored = false;
+    double E = 0, G = 0;
+
+    // loads / wave / morison
+    double* d_Fstatic = nullptr;
+    bool have_wave = false, have_morison = false, gp_valid = false;
+    WaveAiry wv{};
+    double rho = 0, Cd = 0, Cm = 0;
+    int ng = 0;
+    double *d_gsw = nullptr, *d_gp = nullptr;
+    StressPts sp{};
+
+    // scan buffers (capacity cap_ldP phases)
+    int cap_ldP = 0;
+    bool cap_details = false;
+    double *d_t = nullptr, *d_trig = nullptr, *d_Fm = nullptr, *d_X = nullptr, *d_Ffix = nullptr, *d_rows = nullptr;
+    double *d_totpart = nullptr, *d_part_util = nullptr, *d_part_vm = nullptr, *d_part_disp = nullptr, *d_react = nullptr;
+    double *d_table = nullptr, *d_details = nullptr, *d_Fload = nullptr, *d_argval = nullptr, *d_tmp = nullptr, *d_res = nullptr;
+    size_t fload_elems = 0, tmp_elems = 0;
+    int *d_part_mem = nullptr, *d_part_node = nullptr;
+    long long* d_argidx = nullptr;
+    int lastP = 0, last_ldP = 0;
+    bool last_morison = false, last_fem = false;
+    double last_fy = 355.0;
+
+    cudaEvent_t ev0[JK_NTIMERS], ev1[JK_NTIMERS];
+    bool ev_set[JK_NTIMERS];
+};
+
+#define JK_FAIL(h, code, ...)                                    \
+    do {                                                         \
+        char _b[512];                                            \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                   \
+        if (h) (h)->err = _b; else g_err = _b;                   \
+        return (code);                                           \
+    } while (0)
+
+#define CUDA_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) JK_FAIL(h, JK_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                          \
+    do {                                                                                         \
+        (h)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess) JK_FAIL(h, JK_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+}
+template <typename T>
+static void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static void tic(jk_handle_t h, int id) { cudaEventRecord(h->ev0[id], h->stream); }
+static void toc(jk_handle_t h, int id) { cudaEventRecord(h->ev1[id], h->stream); h->ev_set[id] = true; }
+
+extern "C" int jk_version(void) { return 100; }
+
+extern "C" const char* jk_last_error(jk_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+extern "C" int64_t jk_launch_count(jk_handle_t h) { return h ? h->launches : 0; }
+extern "C" void* jk_stream(jk_handle_t h) { return h ? (void*)h->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xyz, int n_members,
+                         const int32_t* conn, const int32_t* sec_id, int n_sec, const double* sec_props,
+                         jk_handle_t* out) {
+    if (!out) JK_FAIL((jk_handle_t)nullptr, JK_EINVAL, "jk_create: out is NULL");
+    *out = nullptr;
+    if (n_nodes <= 0 || n_members <= 0 || n_sec <= 0 || !xyz || !conn || !sec_id || !sec_props)
+        JK_FAIL((jk_handle_t)nullptr, JK_EINVAL, "jk_create: empty or NULL geometry (n_nodes=%d n_members=%d n_sec=%d)", n_nodes, n_members, n_sec);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        JK_FAIL((jk_handle_t)nullptr, JK_ENODEVICE, "jk_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) JK_FAIL((jk_handle_t)nullptr, JK_EINVAL, "jk_create: device %d out of range (%d devices)", device, ndev);
+    for (int m = 0; m < n_members; ++m) {
+        int a = conn[2 * m], b = conn[2 * m + 1];
+        if (a < 0 || a >= n_nodes || b < 0 || b >= n_nodes || a == b)
+            JK_FAIL((jk_handle_t)nullptr, JK_EINVAL, "jk_create: member %d has invalid end nodes (%d, %d)", m, a, b);
+        if (sec_id[m] < 0 || sec_id[m] >= n_sec) JK_FAIL((jk_handle_t)nullptr, JK_EINVAL, "jk_create: member %d has invalid section %d", m, sec_id[m]);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+        JK_FAIL((jk_handle_t)nullptr, JK_ENODEVICE, "jk_create: device %d is not sm_100-class (this library is built for sm_100a only)", device);
+
+    jk_handle_t h = new jk_handle_s();
+    h->device = device;
+    cudaSetDevice(device);
+    if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+    else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; JK_FAIL((jk_handle_t)nullptr, JK_ECUDA, "jk_create: cudaStreamCreate failed"); } h->own_stream = true; }
+    for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); h->ev_set[i] = false; }
+    h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
+    h->h_xyz.assign(xyz, xyz + 3 * (size_t)n_nodes);
+    h->h_conn.assign(conn, conn + 2 * (size_t)n_members);
+    h->h_sec.assign(sec_id, sec_id + n_members);
+    // node -> (member, end) adjacency in member order
+    h->h_adj_ptr.assign(n_nodes + 1, 0);
+    for (int m = 0; m < n_members; ++m) { h->h_adj_ptr[conn[2 * m] + 1]++; h->h_adj_ptr[conn[2 * m + 1] + 1]++; }
+    for (int i = 0; i < n_nodes; ++i) h->h_adj_ptr[i + 1] += h->h_adj_ptr[i];
+    h->h_adj.resize(2 * (size_t)n_members);
+    { std::vector<int> fill(h->h_adj_ptr.begin(), h->h_adj_ptr.end() - 1);
+      for (int m = 0; m < n_members; ++m) for (int e = 0; e < 2; ++e) h->h_adj[fill[conn[2 * m + e]]++] = (m << 1) | e; }
+    for (int i = 0; i < 8; ++i) { double rad = (45.0 * i) * (M_PI / 180.0); h->sp.cs[i] = cos(rad); h->sp.sn[i] = sin(rad); }
+
+    *out = h;   // from here on errors are reported on the handle; caller destroys it
+    CUDA_TRY(h, dev_alloc(&h->d_xyz, 3 * (size_t)n_nodes));
+    CUDA_TRY(h, dev_alloc(&h->d_conn, 2 * (size_t)n_members));
+    CUDA_TRY(h, dev_alloc(&h->d_sec, (size_t)n_members));
+    CUDA_TRY(h, dev_alloc(&h->d_secp, (size_t)n_sec * JK_SEC_NPROP));
+    CUDA_TRY(h, dev_alloc(&h->d_mc, (size_t)n_members * MC_STRIDE));
+    CUDA_TRY(h, dev_alloc(&h->d_Ke, (size_t)n_members * 144));
+    CUDA_TRY(h, dev_alloc(&h->d_Kl, (size_t)n_members * 144));
+    CUDA_TRY(h, dev_alloc(&h->d_adj_ptr, (size_t)n_nodes + 1));
+    CUDA_TRY(h, dev_alloc(&h->d_adj, 2 * (size_t)n_members));
+    CUDA_TRY(h, dev_alloc(&h->d_Fstatic, 6 * (size_t)n_nodes));
+    CUDA_TRY(h, dev_alloc(&h->d_info, 1));
+    CUDA_TRY(h, dev_alloc(&h->d_argval, 1));
+    CUDA_TRY(h, dev_alloc(&h->d_argidx, 1));
+    CUDA_TRY(h, dev_alloc(&h->d_res, 2));
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_xyz, xyz, 3 * (size_t)n_nodes * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_conn, conn, 2 * (size_t)n_members * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_sec, sec_id, (size_t)n_members * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_secp, sec_props, (size_t)n_sec * JK_SEC_NPROP * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_adj_ptr, h->h_adj_ptr.data(), ((size_t)n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_adj, h->h_adj.data(), 2 * (size_t)n_members * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_Fstatic, 0, 6 * (size_t)n_nodes * sizeof(double), s));
+    // opt in to large dynamic shared memory once
+    CUDA_TRY(h, cudaFuncSetAttribute(k_trailing_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_panel_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_tile_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INVERSE_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return JK_OK;
+}
+
+extern "C" int jk_destroy(jk_handle_t h) {
+    if (!h) return JK_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    dev_free(h->d_xyz); dev_free(h->d_secp); dev_free(h->d_mc); dev_free(h->d_Ke); dev_free(h->d_Kl);
+    dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
+    dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
+    dev_free(h->d_blocks); dev_free(h->d_contrib); dev_free(h->d_tiles); dev_free(h->d_Linv); dev_free(h->d_info);
+    dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp);
+    dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
+    dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
+    dev_free(h->d_table); dev_free(h->d_details); dev_free(h->d_Fload); dev_free(h->d_argval); dev_free(h->d_tmp); dev_free(h->d_res);
+    dev_free(h->d_part_mem); dev_free(h->d_part_node); dev_free(h->d_argidx);
+    for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return JK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse Cuthill-McKee over the free nodes (graph = members with both ends free)
+// ------------------------------------------------------------------------------------------------
+static void rcm_order(int Nn, const std::vector<int>& conn, const std::vector<char>& is_fixed, std::vector<int>& order) {
+    int M = (int)conn.size() / 2;
+    std::vector<std::vector<int>> nb(Nn);
+    for (int m = 0; m < M; ++m) {
+        int a = conn[2 * m], b = conn[2 * m + 1];
+        if (is_fixed[a] || is_fixed[b]) continue;
+        nb[a].push_back(b); nb[b].push_back(a);
+    }
+    for (auto& v : nb) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    std::vector<int> deg(Nn);
+    for (int i = 0; i < Nn; ++i) deg[i] = (int)nb[i].size();
+    std::vector<char> visited(Nn, 0);
+    std::vector<int> level(Nn, -1);
+    order.clear();
+    auto bfs_levels = [&](int root, std::vector<int>& comp) {   // returns eccentricity; comp = BFS order
+        comp.clear();
+        std::vector<int> touched;
+        std::queue<int> q;
+        level[root] = 0; q.push(root); touched.push_back(root);
+        int ecc = 0;
+        while (!q.empty()) {
+            int u = q.front(); q.pop(); comp.push_back(u);
+            ecc = std::max(ecc, level[u]);
+            for (int v : nb[u]) if (level[v] < 0) { level[v] = level[u] + 1; q.push(v); touched.push_back(v); }
+        }
+        return ecc;
+    };
+    std::vector<int> comp, comp2;
+    for (int seed = 0; seed < Nn; ++seed) {
+        if (is_fixed[seed] || visited[seed]) continue;
+        // pseudo-peripheral root (George-Liu)
+        int root = seed;
+        int ecc = bfs_levels(root, comp);
+        for (int it = 0; it < 8; ++it) {
+            int best = -1;
+            for (int u : comp) if (level[u] == ecc && (best < 0 || deg[u] < deg[best])) best = u;
+            for (int u : comp) level[u] = -1;
+            int ecc2 = bfs_levels(best, comp2);
+            if (ecc2 > ecc) { root = best; ecc = ecc2; comp.swap(comp2); }
+            else { for (int u : comp2) level[u] = -1; bfs_levels(root, comp); break; }
+        }
+        for (int u : comp) level[u] = -1;
+        // Cuthill-McKee from root: neighbours by increasing degree
+        std::vector<int> cm;
+        std::queue<int> q;
+        visited[root] = 1; q.push(root);
+        while (!q.empty()) {
+            int u = q.front(); q.pop(); cm.push_back(u);
+            std::vector<int> nx;
+            for (int v : nb[u]) if (!visited[v]) { visited[v] = 1; nx.push_back(v); }
+            std::sort(nx.begin(), nx.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
+            for (int v : nx) q.push(v);
+        }
+        order.insert(order.end(), cm.rbegin(), cm.rend());
+    }
+}
+
+extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_nodes, int ordering, int solver) {
+    if (!h) return JK_EINVAL;
+    if (n_fixed <= 0 || !fixed_nodes) JK_FAIL(h, JK_EINVAL, "jk_set_supports: at least one fixed node is required (K_ff would be singular)");
+    cudaSetDevice(h->device);
+    std::vector<char> is_fixed(h->Nn, 0);
+    h->h_fixed.clear();
+    for (int i = 0; i < n_fixed; ++i) {
+        int f = fixed_nodes[i];
+        if (f < 0 || f >= h->Nn) JK_FAIL(h, JK_EINVAL, "jk_set_supports: fixed node %d out of range", f);
+        if (!is_fixed[f]) { is_fixed[f] = 1; h->h_fixed.push_back(f); }
+    }
+    h->n_fixed = (int)h->h_fixed.size();
+    h->n_free_nodes = h->Nn - h->n_fixed;
+    if (h->n_free_nodes <= 0) JK_FAIL(h, JK_EINVAL, "jk_set_supports: every node is fixed");
+    if (ordering == JK_ORDER_RCM) rcm_order(h->Nn, h->h_conn, is_fixed, h->h_free_nodes);
+    else { h->h_free_nodes.clear(); for (int i = 0; i < h->Nn; ++i) if (!is_fixed[i]) h->h_free_nodes.push_back(i); }
+    if ((int)h->h_free_nodes.size() != h->n_free_nodes) JK_FAIL(h, JK_EINVAL, "jk_set_supports: internal ordering error");
+    h->h_node2slot.assign(h->Nn, 0);
+    for (int i = 0; i < h->n_fixed; ++i) h->h_node2slot[h->h_fixed[i]] = -1 - i;
+    for (int s = 0; s < h->n_free_nodes; ++s) h->h_node2slot[h->h_free_nodes[s]] = s;
+    h->n_free = 6 * h->n_free_nodes;
+    h->NT = ceil_div(h->n_free, NB);
+    h->n_pad = h->NT * NB;
+    h->solver = solver;
+
+    // 6x6 block list of K_ff with contributions in member order (deterministic assembly)
+    struct Contrib { long long key; int member, quad; };
+    std::vector<Contrib> cs;
+    cs.reserve(3 * (size_t)h->M);
+    int bw = 0;
+    auto span = [&](int rs, int cslot) { int I = (6 * rs + 5) / NB, J = (6 * cslot) / NB; bw = std::max(bw, I - J); };
+    for (int m = 0; m < h->M; ++m) {
+        int s0 = h->h_node2slot[h->h_conn[2 * m]], s1 = h->h_node2slot[h->h_conn[2 * m + 1]];
+        if (s0 >= 0) { cs.push_back({(long long)s0 * h->n_free_nodes + s0, m, 0}); span(s0, s0); }
+        if (s1 >= 0) { cs.push_back({(long long)s1 * h->n_free_nodes + s1, m, 3}); span(s1, s1); }
+        if (s0 >= 0 && s1 >= 0) {
+            if (s0 > s1) { cs.push_back({(long long)s0 * h->n_free_nodes + s1, m, (0 << 1) | 1}); span(s0, s1); }
+            else { cs.push_back({(long long)s1 * h->n_free_nodes + s0, m, (1 << 1) | 0}); span(s1, s0); }
+        }
+    }
+    std::stable_sort(cs.begin(), cs.end(), [](const Contrib& a, const Contrib& b) { return a.key < b.key; });
+    std::vector<KBlock> blocks;
+    std::vector<int2> contrib(cs.size());
+    for (size_t i = 0; i < cs.size(); ++i) {
+        contrib[i] = make_int2(cs[i].member, cs[i].quad);
+        if (i == 0 || cs[i].key != cs[i - 1].key) {
+            KBlock kb; kb.row_slot = (int)(cs[i].key / h->n_free_nodes); kb.col_slot = (int)(cs[i].key % h->n_free_nodes);
+            kb.start = (int)i; kb.count = 0; blocks.push_back(kb);
+        }
+        blocks.back().count++;
+    }
+    // free nodes with no member at all would make K_ff singular; report it now
+    { std::vector<char> touched(h->n_free_nodes, 0);
+      for (auto& b : blocks) if (b.row_slot == b.col_slot) touched[b.row_slot] = 1;
+      for (int s = 0; s < h->n_free_nodes; ++s) if (!touched[s]) JK_FAIL(h, JK_EINVAL, "jk_set_supports: free node %d has no member attached", h->h_free_nodes[s]); }
+    h->nblocks = (int)blocks.size();
+    h->bw = (solver == JK_SOLVER_DENSE) ? (h->NT - 1) : std::min(bw, h->NT - 1);
+    h->tiles_elems = (size_t)h->NT * (size_t)(h->bw + 1) * NB * NB;
+
+    CUDA_TRY(h, dev_alloc(&h->d_node2slot, (size_t)h->Nn));
+    CUDA_TRY(h, dev_alloc(&h->d_fixed_nodes, (size_t)h->n_fixed));
+    CUDA_TRY(h, dev_alloc(&h->d_free_nodes, (size_t)h->n_free_nodes));
+    CUDA_TRY(h, dev_alloc(&h->d_blocks, blocks.size()));
+    CUDA_TRY(h, dev_alloc(&h->d_contrib, contrib.size()));
+    CUDA_TRY(h, dev_alloc(&h->d_tiles, h->tiles_elems));
+    CUDA_TRY(h, dev_alloc(&h->d_Linv, (size_t)h->NT * NB * NB));
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_node2slot, h->h_node2slot.data(), (size_t)h->Nn * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_blocks, blocks.data(), blocks.size() * sizeof(KBlock), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_contrib, contrib.data(), contrib.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->have_supports = true; h->assembled = false; h->factored = false;
+    // buffers sized by n_pad / n_fixed must be rebuilt
+    h->cap_ldP = 0;
+    return JK_OK;
+}
+
+extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
+    if (!h) return JK_EINVAL;
+    if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "jk_assemble: call jk_set_supports first");
+    if (!(E > 0) || !(G > 0)) JK_FAIL(h, JK_EINVAL, "jk_assemble: E and G must be positive");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    h->E = E; h->G = G;
+    tic(h, JK_T_ASSEMBLE);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_tiles, 0, h->tiles_elems * sizeof(double), s));
+    k_member_setup<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, h->d_xyz, h->d_conn, h->d_sec, h->d_secp, JK_SEC_NPROP, E, G, h->d_mc, h->d_Ke, h->d_Kl);
+    LAUNCH_CHECK(h);
+    k_assemble_blocks<<<h->nblocks, 64, 0, s>>>(h->nblocks, h->d_blocks, h->d_contrib, h->d_Ke, h->d_tiles, h->bw);
+    LAUNCH_CHECK(h);
+    if (h->n_pad > h->n_free) { k_pad_identity<<<1, NB, 0, s>>>(h->n_free, h->n_pad, h->d_tiles, h->bw); LAUNCH_CHECK(h); }
+    toc(h, JK_T_ASSEMBLE);
+    h->assembled = true; h->factored = false;
+    return JK_OK;
+}
+
+extern "C" int jk_factor(jk_handle_t h) {
+    if (!h) return JK_EINVAL;
+    if (!h->assembled) JK_FAIL(h, JK_ESTATE, "jk_factor: call jk_assemble first");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    tic(h, JK_T_FACTOR);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), s));
+    for (int k = 0; k < h->NT; ++k) {
+        int w = std::min(h->bw, h->NT - 1 - k);
+        k_potrf_tile<<<1, 256, 0, s>>>(h->d_tiles, k, h->bw, h->d_info);
+        LAUNCH_CHECK(h);
+        if (w > 0) {
+            k_panel_trsm<<<w, NB, PANEL_SMEM, s>>>(h->d_tiles, k, h->bw);
+            LAUNCH_CHECK(h);
+            k_trailing_update<<<w * (w + 1) / 2, 128, UPDATE_SMEM, s>>>(h->d_tiles, k, w, h->bw);
+            LAUNCH_CHECK(h);
+        }
+    }
+    k_tile_inverse<<<h->NT, 256, INVERSE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->bw);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_FACTOR);
+    int info = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (info != 0) {
+        h->assembled = false;   // tiles were overwritten
+        JK_FAIL(h, JK_ENOTSPD, "jk_factor: K_ff is not positive definite (pivot %d <= 0): structure is a mechanism or badly supported", info - 1);
+    }
+    h->factored = true;
+    h->assembled = false;       // the tile storage now holds L
+    return JK_OK;
+}
+
+extern "C" int jk_set_static_load(jk_handle_t h, const double* F) {
+    if (!h || !F) return JK_EINVAL;
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_Fstatic, F, 6 * (size_t)h->Nn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return JK_OK;
+}
+
+extern "C" int jk_set_wave_airy(jk_handle_t h, double a, double k, double omega, double d, double U_c, double dt) {
+    if (!h) return JK_EINVAL;
+    if (!(k > 0) || !(omega > 0) || !(d > 0) || !(dt > 0)) JK_FAIL(h, JK_EINVAL, "jk_set_wave_airy: k, omega, d, dt must be positive");
+    h->wv.a = a; h->wv.k = k; h->wv.omega = omega; h->wv.d = d; h->wv.Uc = U_c; h->wv.dt = dt; h->wv.inv_dt = 1.0 / dt;
+    h->have_wave = true; h->gp_valid = false;
+    return JK_OK;
+}
+
+extern "C" int jk_set_wave_fourier(jk_handle_t h, double, double, double, double, double, int, const double*, const double*) {
+    if (!h) return JK_EINVAL;
+    JK_FAIL(h, JK_EINVAL, "jk_set_wave_fourier: Fourier-series kinematics are not built in this round (Airy closed form only)");
+}
+
+extern "C" int jk_set_morison(jk_handle_t h, double theta_wave, double theta_current, double rho, double Cd, double Cm,
+                              int n_gauss, const double* gauss_s, const double* gauss_w) {
+    if (!h || !gauss_s || !gauss_w) return JK_EINVAL;
+    if (n_gauss <= 0 || n_gauss > 64) JK_FAIL(h, JK_EINVAL, "jk_set_morison: n_gauss must be in 1..64");
+    cudaSetDevice(h->device);
+    h->rho = rho; h->Cd = Cd; h->Cm = Cm; h->ng = n_gauss;
+    h->wv.cos_w = cos(theta_wave); h->wv.sin_w = sin(theta_wave);
+    h->wv.uc_cos_c = cos(theta_current); h->wv.uc_sin_c = sin(theta_current);   // multiplied by U_c at launch
+    std::vector<double> gsw(2 * (size_t)n_gauss);
+    for (int i = 0; i < n_gauss; ++i) { gsw[i] = gauss_s[i]; gsw[n_gauss + i] = gauss_w[i]; }
+    CUDA_TRY(h, dev_alloc(&h->d_gsw, gsw.size()));
+    CUDA_TRY(h, dev_alloc(&h->d_gp, (size_t)h->M * n_gauss * GP_STRIDE));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_gsw, gsw.data(), gsw.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_morison = true; h->gp_valid = false;
+    return JK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan buffers
+// ------------------------------------------------------------------------------------------------
+static int ensure_buffers(jk_handle_t h, int P, bool need_fem, bool need_details) {
+    int ldP = ceil_div(P, SLAB) * SLAB;
+    bool need = ldP > h->cap_ldP || (need_details && !h->cap_details) || (need_fem && !h->d_X);
+    if (!need) return JK_OK;
+    ldP = std::max(ldP, h->cap_ldP);
+    size_t l = (size_t)ldP;
+    int n_mchunk = ceil_div(h->M, MCHUNK), n_nchunk = ceil_div(h->Nn, NCHUNK);
+    CUDA_TRY(h, dev_alloc(&h->d_t, l));
+    CUDA_TRY(h, dev_alloc(&h->d_trig, 4 * l));
+    CUDA_TRY(h, dev_alloc(&h->d_Fm, (size_t)h->M * 6 * l));
+    CUDA_TRY(h, dev_alloc(&h->d_totpart, (size_t)n_mchunk * 9 * l));
+    CUDA_TRY(h, dev_alloc(&h->d_table, l * JK_TABLE_NCOL));
+    if (need_details || h->cap_details) { CUDA_TRY(h, dev_alloc(&h->d_details, (size_t)h->M * 4 * l)); h->cap_details = true; }
+    if (need_fem || h->d_X) {
+        if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "supports not set");
+        CUDA_TRY(h, dev_alloc(&h->d_X, (size_t)h->n_pad * l));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_X, 0, (size_t)h->n_pad * l * sizeof(double), h->stream));
+        CUDA_TRY(h, dev_alloc(&h->d_Ffix, (size_t)h->n_fixed * 6 * l));
+        CUDA_TRY(h, dev_alloc(&h->d_react, (size_t)h->n_fixed * 6 * l));
+        CUDA_TRY(h, dev_alloc(&h->d_rows, (size_t)h->M * JK_MEMBER_NCOL * l));
+        CUDA_TRY(h, dev_alloc(&h->d_part_util, (size_t)n_mchunk * l));
+        CUDA_TRY(h, dev_alloc(&h->d_part_vm, (size_t)n_mchunk * l));
+        CUDA_TRY(h, dev_alloc(&h->d_part_mem, (size_t)n_mchunk * l));
+        CUDA_TRY(h, dev_alloc(&h->d_part_disp, (size_t)n_nchunk * l));
+        CUDA_TRY(h, dev_alloc(&h->d_part_node, (size_t)n_nchunk * l));
+    }
+    h->cap_ldP = ldP;
+    return JK_OK;
+}
+
+static int ensure_tmp(jk_handle_t h, size_t n) {
+    if (n <= h->tmp_elems) return JK_OK;
+    CUDA_TRY(h, dev_alloc(&h->d_tmp, n));
+    h->tmp_elems = n;
+    return JK_OK;
+}
+
+static WaveAiry launch_wave(jk_handle_t h) {
+    WaveAiry w = h->wv;
+    w.uc_cos_c = h->wv.Uc * h->wv.uc_cos_c;   // U_c * cos(theta_c), GUI.py:582
+    w.uc_sin_c = h->wv.Uc * h->wv.uc_sin_c;
+    return w;
+}
+
+// Morison stage for the phases already in d_t: trig tables, Gauss-point tables (once per wave), K1
+static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
+    cudaStream_t s = h->stream;
+    WaveAiry w = launch_wave(h);
+    tic(h, JK_T_WAVE_SETUP);
+    if (!h->gp_valid) {
+        int n = h->M * h->ng;
+        k_gauss_setup_airy<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_gp);
+        LAUNCH_CHECK(h);
+        h->gp_valid = true;
+    }
+    k_phase_setup<<<ceil_div(ldP, 128), 128, 0, s>>>(P, ldP, h->d_t, w.omega, w.dt, h->d_trig);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_WAVE_SETUP);
+    tic(h, JK_T_MORISON);
+    dim3 grid(ceil_div(ldP, PH_TPB), ceil_div(h->M, MCHUNK));
+    size_t smem = ((size_t)MCHUNK * h->ng * GP_STRIDE + MCHUNK * 8 + 2 * h->ng) * sizeof(double);
+    double cD0 = 0.5 * h->rho * h->Cd, cI0 = h->rho * h->Cm;
+    if (details) {
+        CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details);
+    } else {
+        CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_morison_airy<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
+    }
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_MORISON);
+    return JK_OK;
+}
+
+// member constants are produced by jk_assemble; Morison-only use needs them too
+static int ensure_member_consts(jk_handle_t h) {
+    if (h->E > 0) return JK_OK;   // jk_assemble ran
+    // geometry-only constants: run the setup kernel with unit moduli (stiffness entries unused by Morison)
+    k_member_setup<<<ceil_div(h->M, 128), 128, 0, h->stream>>>(h->M, h->d_xyz, h->d_conn, h->d_sec, h->d_secp, JK_SEC_NPROP, 1.0, 1.0, h->d_mc, h->d_Ke, h->d_Kl);
+    LAUNCH_CHECK(h);
+    return JK_OK;
+}
+
+static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool fem) {
+    cudaStream_t s = h->stream;
+    tic(h, JK_T_REDUCE);
+    int n_mchunk = ceil_div(h->M, MCHUNK), n_nchunk = ceil_div(h->Nn, NCHUNK);
+    k_phase_reduce<<<ceil_div(P, 128), 128, 0, s>>>(P, ldP, h->d_t, n_mchunk, morison ? h->d_totpart : nullptr,
+                                                     n_mchunk, fem ? h->d_part_util : nullptr, h->d_part_vm, h->d_part_mem,
+                                                     n_nchunk, fem ? h->d_part_disp : nullptr, h->d_part_node,
+                                                     h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL);
+    LAUNCH_CHECK(h);
+    k_argmax<<<1, 1024, 0, s>>>(P, h->d_table, JK_TABLE_NCOL, morison ? JK_COL_TOTAL_KN : JK_COL_MAX_UTIL, h->d_argval, h->d_argidx);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_REDUCE);
+    return JK_OK;
+}
+
+// solve + post for the right-hand sides already in d_X / d_Ffix
+static int run_fem(jk_handle_t h, int ldP, double fy) {
+    cudaStream_t s = h->stream;
+    int nslab = ldP / SLAB;
+    tic(h, JK_T_SOLVE_FWD);
+    k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_SOLVE_FWD);
+    tic(h, JK_T_SOLVE_BWD);
+    k_slab_sweep<true><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_SOLVE_BWD);
+    tic(h, JK_T_POST);
+    dim3 gm(ceil_div(ldP, PH_TPB), ceil_div(h->M, MCHUNK));
+    k_member_post<<<gm, PH_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
+                                        h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
+    LAUNCH_CHECK(h);
+    dim3 gn(ceil_div(ldP, PH_TPB), ceil_div(h->Nn, NCHUNK));
+    k_node_post<<<gn, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_part_disp, h->d_part_node);
+    LAUNCH_CHECK(h);
+    dim3 gr(ceil_div(ldP, PH_TPB), h->n_fixed);
+    k_node_residual<<<gr, PH_TPB, 0, s>>>(h->n_fixed, h->d_fixed_nodes, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn,
+                                          h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Ffix, h->d_react);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_POST);
+    return JK_OK;
+}
+
+static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
+    int ldP = ceil_div(P, SLAB) * SLAB;
+    cudaStream_t s = h->stream;
+    int rc;
+    if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
+    if ((rc = run_morison(h, P, ldP, false)) != JK_OK) return rc;
+    if (fem) {
+        tic(h, JK_T_RHS);
+        dim3 g(ceil_div(ldP, PH_TPB), h->Nn);
+        k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
+                                         h->d_X, h->d_Ffix, nullptr);
+        LAUNCH_CHECK(h);
+        toc(h, JK_T_RHS);
+        if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
+    }
+    if ((rc = reduce_and_argmax(h, P, ldP, true, fem)) != JK_OK) return rc;
+    h->lastP = P; h->last_ldP = ldP; h->last_morison = true; h->last_fem = fem; h->last_fy = fy;
+    return JK_OK;
+}
+
+static int check_scan_ready(jk_handle_t h, int P, const void* t, bool fem) {
+    if (P <= 0 || !t) JK_FAIL(h, JK_EINVAL, "phase scan: P must be positive and t non-NULL (P=%d)", P);
+    if (!h->have_wave || !h->have_morison) JK_FAIL(h, JK_ESTATE, "phase scan: call jk_set_wave_* and jk_set_morison first");
+    if (fem && !h->factored) JK_FAIL(h, JK_ESTATE, "phase scan: call jk_assemble and jk_factor first");
+    return JK_OK;
+}
+
+extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* critical) {
+    if (!h) return JK_EINVAL;
+    if (P != h->lastP) JK_FAIL(h, JK_EINVAL, "jk_read_table: P=%d does not match the last scan (%d)", P, h->lastP);
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    long long idx = -1;
+    tic(h, JK_T_D2H);
+    if (table) CUDA_TRY(h, cudaMemcpyAsync(table, h->d_table, (size_t)P * JK_TABLE_NCOL * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&idx, h->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    toc(h, JK_T_D2H);
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (critical) *critical = (int64_t)idx;
+    return JK_OK;
+}
+
+static int scan_host(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical, bool fem) {
+    if (!h) return JK_EINVAL;
+    int rc = check_scan_ready(h, P, t, fem);
+    if (rc != JK_OK) return rc;
+    cudaSetDevice(h->device);
+    if ((rc = ensure_buffers(h, P, fem, false)) != JK_OK) return rc;
+    tic(h, JK_T_SCAN_TOTAL);
+    tic(h, JK_T_H2D);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    toc(h, JK_T_H2D);
+    if ((rc = scan_core(h, P, fy, fem)) != JK_OK) return rc;
+    toc(h, JK_T_SCAN_TOTAL);
+    return jk_read_table(h, P, table, critical);
+}
+
+extern "C" int jk_morison_scan(jk_handle_t h, int P, const double* t, double* table, int64_t* critical) {
+    return scan_host(h, P, t, 355.0, table, critical, false);
+}
+
+extern "C" int jk_phase_scan(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical) {
+    if (h && !(fy > 0)) JK_FAIL(h, JK_EINVAL, "jk_phase_scan: fy must be positive");
+    return scan_host(h, P, t, fy, table, critical, true);
+}
+
+extern "C" int jk_phase_scan_dev(jk_handle_t h, int P, const double* t_dev, double fy) {
+    if (!h) return JK_EINVAL;
+    int rc = check_scan_ready(h, P, t_dev, true);
+    if (rc != JK_OK) return rc;
+    if (!(fy > 0)) JK_FAIL(h, JK_EINVAL, "jk_phase_scan_dev: fy must be positive");
+    cudaSetDevice(h->device);
+    if ((rc = ensure_buffers(h, P, true, false)) != JK_OK) return rc;
+    tic(h, JK_T_SCAN_TOTAL);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t_dev, (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = scan_core(h, P, fy, true)) != JK_OK) return rc;
+    toc(h, JK_T_SCAN_TOTAL);
+    return JK_OK;
+}
+
+__global__ void k_nodal_single(int Nn, int ldP, int p, const double* __restrict__ Fm, const int* __restrict__ adj_ptr,
+                               const int* __restrict__ adj, double* __restrict__ nodal) {
+    int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= Nn) return;
+    double f[3] = {0, 0, 0};
+    for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
+        int m = adj[q] >> 1, end = adj[q] & 1;
+        size_t o = ((size_t)m * 6 + 3 * end) * ldP + p;
+        f[0] += Fm[o]; f[1] += Fm[o + ldP]; f[2] += Fm[o + 2 * (size_t)ldP];
+    }
+    nodal[3 * node] = f[0]; nodal[3 * node + 1] = f[1]; nodal[3 * node + 2] = f[2];
+}
+
+__global__ void k_gather_strided(int n, size_t stride, size_t offset, const double* __restrict__ src, double* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(size_t)i * stride + offset];
+}
+
+__global__ void k_gather_U(int Nn, int p, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot, double* __restrict__ U) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * Nn) return;
+    U[i] = load_u(X, node2slot, i / 6, i % 6, p, n_pad);
+}
+
+extern "C" int jk_morison_single(jk_handle_t h, double t, double* nodal_forces, double* totals, double* details) {
+    if (!h) return JK_EINVAL;
+    int rc = check_scan_ready(h, 1, &t, false);
+    if (rc != JK_OK) return rc;
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    if ((rc = ensure_buffers(h, 1, false, details != nullptr)) != JK_OK) return rc;
+    int ldP = SLAB;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_t, &t, sizeof(double), cudaMemcpyHostToDevice, s));
+    if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
+    if ((rc = run_morison(h, 1, ldP, details != nullptr)) != JK_OK) return rc;
+    int n_mchunk = ceil_div(h->M, MCHUNK);
+    if ((rc = ensure_tmp(h, 3 * (size_t)h->Nn + (size_t)n_mchunk * 9 + 4 * (size_t)h->M)) != JK_OK) return rc;
+    double* d_nodal = h->d_tmp;
+    double* d_part = h->d_tmp + 3 * (size_t)h->Nn;
+    double* d_det = d_part + (size_t)n_mchunk * 9;
+    k_nodal_single<<<ceil_div(h->Nn, 128), 128, 0, s>>>(h->Nn, ldP, 0, h->d_Fm, h->d_adj_ptr, h->d_adj, d_nodal);
+    LAUNCH_CHECK(h);
+    // totals: chunk partials of phase 0, summed in chunk (= member) order on the host side of the ABI
+    std::vector<double> part((size_t)n_mchunk * 9);
+    k_gather_strided<<<ceil_div(n_mchunk * 9, 128), 128, 0, s>>>(n_mchunk * 9, (size_t)ldP, 0, h->d_totpart, d_part);
+    LAUNCH_CHECK(h);
+    CUDA_TRY(h, cudaMemcpyAsync(part.data(), d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (totals) for (int k = 0; k < 9; ++k) { double v = 0.0; for (int c = 0; c < n_mchunk; ++c) v += part[(size_t)c * 9 + k]; totals[k] = v; }
+    if (nodal_forces) CUDA_TRY(h, cudaMemcpyAsync(nodal_forces, d_nodal, 3 * (size_t)h->Nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (details) {
+        k_gather_strided<<<ceil_div(h->M * 4, 128), 128, 0, s>>>(h->M * 4, (size_t)ldP, 0, h->d_details, d_det);
+        LAUNCH_CHECK(h);
+        CUDA_TRY(h, cudaMemcpyAsync(details, d_det, 4 * (size_t)h->M * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->lastP = 0;   // scan buffers no longer describe a scan
+    return JK_OK;
+}
+
+extern "C" int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy) {
+    if (!h) return JK_EINVAL;
+    if (nrhs <= 0 || !F) JK_FAIL(h, JK_EINVAL, "jk_solve: nrhs must be positive and F non-NULL");
+    if (!h->factored) JK_FAIL(h, JK_ESTATE, "jk_solve: call jk_assemble and jk_factor first");
+    if (!(fy > 0)) JK_FAIL(h, JK_EINVAL, "jk_solve: fy must be positive");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    int rc;
+    if ((rc = ensure_buffers(h, nrhs, true, false)) != JK_OK) return rc;
+    int ldP = ceil_div(nrhs, SLAB) * SLAB;
+    size_t nF = (size_t)nrhs * 6 * h->Nn;
+    if (nF > h->fload_elems) { CUDA_TRY(h, dev_alloc(&h->d_Fload, nF)); h->fload_elems = nF; }
+    tic(h, JK_T_SCAN_TOTAL);
+    tic(h, JK_T_H2D);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_Fload, F, nF * sizeof(double), cudaMemcpyHostToDevice, s));
+    toc(h, JK_T_H2D);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_t, 0, (size_t)ldP * sizeof(double), s));
+    tic(h, JK_T_RHS);
+    dim3 g(ceil_div(ldP, PH_TPB), h->Nn);
+    k_rhs_from_loads<<<g, PH_TPB, 0, s>>>(h->Nn, nrhs, ldP, h->n_pad, h->d_Fload, h->d_node2slot, h->d_X, h->d_Ffix);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_RHS);
+    if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
+    if ((rc = reduce_and_argmax(h, nrhs, ldP, false, true)) != JK_OK) return rc;
+    toc(h, JK_T_SCAN_TOTAL);
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->lastP = nrhs; h->last_ldP = ldP; h->last_morison = false; h->last_fem = true; h->last_fy = fy;
+    return JK_OK;
+}
+
+extern "C" int jk_fetch_phase(jk_handle_t h, int phase, double* U, double* reactions, double* member_rows,
+                              double* end_forces, double* nodal_forces) {
+    if (!h) return JK_EINVAL;
+    if (h->lastP <= 0) JK_FAIL(h, JK_ESTATE, "jk_fetch_phase: no scan or solve results are resident");
+    if (phase < 0 || phase >= h->lastP) JK_FAIL(h, JK_EINVAL, "jk_fetch_phase: phase %d out of range (0..%d)", phase, h->lastP - 1);
+    if ((U || reactions || member_rows || end_forces) && !h->last_fem) JK_FAIL(h, JK_ESTATE, "jk_fetch_phase: the last scan was Morison-only");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    int ldP = h->last_ldP, rc;
+    size_t nU = 6 * (size_t)h->Nn, nR = 6 * (size_t)h->n_fixed, nM = 7 * (size_t)h->M, nE = 12 * (size_t)h->M, nN = 3 * (size_t)h->Nn;
+    if ((rc = ensure_tmp(h, nU + nR + nM + nE + nN)) != JK_OK) return rc;
+    double *dU = h->d_tmp, *dR = dU + nU, *dM = dR + nR, *dE = dM + nM, *dN = dE + nE;
+    if (U) {
+        k_gather_U<<<ceil_div((int)nU, 128), 128, 0, s>>>(h->Nn, phase, h->n_pad, h->d_X, h->d_node2slot, dU); LAUNCH_CHECK(h);
+        CUDA_TRY(h, cudaMemcpyAsync(U, dU, nU * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (reactions) {
+        k_gather_strided<<<ceil_div((int)nR, 128), 128, 0, s>>>((int)nR, (size_t)ldP, (size_t)phase, h->d_react, dR); LAUNCH_CHECK(h);
+        CUDA_TRY(h, cudaMemcpyAsync(reactions, dR, nR * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (member_rows || end_forces) {
+        k_member_post_single<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, phase, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp,
+                                                               h->last_fy, dM, dE);
+        LAUNCH_CHECK(h);
+        if (member_rows) CUDA_TRY(h, cudaMemcpyAsync(member_rows, dM, nM * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (end_forces) CUDA_TRY(h, cudaMemcpyAsync(end_forces, dE, nE * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (nodal_forces) {
+        if (h->last_morison) { k_nodal_single<<<ceil_div(h->Nn, 128), 128, 0, s>>>(h->Nn, ldP, phase, h->d_Fm, h->d_adj_ptr, h->d_adj, dN); LAUNCH_CHECK(h); }
+        else CUDA_TRY(h, cudaMemsetAsync(dN, 0, nN * sizeof(double), s));
+        CUDA_TRY(h, cudaMemcpyAsync(nodal_forces, dN, nN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return JK_OK;
+}
+
+extern "C" int jk_fetch_member_column(jk_handle_t h, int member, int column, int P, double* out) {
+    if (!h || !out) return JK_EINVAL;
+    if (!h->last_fem || P != h->lastP) JK_FAIL(h, JK_ESTATE, "jk_fetch_member_column: no matching scan results are resident");
+    if (member < 0 || member >= h->M || column < 0 || column >= JK_MEMBER_NCOL) JK_FAIL(h, JK_EINVAL, "jk_fetch_member_column: bad member/column");
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_rows + ((size_t)member * JK_MEMBER_NCOL + column) * h->last_ldP, (size_t)P * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return JK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+extern "C" int jk_get_dims(jk_handle_t h, int32_t* out) {
+    if (!h || !out) return JK_EINVAL;
+    out[0] = h->Nn; out[1] = h->M; out[2] = h->n_fixed; out[3] = h->n_free; out[4] = h->n_pad; out[5] = NB; out[6] = h->bw; out[7] = h->NT;
+    return JK_OK;
+}
+
+extern "C" int jk_get_order(jk_handle_t h, int32_t* free_nodes) {
+    if (!h || !free_nodes) return JK_EINVAL;
+    if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "jk_get_order: supports not set");
+    std::copy(h->h_free_nodes.begin(), h->h_free_nodes.end(), free_nodes);
+    return JK_OK;
+}
+
+extern "C" int jk_get_K(jk_handle_t h, double* K) {
+    if (!h || !K) return JK_EINVAL;
+    if (!(h->E > 0)) JK_FAIL(h, JK_ESTATE, "jk_get_K: call jk_assemble first");
+    cudaSetDevice(h->device);
+    size_t n = 6 * (size_t)h->Nn;
+    if (n * n > ((size_t)1 << 31)) JK_FAIL(h, JK_EINVAL, "jk_get_K: dense K of %zu x %zu is refused (use the tile storage)", n, n);
+    int rc;
+    if ((rc = ensure_tmp(h, n * n)) != JK_OK) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_tmp, 0, n * n * sizeof(double), s));
+    size_t tot = (size_t)h->M * 144;
+    k_dense_K<<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(h->M, h->d_conn, h->d_Ke, h->d_tmp, (int)n);
+    LAUNCH_CHECK(h);
+    CUDA_TRY(h, cudaMemcpyAsync(K, h->d_tmp, n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return JK_OK;
+}
+
+extern "C" int jk_get_elements(jk_handle_t h, double* Ke, double* Kl, double* R, double* L) {
+    if (!h) return JK_EINVAL;
+    if (!(h->E > 0)) JK_FAIL(h, JK_ESTATE, "jk_get_elements: call jk_assemble first");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    if (Ke) CUDA_TRY(h, cudaMemcpyAsync(Ke, h->d_Ke, (size_t)h->M * 144 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (Kl) CUDA_TRY(h, cudaMemcpyAsync(Kl, h->d_Kl, (size_t)h->M * 144 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<double> mc;
+    if (R || L) {
+        mc.resize((size_t)h->M * MC_STRIDE);
+        CUDA_TRY(h, cudaMemcpyAsync(mc.data(), h->d_mc, mc.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    for (int m = 0; m < h->M && (R || L); ++m) {
+        if (R) for (int i = 0; i < 9; ++i) R[(size_t)m * 9 + i] = mc[(size_t)m * MC_STRIDE + MC_R + i];
+        if (L) L[m] = mc[(size_t)m * MC_STRIDE + MC_L];
+    }
+    return JK_OK;
+}
+
+extern "C" int jk_get_timings(jk_handle_t h, double* ms) {
+    if (!h || !ms) return JK_EINVAL;
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < JK_NTIMERS; ++i) {
+        ms[i] = -1.0;
+        if (h->ev_set[i]) { float f = 0; if (cudaEventElapsedTime(&f, h->ev0[i], h->ev1[i]) == cudaSuccess) ms[i] = f; }
+    }
+    return JK_OK;
+}
+
+// max |K u - F| over the free DOFs of all phases of the last scan, relative to max |F|
+__global__ void __launch_bounds__(PH_TPB)
+k_free_residual(int n_free_nodes, const int* __restrict__ free_nodes, int P, int ldP, int n_pad, const double* __restrict__ X,
+                const int* __restrict__ node2slot, const int* __restrict__ conn, const int* __restrict__ adj_ptr,
+                const int* __restrict__ adj, const double* __restrict__ Ke, const double* __restrict__ Fstatic,
+                const double* __restrict__ Fm /* null: loads from Fload */, const double* __restrict__ Fload, int Nn,
+                unsigned long long* __restrict__ out /* [2]: max |r|, max |F| as double bits */) {
+    int sidx = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double rmax = 0.0, fmaxv = 0.0;
+    if (sidx < n_free_nodes && p < P) {
+        int node = free_nodes[sidx];
+        double r[6] = {0, 0, 0, 0, 0, 0}, f[6];
+        for (int c = 0; c < 6; ++c) f[c] = Fm ? Fstatic[6 * node + c] : Fload[(size_t)p * 6 * Nn + 6 * node + c];
+        for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
+            int m = adj[q] >> 1, end = adj[q] & 1;
+            double ue[12];
+            for (int k = 0; k < 6; ++k) {
+                ue[k] = load_u(X, node2slot, conn[2 * m], k, p, n_pad);
+                ue[6 + k] = load_u(X, node2slot, conn[2 * m + 1], k, p, n_pad);
+            }
+            const double* ke = Ke + (size_t)m * 144 + (size_t)(6 * end) * 12;
+            for (int i = 0; i < 6; ++i) { double s = 0.0; for (int j = 0; j < 12; ++j) s = fma(ke[i * 12 + j], ue[j], s); r[i] += s; }
+            if (Fm) { size_t o = ((size_t)m * 6 + 3 * end) * ldP + p; f[0] += Fm[o]; f[1] += Fm[o + ldP]; f[2] += Fm[o + 2 * (size_t)ldP]; }
+        }
+        for (int i = 0; i < 6; ++i) { rmax = fmax(rmax, fabs(r[i] - f[i])); fmaxv = fmax(fmaxv, fabs(f[i])); }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        rmax = fmax(rmax, __shfl_down_sync(0xffffffffu, rmax, off));
+        fmaxv = fmax(fmaxv, __shfl_down_sync(0xffffffffu, fmaxv, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&out[0], (unsigned long long)__double_as_longlong(rmax));
+        atomicMax(&out[1], (unsigned long long)__double_as_longlong(fmaxv));
+    }
+}
+
+extern "C" int jk_residual(jk_handle_t h, double* rel) {
+    if (!h || !rel) return JK_EINVAL;
+    if (!h->last_fem || h->lastP <= 0) JK_FAIL(h, JK_ESTATE, "jk_residual: no FEM results are resident");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_res, 0, 2 * sizeof(double), s));
+    dim3 g(ceil_div(h->lastP, PH_TPB), h->n_free_nodes);
+    k_free_residual<<<g, PH_TPB, 0, s>>>(h->n_free_nodes, h->d_free_nodes, h->lastP, h->last_ldP, h->n_pad, h->d_X, h->d_node2slot,
+                                         h->d_conn, h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Fstatic,
+                                         h->last_morison ? h->d_Fm : nullptr, h->d_Fload, h->Nn, (unsigned long long*)h->d_res);
+    LAUNCH_CHECK(h);
+    double v[2];
+    CUDA_TRY(h, cudaMemcpyAsync(v, h->d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    *rel = v[1] > 0 ? v[0] / v[1] : v[0];
+    return JK_OK;
+}

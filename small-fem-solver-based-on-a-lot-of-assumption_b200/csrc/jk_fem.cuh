@@ -1,0 +1,352 @@
+// jk_fem.cuh -- element construction, deterministic assembly and post-processing kernels.
+//
+// Reference behaviour restated here (file:line = /root/reference/JacketAnalysisGUI_v2.py):
+//   k_member_setup      BeamElement3D.__init__/_compute_transformation_matrix/_compute_local_stiffness  361-422
+//   k_assemble_blocks   FEMSolver._assemble_global_stiffness + apply_boundary_conditions                457-479
+//   k_member_post       BeamElement3D.get_internal_forces + FEMSolver.get_member_internal_forces
+//                       + TubularSection.calc_stress_at_point                                           424-432, 504-533, 147-160
+//   k_reactions         FEMSolver.get_reactions                                                         492-502
+//   k_node_post         max nodal translation of run_analysis                                           2035-2040
+#pragma once
+#include "jk_common.cuh"
+
+namespace jk {
+
+// ----------------------------------------------------------------------------------------------
+// K2a: one thread per member -> constant row, global element matrix Ke (symmetric by construction)
+// ----------------------------------------------------------------------------------------------
+__global__ void k_member_setup(int M, const double* __restrict__ xyz, const int* __restrict__ conn,
+                               const int* __restrict__ sec, const double* __restrict__ secp, int nprop,
+                               double E, double G, double* __restrict__ mc, double* __restrict__ Ke,
+                               double* __restrict__ Kl_out) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    int a = conn[2 * m], b = conn[2 * m + 1];
+    double dx = xyz[3 * b] - xyz[3 * a], dy = xyz[3 * b + 1] - xyz[3 * a + 1], dz = xyz[3 * b + 2] - xyz[3 * a + 2];
+    double L = sqrt(dx * dx + dy * dy + dz * dz);
+    double lx[3] = {dx / L, dy / L, dz / L}, ly[3], lz[3];
+    if (fabs(lx[2]) > 0.999) {   // near-vertical member: ly = z x lx (GUI.py:374-378)
+        ly[0] = -lx[1]; ly[1] = lx[0]; ly[2] = 0.0;
+        double n = sqrt(ly[0] * ly[0] + ly[1] * ly[1] + ly[2] * ly[2]);
+        if (n > 1e-10) { ly[0] /= n; ly[1] /= n; ly[2] /= n; } else { ly[0] = 0.0; ly[1] = 1.0; ly[2] = 0.0; }
+        lz[0] = lx[1] * ly[2] - lx[2] * ly[1];
+        lz[1] = lx[2] * ly[0] - lx[0] * ly[2];
+        lz[2] = lx[0] * ly[1] - lx[1] * ly[0];
+    } else {                      // lz = lx x z, ly = lz x lx (GUI.py:380-382)
+        lz[0] = lx[1]; lz[1] = -lx[0]; lz[2] = 0.0;
+        double n = sqrt(lz[0] * lz[0] + lz[1] * lz[1] + lz[2] * lz[2]);
+        lz[0] /= n; lz[1] /= n; lz[2] /= n;
+        ly[0] = lz[1] * lx[2] - lz[2] * lx[1];
+        ly[1] = lz[2] * lx[0] - lz[0] * lx[2];
+        ly[2] = lz[0] * lx[1] - lz[1] * lx[0];
+    }
+    const double* sp = secp + (size_t)sec[m] * nprop;
+    double Do = sp[0], Ax = sp[1], Iy = sp[2], Iz = sp[3], Ix = sp[4], Ay = sp[5], Az = sp[6], Ro = sp[7];
+    double Lmm = L * 1000.0;
+    double L2 = Lmm * Lmm, L3 = L2 * Lmm;
+    double phy = 0.0, phz = 0.0;
+    if (Ay > 0.0 && Az > 0.0) {   // include_shear (GUI.py:394-396)
+        phy = 12.0 * E * Iz / (G * Az * L2);
+        phz = 12.0 * E * Iy / (G * Ay * L2);
+    }
+    double alpha = E * Ax / Lmm;
+    double bz = E * Iz / ((1.0 + phy) * L3);
+    double by = E * Iy / ((1.0 + phz) * L3);
+    double tors = G * Ix / Lmm;
+    double k12z = 12.0 * bz, k6zL = 6.0 * bz * Lmm, k4z = (4.0 + phy) * bz * L2, k2z = (2.0 - phy) * bz * L2;
+    double k12y = 12.0 * by, k6yL = 6.0 * by * Lmm, k4y = (4.0 + phz) * by * L2, k2y = (2.0 - phz) * by * L2;
+
+    double* c = mc + (size_t)m * MC_STRIDE;
+    c[MC_L] = L;
+    for (int i = 0; i < 3; ++i) { c[MC_E + i] = lx[i]; c[MC_R + i] = lx[i]; c[MC_R + 3 + i] = ly[i]; c[MC_R + 6 + i] = lz[i]; }
+    c[MC_ALPHA] = alpha; c[MC_BZ] = bz; c[MC_BY] = by; c[MC_TORS] = tors; c[MC_PHIY] = phy; c[MC_PHIZ] = phz;
+    c[MC_LMM] = Lmm;
+    double Dm = Do / 1000.0;
+    c[MC_D] = Dm; c[MC_ACROSS] = 3.141592653589793 * (Dm * Dm) / 4.0;
+    c[MC_AX] = Ax; c[MC_IY] = Iy; c[MC_IZ] = Iz; c[MC_IX] = Ix; c[MC_AY] = Ay; c[MC_AZ] = Az; c[MC_RO] = Ro;
+    c[MC_K12Z] = k12z; c[MC_K6ZL] = k6zL; c[MC_K4Z] = k4z; c[MC_K2Z] = k2z;
+    c[MC_K12Y] = k12y; c[MC_K6YL] = k6yL; c[MC_K4Y] = k4y; c[MC_K2Y] = k2y;
+    c[MC_IAX] = 1.0 / Ax; c[MC_IIY] = Iy > 0.0 ? 1.0 / Iy : 0.0; c[MC_IIZ] = Iz > 0.0 ? 1.0 / Iz : 0.0;
+    c[MC_IIX] = Ix > 0.0 ? 1.0 / Ix : 0.0; c[MC_IAY] = Ay > 0.0 ? 1.0 / Ay : 0.0; c[MC_IAZ] = Az > 0.0 ? 1.0 / Az : 0.0;
+    for (int i = 43; i < MC_STRIDE; ++i) c[i] = 0.0;
+
+    // local stiffness, entries as listed at GUI.py:406-421
+    double Kl[12][12];
+    for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) Kl[i][j] = 0.0;
+    Kl[0][0] = Kl[6][6] = alpha;   Kl[0][6] = Kl[6][0] = -alpha;
+    Kl[1][1] = Kl[7][7] = k12z;    Kl[1][7] = Kl[7][1] = -k12z;
+    Kl[1][5] = Kl[5][1] = Kl[1][11] = Kl[11][1] = k6zL;
+    Kl[7][5] = Kl[5][7] = Kl[7][11] = Kl[11][7] = -k6zL;
+    Kl[5][5] = Kl[11][11] = k4z;   Kl[5][11] = Kl[11][5] = k2z;
+    Kl[2][2] = Kl[8][8] = k12y;    Kl[2][8] = Kl[8][2] = -k12y;
+    Kl[2][4] = Kl[4][2] = Kl[2][10] = Kl[10][2] = -k6yL;
+    Kl[8][4] = Kl[4][8] = Kl[8][10] = Kl[10][8] = k6yL;
+    Kl[4][4] = Kl[10][10] = k4y;   Kl[4][10] = Kl[10][4] = k2y;
+    Kl[3][3] = Kl[9][9] = tors;    Kl[3][9] = Kl[9][3] = -tors;
+    if (Kl_out) for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) Kl_out[(size_t)m * 144 + i * 12 + j] = Kl[i][j];
+
+    // Ke = T^T (Kl T), T = blkdiag(R,R,R,R), R rows = lx, ly, lz.  Lower triangle computed, mirrored.
+    double Rm[3][3] = {{lx[0], lx[1], lx[2]}, {ly[0], ly[1], ly[2]}, {lz[0], lz[1], lz[2]}};
+    double W[12][12];
+    for (int i = 0; i < 12; ++i)
+        for (int bb = 0; bb < 4; ++bb)
+            for (int cc = 0; cc < 3; ++cc) {
+                double s = 0.0;
+                for (int j = 0; j < 3; ++j) s = fma(Kl[i][3 * bb + j], Rm[j][cc], s);
+                W[i][3 * bb + cc] = s;
+            }
+    double* ke = Ke + (size_t)m * 144;
+    for (int aa = 0; aa < 4; ++aa)
+        for (int r = 0; r < 3; ++r)
+            for (int col = 0; col <= 3 * aa + r; ++col) {
+                double s = 0.0;
+                for (int i = 0; i < 3; ++i) s = fma(Rm[i][r], W[3 * aa + i][col], s);
+                ke[(3 * aa + r) * 12 + col] = s;
+                ke[col * 12 + (3 * aa + r)] = s;
+            }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2b: deterministic segmented scatter-add.  One CUDA block (64 threads, 36 active) per 6x6 node
+// block of K_ff; its contributions (member, quadrant) are summed in member order.
+// ----------------------------------------------------------------------------------------------
+struct KBlock { int row_slot, col_slot, start, count; };
+
+__global__ void k_assemble_blocks(int nblocks, const KBlock* __restrict__ blocks, const int2* __restrict__ contrib,
+                                  const double* __restrict__ Ke, double* __restrict__ tiles, int bw) {
+    int bi = blockIdx.x;
+    if (bi >= nblocks) return;
+    int tid = threadIdx.x;
+    if (tid >= 36) return;
+    int r = tid / 6, c = tid % 6;
+    KBlock kb = blocks[bi];
+    double s = 0.0;
+    for (int i = 0; i < kb.count; ++i) {
+        int2 ct = contrib[kb.start + i];          // x = member, y = (row quadrant << 1) | col quadrant
+        int qr = (ct.y >> 1) & 1, qc = ct.y & 1;
+        s += Ke[(size_t)ct.x * 144 + (6 * qr + r) * 12 + (6 * qc + c)];
+    }
+    int Rg = 6 * kb.row_slot + r, Cg = 6 * kb.col_slot + c;
+    if (Rg < Cg) return;                           // only the lower triangle is stored
+    int I = Rg / NB, J = Cg / NB;
+    tiles[tile_off(I, J, bw) + (size_t)(Rg % NB) * NB + (Cg % NB)] = s;
+}
+
+// identity on the padded tail of the last diagonal tile so the factor is defined there
+__global__ void k_pad_identity(int n_free, int n_pad, double* __restrict__ tiles, int bw) {
+    int r = n_free + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    int I = r / NB;
+    tiles[tile_off(I, I, bw) + (size_t)(r % NB) * NB + (r % NB)] = 1.0;
+}
+
+// dense K in the reference's DOF order (FEMSolver.K_global accessor / parity tests only).
+// One thread per (member, entry); summation order is not fixed here (atomics) -- the solver never reads this.
+__global__ void k_dense_K(int M, const int* __restrict__ conn, const double* __restrict__ Ke, double* __restrict__ K, int n_dof) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)M * 144) return;
+    int m = (int)(idx / 144), e = (int)(idx % 144), ii = e / 12, jj = e % 12;
+    int di = 6 * conn[2 * m + (ii >= 6)] + (ii % 6), dj = 6 * conn[2 * m + (jj >= 6)] + (jj % 6);
+    atomicAdd(&K[(size_t)di * n_dof + dj], Ke[idx]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// element end forces from element displacements (local axes)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void element_local_forces(const double* __restrict__ c, const double* ue, double* Fl) {
+    double ul[12];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            ul[3 * a + i] = fma(c[MC_R + 3 * i + 2], ue[3 * a + 2], fma(c[MC_R + 3 * i + 1], ue[3 * a + 1], c[MC_R + 3 * i] * ue[3 * a]));
+    const double al = c[MC_ALPHA], to = c[MC_TORS];
+    const double k12z = c[MC_K12Z], k6zL = c[MC_K6ZL], k4z = c[MC_K4Z], k2z = c[MC_K2Z];
+    const double k12y = c[MC_K12Y], k6yL = c[MC_K6YL], k4y = c[MC_K4Y], k2y = c[MC_K2Y];
+    Fl[0] = fma(-al, ul[6], al * ul[0]);
+    Fl[1] = fma(k6zL, ul[11], fma(-k12z, ul[7], fma(k6zL, ul[5], k12z * ul[1])));
+    Fl[2] = fma(-k6yL, ul[10], fma(-k12y, ul[8], fma(-k6yL, ul[4], k12y * ul[2])));
+    Fl[3] = fma(-to, ul[9], to * ul[3]);
+    Fl[4] = fma(k2y, ul[10], fma(k6yL, ul[8], fma(k4y, ul[4], -k6yL * ul[2])));
+    Fl[5] = fma(k2z, ul[11], fma(-k6zL, ul[7], fma(k4z, ul[5], k6zL * ul[1])));
+    Fl[6] = fma(al, ul[6], -al * ul[0]);
+    Fl[7] = fma(-k6zL, ul[11], fma(k12z, ul[7], fma(-k6zL, ul[5], -k12z * ul[1])));
+    Fl[8] = fma(k6yL, ul[10], fma(k12y, ul[8], fma(k6yL, ul[4], -k12y * ul[2])));
+    Fl[9] = fma(to, ul[9], -to * ul[3]);
+    Fl[10] = fma(k4y, ul[10], fma(k6yL, ul[8], fma(k2y, ul[4], -k6yL * ul[2])));
+    Fl[11] = fma(k4z, ul[11], fma(-k6zL, ul[7], fma(k2z, ul[5], k6zL * ul[1])));
+}
+
+// cos/sin of the 8 stress points 0,45,...,315 deg (GUI.py:139-145); filled by the host with libm
+struct StressPts { double cs[8], sn[8]; };
+
+// per-member stress-point coefficients: pt[3*i + {0,1,2}] = y_i/Iz, z_i/Iy, R_i/Ix for the 8 points of
+// TubularSection.get_stress_points (GUI.py:139-145)
+__device__ __forceinline__ void stress_point_coeffs(const double* __restrict__ c, const StressPts& sp, int i, double* pt) {
+    double y = c[MC_RO] * sp.cs[i], z = c[MC_RO] * sp.sn[i];
+    pt[0] = y * c[MC_IIZ];
+    pt[1] = z * c[MC_IIY];
+    pt[2] = sqrt(fma(y, y, z * z)) * c[MC_IIX];
+}
+
+// 7 result fields of one member from its 12 local end forces (GUI.py:514-532)
+__device__ __forceinline__ void member_row(const double* __restrict__ c, const double* __restrict__ pt, const double* Fl,
+                                           double inv_fy, double* row) {
+    // node-1 forces carry the sign flip of GUI.py:428-429
+    double Fx = -Fl[0], Fy = -Fl[1], Fz = -Fl[2], Mx = -Fl[3], My = -Fl[4], Mz = -Fl[5];
+    double sFx = Fx * c[MC_IAX];
+    double tFy = Fy * c[MC_IAY], tFz = Fz * c[MC_IAZ];
+    double tS = fma(tFy, tFy, tFz * tFz);
+    double vm2max = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double sig = fma(Mz, pt[3 * i], fma(My, pt[3 * i + 1], sFx));
+        double tM = Mx * pt[3 * i + 2];
+        double tau2 = fma(tM, tM, tS);
+        double vm2 = fma(3.0, tau2, sig * sig);
+        vm2max = fmax(vm2max, vm2);
+    }
+    double vm = sqrt(vm2max);
+    row[0] = fmax(fabs(Fl[0]), fabs(Fl[6])) * 1e-3;
+    row[1] = fmax(fabs(Fl[1]), fabs(Fl[7])) * 1e-3;
+    row[2] = fmax(fabs(Fl[2]), fabs(Fl[8])) * 1e-3;
+    row[3] = fmax(fabs(Fl[4]), fabs(Fl[10])) * 1e-6;
+    row[4] = fmax(fabs(Fl[5]), fabs(Fl[11])) * 1e-6;
+    row[5] = vm;
+    row[6] = vm * inv_fy;
+}
+
+__device__ __forceinline__ double load_u(const double* __restrict__ X, const int* __restrict__ node2slot,
+                                         int node, int comp, int p, int n_pad) {
+    int s = node2slot[node];
+    return s >= 0 ? X[rhs_off(6 * s + comp, p, n_pad)] : 0.0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K5: block = 128 phases x MCHUNK members.  rows[m][7][ldP]; per-chunk running maxima.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PH_TPB)
+k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
+              const int* __restrict__ conn, const double* __restrict__ mc, StressPts sp, double fy,
+              double* __restrict__ rows, double* __restrict__ part_util, double* __restrict__ part_vm,
+              int* __restrict__ part_mem) {
+    __shared__ double s_mc[MCHUNK * MC_STRIDE];
+    __shared__ int s_slot[MCHUNK * 2];
+    __shared__ double s_pt[MCHUNK * 24];
+    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
+    int nm = min(MCHUNK, M - m0);
+    for (int i = threadIdx.x; i < nm * MC_STRIDE; i += blockDim.x) s_mc[i] = mc[(size_t)m0 * MC_STRIDE + i];
+    for (int i = threadIdx.x; i < nm * 2; i += blockDim.x) s_slot[i] = node2slot[conn[2 * m0 + i]];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nm * 8; i += blockDim.x) stress_point_coeffs(s_mc + (i / 8) * MC_STRIDE, sp, i % 8, s_pt + 3 * i);
+    __syncthreads();
+    const double inv_fy = 1.0 / fy;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ldP) return;
+    const size_t xbase = (size_t)(p / SLAB) * (size_t)n_pad * SLAB + (size_t)(p % SLAB);
+    double best_u = -1.0, best_vm = 0.0; int best_m = 0;
+    for (int mm = 0; mm < nm; ++mm) {
+        const double* c = s_mc + mm * MC_STRIDE;
+        double ue[12], Fl[12], row[7];
+        int s1 = s_slot[2 * mm], s2 = s_slot[2 * mm + 1];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            ue[k] = s1 >= 0 ? X[xbase + (size_t)(6 * s1 + k) * SLAB] : 0.0;
+            ue[6 + k] = s2 >= 0 ? X[xbase + (size_t)(6 * s2 + k) * SLAB] : 0.0;
+        }
+        element_local_forces(c, ue, Fl);
+        member_row(c, s_pt + mm * 24, Fl, inv_fy, row);
+        size_t o = ((size_t)(m0 + mm) * 7) * ldP + p;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) rows[o + (size_t)k * ldP] = row[k];
+        if (row[6] > best_u) { best_u = row[6]; best_vm = row[5]; best_m = m0 + mm; }
+    }
+    size_t po = (size_t)chunk * ldP + p;
+    part_util[po] = best_u; part_vm[po] = best_vm; part_mem[po] = best_m;
+}
+
+// single phase, compact outputs (jk_fetch_phase): rows[M*7], endf[M*12]
+__global__ void k_member_post_single(int M, int p, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
+                                     const int* __restrict__ conn, const double* __restrict__ mc, StressPts sp, double fy,
+                                     double* __restrict__ rows, double* __restrict__ endf) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double* c = mc + (size_t)m * MC_STRIDE;
+    double ue[12], Fl[12], row[7];
+    for (int k = 0; k < 6; ++k) {
+        ue[k] = load_u(X, node2slot, conn[2 * m], k, p, n_pad);
+        ue[6 + k] = load_u(X, node2slot, conn[2 * m + 1], k, p, n_pad);
+    }
+    element_local_forces(c, ue, Fl);
+    double pt[24];
+    for (int i = 0; i < 8; ++i) stress_point_coeffs(c, sp, i, pt + 3 * i);
+    member_row(c, pt, Fl, 1.0 / fy, row);
+    if (rows) for (int k = 0; k < 7; ++k) rows[(size_t)m * 7 + k] = row[k];
+    if (endf) for (int k = 0; k < 12; ++k) endf[(size_t)m * 12 + k] = k < 6 ? -Fl[k] : Fl[k];
+}
+
+// ----------------------------------------------------------------------------------------------
+// max nodal translation per phase: block = 128 phases x NCHUNK nodes
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PH_TPB)
+k_node_post(int Nn, int ldP, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
+            double* __restrict__ part_disp, int* __restrict__ part_node) {
+    int chunk = blockIdx.y, n0 = chunk * NCHUNK;
+    int nn = min(NCHUNK, Nn - n0);
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ldP) return;
+    const size_t xbase = (size_t)(p / SLAB) * (size_t)n_pad * SLAB + (size_t)(p % SLAB);
+    double best = 0.0; int bnode = -1;
+    for (int i = 0; i < nn; ++i) {
+        int s = node2slot[n0 + i];
+        double d = 0.0;
+        if (s >= 0) {
+            double ux = X[xbase + (size_t)(6 * s) * SLAB], uy = X[xbase + (size_t)(6 * s + 1) * SLAB], uz = X[xbase + (size_t)(6 * s + 2) * SLAB];
+            d = sqrt(ux * ux + uy * uy + uz * uz);
+        }
+        if (d > best) { best = d; bnode = n0 + i; }
+    }
+    part_disp[(size_t)chunk * ldP + p] = best;
+    part_node[(size_t)chunk * ldP + p] = bnode;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K u - F at the 6 DOF of selected nodes, matrix-free over the incident members (member order).
+//   mode 0: nodes = fixed nodes, F from Ffix[6*f+c][ldP]           -> reactions (GUI.py:493)
+//   mode 1: nodes = free nodes (by slot), F from the saved RHS copy -> residual diagnostic
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PH_TPB)
+k_node_residual(int n_sel, const int* __restrict__ sel_nodes, int ldP, int n_pad,
+                const double* __restrict__ X, const int* __restrict__ node2slot, const int* __restrict__ conn,
+                const int* __restrict__ adj_ptr, const int* __restrict__ adj, const double* __restrict__ Ke,
+                const double* __restrict__ Fsel /* [n_sel*6][ldP] */, double* __restrict__ out /* [n_sel*6][ldP] */) {
+    int f = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_sel || p >= ldP) return;
+    int node = sel_nodes[f];
+    double r[6] = {0, 0, 0, 0, 0, 0};
+    for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
+        int m = adj[q] >> 1, end = adj[q] & 1;
+        double ue[12];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            ue[k] = load_u(X, node2slot, conn[2 * m], k, p, n_pad);
+            ue[6 + k] = load_u(X, node2slot, conn[2 * m + 1], k, p, n_pad);
+        }
+        const double* ke = Ke + (size_t)m * 144 + (size_t)(6 * end) * 12;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) s = fma(ke[i * 12 + j], ue[j], s);
+            r[i] += s;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        size_t o = (size_t)(6 * f + i) * ldP + p;
+        out[o] = r[i] - Fsel[o];
+    }
+}
+
+}  // namespace jk

@@ -1,0 +1,294 @@
+// jk_morison.cuh -- Morison drag + inertia load integration over members x Gauss points x phases.
+//
+// Reference behaviour restated here (file:line = /root/reference/JacketAnalysisGUI_v2.py):
+//   RaschiiWave.eta / velocity / acceleration / get_kinematics (Airy closed form)   259-296
+//   MorisonCalculator.get_kinematics_3d                                             559-589
+//   MorisonCalculator.compute_all_morison_forces                                    591-682
+//   MorisonCalculator.find_critical_phase (the 8 row columns + first-max)           684-724
+//
+// The phase angle k x_w - omega t is split: cos/sin(k x_w) per Gauss point (phase independent,
+// k_gauss_setup) and cos/sin(omega t), cos/sin(omega (t+dt)) per phase (k_phase_setup); the kernel
+// combines them with the angle-addition formulas.  The forward-difference acceleration
+// (v(t+dt) - v(t)) / dt with the dry test at BOTH times (GUI.py:283-288, 267-270) is kept: a point
+// that is wet at t and dry at t+dt gets a = -v(t)/dt exactly as in the reference.
+#pragma once
+#include "jk_common.cuh"
+
+namespace jk {
+
+// per (member, gauss point): cos(k xw), sin(k xw), Cu = a w cosh(k(z+d))/sinh(kd), Cw (sinh), z
+__global__ void k_gauss_setup_airy(int M, int G, const double* __restrict__ xyz, const int* __restrict__ conn,
+                                   const double* __restrict__ gs, WaveAiry wv, double* __restrict__ gp) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * G) return;
+    int m = idx / G, g = idx % G;
+    int a = conn[2 * m], b = conn[2 * m + 1];
+    double s = gs[g];
+    // pos = coord1 + s * dL (GUI.py:625)
+    double x = xyz[3 * a] + s * (xyz[3 * b] - xyz[3 * a]);
+    double y = xyz[3 * a + 1] + s * (xyz[3 * b + 1] - xyz[3 * a + 1]);
+    double z = xyz[3 * a + 2] + s * (xyz[3 * b + 2] - xyz[3 * a + 2]);
+    double xw = __dadd_rn(__dmul_rn(x, wv.cos_w), __dmul_rn(y, wv.sin_w));   // GUI.py:562
+    double sk, ck;
+    sincos(wv.k * xw, &sk, &ck);
+    double kd = wv.k * wv.d, kz = wv.k * (z + wv.d);                          // GUI.py:277
+    double shkd = sinh(kd);
+    double* o = gp + (size_t)idx * GP_STRIDE;
+    o[0] = ck; o[1] = sk;
+    o[2] = wv.a * wv.omega * cosh(kz) / shkd;                                 // GUI.py:279
+    o[3] = wv.a * wv.omega * sinh(kz) / shkd;                                 // GUI.py:280
+    o[4] = z;
+}
+
+// per phase: cos/sin(omega t), cos/sin(omega (t + dt)) -> trig[4][ldP]; padded phases repeat the last t
+__global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, double omega, double dt, double* __restrict__ trig) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ldP) return;
+    double tt = t[min(p, P - 1)];
+    double s0, c0, s1, c1;
+    sincos(omega * tt, &s0, &c0);
+    sincos(omega * (tt + dt), &s1, &c1);
+    trig[p] = c0; trig[ldP + p] = s0; trig[2 * (size_t)ldP + p] = c1; trig[3 * (size_t)ldP + p] = s1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: block = 128 phases (one thread each) x MCHUNK members.
+//   Fm[m][6][ldP]          member end forces F1 (node1), F2 (node2) after linear lumping (GUI.py:658-659)
+//   totpart[chunk][9][ldP] chunk partial sums of drag / inertia / (drag+inertia) in member order
+//   details[m][4][ldP]     optional drag_kN, inertia_kN, total_kN, submerged_length (GUI.py:668-674)
+// ----------------------------------------------------------------------------------------------
+template <bool DETAILS>
+__global__ void __launch_bounds__(PH_TPB)
+k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
+               const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
+               WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
+               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details) {
+    extern __shared__ __align__(16) double smem[];
+    double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
+    double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][8]: e0 e1 e2 cD cI L
+    double* s_g = s_m + MCHUNK * 8;                        // s[G], w[G]
+    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
+    int nm = min(MCHUNK, M - m0);
+    for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        const double* c = mc + (size_t)(m0 + i) * MC_STRIDE;
+        s_m[8 * i + 0] = c[MC_E]; s_m[8 * i + 1] = c[MC_E + 1]; s_m[8 * i + 2] = c[MC_E + 2];
+        s_m[8 * i + 3] = cD0 * c[MC_D];                    // 0.5*rho*Cd*D      (GUI.py:649)
+        s_m[8 * i + 4] = cI0 * c[MC_ACROSS];               // rho*Cm*A_cross    (GUI.py:652)
+        s_m[8 * i + 5] = c[MC_L];
+    }
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_g[i] = gsw[i];
+    __syncthreads();
+
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ldP) return;
+    const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
+    double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
+
+    for (int mm = 0; mm < nm; ++mm) {
+        const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
+        const double cD = s_m[8 * mm + 3], cI = s_m[8 * mm + 4], L = s_m[8 * mm + 5];
+        double F1[3] = {0, 0, 0}, F2[3] = {0, 0, 0}, md[3] = {0, 0, 0}, mi[3] = {0, 0, 0};
+        double sub = 0.0;
+        const double* gpm = s_gp + mm * G * GP_STRIDE;
+        for (int g = 0; g < G; ++g) {
+            const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1];
+            const double Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3], z = gpm[g * GP_STRIDE + 4];
+            // cos / sin of (k xw - omega t) at t and t + dt
+            const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
+            const double eta0 = wv.a * c0;                                     // GUI.py:265
+            if (z > eta0) continue;                                            // dry at t (GUI.py:292, 627)
+            const double c1 = fma(skx, sw1, ckx * cw1), s1 = fma(skx, cw1, -(ckx * sw1));
+            const double eta1 = wv.a * c1;
+            const bool wet1 = !(z > eta1);                                     // GUI.py:269 at t + dt
+            const double u0 = fma(Cu, c0, wv.Uc), w0 = Cw * s0;                // GUI.py:279-281
+            const double u1 = wet1 ? fma(Cu, c1, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1 : 0.0;
+            const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;   // GUI.py:288
+            const double uwo = u0 - wv.Uc;                                     // GUI.py:573
+            const double U0 = fma(uwo, wv.cos_w, wv.uc_cos_c), U1 = fma(uwo, wv.sin_w, wv.uc_sin_c), U2 = w0;
+            const double A0 = du * wv.cos_w, A1 = du * wv.sin_w, A2 = dw;
+            const double Ue = fma(U2, e2, fma(U1, e1, U0 * e0));
+            const double Ae = fma(A2, e2, fma(A1, e1, A0 * e0));
+            const double Up0 = fma(-Ue, e0, U0), Up1 = fma(-Ue, e1, U1), Up2 = fma(-Ue, e2, U2);   // GUI.py:641
+            const double Ap0 = fma(-Ae, e0, A0), Ap1 = fma(-Ae, e1, A1), Ap2 = fma(-Ae, e2, A2);   // GUI.py:642
+            const double mag = sqrt(fma(Up2, Up2, fma(Up1, Up1, Up0 * Up0)));
+            const double s = s_g[g], w = s_g[G + g];
+            const double Lw = L * w;
+            const double kd_ = (mag > 1e-10) ? cD * mag * Lw : 0.0;            // GUI.py:648-651
+            const double ki_ = cI * Lw;
+            const double fd0 = kd_ * Up0, fd1 = kd_ * Up1, fd2 = kd_ * Up2;
+            const double fi0 = ki_ * Ap0, fi1 = ki_ * Ap1, fi2 = ki_ * Ap2;
+            const double ft0 = fd0 + fi0, ft1 = fd1 + fi1, ft2 = fd2 + fi2;
+            md[0] += fd0; md[1] += fd1; md[2] += fd2;
+            mi[0] += fi0; mi[1] += fi1; mi[2] += fi2;
+            const double s1m = 1.0 - s;
+            F1[0] = fma(s1m, ft0, F1[0]); F1[1] = fma(s1m, ft1, F1[1]); F1[2] = fma(s1m, ft2, F1[2]);
+            F2[0] = fma(s, ft0, F2[0]); F2[1] = fma(s, ft1, F2[1]); F2[2] = fma(s, ft2, F2[2]);
+            if (DETAILS) sub += Lw;
+        }
+        size_t o = ((size_t)(m0 + mm) * 6) * ldP + p;
+        Fm[o] = F1[0]; Fm[o + ldP] = F1[1]; Fm[o + 2 * (size_t)ldP] = F1[2];
+        Fm[o + 3 * (size_t)ldP] = F2[0]; Fm[o + 4 * (size_t)ldP] = F2[1]; Fm[o + 5 * (size_t)ldP] = F2[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { td[k] += md[k]; ti[k] += mi[k]; tm[k] += md[k] + mi[k]; }   // GUI.py:664-666
+        if (DETAILS) {
+            size_t od = ((size_t)(m0 + mm) * 4) * ldP + p;
+            double mt0 = md[0] + mi[0], mt1 = md[1] + mi[1], mt2 = md[2] + mi[2];
+            details[od] = sqrt(md[0] * md[0] + md[1] * md[1] + md[2] * md[2]) / 1000.0;
+            details[od + ldP] = sqrt(mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]) / 1000.0;
+            details[od + 2 * (size_t)ldP] = sqrt(mt0 * mt0 + mt1 * mt1 + mt2 * mt2) / 1000.0;
+            details[od + 3 * (size_t)ldP] = sub;
+        }
+    }
+    size_t ot = ((size_t)chunk * 9) * ldP + p;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        totpart[ot + (size_t)k * ldP] = td[k];
+        totpart[ot + (size_t)(3 + k) * ldP] = ti[k];
+        totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// RHS gather: thread = (node, phase).  Sums the member-end forces of the node's incident members in
+// member order (the reference's accumulation order, GUI.py:661-662), adds the static load and writes
+// the solver right-hand side (free nodes) or the load at the supports (fixed nodes, for reactions).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PH_TPB)
+k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const int* __restrict__ adj_ptr,
+             const int* __restrict__ adj, const int* __restrict__ node2slot, const double* __restrict__ Fstatic,
+             double* __restrict__ B, double* __restrict__ Ffix, double* __restrict__ nodal /* [Nn*3] single phase or null */) {
+    int node = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= Nn || p >= ldP) return;
+    double f[3] = {0, 0, 0};
+    for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
+        int m = adj[q] >> 1, end = adj[q] & 1;
+        size_t o = ((size_t)m * 6 + 3 * end) * ldP + p;
+        f[0] += Fm[o]; f[1] += Fm[o + ldP]; f[2] += Fm[o + 2 * (size_t)ldP];
+    }
+    if (nodal && p == 0) { nodal[3 * node] = f[0]; nodal[3 * node + 1] = f[1]; nodal[3 * node + 2] = f[2]; }
+    int s = node2slot[node];
+    if (s >= 0) {
+        if (!B) return;
+        size_t o = rhs_off(6 * s, p, n_pad);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + f[c];
+#pragma unroll
+        for (int c = 3; c < 6; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c];
+    } else {
+        if (!Ffix) return;
+        int fi = -1 - s;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + f[c];
+#pragma unroll
+        for (int c = 3; c < 6; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c];
+    }
+}
+
+// caller-built load cases (jk_solve): F[p][6*Nn] host layout already on device -> B / Ffix
+__global__ void __launch_bounds__(PH_TPB)
+k_rhs_from_loads(int Nn, int P, int ldP, int n_pad, const double* __restrict__ F, const int* __restrict__ node2slot,
+                 double* __restrict__ B, double* __restrict__ Ffix) {
+    int node = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= Nn || p >= ldP) return;
+    int pp = min(p, P - 1);
+    int s = node2slot[node];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double v = F[(size_t)pp * 6 * Nn + 6 * node + c];
+        if (s >= 0) B[rhs_off(6 * s + c, p, n_pad)] = v;
+        else Ffix[(size_t)(6 * (-1 - s) + c) * ldP + p] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// per-phase table row from the chunk partials (chunk order = member / node order => deterministic)
+// ----------------------------------------------------------------------------------------------
+__global__ void k_phase_reduce(int P, int ldP, const double* __restrict__ t,
+                               int n_mchunk, const double* __restrict__ totpart,
+                               int n_pchunk, const double* __restrict__ part_util, const double* __restrict__ part_vm,
+                               const int* __restrict__ part_mem,
+                               int n_nchunk, const double* __restrict__ part_disp, const int* __restrict__ part_node,
+                               int n_fixed, const double* __restrict__ react,
+                               double* __restrict__ table, int ncol) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double* row = table + (size_t)p * ncol;
+    for (int c = 0; c < ncol; ++c) row[c] = 0.0;
+    row[0] = t[p];
+    if (totpart) {
+        double v[9];
+        for (int k = 0; k < 9; ++k) {
+            double s = 0.0;
+            for (int ch = 0; ch < n_mchunk; ++ch) s += totpart[((size_t)ch * 9 + k) * ldP + p];
+            v[k] = s;
+        }
+        row[2] = sqrt(v[6] * v[6] + v[7] * v[7] + v[8] * v[8]) / 1000.0;     // GUI.py:701, 708
+        row[3] = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 1000.0;
+        row[4] = sqrt(v[3] * v[3] + v[4] * v[4] + v[5] * v[5]) / 1000.0;
+        row[5] = v[6] / 1000.0; row[6] = v[7] / 1000.0; row[7] = v[8] / 1000.0;
+    }
+    if (part_disp) {
+        double best = 0.0; int bn = -1;
+        for (int ch = 0; ch < n_nchunk; ++ch) {
+            double d = part_disp[(size_t)ch * ldP + p];
+            if (d > best) { best = d; bn = part_node[(size_t)ch * ldP + p]; }
+        }
+        row[8] = best; row[9] = (double)bn;
+    }
+    if (part_util) {
+        double best = -1.0, bvm = 0.0; int bm = -1;
+        for (int ch = 0; ch < n_pchunk; ++ch) {
+            double u = part_util[(size_t)ch * ldP + p];
+            if (u > best) { best = u; bvm = part_vm[(size_t)ch * ldP + p]; bm = part_mem[(size_t)ch * ldP + p]; }
+        }
+        row[10] = best; row[11] = (double)bm; row[12] = bvm;
+    }
+    if (react) {
+        for (int c = 0; c < 3; ++c) {
+            double s = 0.0;
+            for (int f = 0; f < n_fixed; ++f) s += react[(size_t)(6 * f + c) * ldP + p];
+            row[13 + c] = s;
+        }
+    }
+}
+
+// K6: first index of the maximum of table[:, col] (Python max(key=...) semantics, GUI.py:717).
+// One block; per-thread strided scan, warp-shuffle reduce, then across warps.
+__global__ void k_argmax(int P, const double* __restrict__ table, int ncol, int col, double* __restrict__ out_val,
+                         long long* __restrict__ out_idx) {
+    double best = 0.0; long long bi = -1;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        double v = table[(size_t)p * ncol + col];
+        if (bi < 0 || v > best) { best = v; bi = p; }
+    }
+    auto better = [](double v, long long i, double bv, long long b) {
+        if (i < 0) return false;
+        if (b < 0) return true;
+        return v > bv || (v == bv && i < b);
+    };
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, best, off);
+        long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (lane == 0) { s_v[warp] = best; s_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        int nw = (blockDim.x + 31) / 32;
+        best = lane < nw ? s_v[lane] : 0.0; bi = lane < nw ? s_i[lane] : -1;
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, best, off);
+            long long oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { *out_val = best; *out_idx = bi; }
+    }
+}
+
+}  // namespace jk

@@ -1,0 +1,212 @@
+"""Engine: one GPU handle (include/jacket_b200.h) per structure.
+
+Owns the call order of the C ABI (create -> supports -> assemble -> factor ->
+loads / wave / Morison -> scan) and caches what has already been sent so the
+reference-style facade classes can be used in any order the GUI uses them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+
+def default_device():
+    for key in ("JK_DEVICE", "LOCAL_RANK"):
+        if key in os.environ:
+            return int(os.environ[key])
+    return 0
+
+
+class Engine:
+    def __init__(self, structure, device=None, stream=None, ordering="rcm", solver="banded"):
+        self.structure = structure
+        self.lib = L.lib()
+        self.device = default_device() if device is None else int(device)
+        self.ordering = {"rcm": L.ORDER_RCM, "natural": L.ORDER_NATURAL}[ordering]
+        self.solver = {"banded": L.SOLVER_BANDED, "dense": L.SOLVER_DENSE}[solver]
+        xyz, conn, sec_id, props, sections = structure.pack()
+        self.xyz, self.conn, self.sec_id, self.sections = xyz, conn, sec_id, sections
+        self.n_nodes, self.n_members = xyz.shape[0], conn.shape[0]
+        self.h = C.c_void_p()
+        rc = self.lib.jk_create(self.device, C.c_void_p(stream or 0), self.n_nodes, L.dptr(xyz), self.n_members,
+                                L.iptr(conn), L.iptr(sec_id), props.shape[0], L.dptr(props), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.jk_last_error(self.h if self.h.value else None)
+            if self.h.value:
+                self.lib.jk_destroy(self.h)
+                self.h = C.c_void_p()
+            raise L.JacketError(rc, msg.decode() if msg else "")
+        self._fixed = None
+        self._moduli = None
+        self._factored = False
+        self._static = None
+        self._wave_sig = None
+        self._morison_sig = None
+        self.fixed_idx = None
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.jk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        L.check(rc, self.h)
+
+    # -- FEM side ---------------------------------------------------------------
+    def set_supports(self, fixed_idx):
+        fixed_idx = L.i32(fixed_idx)
+        key = tuple(int(i) for i in fixed_idx)
+        if key == self._fixed:
+            return
+        self._ck(self.lib.jk_set_supports(self.h, len(fixed_idx), L.iptr(fixed_idx), self.ordering, self.solver))
+        self._fixed, self.fixed_idx = key, fixed_idx
+        self._assembled_for = None
+        self._factored = False
+
+    def assemble(self, E, G):
+        self._ck(self.lib.jk_assemble(self.h, float(E), float(G)))
+        self._moduli = (float(E), float(G))
+        self._factored = False
+
+    def factor(self):
+        self._ck(self.lib.jk_factor(self.h))
+        self._factored = True
+
+    def ensure_factored(self, fixed_idx, E, G):
+        self.set_supports(fixed_idx)
+        if not self._factored or self._moduli != (float(E), float(G)):
+            self.assemble(E, G)
+            self.factor()
+
+    def set_static_load(self, F):
+        F = L.f64(F).reshape(-1)
+        assert F.shape[0] == 6 * self.n_nodes
+        self._ck(self.lib.jk_set_static_load(self.h, L.dptr(F)))
+
+    # -- Morison side -----------------------------------------------------------
+    def set_wave(self, wave):
+        sig = wave.signature()
+        if sig != self._wave_sig:
+            self._ck(self.lib.jk_set_wave_airy(self.h, *wave.device_args()))
+            self._wave_sig = sig
+
+    def set_morison(self, theta_wave, theta_current, rho, Cd, Cm, n_gauss=15):
+        sig = (float(theta_wave), float(theta_current), float(rho), float(Cd), float(Cm), int(n_gauss))
+        if sig != self._morison_sig:
+            xi, wts = np.polynomial.legendre.leggauss(n_gauss)   # same rule as GUI.py:615-617
+            s = L.f64((xi + 1.0) / 2.0)
+            w = L.f64(wts / 2.0)
+            self._ck(self.lib.jk_set_morison(self.h, *sig[:5], n_gauss, L.dptr(s), L.dptr(w)))
+            self._morison_sig = sig
+
+    # -- scans ------------------------------------------------------------------
+    def morison_scan(self, t):
+        t = L.f64(t).reshape(-1)
+        table = np.zeros((t.shape[0], L.TABLE_NCOL))
+        crit = C.c_int64(-1)
+        self._ck(self.lib.jk_morison_scan(self.h, t.shape[0], L.dptr(t), L.dptr(table), C.byref(crit)))
+        return table, int(crit.value)
+
+    def morison_single(self, t, want_details=True):
+        nodal = np.zeros((self.n_nodes, 3))
+        totals = np.zeros(9)
+        details = np.zeros((self.n_members, L.DETAIL_NCOL)) if want_details else None
+        self._ck(self.lib.jk_morison_single(self.h, float(t), L.dptr(nodal), L.dptr(totals), L.dptr(details)))
+        return nodal, totals, details
+
+    def phase_scan(self, t, fy):
+        t = L.f64(t).reshape(-1)
+        table = np.zeros((t.shape[0], L.TABLE_NCOL))
+        crit = C.c_int64(-1)
+        self._ck(self.lib.jk_phase_scan(self.h, t.shape[0], L.dptr(t), float(fy), L.dptr(table), C.byref(crit)))
+        return table, int(crit.value)
+
+    def phase_scan_dev(self, P, t_dev_ptr, fy):
+        self._ck(self.lib.jk_phase_scan_dev(self.h, int(P), C.c_void_p(t_dev_ptr), float(fy)))
+
+    def read_table(self, P):
+        table = np.zeros((P, L.TABLE_NCOL))
+        crit = C.c_int64(-1)
+        self._ck(self.lib.jk_read_table(self.h, P, L.dptr(table), C.byref(crit)))
+        return table, int(crit.value)
+
+    def solve(self, F, fy=355.0):
+        F = L.f64(F).reshape(-1, 6 * self.n_nodes)
+        self._ck(self.lib.jk_solve(self.h, F.shape[0], L.dptr(F), float(fy)))
+
+    def fetch_phase(self, p, U=True, reactions=True, rows=True, end_forces=False, nodal=False):
+        n_fixed = len(self._fixed) if self._fixed else 0
+        out = {}
+        aU = np.zeros(6 * self.n_nodes) if U else None
+        aR = np.zeros((n_fixed, 6)) if reactions else None
+        aM = np.zeros((self.n_members, L.MEMBER_NCOL)) if rows else None
+        aE = np.zeros((self.n_members, 12)) if end_forces else None
+        aN = np.zeros((self.n_nodes, 3)) if nodal else None
+        self._ck(self.lib.jk_fetch_phase(self.h, int(p), L.dptr(aU), L.dptr(aR), L.dptr(aM), L.dptr(aE), L.dptr(aN)))
+        out.update(U=aU, reactions=aR, rows=aM, end_forces=aE, nodal_forces=aN)
+        return out
+
+    def member_column(self, member, column, P):
+        out = np.zeros(P)
+        self._ck(self.lib.jk_fetch_member_column(self.h, int(member), int(column), int(P), L.dptr(out)))
+        return out
+
+    # -- introspection ----------------------------------------------------------
+    def dims(self):
+        d = np.zeros(8, dtype=np.int32)
+        self._ck(self.lib.jk_get_dims(self.h, L.iptr(d)))
+        return dict(zip(("n_nodes", "n_members", "n_fixed", "n_free_dof", "n_pad", "tile", "band_tiles", "n_tiles"),
+                        (int(v) for v in d)))
+
+    def order(self):
+        d = self.dims()
+        o = np.zeros(d["n_nodes"] - d["n_fixed"], dtype=np.int32)
+        self._ck(self.lib.jk_get_order(self.h, L.iptr(o)))
+        return o
+
+    def dense_K(self):
+        n = 6 * self.n_nodes
+        K = np.zeros((n, n))
+        self._ck(self.lib.jk_get_K(self.h, L.dptr(K)))
+        return K
+
+    def elements(self):
+        M = self.n_members
+        Ke, Kl, R, Ln = np.zeros((M, 12, 12)), np.zeros((M, 12, 12)), np.zeros((M, 3, 3)), np.zeros(M)
+        self._ck(self.lib.jk_get_elements(self.h, L.dptr(Ke), L.dptr(Kl), L.dptr(R), L.dptr(Ln)))
+        return Ke, Kl, R, Ln
+
+    def timings(self):
+        ms = np.zeros(L.NTIMERS)
+        self._ck(self.lib.jk_get_timings(self.h, L.dptr(ms)))
+        return dict(zip(L.TIMER_NAMES, (float(v) for v in ms)))
+
+    def residual(self):
+        r = C.c_double(0.0)
+        self._ck(self.lib.jk_residual(self.h, C.byref(r)))
+        return float(r.value)
+
+    def launch_count(self):
+        return int(self.lib.jk_launch_count(self.h))
+
+    def stream(self):
+        return self.lib.jk_stream(self.h)
+
+
+def get_engine(structure, **kw):
+    """The structure's engine, created on first use (one handle per structure and GPU)."""
+    eng = getattr(structure, "_engine", None)
+    if eng is None or (kw and any(getattr(eng, k, None) != v for k, v in kw.items() if k == "device")):
+        eng = Engine(structure, **kw)
+        structure._engine = eng
+    return eng

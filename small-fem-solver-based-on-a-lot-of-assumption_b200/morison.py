@@ -1,0 +1,66 @@
+"""MorisonCalculator -- drop-in for GUI.py:539-724, evaluated on the GPU.
+
+``compute_all_morison_forces`` and ``find_critical_phase`` return the same
+dictionaries as the reference; the arithmetic runs in csrc/jk_morison.cuh.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .engine import get_engine
+
+
+def phase_times(T, n_steps):
+    """t_i = i*T/n_steps, evaluated like the reference does (GUI.py:696)."""
+    return np.array([i * T / n_steps for i in range(n_steps)], dtype=np.float64)
+
+
+def fill_phase_deg(table, omega):
+    """Column 1 of the table, bit-identical to GUI.py:697-698."""
+    table[:, 1] = np.degrees(omega * table[:, 0]) % 360
+    return table
+
+
+class MorisonCalculator:
+    def __init__(self, structure, wave, wave_direction=0.0, current_direction=0.0,
+                 Cd=0.7, Cm=2.0, rho_water=1025):
+        self.structure, self.wave = structure, wave
+        self.wave_dir_deg, self.current_dir_deg = wave_direction, current_direction
+        self.theta_wave = np.deg2rad(90.0 - wave_direction)       # compass -> math angle (GUI.py:555)
+        self.theta_current = np.deg2rad(90.0 - current_direction)
+        self.Cd, self.Cm, self.rho = Cd, Cm, rho_water
+
+    # ------------------------------------------------------------------------
+    def _engine(self, n_gauss=15):
+        eng = get_engine(self.structure)
+        eng.set_wave(self.wave)
+        eng.set_morison(self.theta_wave, self.theta_current, self.rho, self.Cd, self.Cm, n_gauss)
+        return eng
+
+    def compute_all_morison_forces(self, t=0.0, n_gauss=15):
+        eng = self._engine(n_gauss)
+        nodal, totals, details = eng.morison_single(t, want_details=True)
+        st = self.structure
+        nodal_forces = {}
+        for i, name in enumerate(st.node_list):
+            v = np.zeros(6)
+            v[:3] = nodal[i]
+            nodal_forces[name] = v
+        member_details = [dict(member=m["name"], **{c: details[i, j] for j, c in enumerate(L.DETAIL_COLUMNS)})
+                          for i, m in enumerate(st.members)]
+        return {"nodal_forces": nodal_forces, "total_drag": totals[0:3].copy(), "total_inertia": totals[3:6].copy(),
+                "total_morison": totals[6:9].copy(), "member_details": member_details}
+
+    def scan_table(self, n_steps=36, t=None):
+        """The Morison columns of the per-phase table as an array [P, 16] plus the critical index."""
+        eng = self._engine()
+        t = phase_times(self.wave.T, n_steps) if t is None else np.asarray(t, dtype=np.float64)
+        table, crit = eng.morison_scan(t)
+        return fill_phase_deg(table, self.wave.omega), crit
+
+    def find_critical_phase(self, n_steps=36):
+        table, crit = self.scan_table(n_steps)
+        keys = L.TABLE_COLUMNS[:8]
+        rows = [dict(zip(keys, (float(v) for v in table[i, :8]))) for i in range(table.shape[0])]
+        return {"all_phases": rows, "critical": rows[crit], "T": self.wave.T, "omega": self.wave.omega}

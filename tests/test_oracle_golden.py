@@ -1,0 +1,132 @@
+"""The oracle (oracle/jacket_oracle.py) pinned against vectors produced by the reference's own classes
+(tests/golden/make_golden.py).  CPU only.  Tolerances are far below the 1e-9 parity bar because the oracle
+follows the reference's operation order."""
+import numpy as np
+
+from conftest import golden_params, oracle_model, relmax
+from oracle import jacket_oracle as orc
+
+TIGHT = 5e-13
+
+
+def _wave(p):
+    return orc.AiryWave(p["H"], p["T"], p["d"], p["U_c"])
+
+
+def _mor_kw(p):
+    return dict(wave_direction=p["wave_dir"], current_direction=p["current_dir"], Cd=p["Cd"], Cm=p["Cm"],
+                rho_water=p["rho_water"])
+
+
+def test_dispersion_and_pinned_constants(golden):
+    name, g = golden
+    p = golden_params(g)
+    w = _wave(p)
+    assert w.k == g["wave_k"].item() and w.omega == g["wave_omega"].item() and w.L == g["wave_L"].item()
+    if name == "default3_airy":   # values quoted in BASELINE.md section 3
+        assert w.k == 0.046430003773529516 and w.omega == 0.6684239688488921 and w.L == 135.32597020295162
+
+
+def test_morison_single_phase(golden):
+    _, g = golden
+    p = golden_params(g)
+    m = oracle_model(g)
+    for tag in ("t0", "t1"):
+        out = orc.morison_phases(m, _wave(p), [g[f"mor_{tag}_t"].item()], want_details=True, **_mor_kw(p))
+        tot = np.concatenate([out["total_drag"][0], out["total_inertia"][0], out["total_morison"][0]])
+        assert relmax(out["nodal_forces"][0], g[f"mor_{tag}_nodal"]) < TIGHT
+        assert relmax(tot, g[f"mor_{tag}_totals"]) < TIGHT
+        assert relmax(out["member_details"][0], g[f"mor_{tag}_details"]) < TIGHT
+
+
+def test_pinned_t0_total(golden):
+    name, g = golden
+    if name != "default3_airy":
+        return
+    np.testing.assert_allclose(g["mor_t0_totals"][6:9], [3392202.8797103227, 4344665.94447964, -433561.4819033571], rtol=1e-15)
+
+
+def test_phase_scan_tables_and_critical_index(golden):
+    name, g = golden
+    p = golden_params(g)
+    m = oracle_model(g)
+    for key in [k for k in g if k.startswith("scan") and k.endswith("_table")]:
+        n = int(key[4:-6])
+        t = orc.phase_times(p["T"], n)
+        out = orc.morison_phases(m, _wave(p), t, **_mor_kw(p))
+        tab, crit = orc.phase_table(out, t, g["wave_omega"].item())
+        assert crit == int(g[f"scan{n}_critical"])             # bit-exact index
+        assert np.array_equal(tab[:, 0], g[key][:, 0])           # t_i
+        assert np.array_equal(tab[:, 1], g[key][:, 1])           # phase_deg
+        assert relmax(tab[:, 2:], g[key][:, 2:]) < TIGHT
+    if name == "default3_airy":
+        assert int(g["scan36_critical"]) == 35 and int(g["scan360_critical"]) == 353
+        assert abs(g["scan36_table"][35, 2] - 5799.185270933482) < 1e-9
+
+
+def test_elements_and_assembly(golden):
+    _, g = golden
+    p = golden_params(g)
+    fem = orc.FEM(oracle_model(g), p["E"], p["nu"])
+    assert relmax(fem.K_local, g["Kl"]) < 1e-15
+    assert relmax(fem.R, g["T3"]) < 1e-15
+    assert relmax(fem.K_elem, g["Ke"]) < 1e-14
+    if g["K_global"].size:
+        assert relmax(fem.K_global, g["K_global"]) < 1e-14
+
+
+def _fem_inputs(g, p, fem, nodal):
+    inter, sw = fem.static_loads(p["wave_dir"], p["F_axial"], p["F_shear"], p["M_moment"], p["M_torsion"],
+                                 str(p["self_weight_mode"]), p["custom_sw"])
+    return fem.load_matrix(nodal, inter, sw)
+
+
+def test_fem_t0(golden):
+    name, g = golden
+    p = golden_params(g)
+    m = oracle_model(g)
+    fem = orc.FEM(m, p["E"], p["nu"])
+    F = _fem_inputs(g, p, fem, g["mor_t0_nodal"][None])
+    assert relmax(F[0], g["fem_t0_F"]) < 1e-14
+    U = fem.solve(F)
+    assert relmax(U[0], g["fem_t0_U"]) < 1e-10
+    assert relmax(fem.reactions(U, F)[0], g["fem_t0_reactions"]) < 1e-10
+    mf = fem.member_forces(U, p["fy"])
+    rows = np.stack([mf[k][0] for k in ("Fx_max_kN", "Fy_max_kN", "Fz_max_kN", "My_max_kNm", "Mz_max_kNm",
+                                        "von_mises_max_MPa", "utilization")], axis=1)
+    for c in range(7):
+        assert relmax(rows[:, c], g["fem_t0_rows"][:, c]) < 1e-10
+    assert relmax(mf["length_m"], g["fem_t0_length_m"]) < 1e-15
+    if name == "default3_airy":
+        assert abs(np.max(g["fem_t0_rows"][:, 6]) - 0.2147147837812134) < 1e-12
+        tr = np.linalg.norm(g["fem_t0_U"].reshape(-1, 6)[:, :3], axis=1)
+        assert abs(np.max(tr) - 68.22044893416346) < 1e-9
+
+
+def test_per_phase_fem(golden):
+    _, g = golden
+    p = golden_params(g)
+    m = oracle_model(g)
+    P = int(g["phasefem_P"])
+    t = orc.phase_times(p["T"], P)[g["phasefem_idx"]]
+    res = orc.phase_scan(m, _wave(p), t, E=p["E"], nu=p["nu"], fy=p["fy"], F_axial_kN=p["F_axial"],
+                         F_shear_kN=p["F_shear"], M_moment_kNm=p["M_moment"], M_torsion_kNm=p["M_torsion"],
+                         self_weight=str(p["self_weight_mode"]), custom_sw_tonnes=p["custom_sw"], **_mor_kw(p))
+    assert relmax(res["F"], g["phasefem_F"]) < 1e-14
+    for i in range(len(t)):
+        assert relmax(res["U"][i], g["phasefem_U"][i]) < 1e-10
+        assert relmax(res["reactions"][i], g["phasefem_reactions"][i]) < 1e-10
+        for c, k in enumerate(("Fx_max_kN", "Fy_max_kN", "Fz_max_kN", "My_max_kNm", "Mz_max_kNm",
+                               "von_mises_max_MPa", "utilization")):
+            assert relmax(res["members"][k][i], g["phasefem_rows"][i][:, c]) < 1e-10
+
+
+def test_equilibrium_invariant(golden):
+    """sum of reactions + sum of applied forces = 0 (independent of any oracle)."""
+    _, g = golden
+    F = g["phasefem_F"].reshape(g["phasefem_F"].shape[0], -1, 6)
+    R = g["phasefem_reactions"]
+    applied = F[:, :, :3].sum(axis=1)
+    # loads on the fixed nodes are part of F and also appear (negated) in R = K U - F
+    total = applied + R[:, :, :3].sum(axis=1)
+    assert np.max(np.abs(total)) / np.max(np.abs(applied)) < 1e-9
