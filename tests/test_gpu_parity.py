@@ -1,0 +1,229 @@
+"""Parity of the CUDA path (through the Python facade -> ctypes -> C ABI) against (a) the golden vectors produced
+by the reference's own classes and (b) the oracle on seeded inputs.  Needs a B200: `pytest -m gpu`.
+
+Parity metric (hard part 3): max|delta| / max|ref| per field per phase <= 1e-9; critical index exact."""
+import numpy as np
+import pytest
+
+from conftest import golden_params, oracle_model, product_structure, relmax
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+ROWS = ("Fx_max_kN", "Fy_max_kN", "Fz_max_kN", "My_max_kNm", "Mz_max_kNm", "von_mises_max_MPa", "utilization")
+
+
+def _wave(jb, ap):
+    return jb.RaschiiWave(ap.H, ap.T, ap.d, ap.U_c, "Airy", ap.N_harm)
+
+
+def _morison(jb, st, ap):
+    return jb.MorisonCalculator(st, _wave(jb, ap), ap.wave_dir, ap.current_dir, ap.Cd, ap.Cm, ap.rho_water)
+
+
+def test_wave_constants(golden):
+    import jacket_b200 as jb
+    _, g = golden
+    _, ap = product_structure(g)
+    w = _wave(jb, ap)
+    assert w.k == g["wave_k"].item() and w.omega == g["wave_omega"].item() and w.L == g["wave_L"].item()
+    assert w.actual_model == "Airy (fallback)" and w.actual_N == 1
+
+
+def test_morison_single_phase_vs_reference(golden):
+    import jacket_b200 as jb
+    _, g = golden
+    st, ap = product_structure(g)
+    mor = _morison(jb, st, ap)
+    for tag in ("t0", "t1"):
+        r = mor.compute_all_morison_forces(g[f"mor_{tag}_t"].item())
+        nodal = np.array([r["nodal_forces"][n][:3] for n in st.node_list])
+        assert all(r["nodal_forces"][n].shape == (6,) and not r["nodal_forces"][n][3:].any() for n in st.node_list)
+        tot = np.concatenate([r["total_drag"], r["total_inertia"], r["total_morison"]])
+        det = np.array([[d[k] for k in ("drag_kN", "inertia_kN", "total_kN", "submerged_length")] for d in r["member_details"]])
+        assert relmax(nodal, g[f"mor_{tag}_nodal"]) < TOL
+        assert relmax(tot, g[f"mor_{tag}_totals"]) < TOL
+        for c in range(4):
+            assert relmax(det[:, c], g[f"mor_{tag}_details"][:, c]) < TOL
+        assert [d["member"] for d in r["member_details"]] == [m["name"] for m in st.members]
+
+
+def test_find_critical_phase_vs_reference(golden):
+    import jacket_b200 as jb
+    name, g = golden
+    st, ap = product_structure(g)
+    mor = _morison(jb, st, ap)
+    for key in [k for k in g if k.startswith("scan") and k.endswith("_table")]:
+        n = int(key[4:-6])
+        res = mor.find_critical_phase(n_steps=n)
+        tab = np.array([[row[k] for k in ("t", "phase_deg", "total_kN", "drag_kN", "inertia_kN", "Fx_kN", "Fy_kN", "Fz_kN")]
+                        for row in res["all_phases"]])
+        crit = res["all_phases"].index(res["critical"])
+        assert crit == int(g[f"scan{n}_critical"])                 # bit-exact critical phase (incl. FD spike, idx 353)
+        assert np.array_equal(tab[:, 0], g[key][:, 0]) and np.array_equal(tab[:, 1], g[key][:, 1])
+        for c in range(2, 8):
+            assert relmax(tab[:, c], g[key][:, c]) < TOL
+        # every phase individually, relative to that phase's own total force
+        scale = np.maximum(np.abs(g[key][:, 2:3]), 1e-300)
+        assert np.max(np.abs(tab[:, 2:] - g[key][:, 2:]) / scale) < 1e-8
+        assert res["T"] == ap.T and res["omega"] == g["wave_omega"].item()
+
+
+def test_elements_and_K_vs_reference(golden):
+    import jacket_b200 as jb
+    _, g = golden
+    st, ap = product_structure(g)
+    fem = jb.FEMSolver(st, ap.E, ap.nu)
+    els = fem.elements
+    Ke = np.array([e.K_global for e in els]); Kl = np.array([e.K_local for e in els]); T3 = np.array([e.T[:3, :3] for e in els])
+    assert relmax(Kl, g["Kl"]) < 1e-14 and relmax(T3, g["T3"]) < 1e-14 and relmax(Ke, g["Ke"]) < 1e-13
+    assert np.array_equal(Ke, np.transpose(Ke, (0, 2, 1)))          # symmetric by construction
+    if g["K_global"].size:
+        K = fem.K_global
+        assert K.shape == g["K_global"].shape and relmax(K, g["K_global"]) < 1e-13
+
+
+@pytest.mark.parametrize("ordering,solver", [("rcm", "banded"), ("natural", "banded"), ("rcm", "dense"), ("natural", "dense")])
+def test_fem_solver_facade_t0_vs_reference(golden, ordering, solver):
+    """FEMSolver used the way run_analysis uses it (writable F_global), all orderings / storages."""
+    import jacket_b200 as jb
+    _, g = golden
+    st, ap = product_structure(g)
+    fem = jb.FEMSolver(st, ap.E, ap.nu, ordering=ordering, solver=solver)
+    fem.F_global[:] = g["fem_t0_F"]
+    fem.apply_boundary_conditions(st.get_bottom_nodes())
+    assert np.array_equal(np.sort(fem.fixed_dofs), np.sort((6 * g["fixed"][:, None] + np.arange(6)).ravel()))
+    U = fem.solve()
+    assert relmax(U, g["fem_t0_U"]) < TOL
+    assert not U[fem.fixed_dofs].any()
+    reac = fem.get_reactions()
+    R = np.array([reac[n] for n in st.get_bottom_nodes()])
+    assert relmax(R, g["fem_t0_reactions"]) < TOL
+    rows = fem.get_member_internal_forces(ap.fy)
+    arr = np.array([[r[k] for k in ROWS] for r in rows])
+    for c in range(7):
+        assert relmax(arr[:, c], g["fem_t0_rows"][:, c]) < TOL
+    assert relmax([r["length_m"] for r in rows], g["fem_t0_length_m"]) < 1e-15
+    assert [r["member"] for r in rows] == [m["name"] for m in st.members]
+    st._engine.close(); st._engine = None
+
+
+def test_run_analysis_vs_reference(golden):
+    """The GUI's analysis step end to end (GUI.py:1827-2082) at t = 0."""
+    import jacket_b200 as jb
+    name, g = golden
+    st, ap = product_structure(g)
+    nodes = {n: st.nodes[n] for n in st.node_list}
+    members = [{"name": m["name"], "node1": m["node1"], "node2": m["node2"], "type": m["type"]} for m in st.members]
+    ap.do_phase_scan = name == "default3_airy"
+    res = jb.run_analysis(nodes, members, st.get_bottom_nodes(), st.get_top_nodes(), ap)
+    assert set(res) >= {"U", "reactions", "internal_forces", "structure", "max_util", "morison_results", "critical_phase", "wave_info"}
+    assert relmax(res["U"], g["fem_t0_U"]) < TOL
+    assert abs(res["max_util"] - np.max(g["fem_t0_rows"][:, 6])) < TOL * np.max(g["fem_t0_rows"][:, 6])
+    if name == "default3_airy":
+        assert res["critical_phase"]["t"] == g["scan36_table"][35, 0]
+        assert abs(res["critical_phase"]["total_kN"] - 5799.185270933482) < 1e-6
+        worst = max(res["internal_forces"], key=lambda r: r["utilization"])
+        assert worst["member"] == "XBr_HBC2-B3"
+
+
+def test_phase_scan_vs_reference(golden):
+    """The hot path: Morison + FEM for every phase; rows of the phases the reference was replayed at."""
+    import jacket_b200 as jb
+    _, g = golden
+    st, ap = product_structure(g)
+    P = int(g["phasefem_P"])
+    res = jb.phase_scan(st, _wave(jb, ap), P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
+                        rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, params=ap)
+    assert res.table.shape == (P, 16)
+    key = f"scan{P}_table"
+    assert res.critical_index == int(g[f"scan{P}_critical"])
+    assert np.array_equal(res.table[:, 0], g[key][:, 0]) and np.array_equal(res.table[:, 1], g[key][:, 1])
+    for c in range(2, 8):
+        assert relmax(res.table[:, c], g[key][:, c]) < TOL
+    for k, i in enumerate(g["phasefem_idx"]):
+        ph = res.phase(int(i), end_forces=True)
+        assert relmax(ph["U"], g["phasefem_U"][k]) < TOL
+        R = np.array([ph["reactions"][n] for n in st.get_bottom_nodes()])
+        assert relmax(R, g["phasefem_reactions"][k]) < TOL
+        arr = np.array([[r[c] for c in ROWS] for r in ph["internal_forces"]])
+        for c in range(7):
+            assert relmax(arr[:, c], g["phasefem_rows"][k][:, c]) < TOL
+        # per-phase summary columns of the table agree with the full rows
+        row = res.row(int(i))
+        assert abs(row["max_util"] - arr[:, 6].max()) <= 1e-12 * arr[:, 6].max()
+        assert int(row["max_util_member"]) == int(np.argmax(g["phasefem_rows"][k][:, 6]))
+        tr = np.linalg.norm(g["phasefem_U"][k].reshape(-1, 6)[:, :3], axis=1)
+        assert abs(row["max_disp_mm"] - tr.max()) < TOL * tr.max() and int(row["max_disp_node"]) == int(np.argmax(tr))
+        assert relmax([row["sum_Rx"], row["sum_Ry"], row["sum_Rz"]], g["phasefem_reactions"][k][:, :3].sum(axis=0)) < TOL
+        # Morison nodal loads of that phase: F = static + Morison  =>  compare with the reference's F_global
+        F = jb.static_load(st, ap).reshape(-1, 6).copy()
+        F[:, :3] += ph["nodal_forces"]
+        assert relmax(F.ravel(), g["phasefem_F"][k]) < TOL
+    # member time series
+    worst = int(np.argmax(g["phasefem_rows"][0][:, 6]))
+    series = res.member_series(worst, "utilization")
+    assert relmax(series[g["phasefem_idx"]], g["phasefem_rows"][:, worst, 6]) < TOL
+    assert res.engine.residual() < 1e-10
+
+
+def test_mid_size_vs_oracle():
+    """8 legs x 12 bays (584 members, 1152 free DOF, 18 tiles), 96 phases, banded RCM vs the oracle's dense LU."""
+    import jacket_b200 as jb
+    from oracle import jacket_oracle as orc
+    ap = jb.AnalysisParams(H=12.0, T=10.5, U_c=1.1, wave_dir=65.0, current_dir=110.0, wave_model="Airy")
+    nodes, members, fixed, top = jb.generate_jacket(8, 12)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    P = 96
+    res = jb.phase_scan(st, _wave(jb, ap), P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
+                        rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, params=ap)
+    d = res.engine.dims()
+    assert d["n_free_dof"] == 6 * (len(nodes) - len(fixed)) and d["band_tiles"] < d["n_tiles"] - 1
+    xyz, conn, sec_id, _, sections = st.pack()
+    model = orc.Model(xyz, conn, sec_id, [(s.D_outer, s.t, s.rho_steel) for s in sections], st.indices(fixed), st.indices(top))
+    ref = orc.phase_scan(model, orc.AiryWave(ap.H, ap.T, ap.d, ap.U_c), orc.phase_times(ap.T, P), wave_direction=ap.wave_dir,
+                         current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm, rho_water=ap.rho_water, E=ap.E, nu=ap.nu,
+                         fy=ap.fy, F_axial_kN=ap.F_axial, F_shear_kN=ap.F_shear, self_weight="calculated")
+    assert res.critical_index == ref["critical"]
+    for c in range(2, 8):
+        assert relmax(res.table[:, c], ref["table"][:, c]) < TOL
+    assert relmax(res.table[:, 10], ref["members"]["utilization"].max(axis=1)) < TOL
+    assert np.array_equal(res.table[:, 11].astype(int), ref["members"]["utilization"].argmax(axis=1))
+    for i in (0, 17, ref["critical"], P - 1):
+        ph = res.phase(i)
+        assert relmax(ph["U"], ref["U"][i]) < TOL
+        R = np.array([ph["reactions"][n] for n in fixed])
+        assert relmax(R, ref["reactions"][i]) < TOL
+        util = np.array([r["utilization"] for r in ph["internal_forces"]])
+        assert relmax(util, ref["members"]["utilization"][i]) < TOL
+    assert res.engine.residual() < 1e-10
+
+
+def test_dense_storage_matches_banded():
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    out = {}
+    for solver in ("banded", "dense"):
+        nodes, members, fixed, top = jb.generate_jacket(6, 8)
+        st = jb.build_structure(nodes, members, fixed, top, ap)
+        jb.get_engine(st, solver=solver, ordering="rcm")
+        res = jb.phase_scan(st, _wave(jb, ap), 40, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+        out[solver] = (res.table.copy(), res.phase(7)["U"], res.engine.dims())
+    assert out["dense"][2]["band_tiles"] == out["dense"][2]["n_tiles"] - 1 > out["banded"][2]["band_tiles"]
+    assert relmax(out["banded"][0][:, 2:], out["dense"][0][:, 2:]) < 1e-10
+    assert relmax(out["banded"][1], out["dense"][1]) < 1e-10
+
+
+def test_errors_are_loud():
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    nodes, members, fixed, top = jb.generate_jacket(3, 2)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    eng = jb.get_engine(st)
+    with pytest.raises(jb.JacketError):                      # scan before wave / factor
+        eng.phase_scan(np.zeros(4), 355.0)
+    # a mechanism: unsupported structure -> K_ff not positive definite (the reference would lstsq, GUI.py:486-487)
+    nodes2 = dict(nodes); nodes2["LOOSE"] = np.array([100.0, 0.0, -10.0]); nodes2["LOOSE2"] = np.array([101.0, 0.0, -10.0])
+    members2 = members + [{"name": "m_loose", "node1": "LOOSE", "node2": "LOOSE2", "type": "brace"}]
+    st2 = jb.build_structure(nodes2, members2, fixed, top, ap)
+    with pytest.raises(jb.NotPositiveDefinite):
+        jb.FEMSolver(st2, ap.E, ap.nu).apply_boundary_conditions(fixed)
