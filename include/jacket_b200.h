@@ -185,6 +185,11 @@ int jk_residual(jk_handle_t h, double* rel_residual);
 /* kernels launched by this handle since creation (bench "gpu_launches") */
 int64_t jk_launch_count(jk_handle_t h);
 void* jk_stream(jk_handle_t h);
+/* device pointers of the last scan's table [P*JK_TABLE_NCOL] and of the (max value, first index) pair
+ * produced by the on-device argmax -- for device-to-device collectives (NCCL) without a host round trip */
+void* jk_table_dev(jk_handle_t h);
+void* jk_critical_value_dev(jk_handle_t h);
+void* jk_critical_index_dev(jk_handle_t h);
 
 #ifdef __cplusplus
 }

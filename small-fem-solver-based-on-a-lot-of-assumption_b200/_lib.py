@@ -81,6 +81,9 @@ def _sig(lib):
     lib.jk_launch_count.restype = C.c_int64
     lib.jk_stream.argtypes = [H]
     lib.jk_stream.restype = C.c_void_p
+    for name in ("jk_table_dev", "jk_critical_value_dev", "jk_critical_index_dev"):
+        getattr(lib, name).argtypes = [H]
+        getattr(lib, name).restype = C.c_void_p
     for name in ("jk_create", "jk_destroy", "jk_set_supports", "jk_assemble", "jk_factor", "jk_set_static_load",
                  "jk_set_wave_airy", "jk_set_wave_fourier", "jk_set_morison", "jk_morison_scan", "jk_morison_single",
                  "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_fetch_phase",

@@ -114,6 +114,9 @@ extern "C" int jk_version(void) { return 100; }
 extern "C" const char* jk_last_error(jk_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
 extern "C" int64_t jk_launch_count(jk_handle_t h) { return h ? h->launches : 0; }
 extern "C" void* jk_stream(jk_handle_t h) { return h ? (void*)h->stream : nullptr; }
+extern "C" void* jk_table_dev(jk_handle_t h) { return h ? (void*)h->d_table : nullptr; }
+extern "C" void* jk_critical_value_dev(jk_handle_t h) { return h ? (void*)h->d_argval : nullptr; }
+extern "C" void* jk_critical_index_dev(jk_handle_t h) { return h ? (void*)h->d_argidx : nullptr; }
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xyz, int n_members,

@@ -1,0 +1,116 @@
+"""Multi-GPU phase sharding.
+
+Phases are independent units: rank r of g evaluates the contiguous block
+[r*P_local, (r+1)*P_local) of a P_local*g-phase scan on its own GPU (geometry and the
+factor of K are replicated -- identical on every rank, the assembly is deterministic).
+The only exchange is the final critical-phase reduction: one (max total_kN, first index)
+pair per rank through an NCCL all-gather (16 B per rank over NVLink), merged with the
+reference's first-maximum rule (GUI.py:717), plus an optional gather of the per-phase
+table.  torch.distributed is plumbing only (process group, NCCL / gloo transport).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .morison import fill_phase_deg
+
+
+def shard_bounds(n_total, world_size, rank):
+    """Contiguous block of rank ``rank``: sizes differ by at most one, earlier ranks take the remainder."""
+    base, rem = divmod(n_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_times(T, n_total, world_size, rank):
+    """t_i = i*T/n_total for the rank's block, evaluated exactly like GUI.py:696."""
+    lo, hi = shard_bounds(n_total, world_size, rank)
+    return np.array([i * T / n_total for i in range(lo, hi)], dtype=np.float64), lo
+
+
+def merge_critical(values, indices):
+    """First maximum over ranks: larger value wins, ties go to the smaller global index; NaN never wins."""
+    best_v, best_i = None, -1
+    for v, i in zip(values, indices):
+        if i < 0 or v != v:
+            continue
+        if best_v is None or v > best_v or (v == best_v and i < best_i):
+            best_v, best_i = float(v), int(i)
+    return best_v, best_i
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_views(engine, P):
+    """torch views (no copy) of the table [P,16], the critical value [1] and index [1] of the last scan."""
+    import torch
+    lib = engine.lib
+    dev = f"cuda:{engine.device}"
+    table = torch.as_tensor(_DevArray(lib.jk_table_dev(engine.h), (P, L.TABLE_NCOL), "<f8"), device=dev)
+    val = torch.as_tensor(_DevArray(lib.jk_critical_value_dev(engine.h), (1,), "<f8"), device=dev)
+    idx = torch.as_tensor(_DevArray(lib.jk_critical_index_dev(engine.h), (1,), "<i8"), device=dev)
+    return table, val, idx
+
+
+def allgather_critical(local_value, local_global_index, group=None, device=None):
+    """All-gather one (value, global index) pair per rank and merge.  Works on NCCL (device tensors) and gloo (CPU)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return merge_critical([float(local_value)], [int(local_global_index)])
+    ws = dist.get_world_size(group)
+    if isinstance(local_value, torch.Tensor):
+        pair = torch.stack([local_value.reshape(()).to(torch.float64), local_global_index.reshape(()).to(torch.float64)])
+    else:
+        pair = torch.tensor([float(local_value), float(local_global_index)], dtype=torch.float64, device=device or "cpu")
+    out = torch.empty(ws * 2, dtype=torch.float64, device=pair.device)   # flat: gloo and NCCL both accept it
+    dist.all_gather_into_tensor(out, pair, group=group)
+    out = out.cpu().numpy().reshape(ws, 2)
+    return merge_critical(out[:, 0], out[:, 1].astype(np.int64))
+
+
+def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=None, gather_table=True,
+                       t_dev=None, t_host=None):
+    """One rank's part of an n_total-phase scan + the cross-rank critical-phase reduction.
+
+    Returns dict(local_table (torch view on device), offset, critical_value, critical_index (global),
+    table (global [n_total,16] numpy on every rank if gather_table else None)).
+    With t_dev (a device pointer holding this rank's times) nothing crosses PCIe before the reduction.
+    """
+    import torch
+    import torch.distributed as dist
+    lo, hi = shard_bounds(n_total, world_size, rank)
+    P = hi - lo
+    if t_dev is not None:
+        engine.phase_scan_dev(P, t_dev, fy)
+    else:
+        if t_host is None:
+            t_host, _ = shard_times(wave.T, n_total, world_size, rank)
+        engine.phase_scan(t_host, fy)
+    table, val, idx = device_views(engine, P)
+    stream = torch.cuda.ExternalStream(engine.stream(), device=f"cuda:{engine.device}")
+    with torch.cuda.stream(stream):
+        cval, cidx = allgather_critical(val, idx + lo, group=group)
+        full = None
+        if gather_table:
+            if world_size > 1:
+                sizes = [shard_bounds(n_total, world_size, r) for r in range(world_size)]
+                if all(h - l == P for l, h in sizes):
+                    buf = torch.empty(n_total * L.TABLE_NCOL, dtype=torch.float64, device=table.device)
+                    dist.all_gather_into_tensor(buf, table.contiguous().reshape(-1), group=group)
+                    buf = buf.reshape(n_total, L.TABLE_NCOL)
+                else:
+                    parts = [torch.empty((h - l, L.TABLE_NCOL), dtype=torch.float64, device=table.device) for l, h in sizes]
+                    dist.all_gather(parts, table.contiguous(), group=group)
+                    buf = torch.cat(parts)
+                full = buf.cpu().numpy()
+            else:
+                full = table.cpu().numpy()
+            fill_phase_deg(full, wave.omega)
+    return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
