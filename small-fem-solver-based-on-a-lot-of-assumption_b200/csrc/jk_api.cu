@@ -7,12 +7,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
 #include <string>
 #include <vector>
 
 #include "jk_chol.cuh"
+#include "jk_chol_cluster.cuh"
 #include "jk_common.cuh"
 #include "jk_fem.cuh"
 #include "jk_morison.cuh"
@@ -44,7 +46,8 @@ struct jk_handle_s {
     KBlock* d_blocks = nullptr;
     int2* d_contrib = nullptr;
     int nblocks = 0;
-    double *d_tiles = nullptr, *d_Linv = nullptr;
+    double *d_tiles = nullptr, *d_Linv = nullptr, *d_dinv = nullptr;
+    int factor_path = 0;   // 0 = auto (cluster kernel for narrow bands), 1 = per-column launches
     size_t tiles_elems = 0;
     int* d_info = nullptr;
     bool assembled = false, factored = false;
@@ -186,6 +189,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, cudaFuncSetAttribute(k_trailing_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_panel_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_tile_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INVERSE_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_band_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_CLUSTER_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -199,7 +203,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_xyz); dev_free(h->d_secp); dev_free(h->d_mc); dev_free(h->d_Ke); dev_free(h->d_Kl);
     dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
-    dev_free(h->d_blocks); dev_free(h->d_contrib); dev_free(h->d_tiles); dev_free(h->d_Linv); dev_free(h->d_info);
+    dev_free(h->d_blocks); dev_free(h->d_contrib); dev_free(h->d_tiles); dev_free(h->d_Linv); dev_free(h->d_dinv); dev_free(h->d_info);
     dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
@@ -337,6 +341,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     CUDA_TRY(h, dev_alloc(&h->d_contrib, contrib.size()));
     CUDA_TRY(h, dev_alloc(&h->d_tiles, h->tiles_elems));
     CUDA_TRY(h, dev_alloc(&h->d_Linv, (size_t)h->NT * NB * NB));
+    CUDA_TRY(h, dev_alloc(&h->d_dinv, (size_t)h->NT * 512));
     cudaStream_t s = h->stream;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_node2slot, h->h_node2slot.data(), (size_t)h->Nn * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -376,15 +381,35 @@ extern "C" int jk_factor(jk_handle_t h) {
     cudaStream_t s = h->stream;
     tic(h, JK_T_FACTOR);
     CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), s));
-    for (int k = 0; k < h->NT; ++k) {
-        int w = std::min(h->bw, h->NT - 1 - k);
-        k_potrf_tile<<<1, 256, 0, s>>>(h->d_tiles, k, h->bw, h->d_info);
+    // narrow band: one persistent cluster kernel (latency chain); wide band / dense: per-column launches
+    const bool use_cluster = (h->factor_path == 0) && (h->bw <= 16);
+    if (use_cluster) {
+        long long* prof = nullptr;
+        const bool want_prof = getenv("JK_CHOL_PROFILE") != nullptr;
+        if (want_prof) { CUDA_TRY(h, cudaMalloc((void**)&prof, (size_t)h->NT * 8 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(prof, 0, (size_t)h->NT * 8 * sizeof(long long), s)); }
+        k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(h->d_tiles, h->d_dinv, h->NT, h->bw, h->d_info, prof);
         LAUNCH_CHECK(h);
-        if (w > 0) {
-            k_panel_trsm<<<w, NB, PANEL_SMEM, s>>>(h->d_tiles, k, h->bw);
+        if (want_prof) {   // debug aid: average clock deltas between the phase stamps of CTA 0
+            std::vector<long long> hp((size_t)h->NT * 8);
+            CUDA_TRY(h, cudaMemcpyAsync(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            cudaFree(prof);
+            double acc[6] = {0, 0, 0, 0, 0, 0}; int n = 0;
+            for (int k = 8; k + 8 < h->NT; ++k, ++n) for (int i = 0; i < 6; ++i) acc[i] += (double)(hp[(size_t)k * 8 + i + 1] - hp[(size_t)k * 8 + i]);
+            if (n > 0) fprintf(stderr, "[jk chol profile] clocks/column: panel %.0f | sync %.0f | B-load+update %.0f | potrf %.0f | store+other tiles %.0f | sync %.0f\n",
+                               acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n);
+        }
+    } else {
+        for (int k = 0; k < h->NT; ++k) {
+            int w = std::min(h->bw, h->NT - 1 - k);
+            k_potrf_tile<<<1, 256, 0, s>>>(h->d_tiles, k, h->bw, h->d_info);
             LAUNCH_CHECK(h);
-            k_trailing_update<<<w * (w + 1) / 2, 128, UPDATE_SMEM, s>>>(h->d_tiles, k, w, h->bw);
-            LAUNCH_CHECK(h);
+            if (w > 0) {
+                k_panel_trsm<<<w, NB, PANEL_SMEM, s>>>(h->d_tiles, k, h->bw);
+                LAUNCH_CHECK(h);
+                k_trailing_update<<<w * (w + 1) / 2, 128, UPDATE_SMEM, s>>>(h->d_tiles, k, w, h->bw);
+                LAUNCH_CHECK(h);
+            }
         }
     }
     k_tile_inverse<<<h->NT, 256, INVERSE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->bw);

@@ -1,0 +1,323 @@
+// jk_chol_cluster.cuh -- the whole tile-banded Cholesky in ONE persistent kernel on a thread-block
+// cluster (8 CTAs on 8 SMs of one GPC, hardware cluster barriers between phases).
+//
+// The factorisation of a narrow band is a latency chain (n pivots in sequence), not a throughput
+// problem: the first version spent 60 us per tile column on three kernel launches.  Here a column
+// costs two cluster barriers:
+//
+//   phase A(k)  panel:   tiles (k+1..k+w, k) <- A * L_kk^{-T}       one tile per CTA, warp-local blocked
+//                                                                   TRSM on DMMA with the 16x16 diagonal-
+//                                                                   block inverses produced by the potrf
+//   phase B(k)  update:  tile (i,j) -= L_ik L_jk^T, k < j <= i <= k+w   DMMA, tiles dealt round-robin;
+//               CTA 0 takes tile (k+1,k+1) first, keeps it in shared memory and factors it at once
+//               (lookahead: the next potrf overlaps the rest of this column's update).
+//
+// potrf of a 64x64 tile: eight 8-column panels, see potrf64_smem.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "jk_chol.cuh"
+
+namespace jk {
+
+constexpr int CHOL_CLUSTER = 8;
+constexpr int CHOL_THREADS = 256;
+constexpr int DI_LD = 12;                                   // row stride of an 8x8 inverse block in smem (== 12 mod 16: conflict-free)
+constexpr int DI_BLK = 8 * DI_LD;
+constexpr size_t CHOL_CLUSTER_SMEM = (size_t)(3 * NB * LS_LD + 8 * DI_BLK) * sizeof(double);
+
+// 1/d and 1/sqrt(d) to ~1 ulp from the MUFU seeds (rel. error ~2^-22) and ONE cubic correction each:
+// a chain of 3-4 dependent FMAs instead of the 8-10 of the library routines.  d must be a normal positive number.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    double p = fma(e, e, e);
+    return fma(y, p, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double t = d * y;
+    double e = fma(-t, y, 1.0);
+    double p = fma(0.375, e, 0.5);
+    double q = y * e;
+    return fma(q, p, y);
+}
+
+// Cholesky of the 64x64 tile T (smem, row stride LS_LD, lower triangle) in place.  Di[8][8][DI_LD]
+// receives the inverses of the eight 8x8 diagonal blocks of L.  All 256 threads of the CTA call this.
+//
+// Eight 8-column panels.  Per panel: warp 0 factors the 8x8 diagonal block entirely in registers (every
+// lane the same values, no communication).  The pivot recurrence is square-root free (LDL^T form:
+// d' = d11 - d10^2 / d00 needs only the reciprocal), the column scaling by 1/sqrt(d) happens off the
+// chain.  Then one DMMA phase solves the rows below against the block inverse and one DMMA phase applies
+// the rank-8 update to the trailing block.
+__device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, int* __restrict__ info, int pivot_base) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = 8 * p;
+        double* Dp = Di + p * DI_BLK;
+        if (warp == 0) {
+            double d[8][8], m[8][8], rs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) d[i][j] = T[(c0 + i) * LS_LD + c0 + j];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double dc = d[c][c];
+                if (!(dc > 0.0)) { if (!bad && lane == 0) atomicCAS(info, 0, pivot_base + c0 + c + 1); bad = true; dc = 1.0; }
+                const double inv = fast_rcp(dc);
+                rs[c] = fast_rsqrt(dc);
+                double t[8];
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i) t[i] = d[i][c] * inv;
+#pragma unroll
+                for (int j = c + 1; j < 8; ++j)
+#pragma unroll
+                    for (int i = j; i < 8; ++i) {
+                        if (i == j && j == c + 1) d[i][j] = fma(-(d[i][c] * d[i][c]), inv, d[i][j]);   // next pivot: shortest chain
+                        else d[i][j] = fma(-d[i][c], t[j], d[i][j]);
+                    }
+                d[c][c] = dc;
+            }
+            // L = Ltilde D^(1/2): scale the columns off the pivot chain
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i) d[i][c] *= rs[c];
+                d[c][c] *= rs[c];
+            }
+            // M = L^-1 (lower) by forward substitution, 1/L_jj = rs_j
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                m[j][j] = rs[j];
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int kk = j; kk < i; ++kk) sacc = fma(d[i][kk], m[kk][j], sacc);
+                    m[i][j] = -sacc * rs[i];
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j <= i) T[(c0 + i) * LS_LD + c0 + j] = d[i][j];
+                        Dp[i * DI_LD + j] = (j <= i) ? m[i][j] : 0.0;
+                    }
+            }
+        }
+        __syncthreads();
+        const int nmt = 7 - p;                              // 8-row tiles below the diagonal block
+        if (nmt == 0) break;
+        // ---- rows below: X = A * M^T (in place), one 8-row tile per warp ----
+        if (warp < nmt) {
+            const int row0 = c0 + 8 + 8 * warp;
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int k4 = 0; k4 < 2; ++k4)
+                dmma(x0, x1, T[(row0 + fr) * LS_LD + c0 + 4 * k4 + fk], Dp[fr * DI_LD + 4 * k4 + fk]);
+            __syncwarp();
+            T[(row0 + fr) * LS_LD + c0 + 2 * fk] = x0;
+            T[(row0 + fr) * LS_LD + c0 + 2 * fk + 1] = x1;
+        }
+        __syncthreads();
+        // ---- trailing block: C(mi,nj) -= X_mi X_nj^T for the lower triangle of 8x8 tiles ----
+        const int ntile = nmt * (nmt + 1) / 2;
+        for (int t = warp; t < ntile; t += CHOL_THREADS / 32) {
+            int mi = 0;
+            while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
+            const int nj = t - mi * (mi + 1) / 2;
+            const int ri = c0 + 8 + 8 * mi, rj = c0 + 8 + 8 * nj;
+            double* cp = T + (ri + fr) * LS_LD + rj + 2 * fk;
+            double c0v = cp[0], c1v = cp[1];
+#pragma unroll
+            for (int k4 = 0; k4 < 2; ++k4)
+                dmma(c0v, c1v, -T[(ri + fr) * LS_LD + c0 + 4 * k4 + fk], T[(rj + fr) * LS_LD + c0 + 4 * k4 + fk]);
+            cp[0] = c0v; cp[1] = c1v;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void store_tile(double* __restrict__ g, const double* __restrict__ T, int tid, int nthreads) {
+    for (int q = tid; q < NB * (NB / 2); q += nthreads) {
+        int r = q / (NB / 2), cc = q % (NB / 2);
+        *reinterpret_cast<double2*>(g + r * NB + 2 * cc) = make_double2(T[r * LS_LD + 2 * cc], T[r * LS_LD + 2 * cc + 1]);
+    }
+}
+
+// tile (row-block of As) <- As * L^{-T}, warp-local: warp w owns rows 8w..8w+7 of As.  Blocked by 8 columns with
+// the 8x8 diagonal-block inverses Di of L (Ls): X_b = A_b M_b^T ; A_b2 -= X_b L_{b2,b}^T (b2 > b).
+__device__ __forceinline__ void trsm64_warp(double* __restrict__ As, const double* __restrict__ Ls, const double* __restrict__ Di) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    double* arow = As + (8 * warp + fr) * LS_LD;
+#pragma unroll 1
+    for (int b = 0; b < 8; ++b) {
+        double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < 2; ++k4) dmma(x0, x1, arow[8 * b + 4 * k4 + fk], Di[b * DI_BLK + fr * DI_LD + 4 * k4 + fk]);
+        __syncwarp();
+        arow[8 * b + 2 * fk] = x0; arow[8 * b + 2 * fk + 1] = x1;
+        __syncwarp();
+        const double a0 = -arow[8 * b + fk], a1 = -arow[8 * b + 4 + fk];
+        for (int b2 = b + 1; b2 < 8; ++b2) {
+            double* cp = arow + 8 * b2 + 2 * fk;
+            double c0v = cp[0], c1v = cp[1];
+            dmma(c0v, c1v, a0, Ls[(8 * b2 + fr) * LS_LD + 8 * b + fk]);
+            dmma(c0v, c1v, a1, Ls[(8 * b2 + fr) * LS_LD + 8 * b + 4 + fk]);
+            cp[0] = c0v; cp[1] = c1v;
+        }
+        __syncwarp();
+    }
+}
+
+// acc(8 rows x 64 cols per warp) = As * Bs^T over the full 64-deep contraction
+__device__ __forceinline__ void gemm64_nt(const double* __restrict__ As, const double* __restrict__ Bs, double (&acc)[8][2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const double* ap = As + (8 * warp + fr) * LS_LD + fk;
+    const double* bp = Bs + fr * LS_LD + fk;
+#pragma unroll 4
+    for (int k4 = 0; k4 < NB / 4; ++k4) {
+        double av = ap[4 * k4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma(acc[nt][0], acc[nt][1], av, bp[nt * 8 * LS_LD + 4 * k4]);
+    }
+}
+
+__global__ void __cluster_dims__(CHOL_CLUSTER, 1, 1) __launch_bounds__(CHOL_THREADS, 1)
+k_band_chol_cluster(double* __restrict__ tiles, double* __restrict__ dinv /* [NT][8][8][8] */, int NT, int bw, int* __restrict__ info,
+                    long long* __restrict__ prof /* optional [NT][8] clock stamps of CTA 0 (debug) */) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = As + NB * LS_LD;
+    double* Cs = Bs + NB * LS_LD;
+    double* Di = Cs + NB * LS_LD;                            // [8][8][DI_LD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int cta = (int)cluster.block_rank();
+
+    auto store_dinv = [&](int k) {
+        double* g = dinv + (size_t)k * 512;
+        for (int q = tid; q < 512; q += CHOL_THREADS) { int b = q >> 6, r = (q >> 3) & 7, c = q & 7; g[q] = Di[b * DI_BLK + r * DI_LD + c]; }
+    };
+    auto load_dinv = [&](int k) {
+        const double* g = dinv + (size_t)k * 512;
+        for (int q = tid; q < 512; q += CHOL_THREADS) { int b = q >> 6, r = (q >> 3) & 7, c = q & 7; Di[b * DI_BLK + r * DI_LD + c] = __ldcg(g + q); }
+    };
+
+    if (cta == 0) {                                          // prologue: potrf(0)
+        load_tile_async(Cs, tiles + tile_off(0, 0, bw), tid, CHOL_THREADS);
+        cp_async_commit(); cp_async_wait<0>();
+        __syncthreads();
+        potrf64_smem(Cs, Di, info, 0);
+        store_tile(tiles + tile_off(0, 0, bw), Cs, tid, CHOL_THREADS);
+        store_dinv(0);
+    }
+    cluster.sync();
+
+#define JK_STAMP(i) do { if (prof && cta == 0 && tid == 0) prof[(size_t)k * 8 + (i)] = clock64(); } while (0)
+    for (int k = 0; k + 1 < NT; ++k) {
+        const int w = min(bw, NT - 1 - k);
+        JK_STAMP(0);
+        // ---------------- phase A: panel ----------------
+        if (cta < w) {
+            load_tile_async(Bs, tiles + tile_off(k, k, bw), tid, CHOL_THREADS);
+            cp_async_commit();
+            load_dinv(k);
+        }
+        for (int q = cta; q < w; q += CHOL_CLUSTER) {
+            double* g = tiles + tile_off(k + 1 + q, k, bw);
+            load_tile_async(As, g, tid, CHOL_THREADS);
+            cp_async_commit(); cp_async_wait<0>();
+            __syncthreads();
+            trsm64_warp(As, Bs, Di);
+            __syncthreads();
+            store_tile(g, As, tid, CHOL_THREADS);
+            __syncthreads();
+        }
+        JK_STAMP(1);
+        cluster.sync();
+        JK_STAMP(2);
+        // ---------------- phase B: trailing update (+ lookahead potrf on CTA 0) ----------------
+        const int ntile = w * (w + 1) / 2;
+        if (cta == 0) {
+            load_tile_async(Cs, tiles + tile_off(k + 1, k + 1, bw), tid, CHOL_THREADS);
+            if (w >= 1) load_tile_async(As, tiles + tile_off(k + 1, k, bw), tid, CHOL_THREADS);
+            cp_async_commit(); cp_async_wait<0>();
+            __syncthreads();
+            if (w >= 1) {
+                // D_{k+1} -= L_{k+1,k} L_{k+1,k}^T, lower 8x8 tiles only; row blocks paired (w, 7-w) per SM sub-partition
+                const int rb = (warp < 4) ? warp : 11 - warp;
+                const double* ap = As + (8 * rb + fr) * LS_LD + fk;
+                const double* bp = As + fr * LS_LD + fk;
+                double acc[8][2];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll 2
+                for (int k4 = 0; k4 < NB / 4; ++k4) {
+                    const double av = ap[4 * k4];
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                        if (nt <= rb) dmma(acc[nt][0], acc[nt][1], av, bp[nt * 8 * LS_LD + 4 * k4]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    if (nt <= rb) {
+                        double* cp = Cs + (8 * rb + fr) * LS_LD + 8 * nt + 2 * fk;
+                        cp[0] -= acc[nt][0]; cp[1] -= acc[nt][1];
+                    }
+                __syncthreads();
+            }
+            JK_STAMP(3);
+            potrf64_smem(Cs, Di, info, (k + 1) * NB);
+            JK_STAMP(4);
+            store_tile(tiles + tile_off(k + 1, k + 1, bw), Cs, tid, CHOL_THREADS);
+            store_dinv(k + 1);
+        }
+        // remaining tiles t = 1..ntile-1 dealt to CTAs 1..7 (CTA 0 joins only if the band is wide)
+        const int nworkers = (ntile - 1 > 4 * (CHOL_CLUSTER - 1)) ? CHOL_CLUSTER : CHOL_CLUSTER - 1;
+        const int me = (nworkers == CHOL_CLUSTER) ? cta : cta - 1;
+        if (me >= 0) {
+            for (int t = 1 + me; t < ntile; t += nworkers) {
+                int bi = 0;
+                while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+                const int bj = t - bi * (bi + 1) / 2;
+                const int i = k + 1 + bi, j = k + 1 + bj;
+                load_tile_async(As, tiles + tile_off(i, k, bw), tid, CHOL_THREADS);
+                load_tile_async(Bs, tiles + tile_off(j, k, bw), tid, CHOL_THREADS);
+                cp_async_commit(); cp_async_wait<0>();
+                __syncthreads();
+                double acc[8][2];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+                gemm64_nt(As, Bs, acc);
+                double* gc = tiles + tile_off(i, j, bw);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    double2* p = reinterpret_cast<double2*>(gc + (8 * warp + fr) * NB + 8 * nt + 2 * fk);
+                    double2 v = __ldcg(p);
+                    v.x -= acc[nt][0]; v.y -= acc[nt][1];
+                    *p = v;
+                }
+                __syncthreads();
+            }
+        }
+        JK_STAMP(5);
+        cluster.sync();
+        JK_STAMP(6);
+    }
+#undef JK_STAMP
+}
+
+}  // namespace jk
