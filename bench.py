@@ -299,14 +299,14 @@ def run_ours(args):
     def step_resident():
         """inputs already in HBM: assemble + factor + scan + cross-rank reduction"""
         eng.assemble(E, G)
-        eng.factor()
+        eng.factor(overlap=True)      # side stream: runs concurrently with the Morison + load stage of the scan
         return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=(world > 1), t_dev=t_dev.data_ptr())
 
     def step_e2e():
         """host buffers in, host table out, through the public API"""
         eng.set_static_load(F_static)
         eng.assemble(E, G)
-        eng.factor()
+        eng.factor(overlap=True)
         return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=True, t_host=t_host)
 
     def barrier():

@@ -125,6 +125,10 @@ int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_nodes, int 
 int jk_assemble(jk_handle_t h, double E, double G);
 /* factor half of np.linalg.solve (GUI.py:485): blocked Cholesky, once per structure */
 int jk_factor(jk_handle_t h);
+/* Asynchronous variant: queued on the handle's side stream; the next scan overlaps its Morison + load stage with the
+ * factorisation and joins before the triangular sweeps.  A non-positive pivot is reported by that scan's
+ * jk_phase_scan / jk_read_table / jk_solve (JK_ENOTSPD). */
+int jk_factor_begin(jk_handle_t h);
 
 /* F_global contributions that do not depend on the phase (interface loads
  * GUI.py:1962-1977 and self-weight GUI.py:1994-2012), built by the host. */

@@ -59,6 +59,7 @@ def _sig(lib):
     lib.jk_set_supports.argtypes = [H, C.c_int, _ip, C.c_int, C.c_int]
     lib.jk_assemble.argtypes = [H, C.c_double, C.c_double]
     lib.jk_factor.argtypes = [H]
+    lib.jk_factor_begin.argtypes = [H]
     lib.jk_set_static_load.argtypes = [H, _dp]
     lib.jk_set_wave_airy.argtypes = [H] + [C.c_double] * 6
     lib.jk_set_wave_fourier.argtypes = [H] + [C.c_double] * 5 + [C.c_int, _dp, _dp]
@@ -84,7 +85,7 @@ def _sig(lib):
     for name in ("jk_table_dev", "jk_critical_value_dev", "jk_critical_index_dev"):
         getattr(lib, name).argtypes = [H]
         getattr(lib, name).restype = C.c_void_p
-    for name in ("jk_create", "jk_destroy", "jk_set_supports", "jk_assemble", "jk_factor", "jk_set_static_load",
+    for name in ("jk_create", "jk_destroy", "jk_set_supports", "jk_assemble", "jk_factor", "jk_factor_begin", "jk_set_static_load",
                  "jk_set_wave_airy", "jk_set_wave_fourier", "jk_set_morison", "jk_morison_scan", "jk_morison_single",
                  "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_fetch_phase",
                  "jk_fetch_member_column", "jk_get_dims", "jk_get_order", "jk_get_K", "jk_get_elements",

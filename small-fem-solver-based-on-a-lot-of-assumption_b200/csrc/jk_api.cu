@@ -27,6 +27,9 @@ struct jk_handle_s {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream2 = nullptr;        // side stream: the factorisation runs here, concurrently with the Morison stage
+    cudaEvent_t ev_fork = nullptr, ev_factor = nullptr;
+    bool factor_inflight = false;
     std::string err;
     int64_t launches = 0;
 
@@ -109,8 +112,8 @@ template <typename T>
 static void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-static void tic(jk_handle_t h, int id) { cudaEventRecord(h->ev0[id], h->stream); }
-static void toc(jk_handle_t h, int id) { cudaEventRecord(h->ev1[id], h->stream); h->ev_set[id] = true; }
+static void tic(jk_handle_t h, int id, cudaStream_t s = nullptr) { cudaEventRecord(h->ev0[id], s ? s : h->stream); }
+static void toc(jk_handle_t h, int id, cudaStream_t s = nullptr) { cudaEventRecord(h->ev1[id], s ? s : h->stream); h->ev_set[id] = true; }
 
 extern "C" int jk_version(void) { return 100; }
 
@@ -149,6 +152,9 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; JK_FAIL((jk_handle_t)nullptr, JK_ECUDA, "jk_create: cudaStreamCreate failed"); } h->own_stream = true; }
     for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); h->ev_set[i] = false; }
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi); }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming);
     h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
     h->h_xyz.assign(xyz, xyz + 3 * (size_t)n_nodes);
     h->h_conn.assign(conn, conn + 2 * (size_t)n_members);
@@ -210,6 +216,9 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_table); dev_free(h->d_details); dev_free(h->d_Fload); dev_free(h->d_argval); dev_free(h->d_tmp); dev_free(h->d_res);
     dev_free(h->d_part_mem); dev_free(h->d_part_node); dev_free(h->d_argidx);
     for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_factor) cudaEventDestroy(h->ev_factor);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JK_OK;
@@ -361,6 +370,7 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     if (!(E > 0) || !(G > 0)) JK_FAIL(h, JK_EINVAL, "jk_assemble: E and G must be positive");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
+    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0)); h->factor_inflight = false; }
     h->E = E; h->G = G;
     tic(h, JK_T_ASSEMBLE);
     CUDA_TRY(h, cudaMemsetAsync(h->d_tiles, 0, h->tiles_elems * sizeof(double), s));
@@ -374,12 +384,9 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     return JK_OK;
 }
 
-extern "C" int jk_factor(jk_handle_t h) {
-    if (!h) return JK_EINVAL;
-    if (!h->assembled) JK_FAIL(h, JK_ESTATE, "jk_factor: call jk_assemble first");
-    cudaSetDevice(h->device);
-    cudaStream_t s = h->stream;
-    tic(h, JK_T_FACTOR);
+// launches the factorisation on stream s (no host synchronisation)
+static int launch_factor(jk_handle_t h, cudaStream_t s) {
+    tic(h, JK_T_FACTOR, s);
     CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), s));
     // narrow band: one persistent cluster kernel (latency chain); wide band / dense: per-column launches
     const bool use_cluster = (h->factor_path == 0) && (h->bw <= 16);
@@ -414,16 +421,52 @@ extern "C" int jk_factor(jk_handle_t h) {
     }
     k_tile_inverse<<<h->NT, 256, INVERSE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->bw);
     LAUNCH_CHECK(h);
-    toc(h, JK_T_FACTOR);
+    toc(h, JK_T_FACTOR, s);
+    return JK_OK;
+}
+
+// host-side completion of an asynchronous factorisation: pivot check.  Call only after the streams were synchronised.
+static int finish_factor(jk_handle_t h) {
+    if (!h->factor_inflight) return JK_OK;
+    h->factor_inflight = false;
     int info = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream2));
+    CUDA_TRY(h, cudaMemcpy(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) {
-        h->assembled = false;   // tiles were overwritten
-        JK_FAIL(h, JK_ENOTSPD, "jk_factor: K_ff is not positive definite (pivot %d <= 0): structure is a mechanism or badly supported", info - 1);
+        h->factored = false;
+        JK_FAIL(h, JK_ENOTSPD, "K_ff is not positive definite (pivot %d <= 0): structure is a mechanism or badly supported", info - 1);
     }
-    h->factored = true;
+    return JK_OK;
+}
+
+extern "C" int jk_factor(jk_handle_t h) {
+    if (!h) return JK_EINVAL;
+    if (!h->assembled) JK_FAIL(h, JK_ESTATE, "jk_factor: call jk_assemble first");
+    cudaSetDevice(h->device);
+    int rc = launch_factor(h, h->stream);
+    if (rc != JK_OK) return rc;
     h->assembled = false;       // the tile storage now holds L
+    h->factored = true;
+    h->factor_inflight = true;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return finish_factor(h);
+}
+
+// Asynchronous variant: the factorisation is queued on the handle's side stream (after everything already queued on
+// the main stream) and the call returns at once.  The next scan runs its Morison + load stage concurrently and joins
+// before the triangular sweeps; a non-positive pivot is reported by that scan's jk_read_table / jk_phase_scan.
+extern "C" int jk_factor_begin(jk_handle_t h) {
+    if (!h) return JK_EINVAL;
+    if (!h->assembled) JK_FAIL(h, JK_ESTATE, "jk_factor_begin: call jk_assemble first");
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    int rc = launch_factor(h, h->stream2);
+    if (rc != JK_OK) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream2));
+    h->assembled = false;
+    h->factored = true;
+    h->factor_inflight = true;
     return JK_OK;
 }
 
@@ -571,6 +614,7 @@ static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool f
 static int run_fem(jk_handle_t h, int ldP, double fy) {
     cudaStream_t s = h->stream;
     int nslab = ldP / SLAB;
+    if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0));   // join the side stream
     tic(h, JK_T_SOLVE_FWD);
     k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad);
     LAUNCH_CHECK(h);
@@ -634,7 +678,7 @@ extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* criti
     toc(h, JK_T_D2H);
     CUDA_TRY(h, cudaStreamSynchronize(s));
     if (critical) *critical = (int64_t)idx;
-    return JK_OK;
+    return finish_factor(h);
 }
 
 static int scan_host(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical, bool fem) {
@@ -762,7 +806,7 @@ extern "C" int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy) {
     toc(h, JK_T_SCAN_TOTAL);
     CUDA_TRY(h, cudaStreamSynchronize(s));
     h->lastP = nrhs; h->last_ldP = ldP; h->last_morison = false; h->last_fem = true; h->last_fy = fy;
-    return JK_OK;
+    return finish_factor(h);
 }
 
 extern "C" int jk_fetch_phase(jk_handle_t h, int phase, double* U, double* reactions, double* member_rows,

@@ -78,8 +78,10 @@ class Engine:
         self._moduli = (float(E), float(G))
         self._factored = False
 
-    def factor(self):
-        self._ck(self.lib.jk_factor(self.h))
+    def factor(self, overlap=False):
+        """Blocked Cholesky.  overlap=True queues it on the side stream so the next scan's Morison stage runs
+        concurrently (a non-SPD matrix is then reported by that scan)."""
+        self._ck(self.lib.jk_factor_begin(self.h) if overlap else self.lib.jk_factor(self.h))
         self._factored = True
 
     def ensure_factored(self, fixed_idx, E, G):
