@@ -13,7 +13,7 @@ namespace jk {
 constexpr int LS_LD = NB + 4;     // smem row stride of an L tile  (== 4 mod 16 -> conflict-free DMMA fragment loads)
 constexpr int XS_LD = SLAB + 4;   // smem row stride of an X tile
 constexpr int SOLVE_STAGES = 3;
-constexpr int SOLVE_THREADS = 128;
+constexpr int SOLVE_THREADS = 256;   // 8 warps: warp w owns rows 8w..8w+7 of the tile row, all SLAB columns
 constexpr size_t SOLVE_SMEM = (size_t)SOLVE_STAGES * (NB * LS_LD + NB * XS_LD) * sizeof(double) + (size_t)NB * XS_LD * sizeof(double);
 constexpr size_t UPDATE_SMEM = (size_t)2 * NB * LS_LD * sizeof(double);
 
@@ -243,8 +243,9 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
     // prologue: STAGES-1 items in flight
     for (int s = 0; s < SOLVE_STAGES - 1; ++s) { issue(it_load, s); cp_async_commit(); it_load.next(); }
 
-    double acc[2][4][2];
-    double bk[2][4][2];
+    double acc[4][2];
+    double bk[4][2];
+    const int row = 8 * warp + fr;                             // this lane's row inside the tile
     int n = 0;                                                 // item counter
     bool new_step = true;
     while (!it.done()) {
@@ -252,20 +253,27 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         if (new_step) {
             // right-hand side rows of this step (fragment layout), issued early
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    int r = 16 * warp + 8 * mt + fr, c = 8 * nt + 2 * fk;
-                    double2 v = *reinterpret_cast<const double2*>(Xslab + ((size_t)it.k * NB + r) * SLAB + c);
-                    bk[mt][nt][0] = v.x; bk[mt][nt][1] = v.y;
-                    acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-                }
+            for (int nt = 0; nt < 4; ++nt) {
+                double2 v = *reinterpret_cast<const double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + 8 * nt + 2 * fk);
+                bk[nt][0] = v.x; bk[nt][1] = v.y;
+                acc[nt][0] = acc[nt][1] = 0.0;
+            }
             new_step = false;
         }
         cp_async_wait<SOLVE_STAGES - 2>();
         __syncthreads();                                       // item n landed; everyone is done with item n-1
-        issue(it_load, (n + SOLVE_STAGES - 1) % SOLVE_STAGES);
-        cp_async_commit();
+        // The copies of item n+STAGES-1 (into the stage item n-1 just released) are issued INSIDE the DMMA loop below,
+        // one 16-byte chunk per thread per k-step, so the tensor pipe never waits for a copy-issue phase.
+        const int lstage = (n + SOLVE_STAGES - 1) % SOLVE_STAGES;
+        const bool ld_l = !it_load.done();
+        const bool ld_x = ld_l && !it_load.is_diag() && !it_load.x_in_smem();
+        const double* lsrc = nullptr; const double* xsrc = nullptr;
+        if (ld_l) lsrc = (it_load.is_diag() ? (Linv + (size_t)it_load.k * NB * NB)
+                                            : (tiles + (BWD ? tile_off(it_load.j, it_load.k, bw) : tile_off(it_load.k, it_load.j, bw))))
+                         + (tid >> 5) * NB + 2 * (tid & 31);
+        if (ld_x) xsrc = Xslab + (size_t)it_load.j * NB * SLAB + (tid >> 4) * SLAB + 2 * (tid & 15);
+        double* ldst = Ls + lstage * NB * LS_LD + (tid >> 5) * LS_LD + 2 * (tid & 31);
+        double* xdst = Xs + lstage * NB * XS_LD + (tid >> 4) * XS_LD + 2 * (tid & 15);
         it_load.next();
 
         const double* ls = Ls + stage * NB * LS_LD;
@@ -273,48 +281,41 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         if (it.is_diag()) {
             // t = B_k - acc  -> Ts, then acc = Linv * t
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    int r = 16 * warp + 8 * mt + fr, c = 8 * nt + 2 * fk;
-                    Ts[r * XS_LD + c] = bk[mt][nt][0] - acc[mt][nt][0];
-                    Ts[r * XS_LD + c + 1] = bk[mt][nt][1] - acc[mt][nt][1];
-                    acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-                }
+            for (int nt = 0; nt < 4; ++nt) {
+                Ts[row * XS_LD + 8 * nt + 2 * fk] = bk[nt][0] - acc[nt][0];
+                Ts[row * XS_LD + 8 * nt + 2 * fk + 1] = bk[nt][1] - acc[nt][1];
+                acc[nt][0] = acc[nt][1] = 0.0;
+            }
             __syncthreads();
             xs = Ts;
         } else {
             xs = it.x_in_smem() ? Ts : (Xs + stage * NB * XS_LD);
         }
         // acc += op(L) * xs, op = identity (forward) or transpose (backward)
-        const double* a_base = BWD ? (ls + fk * LS_LD + 16 * warp + fr) : (ls + (16 * warp + fr) * LS_LD + fk);
+        const double* a_base = BWD ? (ls + fk * LS_LD + row) : (ls + row * LS_LD + fk);
         const double* b_base = xs + fk * XS_LD + fr;
-#pragma unroll 4
+#pragma unroll
         for (int k4 = 0; k4 < NB / 4; ++k4) {
-            double a0, a1;
-            if (BWD) { a0 = a_base[4 * k4 * LS_LD]; a1 = a_base[4 * k4 * LS_LD + 8]; }
-            else { a0 = a_base[4 * k4]; a1 = a_base[8 * LS_LD + 4 * k4]; }
+            // 256 threads x (8 L chunks + 4 X chunks) of 16 B = one 64x64 L tile + one 64x32 X tile
+            if (k4 < 8) { if (ld_l) cp_async16(ldst + k4 * 8 * LS_LD, lsrc + k4 * 8 * NB); }
+            else if (k4 < 12) { if (ld_x) cp_async16(xdst + (k4 - 8) * 16 * XS_LD, xsrc + (k4 - 8) * 16 * SLAB); }
+            const double a0 = BWD ? a_base[4 * k4 * LS_LD] : a_base[4 * k4];
             double b[4];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) b[nt] = b_base[4 * k4 * XS_LD + 8 * nt];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                dmma(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
-                dmma(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
-            }
+            for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], a0, b[nt]);
         }
+        cp_async_commit();
         if (it.is_diag()) {
             // acc is X_k: store to the slab (in place) and keep it in Ts as the newest tile
             __syncthreads();                                   // all warps finished reading Ts (= t)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    int r = 16 * warp + 8 * mt + fr, c = 8 * nt + 2 * fk;
-                    double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-                    *reinterpret_cast<double2*>(Xslab + ((size_t)it.k * NB + r) * SLAB + c) = v;
-                    Ts[r * XS_LD + c] = v.x; Ts[r * XS_LD + c + 1] = v.y;
-                }
+            for (int nt = 0; nt < 4; ++nt) {
+                double2 v = make_double2(acc[nt][0], acc[nt][1]);
+                *reinterpret_cast<double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + 8 * nt + 2 * fk) = v;
+                Ts[row * XS_LD + 8 * nt + 2 * fk] = v.x; Ts[row * XS_LD + 8 * nt + 2 * fk + 1] = v.y;
+            }
             new_step = true;
         }
         it.next();
