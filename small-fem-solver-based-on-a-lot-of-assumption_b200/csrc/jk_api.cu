@@ -43,7 +43,7 @@ struct jk_handle_s {
 
     // supports / ordering / storage
     bool have_supports = false;
-    int n_fixed = 0, n_free_nodes = 0, n_free = 0, n_pad = 0, NT = 0, bw = 0, solver = 0;
+    int n_fixed = 0, n_free_nodes = 0, n_free = 0, n_pad = 0, NT = 0, bw = 0, solver = 0, hb = 0;
     std::vector<int> h_node2slot, h_free_nodes, h_fixed;
     int *d_node2slot = nullptr, *d_fixed_nodes = nullptr, *d_free_nodes = nullptr;
     KBlock* d_blocks = nullptr;
@@ -313,8 +313,8 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     struct Contrib { long long key; int member, quad; };
     std::vector<Contrib> cs;
     cs.reserve(3 * (size_t)h->M);
-    int bw = 0;
-    auto span = [&](int rs, int cslot) { int I = (6 * rs + 5) / NB, J = (6 * cslot) / NB; bw = std::max(bw, I - J); };
+    int bw = 0, hb = 0;
+    auto span = [&](int rs, int cslot) { int I = (6 * rs + 5) / NB, J = (6 * cslot) / NB; bw = std::max(bw, I - J); hb = std::max(hb, 6 * (rs - cslot) + 5); };
     for (int m = 0; m < h->M; ++m) {
         int s0 = h->h_node2slot[h->h_conn[2 * m]], s1 = h->h_node2slot[h->h_conn[2 * m + 1]];
         if (s0 >= 0) { cs.push_back({(long long)s0 * h->n_free_nodes + s0, m, 0}); span(s0, s0); }
@@ -341,6 +341,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
       for (int s = 0; s < h->n_free_nodes; ++s) if (!touched[s]) JK_FAIL(h, JK_EINVAL, "jk_set_supports: free node %d has no member attached", h->h_free_nodes[s]); }
     h->nblocks = (int)blocks.size();
     h->bw = (solver == JK_SOLVER_DENSE) ? (h->NT - 1) : std::min(bw, h->NT - 1);
+    h->hb = hb;   // the Cholesky factor keeps the DOF half-bandwidth of K_ff (no fill outside the band), also in dense storage
     h->tiles_elems = (size_t)h->NT * (size_t)(h->bw + 1) * NB * NB;
 
     CUDA_TRY(h, dev_alloc(&h->d_node2slot, (size_t)h->Nn));
@@ -599,7 +600,7 @@ static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool f
     cudaStream_t s = h->stream;
     tic(h, JK_T_REDUCE);
     int n_mchunk = ceil_div(h->M, MCHUNK), n_nchunk = ceil_div(h->Nn, NCHUNK);
-    k_phase_reduce<<<ceil_div(P, 128), 128, 0, s>>>(P, ldP, h->d_t, n_mchunk, morison ? h->d_totpart : nullptr,
+    k_phase_reduce<<<ceil_div(P, 32), 32 * RED_GROUPS, 0, s>>>(P, ldP, h->d_t, n_mchunk, morison ? h->d_totpart : nullptr,
                                                      n_mchunk, fem ? h->d_part_util : nullptr, h->d_part_vm, h->d_part_mem,
                                                      n_nchunk, fem ? h->d_part_disp : nullptr, h->d_part_node,
                                                      h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL);
@@ -616,19 +617,19 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     int nslab = ldP / SLAB;
     if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0));   // join the side stream
     tic(h, JK_T_SOLVE_FWD);
-    k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad);
+    k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad, h->hb);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SOLVE_FWD);
     tic(h, JK_T_SOLVE_BWD);
-    k_slab_sweep<true><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad);
+    k_slab_sweep<true><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad, h->hb);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SOLVE_BWD);
     tic(h, JK_T_POST);
-    dim3 gm(ceil_div(ldP, PH_TPB), ceil_div(h->M, MCHUNK));
+    dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, PH_TPB));
     k_member_post<<<gm, PH_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
                                         h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
     LAUNCH_CHECK(h);
-    dim3 gn(ceil_div(ldP, PH_TPB), ceil_div(h->Nn, NCHUNK));
+    dim3 gn(ceil_div(h->Nn, NCHUNK), ceil_div(ldP, PH_TPB));
     k_node_post<<<gn, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_part_disp, h->d_part_node);
     LAUNCH_CHECK(h);
     dim3 gr(ceil_div(ldP, PH_TPB), h->n_fixed);

@@ -13,7 +13,9 @@ namespace jk {
 constexpr int LS_LD = NB + 4;     // smem row stride of an L tile  (== 4 mod 16 -> conflict-free DMMA fragment loads)
 constexpr int XS_LD = SLAB + 4;   // smem row stride of an X tile
 constexpr int SOLVE_STAGES = 3;
-constexpr int SOLVE_THREADS = 256;   // 8 warps: warp w owns rows 8w..8w+7 of the tile row, all SLAB columns
+constexpr int SOLVE_NSPLIT = 1;       // column groups per tile row: warps = 8 * NSPLIT, each owns 8 rows x (SLAB / NSPLIT) columns
+constexpr int SOLVE_NT = SLAB / 8 / SOLVE_NSPLIT;   // 8-column DMMA tiles per warp
+constexpr int SOLVE_THREADS = 256 * SOLVE_NSPLIT;
 constexpr size_t SOLVE_SMEM = (size_t)SOLVE_STAGES * (NB * LS_LD + NB * XS_LD) * sizeof(double) + (size_t)NB * XS_LD * sizeof(double);
 constexpr size_t UPDATE_SMEM = (size_t)2 * NB * LS_LD * sizeof(double);
 
@@ -214,7 +216,8 @@ struct SweepIter {
 template <bool BWD>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, double* __restrict__ X,
-             int NT, int bw, int n_pad) {
+             int NT, int bw, int n_pad, int hb /* DOF half-bandwidth of L (reserved) */) {
+    (void)hb;
     extern __shared__ __align__(16) double smem[];
     double* Ls = smem;                                         // [STAGES][NB][LS_LD]
     double* Xs = Ls + SOLVE_STAGES * NB * LS_LD;               // [STAGES][NB][XS_LD]
@@ -243,9 +246,10 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
     // prologue: STAGES-1 items in flight
     for (int s = 0; s < SOLVE_STAGES - 1; ++s) { issue(it_load, s); cp_async_commit(); it_load.next(); }
 
-    double acc[4][2];
-    double bk[4][2];
-    const int row = 8 * warp + fr;                             // this lane's row inside the tile
+    double acc[SOLVE_NT][2];
+    double bk[SOLVE_NT][2];
+    const int row = 8 * (warp % 8) + fr;                       // this lane's row inside the tile
+    const int col0 = (warp / 8) * (SLAB / SOLVE_NSPLIT);        // first column of this warp's column group
     int n = 0;                                                 // item counter
     bool new_step = true;
     while (!it.done()) {
@@ -253,8 +257,8 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         if (new_step) {
             // right-hand side rows of this step (fragment layout), issued early
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                double2 v = *reinterpret_cast<const double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + 8 * nt + 2 * fk);
+            for (int nt = 0; nt < SOLVE_NT; ++nt) {
+                double2 v = *reinterpret_cast<const double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + col0 + 8 * nt + 2 * fk);
                 bk[nt][0] = v.x; bk[nt][1] = v.y;
                 acc[nt][0] = acc[nt][1] = 0.0;
             }
@@ -274,6 +278,8 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         if (ld_x) xsrc = Xslab + (size_t)it_load.j * NB * SLAB + (tid >> 4) * SLAB + 2 * (tid & 15);
         double* ldst = Ls + lstage * NB * LS_LD + (tid >> 5) * LS_LD + 2 * (tid & 31);
         double* xdst = Xs + lstage * NB * XS_LD + (tid >> 4) * XS_LD + 2 * (tid & 15);
+        constexpr int LROWS = SOLVE_THREADS / 32, XROWS = SOLVE_THREADS / 16;   // tile rows covered by one chunk round
+        constexpr int LCH = NB / LROWS, XCH = NB / XROWS;                        // chunk rounds per thread
         it_load.next();
 
         const double* ls = Ls + stage * NB * LS_LD;
@@ -281,9 +287,9 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         if (it.is_diag()) {
             // t = B_k - acc  -> Ts, then acc = Linv * t
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                Ts[row * XS_LD + 8 * nt + 2 * fk] = bk[nt][0] - acc[nt][0];
-                Ts[row * XS_LD + 8 * nt + 2 * fk + 1] = bk[nt][1] - acc[nt][1];
+            for (int nt = 0; nt < SOLVE_NT; ++nt) {
+                Ts[row * XS_LD + col0 + 8 * nt + 2 * fk] = bk[nt][0] - acc[nt][0];
+                Ts[row * XS_LD + col0 + 8 * nt + 2 * fk + 1] = bk[nt][1] - acc[nt][1];
                 acc[nt][0] = acc[nt][1] = 0.0;
             }
             __syncthreads();
@@ -293,28 +299,36 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         }
         // acc += op(L) * xs, op = identity (forward) or transpose (backward)
         const double* a_base = BWD ? (ls + fk * LS_LD + row) : (ls + row * LS_LD + fk);
-        const double* b_base = xs + fk * XS_LD + fr;
+        const double* b_base = xs + fk * XS_LD + col0 + fr;
+        // fragments of step k4+1 are loaded before the DMMAs of step k4 are issued (register double buffer,
+        // static indices after full unrolling) so the tensor pipe never waits on a shared-memory load
+        double af[2], bf[2][SOLVE_NT];
+        af[0] = a_base[0];
+#pragma unroll
+        for (int nt = 0; nt < SOLVE_NT; ++nt) bf[0][nt] = b_base[8 * nt];
 #pragma unroll
         for (int k4 = 0; k4 < NB / 4; ++k4) {
-            // 256 threads x (8 L chunks + 4 X chunks) of 16 B = one 64x64 L tile + one 64x32 X tile
-            if (k4 < 8) { if (ld_l) cp_async16(ldst + k4 * 8 * LS_LD, lsrc + k4 * 8 * NB); }
-            else if (k4 < 12) { if (ld_x) cp_async16(xdst + (k4 - 8) * 16 * XS_LD, xsrc + (k4 - 8) * 16 * SLAB); }
-            const double a0 = BWD ? a_base[4 * k4 * LS_LD] : a_base[4 * k4];
-            double b[4];
+            // copy chunks of item n+2: (LCH + XCH) x 16 B per thread = one 64x64 L tile + one 64x32 X tile per CTA
+            if (k4 < LCH) { if (ld_l) cp_async16(ldst + k4 * LROWS * LS_LD, lsrc + k4 * LROWS * NB); }
+            else if (k4 < LCH + XCH) { if (ld_x) cp_async16(xdst + (k4 - LCH) * XROWS * XS_LD, xsrc + (k4 - LCH) * XROWS * SLAB); }
+            const int cur = k4 & 1, nxt = cur ^ 1;
+            if (k4 + 1 < NB / 4) {
+                af[nxt] = BWD ? a_base[4 * (k4 + 1) * LS_LD] : a_base[4 * (k4 + 1)];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) b[nt] = b_base[4 * k4 * XS_LD + 8 * nt];
+                for (int nt = 0; nt < SOLVE_NT; ++nt) bf[nxt][nt] = b_base[4 * (k4 + 1) * XS_LD + 8 * nt];
+            }
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma(acc[nt][0], acc[nt][1], a0, b[nt]);
+            for (int nt = 0; nt < SOLVE_NT; ++nt) dmma(acc[nt][0], acc[nt][1], af[cur], bf[cur][nt]);
         }
         cp_async_commit();
         if (it.is_diag()) {
             // acc is X_k: store to the slab (in place) and keep it in Ts as the newest tile
             __syncthreads();                                   // all warps finished reading Ts (= t)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int nt = 0; nt < SOLVE_NT; ++nt) {
                 double2 v = make_double2(acc[nt][0], acc[nt][1]);
-                *reinterpret_cast<double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + 8 * nt + 2 * fk) = v;
-                Ts[row * XS_LD + 8 * nt + 2 * fk] = v.x; Ts[row * XS_LD + 8 * nt + 2 * fk + 1] = v.y;
+                *reinterpret_cast<double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + col0 + 8 * nt + 2 * fk) = v;
+                Ts[row * XS_LD + col0 + 8 * nt + 2 * fk] = v.x; Ts[row * XS_LD + col0 + 8 * nt + 2 * fk + 1] = v.y;
             }
             new_step = true;
         }

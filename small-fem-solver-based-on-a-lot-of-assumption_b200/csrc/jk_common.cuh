@@ -77,7 +77,7 @@ struct WaveAiry {
 // mma.sync m8n8k4 f64: A row-major fragment (lane holds A[l/4][l%4]), B "col" fragment
 // (lane holds B[l%4][l/4]), C/D lane holds C[l/4][2*(l%4) + {0,1}].  SASS: DMMA.8x8x4.
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 

@@ -233,7 +233,9 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
     __shared__ double s_mc[MCHUNK * MC_STRIDE];
     __shared__ int s_slot[MCHUNK * 2];
     __shared__ double s_pt[MCHUNK * 24];
-    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
+    // chunk index is the FAST grid dimension: the blocks in flight share one or two 128-phase tiles, whose slice of
+    // the solution (n x 128 doubles = 20 MB at c4) stays L2-resident while every member chunk re-reads its nodes
+    int chunk = blockIdx.x, m0 = chunk * MCHUNK;
     int nm = min(MCHUNK, M - m0);
     for (int i = threadIdx.x; i < nm * MC_STRIDE; i += blockDim.x) s_mc[i] = mc[(size_t)m0 * MC_STRIDE + i];
     for (int i = threadIdx.x; i < nm * 2; i += blockDim.x) s_slot[i] = node2slot[conn[2 * m0 + i]];
@@ -241,7 +243,7 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
     for (int i = threadIdx.x; i < nm * 8; i += blockDim.x) stress_point_coeffs(s_mc + (i / 8) * MC_STRIDE, sp, i % 8, s_pt + 3 * i);
     __syncthreads();
     const double inv_fy = 1.0 / fy;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y * blockDim.x + threadIdx.x;
     if (p >= ldP) return;
     const size_t xbase = (size_t)(p / SLAB) * (size_t)n_pad * SLAB + (size_t)(p % SLAB);
     double best_u = -1.0, best_vm = 0.0; int best_m = 0;
@@ -291,9 +293,9 @@ __global__ void k_member_post_single(int M, int p, int n_pad, const double* __re
 __global__ void __launch_bounds__(PH_TPB)
 k_node_post(int Nn, int ldP, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
             double* __restrict__ part_disp, int* __restrict__ part_node) {
-    int chunk = blockIdx.y, n0 = chunk * NCHUNK;
+    int chunk = blockIdx.x, n0 = chunk * NCHUNK;
     int nn = min(NCHUNK, Nn - n0);
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = blockIdx.y * blockDim.x + threadIdx.x;
     if (p >= ldP) return;
     const size_t xbase = (size_t)(p / SLAB) * (size_t)n_pad * SLAB + (size_t)(p % SLAB);
     double best = 0.0; int bnode = -1;

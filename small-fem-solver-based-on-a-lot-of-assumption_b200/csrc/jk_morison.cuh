@@ -204,27 +204,65 @@ k_rhs_from_loads(int Nn, int P, int ldP, int n_pad, const double* __restrict__ F
 }
 
 // ----------------------------------------------------------------------------------------------
-// per-phase table row from the chunk partials (chunk order = member / node order => deterministic)
+// per-phase table row from the chunk partials.  Block = 32 phases x RED_GROUPS groups: group g folds chunks
+// g, g+RED_GROUPS, ... in ascending order, then the groups are folded in ascending order by group 0, so the
+// summation order is fixed (deterministic) and first-maximum ties resolve to the lowest member / node index.
 // ----------------------------------------------------------------------------------------------
-__global__ void k_phase_reduce(int P, int ldP, const double* __restrict__ t,
-                               int n_mchunk, const double* __restrict__ totpart,
-                               int n_pchunk, const double* __restrict__ part_util, const double* __restrict__ part_vm,
-                               const int* __restrict__ part_mem,
-                               int n_nchunk, const double* __restrict__ part_disp, const int* __restrict__ part_node,
-                               int n_fixed, const double* __restrict__ react,
-                               double* __restrict__ table, int ncol) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+constexpr int RED_GROUPS = 8;
+
+__global__ void __launch_bounds__(32 * RED_GROUPS)
+k_phase_reduce(int P, int ldP, const double* __restrict__ t,
+               int n_mchunk, const double* __restrict__ totpart,
+               int n_pchunk, const double* __restrict__ part_util, const double* __restrict__ part_vm,
+               const int* __restrict__ part_mem,
+               int n_nchunk, const double* __restrict__ part_disp, const int* __restrict__ part_node,
+               int n_fixed, const double* __restrict__ react,
+               double* __restrict__ table, int ncol) {
+    __shared__ double s_sum[RED_GROUPS][9][32];
+    __shared__ double s_val[RED_GROUPS][3][32];
+    __shared__ int s_idx[RED_GROUPS][2][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const bool live = p < P;
+    const int pp = live ? p : P - 1;
+    // chunk ranges are contiguous per group so that group order == chunk order
+    auto range = [&](int n, int& lo, int& hi) { int per = (n + RED_GROUPS - 1) / RED_GROUPS; lo = min(n, g * per); hi = min(n, lo + per); };
+    if (totpart) {
+        int lo, hi; range(n_mchunk, lo, hi);
+        double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int ch = lo; ch < hi; ++ch)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] += totpart[((size_t)ch * 9 + k) * ldP + pp];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_sum[g][k][lane] = v[k];
+    }
+    if (part_util) {
+        int lo, hi; range(n_pchunk, lo, hi);
+        double best = -1.0, bvm = 0.0; int bm = -1;
+        for (int ch = lo; ch < hi; ++ch) {
+            double u = part_util[(size_t)ch * ldP + pp];
+            if (u > best) { best = u; bvm = part_vm[(size_t)ch * ldP + pp]; bm = part_mem[(size_t)ch * ldP + pp]; }
+        }
+        s_val[g][0][lane] = best; s_val[g][1][lane] = bvm; s_idx[g][0][lane] = bm;
+    }
+    if (part_disp) {
+        int lo, hi; range(n_nchunk, lo, hi);
+        double best = 0.0; int bn = -1;
+        for (int ch = lo; ch < hi; ++ch) {
+            double d = part_disp[(size_t)ch * ldP + pp];
+            if (d > best) { best = d; bn = part_node[(size_t)ch * ldP + pp]; }
+        }
+        s_val[g][2][lane] = best; s_idx[g][1][lane] = bn;
+    }
+    __syncthreads();
+    if (g != 0 || !live) return;
     double* row = table + (size_t)p * ncol;
     for (int c = 0; c < ncol; ++c) row[c] = 0.0;
     row[0] = t[p];
     if (totpart) {
         double v[9];
-        for (int k = 0; k < 9; ++k) {
-            double s = 0.0;
-            for (int ch = 0; ch < n_mchunk; ++ch) s += totpart[((size_t)ch * 9 + k) * ldP + p];
-            v[k] = s;
-        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { double s = 0.0; for (int q = 0; q < RED_GROUPS; ++q) s += s_sum[q][k][lane]; v[k] = s; }
         row[2] = sqrt(v[6] * v[6] + v[7] * v[7] + v[8] * v[8]) / 1000.0;     // GUI.py:701, 708
         row[3] = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 1000.0;
         row[4] = sqrt(v[3] * v[3] + v[4] * v[4] + v[5] * v[5]) / 1000.0;
@@ -232,18 +270,12 @@ __global__ void k_phase_reduce(int P, int ldP, const double* __restrict__ t,
     }
     if (part_disp) {
         double best = 0.0; int bn = -1;
-        for (int ch = 0; ch < n_nchunk; ++ch) {
-            double d = part_disp[(size_t)ch * ldP + p];
-            if (d > best) { best = d; bn = part_node[(size_t)ch * ldP + p]; }
-        }
+        for (int q = 0; q < RED_GROUPS; ++q) if (s_val[q][2][lane] > best) { best = s_val[q][2][lane]; bn = s_idx[q][1][lane]; }
         row[8] = best; row[9] = (double)bn;
     }
     if (part_util) {
         double best = -1.0, bvm = 0.0; int bm = -1;
-        for (int ch = 0; ch < n_pchunk; ++ch) {
-            double u = part_util[(size_t)ch * ldP + p];
-            if (u > best) { best = u; bvm = part_vm[(size_t)ch * ldP + p]; bm = part_mem[(size_t)ch * ldP + p]; }
-        }
+        for (int q = 0; q < RED_GROUPS; ++q) if (s_val[q][0][lane] > best) { best = s_val[q][0][lane]; bvm = s_val[q][1][lane]; bm = s_idx[q][0][lane]; }
         row[10] = best; row[11] = (double)bm; row[12] = bvm;
     }
     if (react) {
