@@ -8,7 +8,8 @@ The class surface mirrors the reference's analysis module
 """
 from .sections import TubularSection
 from .structure import CustomJacketStructure, create_default_3leg_jacket, generate_jacket, default_sections
-from .wave import RaschiiWave, g
+from .wave import RaschiiWave, g, enable_nonlinear_waves
+from . import wavefit
 from .morison import MorisonCalculator, phase_times
 from .fem import FEMSolver, BeamElement3D
 from .analysis import (AnalysisParams, PhaseScanResult, phase_scan, phase_scan_from_params, run_analysis,

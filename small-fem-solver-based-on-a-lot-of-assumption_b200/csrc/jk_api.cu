@@ -63,6 +63,10 @@ struct jk_handle_s {
     double rho = 0, Cd = 0, Cm = 0;
     int ng = 0;
     double *d_gsw = nullptr, *d_gp = nullptr;
+    int wave_kind = 0;         // 0 = Airy closed form, 1 = Fourier series
+    int n_harm = 0;
+    double* d_four = nullptr;  // E[Nh], B[Nh], 1/cosh(j k d)[Nh]
+    size_t gp_elems = 0;
     StressPts sp{};
 
     // scan buffers (capacity cap_ldP phases)
@@ -210,7 +214,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
     dev_free(h->d_blocks); dev_free(h->d_contrib); dev_free(h->d_tiles); dev_free(h->d_Linv); dev_free(h->d_dinv); dev_free(h->d_info);
-    dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp);
+    dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
     dev_free(h->d_table); dev_free(h->d_details); dev_free(h->d_Fload); dev_free(h->d_argval); dev_free(h->d_tmp); dev_free(h->d_res);
@@ -483,13 +487,26 @@ extern "C" int jk_set_wave_airy(jk_handle_t h, double a, double k, double omega,
     if (!h) return JK_EINVAL;
     if (!(k > 0) || !(omega > 0) || !(d > 0) || !(dt > 0)) JK_FAIL(h, JK_EINVAL, "jk_set_wave_airy: k, omega, d, dt must be positive");
     h->wv.a = a; h->wv.k = k; h->wv.omega = omega; h->wv.d = d; h->wv.Uc = U_c; h->wv.dt = dt; h->wv.inv_dt = 1.0 / dt;
+    h->wave_kind = 0; h->n_harm = 0;
     h->have_wave = true; h->gp_valid = false;
     return JK_OK;
 }
 
-extern "C" int jk_set_wave_fourier(jk_handle_t h, double, double, double, double, double, int, const double*, const double*) {
-    if (!h) return JK_EINVAL;
-    JK_FAIL(h, JK_EINVAL, "jk_set_wave_fourier: Fourier-series kinematics are not built in this round (Airy closed form only)");
+extern "C" int jk_set_wave_fourier(jk_handle_t h, double k, double omega, double d, double U_c, double dt,
+                                   int n_harm, const double* E, const double* B) {
+    if (!h || !E || !B) return JK_EINVAL;
+    if (!(k > 0) || !(omega > 0) || !(d > 0) || !(dt > 0)) JK_FAIL(h, JK_EINVAL, "jk_set_wave_fourier: k, omega, d, dt must be positive");
+    if (n_harm < 1 || n_harm > FOURIER_MAX_H) JK_FAIL(h, JK_EINVAL, "jk_set_wave_fourier: n_harm must be in 1..%d", FOURIER_MAX_H);
+    cudaSetDevice(h->device);
+    std::vector<double> four(3 * (size_t)n_harm);
+    for (int j = 0; j < n_harm; ++j) { four[j] = E[j]; four[n_harm + j] = B[j]; four[2 * n_harm + j] = 1.0 / cosh((j + 1) * k * d); }
+    CUDA_TRY(h, dev_alloc(&h->d_four, four.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_four, four.data(), four.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->wv.a = E[0]; h->wv.k = k; h->wv.omega = omega; h->wv.d = d; h->wv.Uc = U_c; h->wv.dt = dt; h->wv.inv_dt = 1.0 / dt;
+    h->wave_kind = 1; h->n_harm = n_harm;
+    h->have_wave = true; h->gp_valid = false;
+    return JK_OK;
 }
 
 extern "C" int jk_set_morison(jk_handle_t h, double theta_wave, double theta_current, double rho, double Cd, double Cm,
@@ -503,7 +520,6 @@ extern "C" int jk_set_morison(jk_handle_t h, double theta_wave, double theta_cur
     std::vector<double> gsw(2 * (size_t)n_gauss);
     for (int i = 0; i < n_gauss; ++i) { gsw[i] = gauss_s[i]; gsw[n_gauss + i] = gauss_w[i]; }
     CUDA_TRY(h, dev_alloc(&h->d_gsw, gsw.size()));
-    CUDA_TRY(h, dev_alloc(&h->d_gp, (size_t)h->M * n_gauss * GP_STRIDE));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_gsw, gsw.data(), gsw.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_morison = true; h->gp_valid = false;
@@ -562,9 +578,16 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
     cudaStream_t s = h->stream;
     WaveAiry w = launch_wave(h);
     tic(h, JK_T_WAVE_SETUP);
+    const int Nh = h->n_harm;
+    const size_t gstride = h->wave_kind == 1 ? (size_t)(3 + 2 * Nh) : (size_t)GP_STRIDE;
     if (!h->gp_valid) {
         int n = h->M * h->ng;
-        k_gauss_setup_airy<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_gp);
+        size_t need = (size_t)n * gstride;
+        if (need > h->gp_elems) { CUDA_TRY(h, dev_alloc(&h->d_gp, need)); h->gp_elems = need; }
+        if (h->wave_kind == 1)
+            k_gauss_setup_fourier<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, Nh, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_four, h->d_gp);
+        else
+            k_gauss_setup_airy<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_gp);
         LAUNCH_CHECK(h);
         h->gp_valid = true;
     }
@@ -573,14 +596,25 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
     toc(h, JK_T_WAVE_SETUP);
     tic(h, JK_T_MORISON);
     dim3 grid(ceil_div(ldP, PH_TPB), ceil_div(h->M, MCHUNK));
-    size_t smem = ((size_t)MCHUNK * h->ng * GP_STRIDE + MCHUNK * 8 + 2 * h->ng) * sizeof(double);
     double cD0 = 0.5 * h->rho * h->Cd, cI0 = h->rho * h->Cm;
-    if (details) {
-        CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details);
+    if (h->wave_kind == 1) {
+        size_t smem = ((size_t)FCHUNK * h->ng * gstride + MCHUNK * 8 + 2 * h->ng + 3 * Nh) * sizeof(double);
+        if (details) {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_fourier<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_morison_fourier<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, Nh, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, h->d_four, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details);
+        } else {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_fourier<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_morison_fourier<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, Nh, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, h->d_four, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
+        }
     } else {
-        CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_morison_airy<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
+        size_t smem = ((size_t)MCHUNK * h->ng * GP_STRIDE + MCHUNK * 8 + 2 * h->ng) * sizeof(double);
+        if (details) {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details);
+        } else {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_morison_airy<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
+        }
     }
     LAUNCH_CHECK(h);
     toc(h, JK_T_MORISON);

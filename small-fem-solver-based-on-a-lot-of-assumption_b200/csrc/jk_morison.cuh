@@ -150,6 +150,176 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
 }
 
 // ----------------------------------------------------------------------------------------------
+// Fourier-series kinematics (Stokes / Fenton form; wrapper semantics of the reference's raschii branch,
+// GUI.py:259-281):   eta = sum_j E_j cos(j phi),   u = sum_j B_j cosh(j k zb)/cosh(j k d) cos(j phi) + U_c,
+//                    w = sum_j B_j sinh(j k zb)/cosh(j k d) sin(j phi),   zb = clamp(z + d, 0.01, d + eta - 0.01).
+// For a point more than 1 cm below the instantaneous surface zb = z + d does not depend on the phase, so
+// B_j cosh/sinh(j k (z+d))/cosh(j k d) are tabulated per Gauss point (k_gauss_setup_fourier); the thin clamped
+// layer under the surface takes a direct evaluation.  cos/sin(j phi) come from the Chebyshev recurrence.
+// PARITY UNPINNED (raschii absent): checked against oracle/jacket_oracle.py:fourier_velocity only.
+// ----------------------------------------------------------------------------------------------
+constexpr int FOURIER_MAX_H = 32;
+constexpr int FCHUNK = 8;      // members staged per shared-memory refill of the Fourier kernel
+
+// wave table in device memory: E[Nh], B[Nh], 1/cosh(j k d)[Nh]
+__global__ void k_gauss_setup_fourier(int M, int G, int Nh, const double* __restrict__ xyz, const int* __restrict__ conn,
+                                      const double* __restrict__ gs, WaveAiry wv, const double* __restrict__ four,
+                                      double* __restrict__ gp /* [M][G][3 + 2 Nh] */) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * G) return;
+    int m = idx / G, g = idx % G;
+    int a = conn[2 * m], b = conn[2 * m + 1];
+    double s = gs[g];
+    double x = xyz[3 * a] + s * (xyz[3 * b] - xyz[3 * a]);
+    double y = xyz[3 * a + 1] + s * (xyz[3 * b + 1] - xyz[3 * a + 1]);
+    double z = xyz[3 * a + 2] + s * (xyz[3 * b + 2] - xyz[3 * a + 2]);
+    double xw = __dadd_rn(__dmul_rn(x, wv.cos_w), __dmul_rn(y, wv.sin_w));
+    double sk, ck;
+    sincos(wv.k * xw, &sk, &ck);
+    const int stride = 3 + 2 * Nh;
+    double* o = gp + (size_t)idx * stride;
+    o[0] = ck; o[1] = sk; o[2] = z;
+    double zb = z + wv.d;
+    for (int j = 1; j <= Nh; ++j) {
+        double arg = j * wv.k * zb;
+        o[3 + 2 * (j - 1)] = four[Nh + j - 1] * cosh(arg) * four[2 * Nh + j - 1];
+        o[4 + 2 * (j - 1)] = four[Nh + j - 1] * sinh(arg) * four[2 * Nh + j - 1];
+    }
+}
+
+// direct evaluation for a clamped point: zb given, cos/sin of the fundamental given
+__device__ __forceinline__ void fourier_uw_direct(int Nh, const double* __restrict__ s_four, double k, double zb, double c, double s,
+                                                  double& u, double& w) {
+    double e = exp(k * zb), ei = 1.0 / e;
+    double p = e, q = ei;
+    double cj = c, sj = s, cjm = 1.0, sjm = 0.0;
+    u = 0.0; w = 0.0;
+    for (int j = 1; j <= Nh; ++j) {
+        double bj = s_four[Nh + j - 1] * s_four[2 * Nh + j - 1];
+        u = fma(bj * 0.5 * (p + q), cj, u);
+        w = fma(bj * 0.5 * (p - q), sj, w);
+        p *= e; q *= ei;
+        double cn = fma(2.0 * c, cj, -cjm), sn = fma(2.0 * c, sj, -sjm);
+        cjm = cj; sjm = sj; cj = cn; sj = sn;
+    }
+}
+
+template <bool DETAILS>
+__global__ void __launch_bounds__(PH_TPB)
+k_morison_fourier(int M, int G, int Nh, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
+                  const double* __restrict__ gsw, const double* __restrict__ trig, const double* __restrict__ four,
+                  WaveAiry wv, double cD0, double cI0,
+                  double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details) {
+    extern __shared__ __align__(16) double smem[];
+    const int stride = 3 + 2 * Nh;
+    double* s_gp = smem;                                   // [FCHUNK][G][stride]
+    double* s_m = s_gp + FCHUNK * G * stride;              // [MCHUNK][8]
+    double* s_g = s_m + MCHUNK * 8;                        // s[G], w[G]
+    double* s_four = s_g + 2 * G;                          // E, B, 1/cosh
+    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
+    int nm = min(MCHUNK, M - m0);
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        const double* c = mc + (size_t)(m0 + i) * MC_STRIDE;
+        s_m[8 * i + 0] = c[MC_E]; s_m[8 * i + 1] = c[MC_E + 1]; s_m[8 * i + 2] = c[MC_E + 2];
+        s_m[8 * i + 3] = cD0 * c[MC_D]; s_m[8 * i + 4] = cI0 * c[MC_ACROSS]; s_m[8 * i + 5] = c[MC_L];
+    }
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_g[i] = gsw[i];
+    for (int i = threadIdx.x; i < 3 * Nh; i += blockDim.x) s_four[i] = four[i];
+
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < ldP;
+    const int pp = live ? p : ldP - 1;
+    const double cw0 = trig[pp], sw0 = trig[ldP + pp], cw1 = trig[2 * (size_t)ldP + pp], sw1 = trig[3 * (size_t)ldP + pp];
+    double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
+
+    for (int sub = 0; sub < nm; sub += FCHUNK) {
+        const int ns = min(FCHUNK, nm - sub);
+        __syncthreads();                                   // previous sub-chunk fully consumed
+        for (int i = threadIdx.x; i < ns * G * stride; i += blockDim.x) s_gp[i] = gp[((size_t)(m0 + sub) * G) * stride + i];
+        __syncthreads();
+        if (!live) continue;
+        for (int ms = 0; ms < ns; ++ms) {
+            const int mm = sub + ms;
+            const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
+            const double cD = s_m[8 * mm + 3], cI = s_m[8 * mm + 4], L = s_m[8 * mm + 5];
+            double F1[3] = {0, 0, 0}, F2[3] = {0, 0, 0}, md[3] = {0, 0, 0}, mi[3] = {0, 0, 0};
+            double subl = 0.0;
+            for (int g = 0; g < G; ++g) {
+                const double* q = s_gp + (ms * G + g) * stride;
+                const double ckx = q[0], skx = q[1], z = q[2];
+                const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
+                const double c1 = fma(skx, sw1, ckx * cw1), s1 = fma(skx, cw1, -(ckx * sw1));
+                // harmonic sums at t and t + dt
+                double eta0 = 0, u0 = 0, w0 = 0, eta1 = 0, u1 = 0, w1 = 0;
+                double a0 = c0, b0 = s0, a0m = 1.0, b0m = 0.0, a1 = c1, b1 = s1, a1m = 1.0, b1m = 0.0;
+                for (int j = 0; j < Nh; ++j) {
+                    const double Ej = s_four[j], ch = q[3 + 2 * j], sh = q[4 + 2 * j];
+                    eta0 = fma(Ej, a0, eta0); u0 = fma(ch, a0, u0); w0 = fma(sh, b0, w0);
+                    eta1 = fma(Ej, a1, eta1); u1 = fma(ch, a1, u1); w1 = fma(sh, b1, w1);
+                    double n0 = fma(2.0 * c0, a0, -a0m), n1 = fma(2.0 * c0, b0, -b0m);
+                    a0m = a0; b0m = b0; a0 = n0; b0 = n1;
+                    n0 = fma(2.0 * c1, a1, -a1m); n1 = fma(2.0 * c1, b1, -b1m);
+                    a1m = a1; b1m = b1; a1 = n0; b1 = n1;
+                }
+                if (z > eta0) continue;                                        // dry at t (GUI.py:269, 292)
+                const double zb = z + wv.d;
+                // thin clamped layer (GUI.py:272): zb = max(0.01, min(z + d, d + eta - 0.01))
+                if (zb < 0.01 || zb > wv.d + eta0 - 0.01)
+                    fourier_uw_direct(Nh, s_four, wv.k, fmax(0.01, fmin(zb, wv.d + eta0 - 0.01)), c0, s0, u0, w0);
+                const bool wet1 = !(z > eta1);
+                if (wet1 && (zb < 0.01 || zb > wv.d + eta1 - 0.01))
+                    fourier_uw_direct(Nh, s_four, wv.k, fmax(0.01, fmin(zb, wv.d + eta1 - 0.01)), c1, s1, u1, w1);
+                u0 += wv.Uc;                                                   // GUI.py:281
+                u1 = wet1 ? u1 + wv.Uc : 0.0; w1 = wet1 ? w1 : 0.0;
+                const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;
+                const double uwo = u0 - wv.Uc;
+                const double U0 = fma(uwo, wv.cos_w, wv.uc_cos_c), U1 = fma(uwo, wv.sin_w, wv.uc_sin_c), U2 = w0;
+                const double A0 = du * wv.cos_w, A1 = du * wv.sin_w, A2 = dw;
+                const double Ue = fma(U2, e2, fma(U1, e1, U0 * e0));
+                const double Ae = fma(A2, e2, fma(A1, e1, A0 * e0));
+                const double Up0 = fma(-Ue, e0, U0), Up1 = fma(-Ue, e1, U1), Up2 = fma(-Ue, e2, U2);
+                const double Ap0 = fma(-Ae, e0, A0), Ap1 = fma(-Ae, e1, A1), Ap2 = fma(-Ae, e2, A2);
+                const double mag = sqrt(fma(Up2, Up2, fma(Up1, Up1, Up0 * Up0)));
+                const double s = s_g[g], w = s_g[G + g];
+                const double Lw = L * w;
+                const double kd_ = (mag > 1e-10) ? cD * mag * Lw : 0.0;
+                const double ki_ = cI * Lw;
+                const double fd0 = kd_ * Up0, fd1 = kd_ * Up1, fd2 = kd_ * Up2;
+                const double fi0 = ki_ * Ap0, fi1 = ki_ * Ap1, fi2 = ki_ * Ap2;
+                const double ft0 = fd0 + fi0, ft1 = fd1 + fi1, ft2 = fd2 + fi2;
+                md[0] += fd0; md[1] += fd1; md[2] += fd2;
+                mi[0] += fi0; mi[1] += fi1; mi[2] += fi2;
+                const double s1m = 1.0 - s;
+                F1[0] = fma(s1m, ft0, F1[0]); F1[1] = fma(s1m, ft1, F1[1]); F1[2] = fma(s1m, ft2, F1[2]);
+                F2[0] = fma(s, ft0, F2[0]); F2[1] = fma(s, ft1, F2[1]); F2[2] = fma(s, ft2, F2[2]);
+                if (DETAILS) subl += Lw;
+            }
+            size_t o = ((size_t)(m0 + mm) * 6) * ldP + p;
+            Fm[o] = F1[0]; Fm[o + ldP] = F1[1]; Fm[o + 2 * (size_t)ldP] = F1[2];
+            Fm[o + 3 * (size_t)ldP] = F2[0]; Fm[o + 4 * (size_t)ldP] = F2[1]; Fm[o + 5 * (size_t)ldP] = F2[2];
+#pragma unroll
+            for (int kq = 0; kq < 3; ++kq) { td[kq] += md[kq]; ti[kq] += mi[kq]; tm[kq] += md[kq] + mi[kq]; }
+            if (DETAILS) {
+                size_t od = ((size_t)(m0 + mm) * 4) * ldP + p;
+                double mt0 = md[0] + mi[0], mt1 = md[1] + mi[1], mt2 = md[2] + mi[2];
+                details[od] = sqrt(md[0] * md[0] + md[1] * md[1] + md[2] * md[2]) / 1000.0;
+                details[od + ldP] = sqrt(mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]) / 1000.0;
+                details[od + 2 * (size_t)ldP] = sqrt(mt0 * mt0 + mt1 * mt1 + mt2 * mt2) / 1000.0;
+                details[od + 3 * (size_t)ldP] = subl;
+            }
+        }
+    }
+    if (!live) return;
+    size_t ot = ((size_t)chunk * 9) * ldP + p;
+#pragma unroll
+    for (int kq = 0; kq < 3; ++kq) {
+        totpart[ot + (size_t)kq * ldP] = td[kq];
+        totpart[ot + (size_t)(3 + kq) * ldP] = ti[kq];
+        totpart[ot + (size_t)(6 + kq) * ldP] = tm[kq];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // RHS gather: thread = (node, phase).  Sums the member-end forces of the node's incident members in
 // member order (the reference's accumulation order, GUI.py:661-662), adds the static load and writes
 // the solver right-hand side (free nodes) or the load at the supports (fixed nodes, for reactions).

@@ -99,7 +99,11 @@ class Engine:
     def set_wave(self, wave):
         sig = wave.signature()
         if sig != self._wave_sig:
-            self._ck(self.lib.jk_set_wave_airy(self.h, *wave.device_args()))
+            if getattr(wave, "kind", "airy") == "fourier":
+                k, om, d, Uc, dt, E, B = wave.fourier_args()
+                self._ck(self.lib.jk_set_wave_fourier(self.h, k, om, d, Uc, dt, len(E), L.dptr(E), L.dptr(B)))
+            else:
+                self._ck(self.lib.jk_set_wave_airy(self.h, *wave.device_args()))
             self._wave_sig = sig
 
     def set_morison(self, theta_wave, theta_current, rho, Cd, Cm, n_gauss=15):

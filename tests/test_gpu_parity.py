@@ -255,3 +255,43 @@ def test_overlapped_factor_matches_blocking():
     e2.set_morison(0.3, 0.3, 1025.0, 0.7, 2.0, 15)
     with pytest.raises(jb.NotPositiveDefinite):
         e2.phase_scan(np.linspace(0.0, 9.0, 8), ap.fy)
+
+
+@pytest.mark.parametrize("model,N,H", [("Stokes", 5, 8.0), ("Fenton", 10, 17.038), ("Airy", 1, 6.0)])
+def test_fourier_series_kinematics_vs_oracle(model, N, H):
+    """Stokes / Fenton path (own fits, opt-in): the CUDA Fourier kernel against the oracle's restatement of the
+    reference's raschii-branch wrapper semantics (GUI.py:259-281) for the SAME coefficients.  Parity vs raschii
+    itself is unpinned (not installable)."""
+    import jacket_b200 as jb
+    from oracle import jacket_oracle as orc
+    ap = jb.AnalysisParams(H=H, wave_model=model, N_harm=N, U_c=1.2, wave_dir=25.0, current_dir=70.0)
+    nodes, members, fixed, top = jb.create_default_3leg_jacket()
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    wave = jb.RaschiiWave(ap.H, ap.T, ap.d, ap.U_c, model, N, nonlinear=True)
+    assert wave.kind == "fourier" and wave.actual_model == model
+    P = 72
+    res = jb.phase_scan(st, wave, P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
+                        rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, params=ap)
+    xyz, conn, sec_id, _, sections = st.pack()
+    model_o = orc.Model(xyz, conn, sec_id, [(s.D_outer, s.t, s.rho_steel) for s in sections], st.indices(fixed), st.indices(top))
+    ow = orc.FourierWave(ap.H, ap.T, ap.d, wave.k, wave.wave.E, wave.wave.B, ap.U_c)
+    ref = orc.phase_scan(model_o, ow, orc.phase_times(ap.T, P), wave_direction=ap.wave_dir, current_direction=ap.current_dir,
+                         Cd=ap.Cd, Cm=ap.Cm, rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, F_axial_kN=ap.F_axial,
+                         F_shear_kN=ap.F_shear, self_weight="calculated", velocity_fn=orc.fourier_velocity)
+    assert res.critical_index == ref["critical"]
+    for c in range(2, 8):
+        assert relmax(res.table[:, c], ref["table"][:, c]) < TOL
+    for i in (0, 11, ref["critical"], P - 1):
+        ph = res.phase(i)
+        assert relmax(ph["U"], ref["U"][i]) < TOL
+        assert relmax(ph["nodal_forces"], ref["morison"]["nodal_forces"][i]) < TOL
+        util = np.array([r["utilization"] for r in ph["internal_forces"]])
+        assert relmax(util, ref["members"]["utilization"][i]) < TOL
+    # single-phase API with member details
+    r1 = jb.MorisonCalculator(st, wave, ap.wave_dir, ap.current_dir, ap.Cd, ap.Cm, ap.rho_water).compute_all_morison_forces(1.7)
+    o1 = orc.morison_phases(model_o, ow, [1.7], ap.wave_dir, ap.current_dir, ap.Cd, ap.Cm, ap.rho_water, velocity_fn=orc.fourier_velocity,
+                            want_details=True)
+    det = np.array([[d[k] for k in ("drag_kN", "inertia_kN", "total_kN", "submerged_length")] for d in r1["member_details"]])
+    for c in range(4):
+        assert relmax(det[:, c], o1["member_details"][0][:, c]) < TOL
+    assert relmax(r1["total_morison"], o1["total_morison"][0]) < TOL
