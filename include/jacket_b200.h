@@ -164,6 +164,18 @@ int jk_phase_scan(jk_handle_t h, int P, const double* t, double fy, double* tabl
 int jk_phase_scan_dev(jk_handle_t h, int P, const double* t_dev, double fy);
 int jk_read_table(jk_handle_t h, int P, double* table, int64_t* critical);
 
+/* Sea-state ensemble (BASELINE configs[4]): n_states Airy sea states (amplitude a = H/2, wave number k from the
+ * dispersion relation GUI.py:197-206, omega = 2 pi / T, math heading theta_wave) x n_phase phases each, evaluated as
+ * ONE batch of n_states*n_phase load cases on the factor already computed.  Depth, current, dt come from
+ * jk_set_wave_airy, current heading / coefficients / Gauss rule from jk_set_morison.  t[n_states*n_phase] are the
+ * case times (state-major).  F_dir (nullable) = two load vectors [2][6*n_nodes] added as cos(theta_wave)*F_dir[0] +
+ * sin(theta_wave)*F_dir[1]: the interface shear that run_analysis applies along the wave heading (GUI.py:1967-1971).
+ * table[n_states*n_phase*JK_TABLE_NCOL]; critical_per_state[n_states] = first phase index of the maximum total_kN
+ * inside each state (GUI.py:717 applied per sea state).  Rows of any case: jk_fetch_phase. */
+int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const double* a, const double* k, const double* omega,
+                     const double* theta_wave, const double* t, const double* F_dir, double fy, double* table,
+                     int64_t* critical_per_state);
+
 /* FEMSolver.solve with caller-built right-hand sides (GUI.py:481-490):
  * F[nrhs*6*n_nodes] (row = load case) -> same pipeline as jk_phase_scan minus Morison. */
 int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy);

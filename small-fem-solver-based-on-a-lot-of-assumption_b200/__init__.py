@@ -12,7 +12,7 @@ from .wave import RaschiiWave, g, enable_nonlinear_waves
 from . import wavefit
 from .morison import MorisonCalculator, phase_times
 from .fem import FEMSolver, BeamElement3D
-from .analysis import (AnalysisParams, PhaseScanResult, phase_scan, phase_scan_from_params, run_analysis,
+from .analysis import (AnalysisParams, PhaseScanResult, EnsembleResult, ensemble_scan, dispersion_wavenumbers, phase_scan, phase_scan_from_params, run_analysis,
                        static_load, interface_load_vector, apply_self_weight, build_structure)
 from .engine import Engine, get_engine
 from ._lib import JacketError, NotPositiveDefinite, TABLE_COLUMNS, MEMBER_COLUMNS, DETAIL_COLUMNS, LIB_PATH

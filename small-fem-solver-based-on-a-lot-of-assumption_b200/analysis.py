@@ -222,3 +222,88 @@ def phase_scan_from_params(nodes, members, fixed_nodes, top_nodes, params: Analy
     wave = RaschiiWave(p.H, p.T, p.d, p.U_c, p.wave_model, p.N_harm)
     return phase_scan(structure, wave, n_steps, wave_direction=p.wave_dir, current_direction=p.current_dir, Cd=p.Cd,
                       Cm=p.Cm, rho_water=p.rho_water, E=p.E, nu=p.nu, fy=p.fy, params=p)
+
+
+# ---------------------------------------------------------------------------------
+# sea-state ensemble (BASELINE configs[4]): many (H, T, direction) states on one factor
+# ---------------------------------------------------------------------------------
+@dataclass
+class EnsembleResult:
+    structure: CustomJacketStructure
+    H: np.ndarray
+    T: np.ndarray
+    wave_dir: np.ndarray
+    k: np.ndarray
+    table: np.ndarray              # [S, n_phase, 16]
+    critical_phase: np.ndarray     # [S] first index of max total_kN inside each state (GUI.py:717 per state)
+    fy: float
+    engine: object = field(repr=False, default=None)
+    columns: tuple = L.TABLE_COLUMNS
+
+    @property
+    def n_states(self):
+        return self.table.shape[0]
+
+    @property
+    def n_phase(self):
+        return self.table.shape[1]
+
+    def critical_rows(self):
+        """[S, 16]: the critical-phase row of every sea state."""
+        return self.table[np.arange(self.n_states), self.critical_phase]
+
+    @property
+    def governing(self):
+        """(state, phase) of the largest member utilisation over the whole ensemble (first maximum)."""
+        u = self.table[:, :, L.TABLE_COLUMNS.index("max_util")]
+        s, p = np.unravel_index(int(np.argmax(u)), u.shape)
+        return int(s), int(p)
+
+    def case(self, state, phase, end_forces=False):
+        got = self.engine.fetch_phase(int(state) * self.n_phase + int(phase), U=True, reactions=True, rows=True,
+                                      end_forces=end_forces, nodal=True)
+        st = self.structure
+        got["reactions"] = {st.node_list[int(n)]: got["reactions"][i].copy() for i, n in enumerate(self.engine.fixed_idx)}
+        got["internal_forces"] = member_rows_to_dicts(st, got.pop("rows"), self.fy, self.engine)
+        return got
+
+
+def dispersion_wavenumbers(T, d):
+    """The reference's Newton iteration (GUI.py:197-206) applied to every period, each with its own stopping test."""
+    from .wave import solve_dispersion
+    return np.array([solve_dispersion(2.0 * np.pi / Ti, d) for Ti in np.asarray(T, dtype=np.float64)])
+
+
+def ensemble_scan(structure, H, T, wave_dir, n_phase=16, *, d=50.0, U_c=0.0, current_direction=0.0, Cd=0.7, Cm=2.0,
+                  rho_water=1025.0, E=210000.0, nu=0.3, fy=355.0, params: AnalysisParams | None = None, n_gauss=15,
+                  dt=0.001, engine=None):
+    """Morison + FEM for n_phase phases of every sea state (H[i], T[i], wave_dir[i]) -- Airy kinematics (the pinned
+    model), current and depth common to all states, one Cholesky factor for the whole ensemble.  With ``params`` the
+    GUI's interface loads and self-weight are applied; the interface shear follows each state's wave direction as
+    run_analysis does (GUI.py:1967-1971)."""
+    H, T, wave_dir = (np.asarray(v, dtype=np.float64).reshape(-1) for v in (H, T, wave_dir))
+    S = H.shape[0]
+    eng = engine or get_engine(structure)
+    G = E / (2 * (1 + nu))
+    eng.ensure_factored(structure.indices(structure.get_bottom_nodes()), E, G)
+    F_dir = None
+    if params is not None:
+        p0 = AnalysisParams(**{**params.__dict__, "F_shear": 0.0})
+        eng.set_static_load(static_load(structure, p0))
+        F_dir = np.zeros((2, structure.n_dof))
+        top = structure.get_top_nodes()
+        for name in top:
+            i = structure.node_index[name]
+            F_dir[0, 6 * i] = params.F_shear * 1000.0 / len(top)
+            F_dir[1, 6 * i + 1] = params.F_shear * 1000.0 / len(top)
+    else:
+        eng.set_static_load(np.zeros(structure.n_dof))
+    k = dispersion_wavenumbers(T, d)
+    omega = 2.0 * np.pi / T
+    wave0 = RaschiiWave(float(H[0]), float(T[0]), d, U_c, "Airy", 1, dt)          # carries depth / current / dt
+    eng.set_wave(wave0)
+    eng.set_morison(0.0, np.deg2rad(90.0 - current_direction), rho_water, Cd, Cm, n_gauss)
+    t = np.array([[i * Ti / n_phase for i in range(n_phase)] for Ti in T])          # GUI.py:696 per state
+    table, crit = eng.ensemble_scan(H / 2.0, k, omega, np.deg2rad(90.0 - wave_dir), t, fy, F_dir)
+    table[:, :, 1] = np.degrees(omega[:, None] * table[:, :, 0]) % 360
+    return EnsembleResult(structure, H, T, wave_dir, k, table, crit, fy, eng)

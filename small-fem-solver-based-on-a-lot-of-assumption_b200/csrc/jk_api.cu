@@ -66,6 +66,7 @@ struct jk_handle_s {
     int wave_kind = 0;         // 0 = Airy closed form, 1 = Fourier series
     int n_harm = 0;
     double* d_four = nullptr;  // E[Nh], B[Nh], 1/cosh(j k d)[Nh]
+    double* d_states = nullptr; long long* d_state_crit = nullptr; int cap_states = 0;   // ensemble: [5][S] parameters
     size_t gp_elems = 0;
     StressPts sp{};
 
@@ -214,7 +215,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
     dev_free(h->d_blocks); dev_free(h->d_contrib); dev_free(h->d_tiles); dev_free(h->d_Linv); dev_free(h->d_dinv); dev_free(h->d_info);
-    dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four);
+    dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four); dev_free(h->d_states); dev_free(h->d_state_crit);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
     dev_free(h->d_table); dev_free(h->d_details); dev_free(h->d_Fload); dev_free(h->d_argval); dev_free(h->d_tmp); dev_free(h->d_res);
@@ -812,6 +813,83 @@ extern "C" int jk_morison_single(jk_handle_t h, double t, double* nodal_forces, 
     CUDA_TRY(h, cudaStreamSynchronize(s));
     h->lastP = 0;   // scan buffers no longer describe a scan
     return JK_OK;
+}
+
+// Sea-state ensemble: n_states Airy sea states x n_phase phases each = one batch of load cases on one factor.
+extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const double* a, const double* k, const double* omega,
+                                const double* theta_wave, const double* t, const double* F_dir, double fy, double* table,
+                                int64_t* critical_per_state) {
+    if (!h) return JK_EINVAL;
+    if (n_states <= 0 || !a || !k || !omega || !theta_wave || !t) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: empty or NULL sea-state arrays");
+    if (n_phase < 8 || n_phase > 4096) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: n_phase must be in 8..4096 (got %d)", n_phase);
+    if ((long long)n_states * n_phase > (1LL << 30)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: too many load cases");
+    if (!h->have_wave || !h->have_morison || h->wave_kind != 0)
+        JK_FAIL(h, JK_ESTATE, "jk_ensemble_scan: call jk_set_wave_airy (depth, current, dt) and jk_set_morison (current heading, coefficients) first");
+    if (!h->factored) JK_FAIL(h, JK_ESTATE, "jk_ensemble_scan: call jk_assemble and jk_factor first");
+    if (!(fy > 0)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: fy must be positive");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    const int C = n_states * n_phase;
+    int rc;
+    if ((rc = ensure_buffers(h, C, true, false)) != JK_OK) return rc;
+    const int ldC = ceil_div(C, SLAB) * SLAB;
+    if (n_states > h->cap_states) {
+        CUDA_TRY(h, dev_alloc(&h->d_states, 5 * (size_t)n_states));
+        CUDA_TRY(h, dev_alloc(&h->d_state_crit, (size_t)n_states));
+        h->cap_states = n_states;
+    }
+    std::vector<double> st(5 * (size_t)n_states);
+    for (int i = 0; i < n_states; ++i) {
+        if (!(k[i] > 0) || !(omega[i] > 0)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: state %d has non-positive k or omega", i);
+        st[i] = a[i]; st[(size_t)n_states + i] = k[i]; st[2 * (size_t)n_states + i] = omega[i];
+        st[3 * (size_t)n_states + i] = cos(theta_wave[i]); st[4 * (size_t)n_states + i] = sin(theta_wave[i]);
+    }
+    double* d_Fdir = nullptr;
+    if (F_dir) {
+        size_t nF = 12 * (size_t)h->Nn;
+        if (nF > h->fload_elems) { CUDA_TRY(h, dev_alloc(&h->d_Fload, nF)); h->fload_elems = nF; }
+        d_Fdir = h->d_Fload;
+        CUDA_TRY(h, cudaMemcpyAsync(d_Fdir, F_dir, nF * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    tic(h, JK_T_SCAN_TOTAL);
+    tic(h, JK_T_H2D);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_states, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t, (size_t)C * sizeof(double), cudaMemcpyHostToDevice, s));
+    toc(h, JK_T_H2D);
+    if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
+    WaveAiry w = launch_wave(h);
+    tic(h, JK_T_MORISON);
+    {
+        dim3 grid(ceil_div(ldC, PH_TPB), ceil_div(h->M, MCHUNK));
+        size_t smem = ((size_t)ENS_MAXS * ENS_EM * h->ng * 4 + ENS_EM * h->ng + MCHUNK * 8 + 2 * h->ng) * sizeof(double);
+        CUDA_TRY(h, cudaFuncSetAttribute(k_morison_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_morison_ensemble<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, C, ldC, n_states, n_phase, h->d_xyz, h->d_conn, h->d_mc, h->d_gsw,
+                                                      h->d_states, h->d_t, w, 0.5 * h->rho * h->Cd, h->rho * h->Cm, h->d_Fm, h->d_totpart);
+        LAUNCH_CHECK(h);
+    }
+    toc(h, JK_T_MORISON);
+    tic(h, JK_T_RHS);
+    {
+        dim3 g(ceil_div(ldC, PH_TPB), h->Nn);
+        k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldC, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic, h->d_X, h->d_Ffix, nullptr,
+                                         d_Fdir, h->d_states, n_states, n_phase, C);
+        LAUNCH_CHECK(h);
+    }
+    toc(h, JK_T_RHS);
+    if ((rc = run_fem(h, ldC, fy)) != JK_OK) return rc;
+    if ((rc = reduce_and_argmax(h, C, ldC, true, true)) != JK_OK) return rc;
+    k_argmax_per_state<<<ceil_div(n_states, 128), 128, 0, s>>>(n_states, n_phase, h->d_table, JK_TABLE_NCOL, JK_COL_TOTAL_KN, h->d_state_crit);
+    LAUNCH_CHECK(h);
+    toc(h, JK_T_SCAN_TOTAL);
+    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy;
+    tic(h, JK_T_D2H);
+    if (table) CUDA_TRY(h, cudaMemcpyAsync(table, h->d_table, (size_t)C * JK_TABLE_NCOL * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<long long> crit(n_states);
+    if (critical_per_state) CUDA_TRY(h, cudaMemcpyAsync(crit.data(), h->d_state_crit, (size_t)n_states * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    toc(h, JK_T_D2H);
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (critical_per_state) for (int i = 0; i < n_states; ++i) critical_per_state[i] = (int64_t)crit[i];
+    return finish_factor(h);
 }
 
 extern "C" int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy) {

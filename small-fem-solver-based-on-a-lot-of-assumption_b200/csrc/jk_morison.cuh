@@ -320,6 +320,135 @@ k_morison_fourier(int M, int G, int Nh, int ldP, const double* __restrict__ gp, 
 }
 
 // ----------------------------------------------------------------------------------------------
+// Sea-state ensemble (BASELINE configs[4]): load case c = (sea state c / n_phase, phase c % n_phase).  Every sea
+// state has its own Airy wave (a, k, omega) and heading, so the per-point tables differ per state: a block of 128
+// cases touches at most 128/n_phase + 1 states and builds their tables for ENS_EM members at a time in shared
+// memory (one sincos + cosh + sinh per point and state, amortised over the state's phases), then runs the same
+// per-point arithmetic as k_morison_airy.  st[5][S] = a, k, omega, cos(theta_w), sin(theta_w).
+// ----------------------------------------------------------------------------------------------
+constexpr int ENS_EM = 8;        // members per table refill
+constexpr int ENS_MAXS = 17;     // states a 128-case block may touch (n_phase >= 8)
+
+__global__ void __launch_bounds__(PH_TPB)
+k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const double* __restrict__ xyz, const int* __restrict__ conn,
+                   const double* __restrict__ mc, const double* __restrict__ gsw, const double* __restrict__ st,
+                   const double* __restrict__ t, WaveAiry wv, double cD0, double cI0,
+                   double* __restrict__ Fm, double* __restrict__ totpart) {
+    extern __shared__ __align__(16) double smem[];
+    double* s_tab = smem;                                   // [ENS_MAXS][ENS_EM][G][4]
+    double* s_z = s_tab + ENS_MAXS * ENS_EM * G * 4;        // [ENS_EM][G]
+    double* s_m = s_z + ENS_EM * G;                         // [MCHUNK][8]
+    double* s_g = s_m + MCHUNK * 8;                         // s[G], w[G]
+    const int chunk = blockIdx.y, m0 = chunk * MCHUNK;
+    const int nm = min(MCHUNK, M - m0);
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        const double* c = mc + (size_t)(m0 + i) * MC_STRIDE;
+        s_m[8 * i + 0] = c[MC_E]; s_m[8 * i + 1] = c[MC_E + 1]; s_m[8 * i + 2] = c[MC_E + 2];
+        s_m[8 * i + 3] = cD0 * c[MC_D]; s_m[8 * i + 4] = cI0 * c[MC_ACROSS]; s_m[8 * i + 5] = c[MC_L];
+    }
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_g[i] = gsw[i];
+    const int c0 = blockIdx.x * blockDim.x;
+    const int cidx = c0 + threadIdx.x;
+    const bool live = cidx < ldC;
+    const int cc = min(cidx, C - 1);
+    const int s_first = min(c0, C - 1) / n_phase, s_last = min(c0 + (int)blockDim.x - 1, C - 1) / n_phase;
+    const int ns = s_last - s_first + 1;
+    const int my_s = cc / n_phase, sl = my_s - s_first;
+    const double a = st[my_s], om = st[2 * (size_t)S + my_s], cw = st[3 * (size_t)S + my_s], sw = st[4 * (size_t)S + my_s];
+    double sw0, cw0, sw1, cw1;
+    { double tt = t[cc]; sincos(om * tt, &sw0, &cw0); sincos(om * (tt + wv.dt), &sw1, &cw1); }
+    double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
+
+    for (int sub = 0; sub < nm; sub += ENS_EM) {
+        const int nsub = min(ENS_EM, nm - sub);
+        __syncthreads();
+        for (int e = threadIdx.x; e < ns * nsub * G; e += blockDim.x) {
+            const int s_i = e / (nsub * G), r = e % (nsub * G), mm = r / G, g = r % G;
+            const int m = m0 + sub + mm;
+            const int na = conn[2 * m], nb = conn[2 * m + 1];
+            const double sg = s_g[g];
+            const double x = xyz[3 * na] + sg * (xyz[3 * nb] - xyz[3 * na]);
+            const double y = xyz[3 * na + 1] + sg * (xyz[3 * nb + 1] - xyz[3 * na + 1]);
+            const double z = xyz[3 * na + 2] + sg * (xyz[3 * nb + 2] - xyz[3 * na + 2]);
+            const int sidx = s_first + s_i;
+            const double a_s = st[sidx], k_s = st[(size_t)S + sidx], om_s = st[2 * (size_t)S + sidx];
+            const double xw = __dadd_rn(__dmul_rn(x, st[3 * (size_t)S + sidx]), __dmul_rn(y, st[4 * (size_t)S + sidx]));
+            double sk, ck;
+            sincos(k_s * xw, &sk, &ck);
+            const double shkd = sinh(k_s * wv.d), kz = k_s * (z + wv.d);
+            double* o = s_tab + ((size_t)(s_i * ENS_EM + mm) * G + g) * 4;
+            o[0] = ck; o[1] = sk; o[2] = a_s * om_s * cosh(kz) / shkd; o[3] = a_s * om_s * sinh(kz) / shkd;
+            if (s_i == 0) s_z[mm * G + g] = z;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int ms = 0; ms < nsub; ++ms) {
+            const int mm = sub + ms;
+            const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
+            const double cD = s_m[8 * mm + 3], cI = s_m[8 * mm + 4], L = s_m[8 * mm + 5];
+            double F1[3] = {0, 0, 0}, F2[3] = {0, 0, 0}, md[3] = {0, 0, 0}, mi[3] = {0, 0, 0};
+            for (int g = 0; g < G; ++g) {
+                const double* q = s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4;
+                const double ckx = q[0], skx = q[1], Cu = q[2], Cw = q[3], z = s_z[ms * G + g];
+                const double c0v = fma(skx, sw0, ckx * cw0), s0v = fma(skx, cw0, -(ckx * sw0));
+                const double eta0 = a * c0v;
+                if (z > eta0) continue;
+                const double c1v = fma(skx, sw1, ckx * cw1), s1v = fma(skx, cw1, -(ckx * sw1));
+                const bool wet1 = !(z > a * c1v);
+                const double u0 = fma(Cu, c0v, wv.Uc), w0 = Cw * s0v;
+                const double u1 = wet1 ? fma(Cu, c1v, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1v : 0.0;
+                const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;
+                const double uwo = u0 - wv.Uc;
+                const double U0 = fma(uwo, cw, wv.uc_cos_c), U1 = fma(uwo, sw, wv.uc_sin_c), U2 = w0;
+                const double A0 = du * cw, A1 = du * sw, A2 = dw;
+                const double Ue = fma(U2, e2, fma(U1, e1, U0 * e0));
+                const double Ae = fma(A2, e2, fma(A1, e1, A0 * e0));
+                const double Up0 = fma(-Ue, e0, U0), Up1 = fma(-Ue, e1, U1), Up2 = fma(-Ue, e2, U2);
+                const double Ap0 = fma(-Ae, e0, A0), Ap1 = fma(-Ae, e1, A1), Ap2 = fma(-Ae, e2, A2);
+                const double mag = sqrt(fma(Up2, Up2, fma(Up1, Up1, Up0 * Up0)));
+                const double sgv = s_g[g], wg = s_g[G + g];
+                const double Lw = L * wg;
+                const double kd_ = (mag > 1e-10) ? cD * mag * Lw : 0.0;
+                const double ki_ = cI * Lw;
+                const double fd0 = kd_ * Up0, fd1 = kd_ * Up1, fd2 = kd_ * Up2;
+                const double fi0 = ki_ * Ap0, fi1 = ki_ * Ap1, fi2 = ki_ * Ap2;
+                const double ft0 = fd0 + fi0, ft1 = fd1 + fi1, ft2 = fd2 + fi2;
+                md[0] += fd0; md[1] += fd1; md[2] += fd2;
+                mi[0] += fi0; mi[1] += fi1; mi[2] += fi2;
+                const double s1m = 1.0 - sgv;
+                F1[0] = fma(s1m, ft0, F1[0]); F1[1] = fma(s1m, ft1, F1[1]); F1[2] = fma(s1m, ft2, F1[2]);
+                F2[0] = fma(sgv, ft0, F2[0]); F2[1] = fma(sgv, ft1, F2[1]); F2[2] = fma(sgv, ft2, F2[2]);
+            }
+            size_t o = ((size_t)(m0 + mm) * 6) * ldC + cidx;
+            Fm[o] = F1[0]; Fm[o + ldC] = F1[1]; Fm[o + 2 * (size_t)ldC] = F1[2];
+            Fm[o + 3 * (size_t)ldC] = F2[0]; Fm[o + 4 * (size_t)ldC] = F2[1]; Fm[o + 5 * (size_t)ldC] = F2[2];
+#pragma unroll
+            for (int kq = 0; kq < 3; ++kq) { td[kq] += md[kq]; ti[kq] += mi[kq]; tm[kq] += md[kq] + mi[kq]; }
+        }
+    }
+    if (!live) return;
+    size_t ot = ((size_t)chunk * 9) * ldC + cidx;
+#pragma unroll
+    for (int kq = 0; kq < 3; ++kq) {
+        totpart[ot + (size_t)kq * ldC] = td[kq];
+        totpart[ot + (size_t)(3 + kq) * ldC] = ti[kq];
+        totpart[ot + (size_t)(6 + kq) * ldC] = tm[kq];
+    }
+}
+
+// first index (within each sea state) of the maximum of table[:, col]; one thread per state
+__global__ void k_argmax_per_state(int S, int n_phase, const double* __restrict__ table, int ncol, int col, long long* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double best = 0.0; int bi = -1;
+    for (int p = 0; p < n_phase; ++p) {
+        double v = table[((size_t)s * n_phase + p) * ncol + col];
+        if (bi < 0 || v > best) { best = v; bi = p; }
+    }
+    out[s] = bi;
+}
+
+// ----------------------------------------------------------------------------------------------
 // RHS gather: thread = (node, phase).  Sums the member-end forces of the node's incident members in
 // member order (the reference's accumulation order, GUI.py:661-662), adds the static load and writes
 // the solver right-hand side (free nodes) or the load at the supports (fixed nodes, for reactions).
@@ -327,11 +456,20 @@ k_morison_fourier(int M, int G, int Nh, int ldP, const double* __restrict__ gp, 
 __global__ void __launch_bounds__(PH_TPB)
 k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const int* __restrict__ adj_ptr,
              const int* __restrict__ adj, const int* __restrict__ node2slot, const double* __restrict__ Fstatic,
-             double* __restrict__ B, double* __restrict__ Ffix, double* __restrict__ nodal /* [Nn*3] single phase or null */) {
+             double* __restrict__ B, double* __restrict__ Ffix, double* __restrict__ nodal /* [Nn*3] single phase or null */,
+             const double* __restrict__ Fdir = nullptr /* ensemble: [2][6*Nn] loads that follow the wave heading */,
+             const double* __restrict__ st = nullptr, int S = 0, int n_phase = 1, int C = 0) {
     int node = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= Nn || p >= ldP) return;
     double f[3] = {0, 0, 0};
+    double fdir[6] = {0, 0, 0, 0, 0, 0};
+    if (Fdir) {   // interface shear is applied along the wave direction of the case's sea state (GUI.py:1967-1971)
+        const int sidx = min(p, C - 1) / n_phase;
+        const double cw = st[3 * (size_t)S + sidx], sw = st[4 * (size_t)S + sidx];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) fdir[c] = fma(cw, Fdir[6 * node + c], sw * Fdir[6 * (size_t)Nn + 6 * node + c]);
+    }
     for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
         int m = adj[q] >> 1, end = adj[q] & 1;
         size_t o = ((size_t)m * 6 + 3 * end) * ldP + p;
@@ -343,16 +481,16 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
         if (!B) return;
         size_t o = rhs_off(6 * s, p, n_pad);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + f[c];
+        for (int c = 0; c < 3; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + fdir[c] + f[c];
 #pragma unroll
-        for (int c = 3; c < 6; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c];
+        for (int c = 3; c < 6; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + fdir[c];
     } else {
         if (!Ffix) return;
         int fi = -1 - s;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + f[c];
+        for (int c = 0; c < 3; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + fdir[c] + f[c];
 #pragma unroll
-        for (int c = 3; c < 6; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c];
+        for (int c = 3; c < 6; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + fdir[c];
     }
 }
 

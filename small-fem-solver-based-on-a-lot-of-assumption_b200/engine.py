@@ -146,6 +146,18 @@ class Engine:
         self._ck(self.lib.jk_read_table(self.h, P, L.dptr(table), C.byref(crit)))
         return table, int(crit.value)
 
+    def ensemble_scan(self, a, k, omega, theta_wave, t, fy, F_dir=None):
+        a, k, omega, theta_wave = (L.f64(v).reshape(-1) for v in (a, k, omega, theta_wave))
+        S = a.shape[0]
+        t = L.f64(t).reshape(S, -1)
+        n_phase = t.shape[1]
+        table = np.zeros((S * n_phase, L.TABLE_NCOL))
+        crit = np.zeros(S, dtype=np.int64)
+        Fd = None if F_dir is None else L.f64(F_dir).reshape(2, 6 * self.n_nodes)
+        self._ck(self.lib.jk_ensemble_scan(self.h, S, n_phase, L.dptr(a), L.dptr(k), L.dptr(omega), L.dptr(theta_wave), L.dptr(t),
+                                           L.dptr(Fd), float(fy), L.dptr(table), crit.ctypes.data_as(C.POINTER(C.c_int64))))
+        return table.reshape(S, n_phase, L.TABLE_NCOL), crit
+
     def solve(self, F, fy=355.0):
         F = L.f64(F).reshape(-1, 6 * self.n_nodes)
         self._ck(self.lib.jk_solve(self.h, F.shape[0], L.dptr(F), float(fy)))

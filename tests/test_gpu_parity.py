@@ -295,3 +295,39 @@ def test_fourier_series_kinematics_vs_oracle(model, N, H):
     for c in range(4):
         assert relmax(det[:, c], o1["member_details"][0][:, c]) < TOL
     assert relmax(r1["total_morison"], o1["total_morison"][0]) < TOL
+
+
+def test_sea_state_ensemble_vs_oracle():
+    """BASELINE configs[4] in small: 12 random sea states x 16 phases on one factor == 12 separate oracle scans."""
+    import jacket_b200 as jb
+    from oracle import jacket_oracle as orc
+    rng = np.random.default_rng(20250101)
+    S, n_phase = 12, 16
+    H = rng.uniform(2.0, 12.0, S); T = rng.uniform(6.0, 16.0, S); wdir = rng.uniform(0.0, 360.0, S)
+    ap = jb.AnalysisParams(wave_model="Airy", U_c=0.8, current_dir=140.0)
+    nodes, members, fixed, top = jb.generate_jacket(5, 7)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    res = jb.ensemble_scan(st, H, T, wdir, n_phase, d=ap.d, U_c=ap.U_c, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
+                           rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, params=ap)
+    assert res.table.shape == (S, n_phase, 16)
+    xyz, conn, sec_id, _, sections = st.pack()
+    model = orc.Model(xyz, conn, sec_id, [(s.D_outer, s.t, s.rho_steel) for s in sections], st.indices(fixed), st.indices(top))
+    fem = orc.FEM(model, ap.E, ap.nu)
+    for s in range(S):
+        ow = orc.AiryWave(H[s], T[s], ap.d, ap.U_c)
+        assert ow.k == res.k[s]
+        ref = orc.phase_scan(model, ow, orc.phase_times(T[s], n_phase), wave_direction=wdir[s], current_direction=ap.current_dir,
+                             Cd=ap.Cd, Cm=ap.Cm, rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, F_axial_kN=ap.F_axial,
+                             F_shear_kN=ap.F_shear, self_weight="calculated", fem=fem)
+        assert int(res.critical_phase[s]) == ref["critical"]
+        assert np.array_equal(res.table[s, :, 0], ref["table"][:, 0]) and np.array_equal(res.table[s, :, 1], ref["table"][:, 1])
+        for c in range(2, 8):
+            assert relmax(res.table[s, :, c], ref["table"][:, c]) < TOL
+        assert relmax(res.table[s, :, 10], ref["members"]["utilization"].max(axis=1)) < TOL
+        if s in (0, 7):
+            got = res.case(s, ref["critical"])
+            assert relmax(got["U"], ref["U"][ref["critical"]]) < TOL
+            R = np.array([got["reactions"][n] for n in fixed])
+            assert relmax(R, ref["reactions"][ref["critical"]]) < TOL
+    gs, gp = res.governing
+    assert res.table[gs, gp, 10] == res.table[:, :, 10].max()
