@@ -37,6 +37,7 @@ WORKLOADS = {
     "c4_jacket10k": (16, 104, 4096),
     "c3_jacket2k": (8, 41, 1024),
     "c2_default3": (None, None, 360),
+    "c5_ensemble": (8, 41, 65536),     # configs[4]: 4096 sea states x 16 phases on the c3 jacket, one factor
 }
 FP64_PEAK_TFLOPS = 37.1    # measured on this pool (profiles/r01_fp64_peaks.json): DMMA m8n8k4 issue peak
 
@@ -63,6 +64,95 @@ def peaks():
         with open(path) as f:
             return json.load(f).get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ensemble_states(n_states, d=50.0, seed=20250101):
+    """H~U[2,16] m, T~U[6,16] s, dir~U[0,360) deg; reject H/L > 0.142 or H/d > 0.78 (README.md:74-76)."""
+    import jacket_b200 as jb
+    rng = np.random.default_rng(seed)
+    H, T, D = [], [], []
+    while len(H) < n_states:
+        h, t, w = rng.uniform(2, 16, 4096), rng.uniform(6, 16, 4096), rng.uniform(0, 360, 4096)
+        k = jb.dispersion_wavenumbers(t, d)
+        ok = (h * k / (2 * np.pi) <= 0.142) & (h / d <= 0.78)
+        H.extend(h[ok]); T.extend(t[ok]); D.extend(w[ok])
+    return np.array(H[:n_states]), np.array(T[:n_states]), np.array(D[:n_states])
+
+
+def run_ensemble(args):
+    """--workload c5_ensemble: assemble + factor once + ONE batch of n_states x 16 load cases per step (per GPU)."""
+    import torch
+    import torch.distributed as dist
+    import jacket_b200 as jb
+    from jacket_b200 import _lib as L
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    n_phase = 16
+    n_states = (args.phases or WORKLOADS[args.workload][2]) // n_phase
+    _, st, wave, p = build_case(args.workload)
+    stream = torch.cuda.Stream(device=dev)
+    eng = jb.Engine(st, device=local_rank, stream=stream.cuda_stream, ordering=args.ordering, solver=args.solver)
+    st._engine = eng
+    H, T, D = ensemble_states(n_states * world)
+    sl = slice(rank * n_states, (rank + 1) * n_states)          # weak scaling: every rank its own block of sea states
+    E, G = p.E, p.E / (2 * (1 + p.nu))
+    eng.set_supports(st.indices(st.get_bottom_nodes()))
+
+    def step():
+        eng.assemble(E, G)
+        eng.factor(overlap=True)
+        return jb.ensemble_scan(st, H[sl], T[sl], D[sl], n_phase, d=p.d, U_c=p.U_c, current_direction=p.current_dir, Cd=p.Cd, Cm=p.Cm,
+                                rho_water=p.rho_water, E=E, nu=p.nu, fy=p.fy, params=p, engine=eng)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ensemble_scan's ensure_factored would refactor if the engine thought it was stale; it is not after factor()
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            res = step()
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    worst = torch.tensor([res.table[:, :, 10].max()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)        # ensemble-wide governing utilisation
+    stage = eng.timings()
+    cases = n_states * n_phase * world
+    if rank == 0:
+        val = cases * args.steps / (float(ms.item()) * 1e-3)
+        dims = eng.dims()
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "members": st.n_members, "free_dof": dims["n_free_dof"], "sea_states_per_gpu": n_states,
+                           "phases_per_state": n_phase, "cases_total": cases, "wave": "Airy (fallback), H~U[2,16] T~U[6,16] dir~U[0,360)",
+                           "step": "assemble + factor once + Morison/solve/post of every (sea state, phase) case; host tables in/out (this IS the e2e path)",
+                           "band_tiles": dims["band_tiles"], "n_tiles": dims["n_tiles"]},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(8 * (5 * n_states + n_states * n_phase + 18 * st.n_nodes)),
+                        "d2h_bytes_per_step": int(n_states * n_phase * L.TABLE_NCOL * 8 + 8 * n_states)},
+                "gpu_launches": int(eng.launch_count() - l0), "clocks": clocks,
+                "stage_ms": {k: stage[k] for k in ("assemble", "factor", "morison", "rhs", "solve_fwd", "solve_bwd", "post", "reduce", "scan_total", "h2d", "d2h")},
+                "governing_utilisation": float(worst.item()), "cpu_baseline": None, "roofline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
 
 
 def build_case(workload):
@@ -432,6 +522,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c5_ensemble":
+        run_ensemble(args)
     else:
         run_ours(args)
 

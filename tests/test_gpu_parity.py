@@ -315,7 +315,7 @@ def test_sea_state_ensemble_vs_oracle():
     fem = orc.FEM(model, ap.E, ap.nu)
     for s in range(S):
         ow = orc.AiryWave(H[s], T[s], ap.d, ap.U_c)
-        assert ow.k == res.k[s]
+        assert abs(ow.k - res.k[s]) <= 4 * np.spacing(ow.k)      # vectorised Newton: array tanh/cosh may differ from the scalar path by an ulp
         ref = orc.phase_scan(model, ow, orc.phase_times(T[s], n_phase), wave_direction=wdir[s], current_direction=ap.current_dir,
                              Cd=ap.Cd, Cm=ap.Cm, rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, F_axial_kN=ap.F_axial,
                              F_shear_kN=ap.F_shear, self_weight="calculated", fem=fem)
