@@ -450,12 +450,7 @@ def run_ours(args):
         items = sum(min(k, bw) + 1 for k in range(NT))
         sweep_flops_exec = items * 2.0 * nb * nb * ldP
         # algorithmic flops of one sweep: 2 * nnz(L within the DOF half-bandwidth) per right-hand side
-        order = eng.order()
-        slot = np.full(st.n_nodes, -1); slot[order] = np.arange(len(order))
-        xyz, conn, *_ = st.pack()
-        s0, s1 = slot[conn[:, 0]], slot[conn[:, 1]]
-        both = (s0 >= 0) & (s1 >= 0)
-        hb = int(6 * np.max(np.abs(s0[both] - s1[both])) + 5)
+        hb = dims["dof_half_bandwidth"]
         nnzL = n * (hb + 1) - hb * (hb + 1) // 2
         sweep_flops_alg = 2.0 * nnzL * P
         kernels = {
@@ -506,7 +501,7 @@ def run_ours(args):
                 "config": {"workload": args.workload, "members": M, "nodes": st.n_nodes, "free_dof": n,
                            "phases_per_gpu": P, "phases_total": n_total, "wave": "Airy (fallback) H=17.038 T=9.4 d=50 Uc=1.7",
                            "solver": args.solver, "ordering": args.ordering, "tile": nb, "band_tiles": bw, "n_tiles": NT,
-                           "dof_half_bandwidth": hb, "parallelism": f"phase-shard x{world}",
+                           "dof_half_bandwidth": hb, "factor_chains": dims["n_chains"], "parallelism": f"phase-shard x{world}",
                            "step": "assemble + Cholesky factor + phase scan (Morison, RHS, 2 sweeps, post, reduce) + cross-rank critical-phase reduction",
                            "l2": "per-step working set ~5 GB (member forces 2.0, solution 0.65, member rows 2.3) >> 126 MB L2: no flush needed"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -191,7 +191,8 @@ int jk_fetch_phase(jk_handle_t h, int phase, double* U, double* reactions,
 int jk_fetch_member_column(jk_handle_t h, int member, int column, int P, double* out);
 
 /* Introspection used by the FEMSolver facade and the parity tests */
-int jk_get_dims(jk_handle_t h, int32_t* out /* n_nodes n_members n_fixed n_free_dof n_pad tile band_tiles n_tiles */);
+int jk_get_dims(jk_handle_t h, int32_t* out /* [12]: n_nodes n_members n_fixed n_free_dof n_pad tile band_tiles n_tiles
+                                                 dof_half_bandwidth n_chains separator_tile_row separator_nodes */);
 int jk_get_order(jk_handle_t h, int32_t* free_nodes /* [n_nodes-n_fixed] solver order */);
 int jk_get_K(jk_handle_t h, double* K /* [n_dof*n_dof] dense, reference DOF order */);
 int jk_get_elements(jk_handle_t h, double* Ke /* [M*144] */, double* Kl /* [M*144] */, double* R /* [M*9] */, double* L /* [M] */);

@@ -46,12 +46,18 @@ struct jk_handle_s {
     int n_fixed = 0, n_free_nodes = 0, n_free = 0, n_pad = 0, NT = 0, bw = 0, solver = 0, hb = 0;
     std::vector<int> h_node2slot, h_free_nodes, h_fixed;
     int *d_node2slot = nullptr, *d_fixed_nodes = nullptr, *d_free_nodes = nullptr;
-    KBlock* d_blocks = nullptr;
-    int2* d_contrib = nullptr;
-    int nblocks = 0;
-    double *d_tiles = nullptr, *d_Linv = nullptr, *d_dinv = nullptr;
+    // The free-free system is stored as one or two tile-banded "chains".  Two chains = the band is split at a
+    // separator S in the middle of the ordering: chain 0 = [A; S] in order, chain 1 = [B; S] in REVERSED order, so
+    // both eliminate towards S and the sequential pivot chain of the factorisation is halved (no extra fill).
+    struct Chain {
+        int NT = 0, kS = 0, bw = 0, hb = 0;   // tile rows, first separator tile row (== NT: none), tile / DOF half-bandwidth
+        int row0 = 0, n_rows = 0;             // first row in the slab, real (unpadded) rows
+        KBlock* d_blocks = nullptr; int2* d_contrib = nullptr; int nblocks = 0;
+        double *d_tiles = nullptr, *d_Linv = nullptr, *d_dinv = nullptr;
+        size_t tiles_elems = 0;
+    } ch[2];
+    int n_chains = 1, nS_nodes = 0;
     int factor_path = 0;   // 0 = auto (cluster kernel for narrow bands), 1 = per-column launches
-    size_t tiles_elems = 0;
     int* d_info = nullptr;
     bool assembled = false, factored = false;
     double E = 0, G = 0;
@@ -214,7 +220,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_xyz); dev_free(h->d_secp); dev_free(h->d_mc); dev_free(h->d_Ke); dev_free(h->d_Kl);
     dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
-    dev_free(h->d_blocks); dev_free(h->d_contrib); dev_free(h->d_tiles); dev_free(h->d_Linv); dev_free(h->d_dinv); dev_free(h->d_info);
+    for (auto& c : h->ch) { dev_free(c.d_blocks); dev_free(c.d_contrib); dev_free(c.d_tiles); dev_free(c.d_Linv); dev_free(c.d_dinv); }
+    dev_free(h->d_info);
     dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four); dev_free(h->d_states); dev_free(h->d_state_crit);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
@@ -306,63 +313,117 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     if (ordering == JK_ORDER_RCM) rcm_order(h->Nn, h->h_conn, is_fixed, h->h_free_nodes);
     else { h->h_free_nodes.clear(); for (int i = 0; i < h->Nn; ++i) if (!is_fixed[i]) h->h_free_nodes.push_back(i); }
     if ((int)h->h_free_nodes.size() != h->n_free_nodes) JK_FAIL(h, JK_EINVAL, "jk_set_supports: internal ordering error");
+    h->n_free = 6 * h->n_free_nodes;
+    h->solver = solver;
+    const int N = h->n_free_nodes;
+    std::vector<int> pos(h->Nn, -1);                       // position of a free node in the linear (RCM / natural) order
+    for (int i = 0; i < N; ++i) pos[h->h_free_nodes[i]] = i;
+    int hbn = 0;                                           // node half-bandwidth of that order
+    for (int m = 0; m < h->M; ++m) {
+        int a = pos[h->h_conn[2 * m]], b = pos[h->h_conn[2 * m + 1]];
+        if (a >= 0 && b >= 0) hbn = std::max(hbn, std::abs(a - b));
+    }
+    // two chains when the band is narrow and long enough: |A|, |B| multiples of 32 nodes (= 3 tiles), separator >= hbn nodes
+    int nA = N, nS = 0, nB = 0;
+    h->n_chains = 1;
+    if (solver == JK_SOLVER_BANDED && getenv("JK_SINGLE_CHAIN") == nullptr && N - hbn >= 4 * 32 && 6 * hbn + 5 <= 12 * NB) {
+        int avail = N - hbn;
+        nA = 32 * (avail / 64);
+        nB = 32 * ((avail - nA) / 32);
+        nS = N - nA - nB;
+        h->n_chains = 2;
+    }
+    h->nS_nodes = nS;
+    // local slot of every free node in its chain(s): chain 0 = [A; S] in order, chain 1 = [rev(B); rev(S)]
+    std::vector<int> slot0(h->Nn, -1), slot1(h->Nn, -1);
+    for (int i = 0; i < nA + nS; ++i) slot0[h->h_free_nodes[i]] = i;
+    if (h->n_chains == 2) for (int i = nA; i < N; ++i) slot1[h->h_free_nodes[i]] = N - 1 - i;   // B: 0..nB-1, S: nB..nB+nS-1 (both reversed)
+    auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
+    c0.n_rows = 6 * (nA + nS); c0.NT = ceil_div(c0.n_rows, NB); c0.kS = (h->n_chains == 2) ? (6 * nA) / NB : c0.NT; c0.row0 = 0;
+    c1.n_rows = (h->n_chains == 2) ? 6 * (nB + nS) : 0; c1.NT = ceil_div(c1.n_rows, NB); c1.kS = (6 * nB) / NB; c1.row0 = c0.NT * NB;
+    h->NT = c0.NT + c1.NT;
+    h->n_pad = h->NT * NB;
+    // node -> first row of the slab (solution lives in chain 0 for A and S nodes, in chain 1 for B nodes)
     h->h_node2slot.assign(h->Nn, 0);
     for (int i = 0; i < h->n_fixed; ++i) h->h_node2slot[h->h_fixed[i]] = -1 - i;
-    for (int s = 0; s < h->n_free_nodes; ++s) h->h_node2slot[h->h_free_nodes[s]] = s;
-    h->n_free = 6 * h->n_free_nodes;
-    h->NT = ceil_div(h->n_free, NB);
-    h->n_pad = h->NT * NB;
-    h->solver = solver;
+    for (int i = 0; i < N; ++i) {
+        int node = h->h_free_nodes[i];
+        h->h_node2slot[node] = (i < nA + nS) ? 6 * slot0[node] : c1.row0 + 6 * slot1[node];
+    }
 
-    // 6x6 block list of K_ff with contributions in member order (deterministic assembly)
+    // 6x6 block lists with contributions in member order (deterministic assembly), one list per chain.
+    // Separator-separator blocks are assembled into chain 0 only (chain 1's trailing block collects -W_B W_B^T).
     struct Contrib { long long key; int member, quad; };
-    std::vector<Contrib> cs;
-    cs.reserve(3 * (size_t)h->M);
-    int bw = 0, hb = 0;
-    auto span = [&](int rs, int cslot) { int I = (6 * rs + 5) / NB, J = (6 * cslot) / NB; bw = std::max(bw, I - J); hb = std::max(hb, 6 * (rs - cslot) + 5); };
-    for (int m = 0; m < h->M; ++m) {
-        int s0 = h->h_node2slot[h->h_conn[2 * m]], s1 = h->h_node2slot[h->h_conn[2 * m + 1]];
-        if (s0 >= 0) { cs.push_back({(long long)s0 * h->n_free_nodes + s0, m, 0}); span(s0, s0); }
-        if (s1 >= 0) { cs.push_back({(long long)s1 * h->n_free_nodes + s1, m, 3}); span(s1, s1); }
-        if (s0 >= 0 && s1 >= 0) {
-            if (s0 > s1) { cs.push_back({(long long)s0 * h->n_free_nodes + s1, m, (0 << 1) | 1}); span(s0, s1); }
-            else { cs.push_back({(long long)s1 * h->n_free_nodes + s0, m, (1 << 1) | 0}); span(s1, s0); }
+    std::vector<char> touched(h->Nn, 0);
+    std::vector<KBlock> blocks[2];
+    std::vector<int2> contribs[2];
+    for (int c = 0; c < h->n_chains; ++c) {
+        const std::vector<int>& sl = c == 0 ? slot0 : slot1;
+        auto& chn = h->ch[c];
+        const long long nn = (long long)N + 1;
+        std::vector<Contrib> cs;
+        cs.reserve(3 * (size_t)h->M);
+        int bw = 0, hb = 0;
+        auto span = [&](int rs, int cslot) { int I = (6 * rs + 5) / NB, J = (6 * cslot) / NB; bw = std::max(bw, I - J); hb = std::max(hb, 6 * (rs - cslot) + 5); };
+        auto in_sep = [&](int node) { int q = pos[node]; return h->n_chains == 2 && q >= nA && q < nA + nS; };
+        for (int m = 0; m < h->M; ++m) {
+            int na = h->h_conn[2 * m], nb = h->h_conn[2 * m + 1];
+            int s0 = sl[na], s1 = sl[nb];
+            bool sepa = in_sep(na), sepb = in_sep(nb);
+            if (s0 >= 0 && !(c == 1 && sepa)) { cs.push_back({(long long)s0 * nn + s0, m, 0}); span(s0, s0); touched[na] = 1; }
+            if (s1 >= 0 && !(c == 1 && sepb)) { cs.push_back({(long long)s1 * nn + s1, m, 3}); span(s1, s1); touched[nb] = 1; }
+            if (s0 >= 0 && s1 >= 0 && !(c == 1 && sepa && sepb)) {
+                if (s0 > s1) { cs.push_back({(long long)s0 * nn + s1, m, (0 << 1) | 1}); span(s0, s1); }
+                else { cs.push_back({(long long)s1 * nn + s0, m, (1 << 1) | 0}); span(s1, s0); }
+            }
         }
-    }
-    std::stable_sort(cs.begin(), cs.end(), [](const Contrib& a, const Contrib& b) { return a.key < b.key; });
-    std::vector<KBlock> blocks;
-    std::vector<int2> contrib(cs.size());
-    for (size_t i = 0; i < cs.size(); ++i) {
-        contrib[i] = make_int2(cs[i].member, cs[i].quad);
-        if (i == 0 || cs[i].key != cs[i - 1].key) {
-            KBlock kb; kb.row_slot = (int)(cs[i].key / h->n_free_nodes); kb.col_slot = (int)(cs[i].key % h->n_free_nodes);
-            kb.start = (int)i; kb.count = 0; blocks.push_back(kb);
+        std::stable_sort(cs.begin(), cs.end(), [](const Contrib& a, const Contrib& b) { return a.key < b.key; });
+        contribs[c].resize(cs.size());
+        for (size_t i = 0; i < cs.size(); ++i) {
+            contribs[c][i] = make_int2(cs[i].member, cs[i].quad);
+            if (i == 0 || cs[i].key != cs[i - 1].key) {
+                KBlock kb; kb.row_slot = (int)(cs[i].key / nn); kb.col_slot = (int)(cs[i].key % nn);
+                kb.start = (int)i; kb.count = 0; blocks[c].push_back(kb);
+            }
+            blocks[c].back().count++;
         }
-        blocks.back().count++;
+        chn.nblocks = (int)blocks[c].size();
+        chn.bw = (solver == JK_SOLVER_DENSE) ? (chn.NT - 1) : std::min(bw, chn.NT - 1);
+        chn.hb = hb;
+        chn.tiles_elems = (size_t)chn.NT * (size_t)(chn.bw + 1) * NB * NB;
     }
-    // free nodes with no member at all would make K_ff singular; report it now
-    { std::vector<char> touched(h->n_free_nodes, 0);
-      for (auto& b : blocks) if (b.row_slot == b.col_slot) touched[b.row_slot] = 1;
-      for (int s = 0; s < h->n_free_nodes; ++s) if (!touched[s]) JK_FAIL(h, JK_EINVAL, "jk_set_supports: free node %d has no member attached", h->h_free_nodes[s]); }
-    h->nblocks = (int)blocks.size();
-    h->bw = (solver == JK_SOLVER_DENSE) ? (h->NT - 1) : std::min(bw, h->NT - 1);
-    h->hb = hb;   // the Cholesky factor keeps the DOF half-bandwidth of K_ff (no fill outside the band), also in dense storage
-    h->tiles_elems = (size_t)h->NT * (size_t)(h->bw + 1) * NB * NB;
+    // a member that joins A and B directly would break the separator (cannot happen when nS >= hbn); free nodes
+    // without any member would make K_ff singular: report both now
+    for (int m = 0; m < h->M && h->n_chains == 2; ++m) {
+        int a = pos[h->h_conn[2 * m]], b = pos[h->h_conn[2 * m + 1]];
+        if (a >= 0 && b >= 0 && ((a < nA && b >= nA + nS) || (b < nA && a >= nA + nS))) JK_FAIL(h, JK_EINVAL, "jk_set_supports: internal separator error");
+    }
+    for (int i = 0; i < N; ++i) if (!touched[h->h_free_nodes[i]]) JK_FAIL(h, JK_EINVAL, "jk_set_supports: free node %d has no member attached", h->h_free_nodes[i]);
+    h->bw = std::max(c0.bw, c1.bw);
+    h->hb = std::max(c0.hb, c1.hb);
+    // row order of the slab for jk_get_order: chain 0 nodes (A, S), then chain 1's own nodes (B reversed)
+    { std::vector<int> ord2(h->h_free_nodes.begin(), h->h_free_nodes.begin() + nA + nS);
+      for (int i = N - 1; i >= nA + nS; --i) ord2.push_back(h->h_free_nodes[i]);
+      h->h_free_nodes.swap(ord2); }
 
     CUDA_TRY(h, dev_alloc(&h->d_node2slot, (size_t)h->Nn));
     CUDA_TRY(h, dev_alloc(&h->d_fixed_nodes, (size_t)h->n_fixed));
     CUDA_TRY(h, dev_alloc(&h->d_free_nodes, (size_t)h->n_free_nodes));
-    CUDA_TRY(h, dev_alloc(&h->d_blocks, blocks.size()));
-    CUDA_TRY(h, dev_alloc(&h->d_contrib, contrib.size()));
-    CUDA_TRY(h, dev_alloc(&h->d_tiles, h->tiles_elems));
-    CUDA_TRY(h, dev_alloc(&h->d_Linv, (size_t)h->NT * NB * NB));
-    CUDA_TRY(h, dev_alloc(&h->d_dinv, (size_t)h->NT * 512));
     cudaStream_t s = h->stream;
+    for (int c = 0; c < 2; ++c) {
+        auto& chn = h->ch[c];
+        if (c >= h->n_chains) { dev_free(chn.d_blocks); dev_free(chn.d_contrib); dev_free(chn.d_tiles); dev_free(chn.d_Linv); dev_free(chn.d_dinv); chn.NT = 0; continue; }
+        CUDA_TRY(h, dev_alloc(&chn.d_blocks, blocks[c].size()));
+        CUDA_TRY(h, dev_alloc(&chn.d_contrib, contribs[c].size()));
+        CUDA_TRY(h, dev_alloc(&chn.d_tiles, chn.tiles_elems));
+        CUDA_TRY(h, dev_alloc(&chn.d_Linv, (size_t)chn.NT * NB * NB));
+        CUDA_TRY(h, dev_alloc(&chn.d_dinv, (size_t)chn.NT * 512));
+        CUDA_TRY(h, cudaMemcpyAsync(chn.d_blocks, blocks[c].data(), blocks[c].size() * sizeof(KBlock), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaMemcpyAsync(chn.d_contrib, contribs[c].data(), contribs[c].size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->d_node2slot, h->h_node2slot.data(), (size_t)h->Nn * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_blocks, blocks.data(), blocks.size() * sizeof(KBlock), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_contrib, contrib.data(), contrib.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     h->have_supports = true; h->assembled = false; h->factored = false;
     // buffers sized by n_pad / n_fixed must be rebuilt
@@ -379,12 +440,15 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0)); h->factor_inflight = false; }
     h->E = E; h->G = G;
     tic(h, JK_T_ASSEMBLE);
-    CUDA_TRY(h, cudaMemsetAsync(h->d_tiles, 0, h->tiles_elems * sizeof(double), s));
     k_member_setup<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, h->d_xyz, h->d_conn, h->d_sec, h->d_secp, JK_SEC_NPROP, E, G, h->d_mc, h->d_Ke, h->d_Kl);
     LAUNCH_CHECK(h);
-    k_assemble_blocks<<<h->nblocks, 64, 0, s>>>(h->nblocks, h->d_blocks, h->d_contrib, h->d_Ke, h->d_tiles, h->bw);
-    LAUNCH_CHECK(h);
-    if (h->n_pad > h->n_free) { k_pad_identity<<<1, NB, 0, s>>>(h->n_free, h->n_pad, h->d_tiles, h->bw); LAUNCH_CHECK(h); }
+    for (int c = 0; c < h->n_chains; ++c) {
+        auto& chn = h->ch[c];
+        CUDA_TRY(h, cudaMemsetAsync(chn.d_tiles, 0, chn.tiles_elems * sizeof(double), s));
+        k_assemble_blocks<<<chn.nblocks, 64, 0, s>>>(chn.nblocks, chn.d_blocks, chn.d_contrib, h->d_Ke, chn.d_tiles, chn.bw);
+        LAUNCH_CHECK(h);
+        if (chn.NT * NB > chn.n_rows) { k_pad_identity<<<1, NB, 0, s>>>(chn.n_rows, chn.NT * NB, chn.d_tiles, chn.bw); LAUNCH_CHECK(h); }
+    }
     toc(h, JK_T_ASSEMBLE);
     h->assembled = true; h->factored = false;
     return JK_OK;
@@ -394,39 +458,58 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
 static int launch_factor(jk_handle_t h, cudaStream_t s) {
     tic(h, JK_T_FACTOR, s);
     CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), s));
-    // narrow band: one persistent cluster kernel (latency chain); wide band / dense: per-column launches
+    // narrow band: persistent cluster kernel(s) (latency chain); wide band / dense: per-column launches
     const bool use_cluster = (h->factor_path == 0) && (h->bw <= 16);
+    auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
     if (use_cluster) {
         long long* prof = nullptr;
         const bool want_prof = getenv("JK_CHOL_PROFILE") != nullptr;
-        if (want_prof) { CUDA_TRY(h, cudaMalloc((void**)&prof, (size_t)h->NT * 8 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(prof, 0, (size_t)h->NT * 8 * sizeof(long long), s)); }
-        k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(h->d_tiles, h->d_dinv, h->NT, h->bw, h->d_info, prof);
-        LAUNCH_CHECK(h);
-        if (want_prof) {   // debug aid: average clock deltas between the phase stamps of CTA 0
-            std::vector<long long> hp((size_t)h->NT * 8);
+        if (want_prof) { CUDA_TRY(h, cudaMalloc((void**)&prof, (size_t)c0.NT * 8 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(prof, 0, (size_t)c0.NT * 8 * sizeof(long long), s)); }
+        CholChain a{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, 0, c0.kS};
+        if (h->n_chains == 2) {
+            // stage 1: both chains eliminate towards the separator, concurrently on two clusters
+            CholChain b{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, 0, c1.kS};
+            k_band_chol_cluster<<<2 * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a, b, h->d_info, prof);
+            LAUNCH_CHECK(h);
+            // stage 2: separator Schur complement = sum of both chains' trailing blocks
+            long long n = 36LL * h->nS_nodes * h->nS_nodes;
+            k_sep_merge_tiles<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c0.d_tiles, c0.bw, c0.kS, c1.d_tiles, c1.bw, c1.kS, h->nS_nodes);
+            LAUNCH_CHECK(h);
+            // stage 3: factor the separator (trailing columns of chain 0)
+            CholChain f{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, c0.kS, c0.NT};
+            k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(f, f, h->d_info, nullptr);
+            LAUNCH_CHECK(h);
+        } else {
+            k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a, a, h->d_info, prof);
+            LAUNCH_CHECK(h);
+        }
+        if (want_prof) {   // debug aid: average clock deltas between the phase stamps of chain 0, CTA 0
+            std::vector<long long> hp((size_t)c0.NT * 8);
             CUDA_TRY(h, cudaMemcpyAsync(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(h, cudaStreamSynchronize(s));
             cudaFree(prof);
             double acc[6] = {0, 0, 0, 0, 0, 0}; int n = 0;
-            for (int k = 8; k + 8 < h->NT; ++k, ++n) for (int i = 0; i < 6; ++i) acc[i] += (double)(hp[(size_t)k * 8 + i + 1] - hp[(size_t)k * 8 + i]);
+            for (int k = 8; k + 8 < c0.kS; ++k, ++n) for (int i = 0; i < 6; ++i) acc[i] += (double)(hp[(size_t)k * 8 + i + 1] - hp[(size_t)k * 8 + i]);
             if (n > 0) fprintf(stderr, "[jk chol profile] clocks/column: panel %.0f | sync %.0f | B-load+update %.0f | potrf %.0f | store+other tiles %.0f | sync %.0f\n",
                                acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n);
         }
     } else {
-        for (int k = 0; k < h->NT; ++k) {
-            int w = std::min(h->bw, h->NT - 1 - k);
-            k_potrf_tile<<<1, 256, 0, s>>>(h->d_tiles, k, h->bw, h->d_info);
+        // per-column launches (dense storage or very wide bands): single chain only
+        for (int k = 0; k < c0.NT; ++k) {
+            int w = std::min(c0.bw, c0.NT - 1 - k);
+            k_potrf_tile<<<1, 256, 0, s>>>(c0.d_tiles, k, c0.bw, h->d_info);
             LAUNCH_CHECK(h);
             if (w > 0) {
-                k_panel_trsm<<<w, NB, PANEL_SMEM, s>>>(h->d_tiles, k, h->bw);
+                k_panel_trsm<<<w, NB, PANEL_SMEM, s>>>(c0.d_tiles, k, c0.bw);
                 LAUNCH_CHECK(h);
-                k_trailing_update<<<w * (w + 1) / 2, 128, UPDATE_SMEM, s>>>(h->d_tiles, k, w, h->bw);
+                k_trailing_update<<<w * (w + 1) / 2, 128, UPDATE_SMEM, s>>>(c0.d_tiles, k, w, c0.bw);
                 LAUNCH_CHECK(h);
             }
         }
     }
-    k_tile_inverse<<<h->NT, 256, INVERSE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->bw);
+    k_tile_inverse<<<c0.NT, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw);
     LAUNCH_CHECK(h);
+    if (h->n_chains == 2) { k_tile_inverse<<<c1.kS, 256, INVERSE_SMEM, s>>>(c1.d_tiles, c1.d_Linv, c1.bw); LAUNCH_CHECK(h); }
     toc(h, JK_T_FACTOR, s);
     return JK_OK;
 }
@@ -651,13 +734,31 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     cudaStream_t s = h->stream;
     int nslab = ldP / SLAB;
     if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0));   // join the side stream
+    auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
+    const int nS6 = 6 * h->nS_nodes;
+    dim3 gsep(ceil_div(ldP, 128), std::max(1, nS6));
     tic(h, JK_T_SOLVE_FWD);
-    k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad, h->hb);
+    if (h->n_chains == 2) {
+        // second chain first: its separator rows collect -L_SB y_B (they start at zero), merged into the first chain's
+        CUDA_TRY(h, cudaMemset2DAsync(h->d_X + ((size_t)c1.row0 + (size_t)c1.kS * NB) * SLAB, (size_t)h->n_pad * SLAB * sizeof(double), 0,
+                                      (size_t)(c1.NT - c1.kS) * NB * SLAB * sizeof(double), (size_t)nslab, s));
+        k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(c1.d_tiles, c1.d_Linv, h->d_X, c1.NT, c1.bw, h->n_pad, c1.row0, c1.kS);
+        LAUNCH_CHECK(h);
+        k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 0);
+        LAUNCH_CHECK(h);
+    }
+    k_slab_sweep<false><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, h->d_X, c0.NT, c0.bw, h->n_pad, c0.row0, c0.NT);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SOLVE_FWD);
     tic(h, JK_T_SOLVE_BWD);
-    k_slab_sweep<true><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(h->d_tiles, h->d_Linv, h->d_X, h->NT, h->bw, h->n_pad, h->hb);
+    k_slab_sweep<true><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, h->d_X, c0.NT, c0.bw, h->n_pad, c0.row0, c0.NT);
     LAUNCH_CHECK(h);
+    if (h->n_chains == 2) {
+        k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 1);
+        LAUNCH_CHECK(h);
+        k_slab_sweep<true><<<nslab, SOLVE_THREADS, SOLVE_SMEM, s>>>(c1.d_tiles, c1.d_Linv, h->d_X, c1.NT, c1.bw, h->n_pad, c1.row0, c1.kS);
+        LAUNCH_CHECK(h);
+    }
     toc(h, JK_T_SOLVE_BWD);
     tic(h, JK_T_POST);
     dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, PH_TPB));
@@ -975,6 +1076,7 @@ extern "C" int jk_fetch_member_column(jk_handle_t h, int member, int column, int
 extern "C" int jk_get_dims(jk_handle_t h, int32_t* out) {
     if (!h || !out) return JK_EINVAL;
     out[0] = h->Nn; out[1] = h->M; out[2] = h->n_fixed; out[3] = h->n_free; out[4] = h->n_pad; out[5] = NB; out[6] = h->bw; out[7] = h->NT;
+    out[8] = h->hb; out[9] = h->n_chains; out[10] = h->ch[0].kS; out[11] = h->nS_nodes;
     return JK_OK;
 }
 

@@ -194,21 +194,34 @@ __global__ void __launch_bounds__(256) k_tile_inverse(const double* __restrict__
 // previous step) stream from L2/HBM through a 3-stage cp.async ring; the newest X tile and the
 // intermediate t stay in shared memory.  The slab's rows are updated in place.
 // ----------------------------------------------------------------------------------------------
+// Walks the tile products of a sweep.  kx = first "special" tile row:
+//   forward : rows k >= kx are PARTIAL -- they only accumulate B_k - sum_{j < kx} L_kj X_j (no diagonal solve);
+//             used for the separator rows of the second chain, whose sums are merged into the first chain.
+//   backward: rows k >= kx are KNOWN   -- already solved (separator solution copied in); the sweep starts at kx-1.
+// kx = NT gives the plain sweep.
 template <bool BWD>
 struct SweepIter {
-    int k, j, NT, bw;
-    __device__ void init(int nt, int b) {
-        NT = nt; bw = b;
-        if (!BWD) { k = 0; j = 0; } else { k = NT - 1; j = NT - 1; }
+    int k, j, NT, bw, kx;
+    __device__ int first_j(int kk) const {
+        if (!BWD) { int lo = max(0, kk - bw), hi = min(kk - 1, kx - 1); return lo <= hi ? lo : kk; }
+        int hi = min(NT - 1, kk + bw); return hi >= kk + 1 ? hi : kk;
+    }
+    __device__ void init(int nt, int b, int kspecial) {
+        NT = nt; bw = b; kx = kspecial;
+        k = BWD ? kx - 1 : 0;
+        j = BWD ? (k >= 0 ? first_j(k) : 0) : first_j(0);
     }
     __device__ bool done() const { return BWD ? (k < 0) : (k >= NT); }
     __device__ bool is_diag() const { return j == k; }
-    __device__ bool x_in_smem() const { return BWD ? (j == k + 1) : (j == k - 1); }
+    __device__ bool partial_row() const { return !BWD && k >= kx; }
+    __device__ bool x_in_smem() const { return BWD ? (j == k + 1 && k + 1 < kx) : (j == k - 1); }
     __device__ void next() {
         if (!BWD) {
-            if (j == k) { ++k; j = max(0, k - bw); } else ++j;
+            if (j == k) { ++k; j = first_j(k); }
+            else { ++j; if (j > min(k - 1, kx - 1)) j = k; }
         } else {
-            if (j == k) { --k; j = min(NT - 1, k + bw); } else --j;
+            if (j == k) { --k; if (k >= 0) j = first_j(k); }
+            else { --j; }
         }
     }
 };
@@ -216,18 +229,18 @@ struct SweepIter {
 template <bool BWD>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, double* __restrict__ X,
-             int NT, int bw, int n_pad, int hb /* DOF half-bandwidth of L (reserved) */) {
-    (void)hb;
+             int NT, int bw, int n_pad /* rows of the whole slab */, int row0 /* first row of this chain in the slab */,
+             int kx /* first partial (forward) / known (backward) tile row, NT for a plain sweep */) {
     extern __shared__ __align__(16) double smem[];
     double* Ls = smem;                                         // [STAGES][NB][LS_LD]
     double* Xs = Ls + SOLVE_STAGES * NB * LS_LD;               // [STAGES][NB][XS_LD]
     double* Ts = Xs + SOLVE_STAGES * NB * XS_LD;               // [NB][XS_LD]  newest X tile / intermediate t
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int fr = lane / 4, fk = lane % 4;
-    double* Xslab = X + (size_t)blockIdx.x * (size_t)n_pad * SLAB;
+    double* Xslab = X + ((size_t)blockIdx.x * (size_t)n_pad + (size_t)row0) * SLAB;
 
     auto issue = [&](const SweepIter<BWD>& it, int stage) {
-        if (it.done()) return;
+        if (it.done() || (it.is_diag() && it.partial_row())) return;
         const double* lsrc = it.is_diag() ? (Linv + (size_t)it.k * NB * NB)
                                           : (tiles + (BWD ? tile_off(it.j, it.k, bw) : tile_off(it.k, it.j, bw)));
         load_tile_async(Ls + stage * NB * LS_LD, lsrc, tid, SOLVE_THREADS);
@@ -242,7 +255,7 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
     };
 
     SweepIter<BWD> it_load, it;
-    it_load.init(NT, bw); it.init(NT, bw);
+    it_load.init(NT, bw, kx); it.init(NT, bw, kx);
     // prologue: STAGES-1 items in flight
     for (int s = 0; s < SOLVE_STAGES - 1; ++s) { issue(it_load, s); cp_async_commit(); it_load.next(); }
 
@@ -269,7 +282,7 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
         // The copies of item n+STAGES-1 (into the stage item n-1 just released) are issued INSIDE the DMMA loop below,
         // one 16-byte chunk per thread per k-step, so the tensor pipe never waits for a copy-issue phase.
         const int lstage = (n + SOLVE_STAGES - 1) % SOLVE_STAGES;
-        const bool ld_l = !it_load.done();
+        const bool ld_l = !it_load.done() && !(it_load.is_diag() && it_load.partial_row());
         const bool ld_x = ld_l && !it_load.is_diag() && !it_load.x_in_smem();
         const double* lsrc = nullptr; const double* xsrc = nullptr;
         if (ld_l) lsrc = (it_load.is_diag() ? (Linv + (size_t)it_load.k * NB * NB)
@@ -284,6 +297,24 @@ k_slab_sweep(const double* __restrict__ tiles, const double* __restrict__ Linv, 
 
         const double* ls = Ls + stage * NB * LS_LD;
         const double* xs;
+        if (it.is_diag() && it.partial_row()) {
+            // partial row: store B_k - sum (no diagonal solve); nothing later in this sweep reads it
+#pragma unroll
+            for (int nt = 0; nt < SOLVE_NT; ++nt) {
+                double2 v = make_double2(bk[nt][0] - acc[nt][0], bk[nt][1] - acc[nt][1]);
+                *reinterpret_cast<double2*>(Xslab + ((size_t)it.k * NB + row) * SLAB + col0 + 8 * nt + 2 * fk) = v;
+            }
+            // no DMMA loop in this item: issue the copies of item n+2 here
+#pragma unroll
+            for (int q = 0; q < LCH; ++q) if (ld_l) cp_async16(ldst + q * LROWS * LS_LD, lsrc + q * LROWS * NB);
+#pragma unroll
+            for (int q = 0; q < XCH; ++q) if (ld_x) cp_async16(xdst + q * XROWS * XS_LD, xsrc + q * XROWS * SLAB);
+            cp_async_commit();
+            new_step = true;
+            it.next();
+            ++n;
+            continue;
+        }
         if (it.is_diag()) {
             // t = B_k - acc  -> Ts, then acc = Linv * t
 #pragma unroll

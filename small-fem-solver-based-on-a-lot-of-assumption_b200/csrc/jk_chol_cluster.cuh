@@ -193,11 +193,23 @@ __device__ __forceinline__ void gemm64_nt(const double* __restrict__ As, const d
     }
 }
 
+// One chain of the factorisation: columns [k_begin, k_end) of a tile-banded matrix are eliminated; the trailing
+// rows (tiles >= k_end) only receive their Schur-complement updates.
+struct CholChain { double* tiles; double* dinv; int NT, bw, k_begin, k_end; };
+
+// Grid = n_chains clusters of CHOL_CLUSTER CTAs; cluster c works on chain[c].  With two chains the band is eliminated
+// from both ends at once (the second chain is the same matrix in reversed order), halving the pivot chain.
 __global__ void __cluster_dims__(CHOL_CLUSTER, 1, 1) __launch_bounds__(CHOL_THREADS, 1)
-k_band_chol_cluster(double* __restrict__ tiles, double* __restrict__ dinv /* [NT][8][8][8] */, int NT, int bw, int* __restrict__ info,
-                    long long* __restrict__ prof /* optional [NT][8] clock stamps of CTA 0 (debug) */) {
+k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
+                    long long* __restrict__ prof /* optional [NT][8] clock stamps of chain 0, CTA 0 (debug) */) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
+    const bool second = blockIdx.x >= CHOL_CLUSTER;
+    const CholChain ch = second ? chain1 : chain0;
+    double* __restrict__ tiles = ch.tiles;
+    double* __restrict__ dinv = ch.dinv;
+    const int NT = ch.NT, bw = ch.bw;
+    if (second) prof = nullptr;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = As + NB * LS_LD;
@@ -216,19 +228,20 @@ k_band_chol_cluster(double* __restrict__ tiles, double* __restrict__ dinv /* [NT
         for (int q = tid; q < 512; q += CHOL_THREADS) { int b = q >> 6, r = (q >> 3) & 7, c = q & 7; Di[b * DI_BLK + r * DI_LD + c] = __ldcg(g + q); }
     };
 
-    if (cta == 0) {                                          // prologue: potrf(0)
-        load_tile_async(Cs, tiles + tile_off(0, 0, bw), tid, CHOL_THREADS);
+    if (cta == 0 && ch.k_begin < ch.k_end) {                 // prologue: potrf(k_begin)
+        load_tile_async(Cs, tiles + tile_off(ch.k_begin, ch.k_begin, bw), tid, CHOL_THREADS);
         cp_async_commit(); cp_async_wait<0>();
         __syncthreads();
-        potrf64_smem(Cs, Di, info, 0);
-        store_tile(tiles + tile_off(0, 0, bw), Cs, tid, CHOL_THREADS);
-        store_dinv(0);
+        potrf64_smem(Cs, Di, info, ch.k_begin * NB);
+        store_tile(tiles + tile_off(ch.k_begin, ch.k_begin, bw), Cs, tid, CHOL_THREADS);
+        store_dinv(ch.k_begin);
     }
     cluster.sync();
 
 #define JK_STAMP(i) do { if (prof && cta == 0 && tid == 0) prof[(size_t)k * 8 + (i)] = clock64(); } while (0)
-    for (int k = 0; k + 1 < NT; ++k) {
+    for (int k = ch.k_begin; k < ch.k_end; ++k) {
         const int w = min(bw, NT - 1 - k);
+        const bool factor_next = (k + 1 < ch.k_end);         // lookahead potrf of the next diagonal tile
         JK_STAMP(0);
         // ---------------- phase A: panel ----------------
         if (cta < w) {
@@ -251,7 +264,7 @@ k_band_chol_cluster(double* __restrict__ tiles, double* __restrict__ dinv /* [NT
         JK_STAMP(2);
         // ---------------- phase B: trailing update (+ lookahead potrf on CTA 0) ----------------
         const int ntile = w * (w + 1) / 2;
-        if (cta == 0) {
+        if (cta == 0 && (w >= 1 || factor_next)) {
             load_tile_async(Cs, tiles + tile_off(k + 1, k + 1, bw), tid, CHOL_THREADS);
             if (w >= 1) load_tile_async(As, tiles + tile_off(k + 1, k, bw), tid, CHOL_THREADS);
             cp_async_commit(); cp_async_wait<0>();
@@ -280,10 +293,10 @@ k_band_chol_cluster(double* __restrict__ tiles, double* __restrict__ dinv /* [NT
                 __syncthreads();
             }
             JK_STAMP(3);
-            potrf64_smem(Cs, Di, info, (k + 1) * NB);
+            if (factor_next) potrf64_smem(Cs, Di, info, (k + 1) * NB);
             JK_STAMP(4);
             store_tile(tiles + tile_off(k + 1, k + 1, bw), Cs, tid, CHOL_THREADS);
-            store_dinv(k + 1);
+            if (factor_next) store_dinv(k + 1);
         }
         // remaining tiles t = 1..ntile-1 dealt to CTAs 1..7 (CTA 0 joins only if the band is wide)
         const int nworkers = (ntile - 1 > 4 * (CHOL_CLUSTER - 1)) ? CHOL_CLUSTER : CHOL_CLUSTER - 1;
@@ -318,6 +331,35 @@ k_band_chol_cluster(double* __restrict__ tiles, double* __restrict__ dinv /* [NT
         JK_STAMP(6);
     }
 #undef JK_STAMP
+}
+
+// Separator merge after the two chains stopped at their separator rows: the Schur complement of the separator is the
+// sum of both chains' contributions.  Chain 1 holds K_SS - W_A W_A^T in its trailing block, chain 0's twin holds
+// -W_B W_B^T with the separator NODES in reversed order (DOF order inside a node unchanged).  Lower triangle only.
+__global__ void k_sep_merge_tiles(double* __restrict__ t0, int bw0, int kS0, const double* __restrict__ t1, int bw1, int kS1, int nS /* nodes */) {
+    const int n = 6 * nS;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * n) return;
+    const int r = (int)(idx / n), c = (int)(idx % n);
+    if (c > r) return;
+    const int r1 = 6 * (nS - 1 - r / 6) + r % 6, c1 = 6 * (nS - 1 - c / 6) + c % 6;
+    const int hi = max(r1, c1), lo = min(r1, c1);
+    const int R0 = kS0 * NB + r, C0 = kS0 * NB + c, R1 = kS1 * NB + hi, C1 = kS1 * NB + lo;
+    if (R0 / NB - C0 / NB > bw0) return;                     // outside the band: both are structurally zero
+    double v = (R1 / NB - C1 / NB > bw1) ? 0.0 : t1[tile_off(R1 / NB, C1 / NB, bw1) + (size_t)(R1 % NB) * NB + (C1 % NB)];
+    t0[tile_off(R0 / NB, C0 / NB, bw0) + (size_t)(R0 % NB) * NB + (C0 % NB)] += v;
+}
+
+// right-hand sides / solutions of the separator rows between the two chains' row blocks of the slab-packed array:
+//   mode 0:  X[row_a + r] += X[row_b + rev(r)]      (forward: add the second chain's partial sums)
+//   mode 1:  X[row_b + rev(r)] = X[row_a + r]        (backward: hand the separator solution to the second chain)
+__global__ void k_sep_exchange(double* __restrict__ X, int n_pad, int ldP, int row_a, int row_b, int nS, int mode) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (p >= ldP || r >= 6 * nS) return;
+    const int r1 = 6 * (nS - 1 - r / 6) + r % 6;
+    const size_t ia = rhs_off(row_a + r, p, n_pad), ib = rhs_off(row_b + r1, p, n_pad);
+    if (mode == 0) X[ia] += X[ib]; else X[ib] = X[ia];
 }
 
 }  // namespace jk

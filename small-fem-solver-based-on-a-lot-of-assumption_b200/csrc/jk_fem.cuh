@@ -219,7 +219,7 @@ __device__ __forceinline__ void member_row(const double* __restrict__ c, const d
 __device__ __forceinline__ double load_u(const double* __restrict__ X, const int* __restrict__ node2slot,
                                          int node, int comp, int p, int n_pad) {
     int s = node2slot[node];
-    return s >= 0 ? X[rhs_off(6 * s + comp, p, n_pad)] : 0.0;
+    return s >= 0 ? X[rhs_off(s + comp, p, n_pad)] : 0.0;   // node2slot holds the node's first ROW of the slab (or -1-f)
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -253,8 +253,8 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
         int s1 = s_slot[2 * mm], s2 = s_slot[2 * mm + 1];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            ue[k] = s1 >= 0 ? X[xbase + (size_t)(6 * s1 + k) * SLAB] : 0.0;
-            ue[6 + k] = s2 >= 0 ? X[xbase + (size_t)(6 * s2 + k) * SLAB] : 0.0;
+            ue[k] = s1 >= 0 ? X[xbase + (size_t)(s1 + k) * SLAB] : 0.0;
+            ue[6 + k] = s2 >= 0 ? X[xbase + (size_t)(s2 + k) * SLAB] : 0.0;
         }
         element_local_forces(c, ue, Fl);
         member_row(c, s_pt + mm * 24, Fl, inv_fy, row);
@@ -303,7 +303,7 @@ k_node_post(int Nn, int ldP, int n_pad, const double* __restrict__ X, const int*
         int s = node2slot[n0 + i];
         double d = 0.0;
         if (s >= 0) {
-            double ux = X[xbase + (size_t)(6 * s) * SLAB], uy = X[xbase + (size_t)(6 * s + 1) * SLAB], uz = X[xbase + (size_t)(6 * s + 2) * SLAB];
+            double ux = X[xbase + (size_t)s * SLAB], uy = X[xbase + (size_t)(s + 1) * SLAB], uz = X[xbase + (size_t)(s + 2) * SLAB];
             d = sqrt(ux * ux + uy * uy + uz * uz);
         }
         if (d > best) { best = d; bnode = n0 + i; }

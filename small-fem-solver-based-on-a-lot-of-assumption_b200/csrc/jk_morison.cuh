@@ -479,7 +479,7 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
     int s = node2slot[node];
     if (s >= 0) {
         if (!B) return;
-        size_t o = rhs_off(6 * s, p, n_pad);
+        size_t o = rhs_off(s, p, n_pad);
 #pragma unroll
         for (int c = 0; c < 3; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + fdir[c] + f[c];
 #pragma unroll
@@ -506,7 +506,7 @@ k_rhs_from_loads(int Nn, int P, int ldP, int n_pad, const double* __restrict__ F
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         double v = F[(size_t)pp * 6 * Nn + 6 * node + c];
-        if (s >= 0) B[rhs_off(6 * s + c, p, n_pad)] = v;
+        if (s >= 0) B[rhs_off(s + c, p, n_pad)] = v;
         else Ffix[(size_t)(6 * (-1 - s) + c) * ldP + p] = v;
     }
 }

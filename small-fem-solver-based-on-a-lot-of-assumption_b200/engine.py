@@ -181,10 +181,10 @@ class Engine:
 
     # -- introspection ----------------------------------------------------------
     def dims(self):
-        d = np.zeros(8, dtype=np.int32)
+        d = np.zeros(12, dtype=np.int32)
         self._ck(self.lib.jk_get_dims(self.h, L.iptr(d)))
-        return dict(zip(("n_nodes", "n_members", "n_fixed", "n_free_dof", "n_pad", "tile", "band_tiles", "n_tiles"),
-                        (int(v) for v in d)))
+        return dict(zip(("n_nodes", "n_members", "n_fixed", "n_free_dof", "n_pad", "tile", "band_tiles", "n_tiles",
+                         "dof_half_bandwidth", "n_chains", "separator_tile_row", "separator_nodes"), (int(v) for v in d)))
 
     def order(self):
         d = self.dims()
