@@ -331,3 +331,35 @@ def test_sea_state_ensemble_vs_oracle():
             assert relmax(R, ref["reactions"][ref["critical"]]) < TOL
     gs, gp = res.governing
     assert res.table[gs, gp, 10] == res.table[:, :, 10].max()
+
+
+def test_two_chain_factorisation_matches_single_chain():
+    """The two-sided elimination (two chains + separator) and the plain single chain give the same solution."""
+    import os
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    out = {}
+    for mode in ("two", "single"):
+        if mode == "single":
+            os.environ["JK_SINGLE_CHAIN"] = "1"
+        try:
+            nodes, members, fixed, top = jb.generate_jacket(8, 30)
+            st = jb.build_structure(nodes, members, fixed, top, ap)
+            res = jb.phase_scan(st, _wave(jb, ap), 48, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+            d = res.engine.dims()
+            out[mode] = (res.table.copy(), res.phase(5)["U"], res.phase(40)["reactions"], d, res.engine.residual())
+            order = res.engine.order()
+            assert sorted(order.tolist()) == sorted(st.indices([n for n in nodes if n not in fixed]).tolist())
+        finally:
+            os.environ.pop("JK_SINGLE_CHAIN", None)
+    assert out["two"][3]["n_chains"] == 2 and out["single"][3]["n_chains"] == 1
+    assert out["two"][3]["separator_nodes"] >= (out["two"][3]["dof_half_bandwidth"] - 5) // 6
+    assert out["two"][0].shape == out["single"][0].shape
+    assert np.array_equal(out["two"][0][:, :8], out["single"][0][:, :8])          # Morison columns do not depend on the solver
+    for c in (8, 10, 12, 13, 14, 15):
+        assert relmax(out["two"][0][:, c], out["single"][0][:, c]) < 1e-10
+    assert np.array_equal(out["two"][0][:, 11], out["single"][0][:, 11])
+    assert relmax(out["two"][1], out["single"][1]) < 1e-10
+    for n in out["two"][2]:
+        assert relmax(out["two"][2][n], out["single"][2][n]) < 1e-10
+    assert out["two"][4] < 1e-9 and out["single"][4] < 1e-9      # max|K u - F| / max|F| over all phases (rounding level)
