@@ -58,30 +58,47 @@ def device_views(engine, P):
     return table, val, idx
 
 
-def allgather_critical(local_value, local_global_index, group=None, device=None):
-    """All-gather one (value, global index) pair per rank and merge.  Works on NCCL (device tensors) and gloo (CPU)."""
+def merge_critical_device(pairs):
+    """First-maximum merge of an all-gathered [world, 2] (value, global index) tensor ON THE DEVICE (no host sync):
+    larger value wins, ties go to the smaller index."""
+    import torch
+    vals, idxs = pairs[:, 0], pairs[:, 1]
+    best = vals.max()
+    idx = torch.where(vals == best, idxs, torch.full_like(idxs, float("inf"))).min()
+    return best, idx
+
+
+def allgather_critical(local_value, local_global_index, group=None, device=None, to_host=True):
+    """All-gather one (value, global index) pair per rank and merge.  Works on NCCL (device tensors) and gloo (CPU).
+    to_host=False keeps the merged pair on the device (two 0-d tensors), so the step stays asynchronous."""
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return merge_critical([float(local_value)], [int(local_global_index)])
-    ws = dist.get_world_size(group)
     if isinstance(local_value, torch.Tensor):
         pair = torch.stack([local_value.reshape(()).to(torch.float64), local_global_index.reshape(()).to(torch.float64)])
     else:
         pair = torch.tensor([float(local_value), float(local_global_index)], dtype=torch.float64, device=device or "cpu")
-    out = torch.empty(ws * 2, dtype=torch.float64, device=pair.device)   # flat: gloo and NCCL both accept it
-    dist.all_gather_into_tensor(out, pair, group=group)
-    out = out.cpu().numpy().reshape(ws, 2)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ws = dist.get_world_size(group)
+        out = torch.empty(ws * 2, dtype=torch.float64, device=pair.device)   # flat: gloo and NCCL both accept it
+        dist.all_gather_into_tensor(out, pair, group=group)
+        out = out.reshape(ws, 2)
+    else:
+        out = pair.reshape(1, 2)
+    if not to_host:
+        return merge_critical_device(out)
+    out = out.cpu().numpy()
     return merge_critical(out[:, 0], out[:, 1].astype(np.int64))
 
 
 def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=None, gather_table=True,
-                       t_dev=None, t_host=None):
+                       t_dev=None, t_host=None, host_results=True):
     """One rank's part of an n_total-phase scan + the cross-rank critical-phase reduction.
 
     Returns dict(local_table (torch view on device), offset, critical_value, critical_index (global),
-    table (global [n_total,16] numpy on every rank if gather_table else None)).
-    With t_dev (a device pointer holding this rank's times) nothing crosses PCIe before the reduction.
+    table (global [n_total,16] on every rank if gather_table else None)).
+    With t_dev (a device pointer holding this rank's times) nothing crosses PCIe before the reduction; with
+    host_results=False nothing crosses it afterwards either (critical pair and gathered table stay device tensors and
+    the call does not synchronise with the host).
     """
     import torch
     import torch.distributed as dist
@@ -96,7 +113,7 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
     table, val, idx = device_views(engine, P)
     stream = torch.cuda.ExternalStream(engine.stream(), device=f"cuda:{engine.device}")
     with torch.cuda.stream(stream):
-        cval, cidx = allgather_critical(val, idx + lo, group=group)
+        cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=host_results)
         full = None
         if gather_table:
             if world_size > 1:
@@ -109,8 +126,11 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
                     parts = [torch.empty((h - l, L.TABLE_NCOL), dtype=torch.float64, device=table.device) for l, h in sizes]
                     dist.all_gather(parts, table.contiguous(), group=group)
                     buf = torch.cat(parts)
-                full = buf.cpu().numpy()
             else:
-                full = table.cpu().numpy()
-            fill_phase_deg(full, wave.omega)
+                buf = table
+            if host_results:
+                full = buf.cpu().numpy()
+                fill_phase_deg(full, wave.omega)
+            else:
+                full = buf
     return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
