@@ -490,7 +490,7 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
             cudaFree(prof);
             double acc[6] = {0, 0, 0, 0, 0, 0}; int n = 0;
             for (int k = 8; k + 8 < c0.kS; ++k, ++n) for (int i = 0; i < 6; ++i) acc[i] += (double)(hp[(size_t)k * 8 + i + 1] - hp[(size_t)k * 8 + i]);
-            if (n > 0) fprintf(stderr, "[jk chol profile] clocks/column: panel %.0f | sync %.0f | B-load+update %.0f | potrf %.0f | store+other tiles %.0f | sync %.0f\n",
+            if (n > 0) fprintf(stderr, "[jk chol profile] CTA0 clocks/column: load %.0f | trsm+store %.0f | arrive+syrk %.0f | potrf %.0f | store+wait(A) %.0f | barrier B %.0f\n",
                                acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n);
         }
     } else {

@@ -239,36 +239,37 @@ k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
     cluster.sync();
 
 #define JK_STAMP(i) do { if (prof && cta == 0 && tid == 0) prof[(size_t)k * 8 + (i)] = clock64(); } while (0)
+    // Split cluster barrier (arrive = release, wait = acquire): CTA 0 arrives on barrier A as soon as L_{k+1,k} is in
+    // global memory and only waits on it after it has factored the next diagonal tile, so the critical chain
+    //   trsm(k+1,k) -> syrk(k+1,k+1) -> potrf(k+1)
+    // never stalls on the other CTAs, whose panel / update work for column k hides under it.
+    auto cluster_arrive = [] { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); };
+    auto cluster_wait = [] { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); };
+    double* Lk = Cs;     // CTA 0: current diagonal factor L_kk (its 8x8 block inverses are in Di)
+    double* Nx = Bs;     // CTA 0: next diagonal tile being built
     for (int k = ch.k_begin; k < ch.k_end; ++k) {
         const int w = min(bw, NT - 1 - k);
         const bool factor_next = (k + 1 < ch.k_end);         // lookahead potrf of the next diagonal tile
-        JK_STAMP(0);
-        // ---------------- phase A: panel ----------------
-        if (cta < w) {
-            load_tile_async(Bs, tiles + tile_off(k, k, bw), tid, CHOL_THREADS);
-            cp_async_commit();
-            load_dinv(k);
-        }
-        for (int q = cta; q < w; q += CHOL_CLUSTER) {
-            double* g = tiles + tile_off(k + 1 + q, k, bw);
-            load_tile_async(As, g, tid, CHOL_THREADS);
-            cp_async_commit(); cp_async_wait<0>();
-            __syncthreads();
-            trsm64_warp(As, Bs, Di);
-            __syncthreads();
-            store_tile(g, As, tid, CHOL_THREADS);
-            __syncthreads();
-        }
-        JK_STAMP(1);
-        cluster.sync();
-        JK_STAMP(2);
-        // ---------------- phase B: trailing update (+ lookahead potrf on CTA 0) ----------------
         const int ntile = w * (w + 1) / 2;
-        if (cta == 0 && (w >= 1 || factor_next)) {
-            load_tile_async(Cs, tiles + tile_off(k + 1, k + 1, bw), tid, CHOL_THREADS);
-            if (w >= 1) load_tile_async(As, tiles + tile_off(k + 1, k, bw), tid, CHOL_THREADS);
-            cp_async_commit(); cp_async_wait<0>();
-            __syncthreads();
+        JK_STAMP(0);
+        if (cta == 0) {
+            // ---------------- critical chain, all operands in this CTA's shared memory ----------------
+            if (w >= 1) {
+                load_tile_async(As, tiles + tile_off(k + 1, k, bw), tid, CHOL_THREADS);
+                load_tile_async(Nx, tiles + tile_off(k + 1, k + 1, bw), tid, CHOL_THREADS);
+                cp_async_commit(); cp_async_wait<0>();
+                __syncthreads();
+                JK_STAMP(1);
+                trsm64_warp(As, Lk, Di);                      // L_{k+1,k} = A L_kk^{-T}
+                __syncthreads();
+                store_tile(tiles + tile_off(k + 1, k, bw), As, tid, CHOL_THREADS);
+                JK_STAMP(2);
+            } else if (factor_next) {                         // decoupled next tile (no panel): just fetch it
+                load_tile_async(Nx, tiles + tile_off(k + 1, k + 1, bw), tid, CHOL_THREADS);
+                cp_async_commit(); cp_async_wait<0>();
+                __syncthreads();
+            }
+            cluster_arrive();                                 // barrier A: L_{k+1,k} published
             if (w >= 1) {
                 // D_{k+1} -= L_{k+1,k} L_{k+1,k}^T, lower 8x8 tiles only; row blocks paired (w, 7-w) per SM sub-partition
                 const int rb = (warp < 4) ? warp : 11 - warp;
@@ -287,22 +288,41 @@ k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt)
                     if (nt <= rb) {
-                        double* cp = Cs + (8 * rb + fr) * LS_LD + 8 * nt + 2 * fk;
+                        double* cp = Nx + (8 * rb + fr) * LS_LD + 8 * nt + 2 * fk;
                         cp[0] -= acc[nt][0]; cp[1] -= acc[nt][1];
                     }
                 __syncthreads();
             }
-            JK_STAMP(3);
-            if (factor_next) potrf64_smem(Cs, Di, info, (k + 1) * NB);
-            JK_STAMP(4);
-            store_tile(tiles + tile_off(k + 1, k + 1, bw), Cs, tid, CHOL_THREADS);
-            if (factor_next) store_dinv(k + 1);
-        }
-        // remaining tiles t = 1..ntile-1 dealt to CTAs 1..7 (CTA 0 joins only if the band is wide)
-        const int nworkers = (ntile - 1 > 4 * (CHOL_CLUSTER - 1)) ? CHOL_CLUSTER : CHOL_CLUSTER - 1;
-        const int me = (nworkers == CHOL_CLUSTER) ? cta : cta - 1;
-        if (me >= 0) {
-            for (int t = 1 + me; t < ntile; t += nworkers) {
+            if (w >= 1 || factor_next) {
+                JK_STAMP(3);
+                if (factor_next) potrf64_smem(Nx, Di, info, (k + 1) * NB);
+                JK_STAMP(4);
+                store_tile(tiles + tile_off(k + 1, k + 1, bw), Nx, tid, CHOL_THREADS);
+                if (factor_next) store_dinv(k + 1);
+                double* tmp = Lk; Lk = Nx; Nx = tmp;
+            }
+            cluster_wait();                                   // barrier A
+        } else {
+            // ---------------- phase A: the other panel tiles (k+2.., k) ----------------
+            if (cta - 1 < w - 1) {
+                load_tile_async(Bs, tiles + tile_off(k, k, bw), tid, CHOL_THREADS);
+                cp_async_commit();
+                load_dinv(k);
+            }
+            for (int q = 1 + (cta - 1); q < w; q += CHOL_CLUSTER - 1) {
+                double* g = tiles + tile_off(k + 1 + q, k, bw);
+                load_tile_async(As, g, tid, CHOL_THREADS);
+                cp_async_commit(); cp_async_wait<0>();
+                __syncthreads();
+                trsm64_warp(As, Bs, Di);
+                __syncthreads();
+                store_tile(g, As, tid, CHOL_THREADS);
+                __syncthreads();
+            }
+            cluster_arrive();
+            cluster_wait();                                   // barrier A: every L_ik of column k is in global memory
+            // ---------------- phase B: trailing update, tiles t = 1.. (tile 0 = (k+1,k+1) belongs to CTA 0) ----------------
+            for (int t = 1 + (cta - 1); t < ntile; t += CHOL_CLUSTER - 1) {
                 int bi = 0;
                 while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
                 const int bj = t - bi * (bi + 1) / 2;
@@ -327,7 +347,7 @@ k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
             }
         }
         JK_STAMP(5);
-        cluster.sync();
+        cluster.sync();                                       // barrier B: column k done
         JK_STAMP(6);
     }
 #undef JK_STAMP
