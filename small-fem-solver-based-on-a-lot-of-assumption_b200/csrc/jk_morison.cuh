@@ -16,6 +16,26 @@
 
 namespace jk {
 
+// Drag + inertia of one wet Gauss point, accumulated into the member sums (GUI.py:633-659).
+//   cdl = 0.5 rho Cd D L w_g,  cil = rho Cm A_cross L w_g  (per member and Gauss point, precomputed)
+//   md += F_drag, mi += F_inertia, F2 += s (F_drag + F_inertia);  F1 = (md + mi) - F2 is formed once per member.
+struct MemberAcc { double md[3], mi[3], F2[3]; };
+__device__ __forceinline__ void morison_point(MemberAcc& A, double U0, double U1, double U2, double A0, double A1, double A2,
+                                              double e0, double e1, double e2, double cdl, double cil, double s) {
+    const double Ue = fma(U2, e2, fma(U1, e1, U0 * e0));
+    const double Ae = fma(A2, e2, fma(A1, e1, A0 * e0));
+    const double Up0 = fma(-Ue, e0, U0), Up1 = fma(-Ue, e1, U1), Up2 = fma(-Ue, e2, U2);   // GUI.py:641
+    const double Ap0 = fma(-Ae, e0, A0), Ap1 = fma(-Ae, e1, A1), Ap2 = fma(-Ae, e2, A2);   // GUI.py:642
+    const double mag = sqrt(fma(Up2, Up2, fma(Up1, Up1, Up0 * Up0)));
+    const double kd = (mag > 1e-10) ? cdl * mag : 0.0;                                     // GUI.py:648-651
+    const double fd0 = kd * Up0, fd1 = kd * Up1, fd2 = kd * Up2;
+    A.md[0] += fd0; A.md[1] += fd1; A.md[2] += fd2;
+    A.mi[0] = fma(cil, Ap0, A.mi[0]); A.mi[1] = fma(cil, Ap1, A.mi[1]); A.mi[2] = fma(cil, Ap2, A.mi[2]);
+    A.F2[0] = fma(s, fma(cil, Ap0, fd0), A.F2[0]);
+    A.F2[1] = fma(s, fma(cil, Ap1, fd1), A.F2[1]);
+    A.F2[2] = fma(s, fma(cil, Ap2, fd2), A.F2[2]);
+}
+
 // per (member, gauss point): cos(k xw), sin(k xw), Cu = a w cosh(k(z+d))/sinh(kd), Cw (sinh), z
 __global__ void k_gauss_setup_airy(int M, int G, const double* __restrict__ xyz, const int* __restrict__ conn,
                                    const double* __restrict__ gs, WaveAiry wv, double* __restrict__ gp) {
@@ -67,6 +87,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
     double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][8]: e0 e1 e2 cD cI L
     double* s_g = s_m + MCHUNK * 8;                        // s[G], w[G]
+    double* s_c = s_g + 2 * G;                             // [MCHUNK][G][2]: cD L w_g, cI L w_g
     int chunk = blockIdx.y, m0 = chunk * MCHUNK;
     int nm = min(MCHUNK, M - m0);
     for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
@@ -79,6 +100,12 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     }
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_g[i] = gsw[i];
     __syncthreads();
+    for (int i = threadIdx.x; i < nm * G; i += blockDim.x) {
+        const int mm = i / G, g = i % G;
+        const double Lw = s_m[8 * mm + 5] * s_g[G + g];
+        s_c[2 * i] = s_m[8 * mm + 3] * Lw; s_c[2 * i + 1] = s_m[8 * mm + 4] * Lw;
+    }
+    __syncthreads();
 
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ldP) return;
@@ -87,10 +114,10 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
 
     for (int mm = 0; mm < nm; ++mm) {
         const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
-        const double cD = s_m[8 * mm + 3], cI = s_m[8 * mm + 4], L = s_m[8 * mm + 5];
-        double F1[3] = {0, 0, 0}, F2[3] = {0, 0, 0}, md[3] = {0, 0, 0}, mi[3] = {0, 0, 0};
+        MemberAcc A = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
         double sub = 0.0;
         const double* gpm = s_gp + mm * G * GP_STRIDE;
+        const double* cm = s_c + mm * G * 2;
         for (int g = 0; g < G; ++g) {
             const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1];
             const double Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3], z = gpm[g * GP_STRIDE + 4];
@@ -105,37 +132,23 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
             const double u1 = wet1 ? fma(Cu, c1, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1 : 0.0;
             const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;   // GUI.py:288
             const double uwo = u0 - wv.Uc;                                     // GUI.py:573
-            const double U0 = fma(uwo, wv.cos_w, wv.uc_cos_c), U1 = fma(uwo, wv.sin_w, wv.uc_sin_c), U2 = w0;
-            const double A0 = du * wv.cos_w, A1 = du * wv.sin_w, A2 = dw;
-            const double Ue = fma(U2, e2, fma(U1, e1, U0 * e0));
-            const double Ae = fma(A2, e2, fma(A1, e1, A0 * e0));
-            const double Up0 = fma(-Ue, e0, U0), Up1 = fma(-Ue, e1, U1), Up2 = fma(-Ue, e2, U2);   // GUI.py:641
-            const double Ap0 = fma(-Ae, e0, A0), Ap1 = fma(-Ae, e1, A1), Ap2 = fma(-Ae, e2, A2);   // GUI.py:642
-            const double mag = sqrt(fma(Up2, Up2, fma(Up1, Up1, Up0 * Up0)));
-            const double s = s_g[g], w = s_g[G + g];
-            const double Lw = L * w;
-            const double kd_ = (mag > 1e-10) ? cD * mag * Lw : 0.0;            // GUI.py:648-651
-            const double ki_ = cI * Lw;
-            const double fd0 = kd_ * Up0, fd1 = kd_ * Up1, fd2 = kd_ * Up2;
-            const double fi0 = ki_ * Ap0, fi1 = ki_ * Ap1, fi2 = ki_ * Ap2;
-            const double ft0 = fd0 + fi0, ft1 = fd1 + fi1, ft2 = fd2 + fi2;
-            md[0] += fd0; md[1] += fd1; md[2] += fd2;
-            mi[0] += fi0; mi[1] += fi1; mi[2] += fi2;
-            const double s1m = 1.0 - s;
-            F1[0] = fma(s1m, ft0, F1[0]); F1[1] = fma(s1m, ft1, F1[1]); F1[2] = fma(s1m, ft2, F1[2]);
-            F2[0] = fma(s, ft0, F2[0]); F2[1] = fma(s, ft1, F2[1]); F2[2] = fma(s, ft2, F2[2]);
-            if (DETAILS) sub += Lw;
+            morison_point(A, fma(uwo, wv.cos_w, wv.uc_cos_c), fma(uwo, wv.sin_w, wv.uc_sin_c), w0,
+                          du * wv.cos_w, du * wv.sin_w, dw, e0, e1, e2, cm[2 * g], cm[2 * g + 1], s_g[g]);
+            if (DETAILS) sub += s_m[8 * mm + 5] * s_g[G + g];
         }
         size_t o = ((size_t)(m0 + mm) * 6) * ldP + p;
-        Fm[o] = F1[0]; Fm[o + ldP] = F1[1]; Fm[o + 2 * (size_t)ldP] = F1[2];
-        Fm[o + 3 * (size_t)ldP] = F2[0]; Fm[o + 4 * (size_t)ldP] = F2[1]; Fm[o + 5 * (size_t)ldP] = F2[2];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { td[k] += md[k]; ti[k] += mi[k]; tm[k] += md[k] + mi[k]; }   // GUI.py:664-666
+        for (int k = 0; k < 3; ++k) {
+            const double mt = A.md[k] + A.mi[k];
+            Fm[o + (size_t)k * ldP] = mt - A.F2[k];                            // F1 = sum (1-s) f   (GUI.py:658)
+            Fm[o + (size_t)(3 + k) * ldP] = A.F2[k];                           // F2 = sum s f       (GUI.py:659)
+            td[k] += A.md[k]; ti[k] += A.mi[k]; tm[k] += mt;                    // GUI.py:664-666
+        }
         if (DETAILS) {
             size_t od = ((size_t)(m0 + mm) * 4) * ldP + p;
-            double mt0 = md[0] + mi[0], mt1 = md[1] + mi[1], mt2 = md[2] + mi[2];
-            details[od] = sqrt(md[0] * md[0] + md[1] * md[1] + md[2] * md[2]) / 1000.0;
-            details[od + ldP] = sqrt(mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]) / 1000.0;
+            double mt0 = A.md[0] + A.mi[0], mt1 = A.md[1] + A.mi[1], mt2 = A.md[2] + A.mi[2];
+            details[od] = sqrt(A.md[0] * A.md[0] + A.md[1] * A.md[1] + A.md[2] * A.md[2]) / 1000.0;
+            details[od + ldP] = sqrt(A.mi[0] * A.mi[0] + A.mi[1] * A.mi[1] + A.mi[2] * A.mi[2]) / 1000.0;
             details[od + 2 * (size_t)ldP] = sqrt(mt0 * mt0 + mt1 * mt1 + mt2 * mt2) / 1000.0;
             details[od + 3 * (size_t)ldP] = sub;
         }
@@ -385,8 +398,8 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
         for (int ms = 0; ms < nsub; ++ms) {
             const int mm = sub + ms;
             const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
-            const double cD = s_m[8 * mm + 3], cI = s_m[8 * mm + 4], L = s_m[8 * mm + 5];
-            double F1[3] = {0, 0, 0}, F2[3] = {0, 0, 0}, md[3] = {0, 0, 0}, mi[3] = {0, 0, 0};
+            const double cDL = s_m[8 * mm + 3] * s_m[8 * mm + 5], cIL = s_m[8 * mm + 4] * s_m[8 * mm + 5];
+            MemberAcc A = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
             for (int g = 0; g < G; ++g) {
                 const double* q = s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4;
                 const double ckx = q[0], skx = q[1], Cu = q[2], Cw = q[3], z = s_z[ms * G + g];
@@ -399,31 +412,18 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
                 const double u1 = wet1 ? fma(Cu, c1v, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1v : 0.0;
                 const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;
                 const double uwo = u0 - wv.Uc;
-                const double U0 = fma(uwo, cw, wv.uc_cos_c), U1 = fma(uwo, sw, wv.uc_sin_c), U2 = w0;
-                const double A0 = du * cw, A1 = du * sw, A2 = dw;
-                const double Ue = fma(U2, e2, fma(U1, e1, U0 * e0));
-                const double Ae = fma(A2, e2, fma(A1, e1, A0 * e0));
-                const double Up0 = fma(-Ue, e0, U0), Up1 = fma(-Ue, e1, U1), Up2 = fma(-Ue, e2, U2);
-                const double Ap0 = fma(-Ae, e0, A0), Ap1 = fma(-Ae, e1, A1), Ap2 = fma(-Ae, e2, A2);
-                const double mag = sqrt(fma(Up2, Up2, fma(Up1, Up1, Up0 * Up0)));
-                const double sgv = s_g[g], wg = s_g[G + g];
-                const double Lw = L * wg;
-                const double kd_ = (mag > 1e-10) ? cD * mag * Lw : 0.0;
-                const double ki_ = cI * Lw;
-                const double fd0 = kd_ * Up0, fd1 = kd_ * Up1, fd2 = kd_ * Up2;
-                const double fi0 = ki_ * Ap0, fi1 = ki_ * Ap1, fi2 = ki_ * Ap2;
-                const double ft0 = fd0 + fi0, ft1 = fd1 + fi1, ft2 = fd2 + fi2;
-                md[0] += fd0; md[1] += fd1; md[2] += fd2;
-                mi[0] += fi0; mi[1] += fi1; mi[2] += fi2;
-                const double s1m = 1.0 - sgv;
-                F1[0] = fma(s1m, ft0, F1[0]); F1[1] = fma(s1m, ft1, F1[1]); F1[2] = fma(s1m, ft2, F1[2]);
-                F2[0] = fma(sgv, ft0, F2[0]); F2[1] = fma(sgv, ft1, F2[1]); F2[2] = fma(sgv, ft2, F2[2]);
+                const double wg = s_g[G + g];
+                morison_point(A, fma(uwo, cw, wv.uc_cos_c), fma(uwo, sw, wv.uc_sin_c), w0, du * cw, du * sw, dw,
+                              e0, e1, e2, cDL * wg, cIL * wg, s_g[g]);
             }
             size_t o = ((size_t)(m0 + mm) * 6) * ldC + cidx;
-            Fm[o] = F1[0]; Fm[o + ldC] = F1[1]; Fm[o + 2 * (size_t)ldC] = F1[2];
-            Fm[o + 3 * (size_t)ldC] = F2[0]; Fm[o + 4 * (size_t)ldC] = F2[1]; Fm[o + 5 * (size_t)ldC] = F2[2];
 #pragma unroll
-            for (int kq = 0; kq < 3; ++kq) { td[kq] += md[kq]; ti[kq] += mi[kq]; tm[kq] += md[kq] + mi[kq]; }
+            for (int kq = 0; kq < 3; ++kq) {
+                const double mt = A.md[kq] + A.mi[kq];
+                Fm[o + (size_t)kq * ldC] = mt - A.F2[kq];
+                Fm[o + (size_t)(3 + kq) * ldC] = A.F2[kq];
+                td[kq] += A.md[kq]; ti[kq] += A.mi[kq]; tm[kq] += mt;
+            }
         }
     }
     if (!live) return;
