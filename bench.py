@@ -40,6 +40,8 @@ WORKLOADS = {
     "c5_ensemble": (8, 41, 65536),     # configs[4]: 4096 sea states x 16 phases on the c3 jacket, one factor
 }
 FP64_PEAK_TFLOPS = 37.1    # measured on this pool (profiles/r01_fp64_peaks.json): DMMA m8n8k4 issue peak
+# dram read+write bytes per launch of the sweep kernels on c4 / 4096 phases, from the ncu --set full captures under profiles/
+SWEEP_TRAFFIC = {"k_slab_sweep": 1.31e9}
 
 
 def parse():
@@ -447,13 +449,16 @@ def run_ours(args):
         M, G15 = st.n_members, 15
         n, nb, bw, NT = dims["n_free_dof"], dims["tile"], dims["band_tiles"], dims["n_tiles"]
         ldP = -(-P // 32) * 32
-        # executed tile products of one sweep (diag + band), each 2*nb*nb*32 flop per 32-column slab
-        items = sum(min(k, bw) + 1 for k in range(NT))
-        sweep_flops_exec = items * 2.0 * nb * nb * ldP
-        # algorithmic flops of one sweep: 2 * nnz(L within the DOF half-bandwidth) per right-hand side
+        # solver statistics from the library: exact nnz(L) of the factor and the flops the sweeps execute per load case
+        # (DMMA k-groups kept by the zero-block masks on the TMA path, all band tile products on the legacy path)
+        sst = eng.solver_stats()
         hb = dims["dof_half_bandwidth"]
-        nnzL = n * (hb + 1) - hb * (hb + 1) // 2
+        sweep_name = "k_sweep" if sst["tma_sweep"] else "k_slab_sweep"
+        sweep_flops_exec = 0.5 * sst["sweep_flops_executed_per_case"] * ldP
+        # algorithmic flops of one sweep: 2 * nnz(L) per right-hand side (one multiply-add per stored non-zero of L)
+        nnzL = sst["nnz_L"]
         sweep_flops_alg = 2.0 * nnzL * P
+        nnz_band = n * (hb + 1) - hb * (hb + 1) // 2       # previous rounds' convention: every entry inside the DOF band
         kernels = {
             "morison": {"ms": stage["morison"], "bound": "fp64", "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS,
                         "achieved": 170.0 * G15 * M * P / (stage["morison"] * 1e-3) * 1e-12},
@@ -478,24 +483,29 @@ def run_ours(args):
         # kernel (k_slab_sweep, forward / backward instantiation) and are counted together; the factorisation is a
         # latency chain on one 8-CTA cluster (8 of 148 SMs) that runs concurrently with the Morison stage.
         sweep_ms = 0.5 * (stage["solve_fwd"] + stage["solve_bwd"])
-        kernels["k_slab_sweep"] = {"ms": sweep_ms, "launches_per_step": 2, "bound": "tensor", "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS,
-                                   "achieved": sweep_flops_alg / (sweep_ms * 1e-3) * 1e-12,
-                                   "executed": sweep_flops_exec / (sweep_ms * 1e-3) * 1e-12}
-        kernels["k_slab_sweep"]["frac"] = kernels["k_slab_sweep"]["achieved"] / FP64_PEAK_TFLOPS
+        kernels[sweep_name] = {"ms": sweep_ms, "launches_per_step": 2, "bound": "tensor", "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS,
+                               "achieved": sweep_flops_alg / (sweep_ms * 1e-3) * 1e-12,
+                               "executed": sweep_flops_exec / (sweep_ms * 1e-3) * 1e-12,
+                               "achieved_band_convention": 2.0 * nnz_band * P / (sweep_ms * 1e-3) * 1e-12,
+                               "nnz_L": nnzL, "nnz_band": nnz_band, "items_per_slab": sst["sweep_items"]}
+        kernels[sweep_name]["frac"] = kernels[sweep_name]["achieved"] / FP64_PEAK_TFLOPS
+        kernels[sweep_name]["frac_executed"] = kernels[sweep_name]["executed"] / FP64_PEAK_TFLOPS
         step_ms = ms_total / args.steps
-        exposed = {"k_slab_sweep": 2 * sweep_ms, "post": stage["post"], "reduce": stage["reduce"],
+        exposed = {sweep_name: 2 * sweep_ms, "post": stage["post"], "reduce": stage["reduce"],
                    "factor": max(0.0, stage["factor"] - stage["morison"] - stage["rhs"]),
                    "morison": min(stage["morison"] + stage["rhs"], stage["factor"])}
-        dom = max(("k_slab_sweep", "morison", "post", "factor"), key=lambda k: exposed[k] if k != "morison" else stage["morison"] * 0.999)
+        dom = max((sweep_name, "morison", "post", "factor"), key=lambda k: exposed[k] if k != "morison" else stage["morison"] * 0.999)
         d = kernels[dom]
         roofline = {"kernel": dom, "bound": "tensor" if d["bound"] in ("tensor", "fp64") else "hbm", "achieved": d["achieved"],
-                    "peak": d["peak"], "unit": d["unit"], "frac": d["frac"], "traffic": 1.31e9 if dom == "k_slab_sweep" and args.workload == "c4_jacket10k" and P == 4096 else None,
+                    "peak": d["peak"], "unit": d["unit"], "frac": d["frac"], "traffic": SWEEP_TRAFFIC.get(dom) if args.workload == "c4_jacket10k" and P == 4096 else None,
                     "executed": d.get("executed"), "launches_per_step": d.get("launches_per_step", 1),
                     "peak_source": ("FP64 pipe, DMMA m8n8k4 issue peak measured on this pool (profiles/r01_fp64_peaks.json); "
                                     "MEASURED_PEAKS.json has no FP64 entry" if d["unit"] == "TFLOP/s" else peak_src),
                     "ms_per_launch": d["ms"], "share_of_step": exposed[dom] / step_ms,
-                    "note": "achieved = algorithmic flops 2*nnz(L_band)*P per sweep; executed adds the zero padding of the 64x64 band tiles; "
-                            "traffic = dram read+write per launch from profiles/r01b (ncu --set full)"}
+                    "frac_executed": d.get("frac_executed"),
+                    "note": "achieved = algorithmic flops 2*nnz(L)*P per sweep direction (exact non-zero count of the factor); executed = "
+                            "DMMA flops issued (k-groups kept by the zero-block masks); traffic = dram read+write per launch from the "
+                            "ncu --set full capture under profiles/ (null until captured for this kernel)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

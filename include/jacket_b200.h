@@ -199,6 +199,16 @@ int jk_get_elements(jk_handle_t h, double* Ke /* [M*144] */, double* Kl /* [M*14
 int jk_get_timings(jk_handle_t h, double* ms /* [JK_NTIMERS] */);
 /* max_i |K u - F|_i / max_i |F|_i over the free DOFs of every phase of the last scan (diagnostic) */
 int jk_residual(jk_handle_t h, double* rel_residual);
+/* Solver statistics after a factorisation: out[0] = non-zeros of L (exact count, lower triangle incl. diagonal),
+ * out[1] = FP64 flops the two triangular sweeps EXECUTE per load case (DMMA k-groups kept by the zero-block masks,
+ * or all tile products of the band on the legacy path), out[2] = sweep items per slab (0 on the legacy path),
+ * out[3] = 1 if the TMA / mbarrier sweep pipeline is active, 0 for the cp.async slab sweep. */
+int jk_solver_stats(jk_handle_t h, double* out /* [4] */);
+/* Host-only introspection of the sweep item list (no device needed; used by the CPU tests): the program the TMA
+ * sweep runs for a chain of n_tiles tile rows, tile half-bandwidth band_tiles, first partial / known tile row kx
+ * (= n_tiles for a plain sweep).  items[6*i..] = row, src, flags, xinfo, next_row, next_init; meta[3] = first known
+ * row, known rows preloaded, top row of the ring numbering.  Returns the item count (items may be NULL to size). */
+int jk_sweep_program(int n_tiles, int band_tiles, int kx, int backward, int32_t* items, int cap_items, int32_t* meta);
 /* kernels launched by this handle since creation (bench "gpu_launches") */
 int64_t jk_launch_count(jk_handle_t h);
 void* jk_stream(jk_handle_t h);

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjacket_b200.so")
+# JK_LIB selects an experimental build of the same sources (kernel A/B runs); default = the in-tree library
+LIB_PATH = os.environ.get("JK_LIB") or os.path.join(_HERE, "libjacket_b200.so")
 
 # keep in sync with include/jacket_b200.h
 SEC_NPROP = 8
@@ -79,6 +80,9 @@ def _sig(lib):
     lib.jk_get_elements.argtypes = [H, _dp, _dp, _dp, _dp]
     lib.jk_get_timings.argtypes = [H, _dp]
     lib.jk_residual.argtypes = [H, _dp]
+    lib.jk_solver_stats.argtypes = [H, _dp]
+    lib.jk_sweep_program.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip]
+    lib.jk_sweep_program.restype = C.c_int
     lib.jk_launch_count.argtypes = [H]
     lib.jk_launch_count.restype = C.c_int64
     lib.jk_stream.argtypes = [H]
@@ -90,7 +94,7 @@ def _sig(lib):
                  "jk_set_wave_airy", "jk_set_wave_fourier", "jk_set_morison", "jk_morison_scan", "jk_morison_single",
                  "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_ensemble_scan", "jk_fetch_phase",
                  "jk_fetch_member_column", "jk_get_dims", "jk_get_order", "jk_get_K", "jk_get_elements",
-                 "jk_get_timings", "jk_residual"):
+                 "jk_get_timings", "jk_residual", "jk_solver_stats"):
         getattr(lib, name).restype = C.c_int
 
 

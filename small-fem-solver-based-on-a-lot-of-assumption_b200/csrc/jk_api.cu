@@ -18,6 +18,7 @@
 #include "jk_common.cuh"
 #include "jk_fem.cuh"
 #include "jk_morison.cuh"
+#include "jk_sweep.cuh"
 
 using namespace jk;
 
@@ -55,7 +56,11 @@ struct jk_handle_s {
         KBlock* d_blocks = nullptr; int2* d_contrib = nullptr; int nblocks = 0;
         double *d_tiles = nullptr, *d_Linv = nullptr, *d_dinv = nullptr;
         size_t tiles_elems = 0;
+        // TMA sweep programs (jk_sweep.cuh): [0] forward, [1] backward.  Item list (host-built) + tile stream (built
+        // from L after every factorisation by k_sweep_build)
+        struct Sweep { int n_items = 0, pre_row = 0, npre = 0, ktop = 0; uint4* d_prog = nullptr; double* d_stream = nullptr; } sw[2];
     } ch[2];
+    bool tma_sweep = false;   // narrow band: sweeps run as the TMA / mbarrier pipeline, otherwise the cp.async slab sweep
     int n_chains = 1, nS_nodes = 0;
     int factor_path = 0;   // 0 = auto (cluster kernel for narrow bands), 1 = per-column launches
     int* d_info = nullptr;
@@ -209,6 +214,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, cudaFuncSetAttribute(k_band_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_CLUSTER_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWB_SMEM));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     return JK_OK;
 }
@@ -220,7 +227,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_xyz); dev_free(h->d_secp); dev_free(h->d_mc); dev_free(h->d_Ke); dev_free(h->d_Kl);
     dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
-    for (auto& c : h->ch) { dev_free(c.d_blocks); dev_free(c.d_contrib); dev_free(c.d_tiles); dev_free(c.d_Linv); dev_free(c.d_dinv); }
+    for (auto& c : h->ch) { dev_free(c.d_blocks); dev_free(c.d_contrib); dev_free(c.d_tiles); dev_free(c.d_Linv); dev_free(c.d_dinv);
+                            for (auto& w : c.sw) { dev_free(w.d_prog); dev_free(w.d_stream); } }
     dev_free(h->d_info);
     dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four); dev_free(h->d_states); dev_free(h->d_state_crit);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
@@ -239,60 +247,143 @@ extern "C" int jk_destroy(jk_handle_t h) {
 // ------------------------------------------------------------------------------------------------
 // reverse Cuthill-McKee over the free nodes (graph = members with both ends free)
 // ------------------------------------------------------------------------------------------------
-static void rcm_order(int Nn, const std::vector<int>& conn, const std::vector<char>& is_fixed, std::vector<int>& order) {
+// member graph restricted to the free nodes
+static void free_graph(int Nn, const std::vector<int>& conn, const std::vector<char>& is_fixed, std::vector<std::vector<int>>& nb) {
     int M = (int)conn.size() / 2;
-    std::vector<std::vector<int>> nb(Nn);
+    nb.assign(Nn, {});
     for (int m = 0; m < M; ++m) {
         int a = conn[2 * m], b = conn[2 * m + 1];
         if (is_fixed[a] || is_fixed[b]) continue;
         nb[a].push_back(b); nb[b].push_back(a);
     }
     for (auto& v : nb) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
-    std::vector<int> deg(Nn);
-    for (int i = 0; i < Nn; ++i) deg[i] = (int)nb[i].size();
-    std::vector<char> visited(Nn, 0);
+}
+
+// Cuthill-McKee from a root SET (in the given order) over the nodes with allowed[v] != 0 that are not yet visited;
+// neighbours are queued by increasing degree.  Appends to out and marks visited.
+static void cm_from(const std::vector<std::vector<int>>& nb, const std::vector<int>& roots, const std::vector<char>& allowed,
+                    std::vector<char>& visited, std::vector<int>& out) {
+    std::queue<int> q;
+    for (int r : roots) if (allowed[r] && !visited[r]) { visited[r] = 1; q.push(r); }
+    std::vector<int> nx;
+    while (!q.empty()) {
+        int u = q.front(); q.pop(); out.push_back(u);
+        nx.clear();
+        for (int v : nb[u]) if (allowed[v] && !visited[v]) { visited[v] = 1; nx.push_back(v); }
+        std::sort(nx.begin(), nx.end(), [&](int a, int b) { return nb[a].size() != nb[b].size() ? nb[a].size() < nb[b].size() : a < b; });
+        for (int v : nx) q.push(v);
+    }
+}
+
+// classic reverse Cuthill-McKee, one pseudo-peripheral root (George-Liu) per connected component
+static void rcm_order(int Nn, const std::vector<std::vector<int>>& nb, const std::vector<char>& is_fixed, std::vector<int>& order) {
+    std::vector<char> visited(Nn, 0), allowed(Nn, 0);
+    for (int i = 0; i < Nn; ++i) allowed[i] = !is_fixed[i];
     std::vector<int> level(Nn, -1);
     order.clear();
     auto bfs_levels = [&](int root, std::vector<int>& comp) {   // returns eccentricity; comp = BFS order
         comp.clear();
-        std::vector<int> touched;
         std::queue<int> q;
-        level[root] = 0; q.push(root); touched.push_back(root);
+        level[root] = 0; q.push(root);
         int ecc = 0;
         while (!q.empty()) {
             int u = q.front(); q.pop(); comp.push_back(u);
             ecc = std::max(ecc, level[u]);
-            for (int v : nb[u]) if (level[v] < 0) { level[v] = level[u] + 1; q.push(v); touched.push_back(v); }
+            for (int v : nb[u]) if (level[v] < 0) { level[v] = level[u] + 1; q.push(v); }
         }
         return ecc;
     };
     std::vector<int> comp, comp2;
     for (int seed = 0; seed < Nn; ++seed) {
         if (is_fixed[seed] || visited[seed]) continue;
-        // pseudo-peripheral root (George-Liu)
         int root = seed;
         int ecc = bfs_levels(root, comp);
         for (int it = 0; it < 8; ++it) {
             int best = -1;
-            for (int u : comp) if (level[u] == ecc && (best < 0 || deg[u] < deg[best])) best = u;
+            for (int u : comp) if (level[u] == ecc && (best < 0 || nb[u].size() < nb[best].size())) best = u;
             for (int u : comp) level[u] = -1;
             int ecc2 = bfs_levels(best, comp2);
             if (ecc2 > ecc) { root = best; ecc = ecc2; comp.swap(comp2); }
             else { for (int u : comp2) level[u] = -1; bfs_levels(root, comp); break; }
         }
         for (int u : comp) level[u] = -1;
-        // Cuthill-McKee from root: neighbours by increasing degree
         std::vector<int> cm;
-        std::queue<int> q;
-        visited[root] = 1; q.push(root);
-        while (!q.empty()) {
-            int u = q.front(); q.pop(); cm.push_back(u);
-            std::vector<int> nx;
-            for (int v : nb[u]) if (!visited[v]) { visited[v] = 1; nx.push_back(v); }
-            std::sort(nx.begin(), nx.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
-            for (int v : nx) q.push(v);
-        }
+        cm_from(nb, {root}, allowed, visited, cm);
         order.insert(order.end(), cm.rbegin(), cm.rend());
+    }
+}
+
+// reverse Cuthill-McKee rooted at the SET of free nodes attached to a support: for a tower the level sets are then the
+// horizontal frames, which gives the minimum bandwidth (a single root makes slanted, wider fronts)
+static void rcm_order_from_supports(int Nn, const std::vector<int>& conn, const std::vector<std::vector<int>>& nb,
+                                    const std::vector<char>& is_fixed, std::vector<int>& order) {
+    std::vector<char> visited(Nn, 0), allowed(Nn, 0), is_root(Nn, 0);
+    for (int i = 0; i < Nn; ++i) allowed[i] = !is_fixed[i];
+    int M = (int)conn.size() / 2;
+    for (int m = 0; m < M; ++m) {
+        int a = conn[2 * m], b = conn[2 * m + 1];
+        if (is_fixed[a] && !is_fixed[b]) is_root[b] = 1;
+        if (is_fixed[b] && !is_fixed[a]) is_root[a] = 1;
+    }
+    std::vector<int> roots;
+    for (int i = 0; i < Nn; ++i) if (is_root[i]) roots.push_back(i);
+    std::sort(roots.begin(), roots.end(), [&](int a, int b) { return nb[a].size() != nb[b].size() ? nb[a].size() < nb[b].size() : a < b; });
+    std::vector<int> cm;
+    cm_from(nb, roots, allowed, visited, cm);
+    for (int i = 0; i < Nn; ++i) if (allowed[i] && !visited[i]) cm_from(nb, {i}, allowed, visited, cm);   // parts not tied to a support
+    order.assign(cm.rbegin(), cm.rend());
+}
+
+// node half-bandwidth and envelope size (sum of row widths) of an ordering
+static void order_quality(int Nn, const std::vector<int>& conn, const std::vector<int>& order, int& hbn, long long& profile) {
+    std::vector<int> pos(Nn, -1), first(order.size());
+    for (size_t i = 0; i < order.size(); ++i) { pos[order[i]] = (int)i; first[i] = (int)i; }
+    hbn = 0;
+    int M = (int)conn.size() / 2;
+    for (int m = 0; m < M; ++m) {
+        int a = pos[conn[2 * m]], b = pos[conn[2 * m + 1]];
+        if (a < 0 || b < 0) continue;
+        int hi = std::max(a, b), lo = std::min(a, b);
+        hbn = std::max(hbn, hi - lo);
+        first[hi] = std::min(first[hi], lo);
+    }
+    profile = 0;
+    for (size_t i = 0; i < order.size(); ++i) profile += (long long)i - first[i];
+}
+
+// Item list of one sweep of one chain (see jk_sweep.cuh).  kx = first partial (forward) / known (backward) tile row,
+// NT for a plain sweep.  Ring slots follow the processing order: seq(k) = k (forward) or ktop - k (backward).
+static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vector<uint4>& prog, int& pre_row, int& npre, int& ktop) {
+    prog.clear();
+    auto push = [&](int row, int src, int flags, int xinfo, int next_row, int next_init) {
+        prog.push_back(make_uint4((unsigned)row, (unsigned)src, (unsigned)flags, (unsigned)xinfo));
+        prog.push_back(make_uint4((unsigned)next_row, (unsigned)next_init, 0u, 0u));
+        prog.push_back(make_uint4(0u, 0u, 0u, 0u));
+    };
+    auto slotinfo = [&](int seq) { return (seq % SW_RING) | (((seq / SW_RING) & 1) << 8); };
+    if (!backward) {
+        pre_row = 0; npre = 0; ktop = 0;
+        for (int k = 0; k < NT; ++k) {
+            const int lo = std::max(0, k - bw), hi = std::min(k - 1, kx - 1);
+            const bool partial = k >= kx, has_next = k + 1 < NT;
+            const int end_flags = SW_ROW_END | (partial ? SW_NO_RING : SW_OUT_FRAG);
+            const int out = (k % SW_RING) << 16;
+            if (hi < lo) { push(k, k, SW_ROW_BEGIN | SW_INIT_RHS | SW_NO_OPERAND | end_flags, out, has_next ? k + 1 : 0, has_next ? 1 : 0); continue; }
+            for (int j = lo; j <= hi; ++j) {
+                int flags = (j == lo ? (SW_ROW_BEGIN | SW_INIT_RHS) : 0) | (j == hi ? end_flags : 0);
+                push(k, j, flags, slotinfo(j) | out, has_next ? k + 1 : 0, (j == hi && has_next) ? 1 : 0);
+            }
+        }
+    } else {
+        npre = kx < NT ? std::min(bw, NT - kx) : 0;
+        pre_row = kx;
+        ktop = kx + npre - 1;
+        for (int k = kx - 1; k >= 0; --k) {
+            const int hi = std::min(NT - 1, std::min(k + bw, ktop));
+            const int out = ((ktop - k) % SW_RING) << 16;
+            push(k, k, SW_ROW_BEGIN | SW_DIAG | (hi < k + 1 ? SW_ROW_END : 0), out, 0, 0);
+            for (int i = hi; i >= k + 1; --i) push(k, i, (i == k + 1 ? SW_ROW_END : 0), slotinfo(ktop - i) | out, 0, 0);
+        }
     }
 }
 
@@ -310,7 +401,20 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     h->n_fixed = (int)h->h_fixed.size();
     h->n_free_nodes = h->Nn - h->n_fixed;
     if (h->n_free_nodes <= 0) JK_FAIL(h, JK_EINVAL, "jk_set_supports: every node is fixed");
-    if (ordering == JK_ORDER_RCM) rcm_order(h->Nn, h->h_conn, is_fixed, h->h_free_nodes);
+    std::vector<std::vector<int>> nbr;
+    if (ordering == JK_ORDER_RCM) {
+        // two candidates: single-root RCM and RCM rooted at the support-adjacent set; keep the narrower band (then the
+        // smaller envelope)
+        free_graph(h->Nn, h->h_conn, is_fixed, nbr);
+        std::vector<int> o1, o2;
+        rcm_order(h->Nn, nbr, is_fixed, o1);
+        rcm_order_from_supports(h->Nn, h->h_conn, nbr, is_fixed, o2);
+        int hb1 = 0, hb2 = 0; long long pr1 = 0, pr2 = 0;
+        order_quality(h->Nn, h->h_conn, o1, hb1, pr1);
+        order_quality(h->Nn, h->h_conn, o2, hb2, pr2);
+        const bool second = getenv("JK_RCM_SINGLE_ROOT") == nullptr && o2.size() == o1.size() && (hb2 < hb1 || (hb2 == hb1 && pr2 < pr1));
+        h->h_free_nodes.swap(second ? o2 : o1);
+    }
     else { h->h_free_nodes.clear(); for (int i = 0; i < h->Nn; ++i) if (!is_fixed[i]) h->h_free_nodes.push_back(i); }
     if ((int)h->h_free_nodes.size() != h->n_free_nodes) JK_FAIL(h, JK_EINVAL, "jk_set_supports: internal ordering error");
     h->n_free = 6 * h->n_free_nodes;
@@ -334,6 +438,27 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         h->n_chains = 2;
     }
     h->nS_nodes = nS;
+    if (h->n_chains == 2 && ordering == JK_ORDER_RCM) {
+        // The second chain eliminates B in REVERSED order (from the far end towards S).  Re-number B by Cuthill-McKee
+        // from the separator outwards: reversed, that is an RCM ordering rooted at S, whose envelope (and so the fill of
+        // that chain's L) is as small as the first chain's.
+        std::vector<char> inB(h->Nn, 0), visited(h->Nn, 0);
+        for (int i = nA + nS; i < N; ++i) inB[h->h_free_nodes[i]] = 1;
+        std::vector<int> roots, cm;
+        for (int i = nA; i < nA + nS; ++i)
+            for (int v : nbr[h->h_free_nodes[i]]) if (inB[v] && !visited[v]) { visited[v] = 1; roots.push_back(v); }
+        for (int v : roots) visited[v] = 0;
+        cm_from(nbr, roots, inB, visited, cm);
+        if ((int)cm.size() == nB) {
+            std::vector<int> trial(h->h_free_nodes);
+            std::copy(cm.begin(), cm.end(), trial.begin() + nA + nS);
+            int hb_old = 0, hb_new = 0; long long pr_old = 0, pr_new = 0;
+            std::vector<int> rev_old(h->h_free_nodes.rbegin(), h->h_free_nodes.rbegin() + nB + nS), rev_new(trial.rbegin(), trial.rbegin() + nB + nS);
+            order_quality(h->Nn, h->h_conn, rev_old, hb_old, pr_old);
+            order_quality(h->Nn, h->h_conn, rev_new, hb_new, pr_new);
+            if (hb_new <= hb_old && pr_new < pr_old) { h->h_free_nodes.swap(trial); for (int i = 0; i < N; ++i) pos[h->h_free_nodes[i]] = i; }
+        }
+    }
     // local slot of every free node in its chain(s): chain 0 = [A; S] in order, chain 1 = [rev(B); rev(S)]
     std::vector<int> slot0(h->Nn, -1), slot1(h->Nn, -1);
     for (int i = 0; i < nA + nS; ++i) slot0[h->h_free_nodes[i]] = i;
@@ -421,6 +546,26 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         CUDA_TRY(h, cudaMemcpyAsync(chn.d_blocks, blocks[c].data(), blocks[c].size() * sizeof(KBlock), cudaMemcpyHostToDevice, s));
         CUDA_TRY(h, cudaMemcpyAsync(chn.d_contrib, contribs[c].data(), contribs[c].size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     }
+    // sweep programs: the TMA pipeline keeps the last SW_RING solved tiles in shared memory, so it needs a narrow band
+    h->tma_sweep = getenv("JK_SWEEP_LEGACY") == nullptr;
+    for (int c = 0; c < h->n_chains; ++c) if (h->ch[c].bw > SW_MAX_BW) h->tma_sweep = false;
+    for (int c = 0; c < 2; ++c)
+        for (int d = 0; d < 2; ++d) {
+            auto& w = h->ch[c].sw[d];
+            dev_free(w.d_prog); dev_free(w.d_stream); w.n_items = 0;
+            if (c >= h->n_chains || !h->tma_sweep) continue;
+            auto& chn = h->ch[c];
+            std::vector<uint4> prog;
+            // the first chain sweeps all its rows (its separator rows are ordinary rows once the chains are merged);
+            // the second chain's separator rows are partial (forward) / known (backward)
+            build_sweep_program(chn.NT, chn.bw, c == 0 ? chn.NT : chn.kS, d == 1, prog, w.pre_row, w.npre, w.ktop);
+            w.n_items = (int)prog.size() / SW_ITEM_U4;
+            if (w.n_items == 0) continue;
+            CUDA_TRY(h, dev_alloc(&w.d_prog, prog.size()));
+            CUDA_TRY(h, dev_alloc(&w.d_stream, (size_t)w.n_items * SW_TILE));
+            CUDA_TRY(h, cudaMemcpyAsync(w.d_prog, prog.data(), prog.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));   // prog is a local
+        }
     CUDA_TRY(h, cudaMemcpyAsync(h->d_node2slot, h->h_node2slot.data(), (size_t)h->Nn * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -510,6 +655,14 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
     k_tile_inverse<<<c0.NT, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw);
     LAUNCH_CHECK(h);
     if (h->n_chains == 2) { k_tile_inverse<<<c1.kS, 256, INVERSE_SMEM, s>>>(c1.d_tiles, c1.d_Linv, c1.bw); LAUNCH_CHECK(h); }
+    if (h->tma_sweep)
+        for (int c = 0; c < h->n_chains; ++c)
+            for (int d = 0; d < 2; ++d) {
+                auto& w = h->ch[c].sw[d];
+                if (w.n_items == 0) continue;
+                k_sweep_build<<<w.n_items, 256, SWB_SMEM, s>>>(w.d_prog, w.d_stream, h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, d);
+                LAUNCH_CHECK(h);
+            }
     toc(h, JK_T_FACTOR, s);
     return JK_OK;
 }
@@ -737,6 +890,51 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
     const int nS6 = 6 * h->nS_nodes;
     dim3 gsep(ceil_div(ldP, 128), std::max(1, nS6));
+    static const bool sweep_prof = getenv("JK_SWEEP_PROFILE") != nullptr;
+    long long* d_prof = nullptr;
+    if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, 4 * 64 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, 4 * 64 * sizeof(long long), s)); }
+    auto sweep = [&](int c, int d) {
+        auto& chn = h->ch[c]; auto& w = chn.sw[d];
+        if (w.n_items > 0) k_sweep<<<nslab, SW_THREADS, SW_SMEM, s>>>(w.d_prog, w.d_stream, h->d_X, w.n_items, h->n_pad, chn.row0, w.pre_row, w.npre, w.ktop,
+                                                                      d_prof ? d_prof + (2 * c + d) * 64 : nullptr);
+    };
+    if (h->tma_sweep) {
+        // same elimination-tree order as below; between its forward and backward sweep a chain's rows hold Z = L_kk Y_k
+        // in fragment order (jk_sweep.cuh)
+        tic(h, JK_T_SOLVE_FWD);
+        if (h->n_chains == 2) {
+            CUDA_TRY(h, cudaMemset2DAsync(h->d_X + ((size_t)c1.row0 + (size_t)c1.kS * NB) * SLAB, (size_t)h->n_pad * SLAB * sizeof(double), 0,
+                                          (size_t)(c1.NT - c1.kS) * NB * SLAB * sizeof(double), (size_t)nslab, s));
+            sweep(1, 0); LAUNCH_CHECK(h);
+            k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 0);
+            LAUNCH_CHECK(h);
+        }
+        sweep(0, 0); LAUNCH_CHECK(h);
+        toc(h, JK_T_SOLVE_FWD);
+        tic(h, JK_T_SOLVE_BWD);
+        sweep(0, 1); LAUNCH_CHECK(h);
+        if (h->n_chains == 2) {
+            k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 1);
+            LAUNCH_CHECK(h);
+            sweep(1, 1); LAUNCH_CHECK(h);
+        }
+        toc(h, JK_T_SOLVE_BWD);
+        if (d_prof) {   // debug aid: where the consumer warps of CTA 0 spend their clocks
+            long long hp[4 * 64];
+            CUDA_TRY(h, cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            cudaFree(d_prof);
+            for (int q = 0; q < 4; ++q) {
+                if (h->ch[q / 2].sw[q % 2].n_items == 0 || q / 2 >= h->n_chains) continue;
+                fprintf(stderr, "[jk sweep profile] chain %d %s: %d items\n", q / 2, q % 2 ? "backward" : "forward", h->ch[q / 2].sw[q % 2].n_items);
+                for (int w = 0; w < 8; ++w) {
+                    const long long* p = hp + q * 64 + w * 8;
+                    fprintf(stderr, "   warp %d: total %lld | wait tile %lld | wait operand %lld | mma loop %lld | row store %lld | k-groups %lld (x2 DMMA pairs) | items %lld\n",
+                            w, p[6], p[0], p[1], p[2], p[3], p[4], p[5]);
+                }
+            }
+        }
+    } else {
     tic(h, JK_T_SOLVE_FWD);
     if (h->n_chains == 2) {
         // second chain first: its separator rows collect -L_SB y_B (they start at zero), merged into the first chain's
@@ -760,6 +958,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         LAUNCH_CHECK(h);
     }
     toc(h, JK_T_SOLVE_BWD);
+    }
     tic(h, JK_T_POST);
     dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, PH_TPB));
     k_member_post<<<gm, PH_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
@@ -1077,6 +1276,85 @@ extern "C" int jk_get_dims(jk_handle_t h, int32_t* out) {
     if (!h || !out) return JK_EINVAL;
     out[0] = h->Nn; out[1] = h->M; out[2] = h->n_fixed; out[3] = h->n_free; out[4] = h->n_pad; out[5] = NB; out[6] = h->bw; out[7] = h->NT;
     out[8] = h->hb; out[9] = h->n_chains; out[10] = h->ch[0].kS; out[11] = h->nS_nodes;
+    return JK_OK;
+}
+
+extern "C" int jk_sweep_program(int n_tiles, int band_tiles, int kx, int backward, int32_t* items, int cap_items, int32_t* meta) {
+    if (n_tiles <= 0 || band_tiles < 0 || band_tiles > SW_MAX_BW || kx < 0 || kx > n_tiles) return JK_EINVAL;
+    std::vector<uint4> prog;
+    int pre_row = 0, npre = 0, ktop = 0;
+    build_sweep_program(n_tiles, band_tiles, kx, backward != 0, prog, pre_row, npre, ktop);
+    const int n = (int)prog.size() / SW_ITEM_U4;
+    if (meta) { meta[0] = pre_row; meta[1] = npre; meta[2] = ktop; }
+    if (items) {
+        if (cap_items < n) return JK_EINVAL;
+        for (int i = 0; i < n; ++i) {
+            const uint4 a = prog[(size_t)i * SW_ITEM_U4], b = prog[(size_t)i * SW_ITEM_U4 + 1];
+            items[6 * i + 0] = (int)a.x; items[6 * i + 1] = (int)a.y; items[6 * i + 2] = (int)a.z; items[6 * i + 3] = (int)a.w;
+            items[6 * i + 4] = (int)b.x; items[6 * i + 5] = (int)b.y;
+        }
+    }
+    return n;
+}
+
+// non-zeros of the factor: chain tiles (rows < row_end, columns < col_end DOFs), lower triangle incl. diagonal
+__global__ void k_count_nnz(const double* __restrict__ tiles, int NT, int bw, int row_end, int col_end, unsigned long long* __restrict__ out) {
+    const int I = blockIdx.x, dJ = blockIdx.y, J = I - dJ;
+    if (J < 0) return;
+    const double* g = tiles + tile_off(I, J, bw);
+    unsigned cnt = 0;
+    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+        int r = I * NB + idx / NB, c = J * NB + idx % NB;
+        if (c <= r && r < row_end && c < col_end && g[idx] != 0.0) ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
+extern "C" int jk_solver_stats(jk_handle_t h, double* out) {
+    if (!h || !out) return JK_EINVAL;
+    if (!h->factored) JK_FAIL(h, JK_ESTATE, "jk_solver_stats: factor first");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0)); }
+    unsigned long long* d_cnt = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d_cnt, sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+    for (int c = 0; c < h->n_chains; ++c) {
+        auto& chn = h->ch[c];
+        // second chain: its separator columns belong to the first chain's factor
+        const int col_end = (c == 1) ? chn.kS * NB : chn.n_rows;
+        k_count_nnz<<<dim3(chn.NT, chn.bw + 1), 256, 0, s>>>(chn.d_tiles, chn.NT, chn.bw, chn.n_rows, col_end, d_cnt);
+        LAUNCH_CHECK(h);
+    }
+    unsigned long long cnt = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    double exec = 0.0; long long items = 0;
+    if (h->tma_sweep) {
+        for (int c = 0; c < h->n_chains; ++c)
+            for (int d = 0; d < 2; ++d) {
+                auto& w = h->ch[c].sw[d];
+                if (w.n_items == 0) continue;
+                std::vector<uint4> prog((size_t)w.n_items * SW_ITEM_U4);
+                CUDA_TRY(h, cudaMemcpyAsync(prog.data(), w.d_prog, prog.size() * sizeof(uint4), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(h, cudaStreamSynchronize(s));
+                for (int i = 0; i < w.n_items; ++i) {
+                    const uint4 m = prog[(size_t)i * SW_ITEM_U4 + 2];
+                    exec += 2.0 * 32.0 * (double)(__builtin_popcount(m.x) + __builtin_popcount(m.y) + __builtin_popcount(m.z) + __builtin_popcount(m.w));
+                }
+                items += w.n_items;
+            }
+    } else {
+        for (int c = 0; c < h->n_chains; ++c) {
+            auto& chn = h->ch[c];
+            long long prods = 0;
+            for (int k = 0; k < chn.NT; ++k) prods += 1 + std::min(k, chn.bw);
+            exec += 2.0 * 2.0 * (double)prods * NB * NB;   // two sweeps, 2 flops per MAC, per right-hand-side column
+        }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    cudaFree(d_cnt);
+    out[0] = (double)cnt; out[1] = exec; out[2] = (double)items; out[3] = h->tma_sweep ? 1.0 : 0.0;
     return JK_OK;
 }
 

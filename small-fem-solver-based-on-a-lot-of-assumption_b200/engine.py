@@ -214,6 +214,13 @@ class Engine:
         self._ck(self.lib.jk_residual(self.h, C.byref(r)))
         return float(r.value)
 
+    def solver_stats(self):
+        """nnz(L), executed sweep flops per load case, sweep items per slab, TMA-pipeline flag."""
+        out = np.zeros(4)
+        self._ck(self.lib.jk_solver_stats(self.h, L.dptr(out)))
+        return {"nnz_L": int(out[0]), "sweep_flops_executed_per_case": float(out[1]), "sweep_items": int(out[2]),
+                "tma_sweep": bool(out[3])}
+
     def launch_count(self):
         return int(self.lib.jk_launch_count(self.h))
 

@@ -363,3 +363,39 @@ def test_two_chain_factorisation_matches_single_chain():
     for n in out["two"][2]:
         assert relmax(out["two"][2][n], out["single"][2][n]) < 1e-10
     assert out["two"][4] < 1e-9 and out["single"][4] < 1e-9      # max|K u - F| / max|F| over all phases (rounding level)
+
+
+@pytest.mark.parametrize("legs,bays,single_chain", [(8, 30, False), (8, 30, True), (5, 6, False), (16, 20, False)])
+def test_tma_sweep_matches_legacy_sweep(legs, bays, single_chain):
+    """The TMA / mbarrier sweep pipeline (Z-form recurrences, zero-block masks) and the cp.async slab sweep solve the
+    same systems; the pipeline executes fewer flops than the band holds."""
+    import os
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    out = {}
+    for mode in ("tma", "legacy"):
+        if mode == "legacy":
+            os.environ["JK_SWEEP_LEGACY"] = "1"
+        if single_chain:
+            os.environ["JK_SINGLE_CHAIN"] = "1"
+        try:
+            nodes, members, fixed, top = jb.generate_jacket(legs, bays)
+            st = jb.build_structure(nodes, members, fixed, top, ap)
+            res = jb.phase_scan(st, _wave(jb, ap), 70, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+            out[mode] = (res.table.copy(), res.phase(3)["U"], res.phase(69)["reactions"], res.engine.solver_stats(), res.engine.residual(),
+                         res.engine.dims())
+        finally:
+            os.environ.pop("JK_SWEEP_LEGACY", None)
+            os.environ.pop("JK_SINGLE_CHAIN", None)
+    st_t, st_l = out["tma"][3], out["legacy"][3]
+    assert st_t["tma_sweep"] and not st_l["tma_sweep"]
+    assert st_t["nnz_L"] == st_l["nnz_L"] > 0
+    assert st_t["sweep_flops_executed_per_case"] < st_l["sweep_flops_executed_per_case"]   # zero-block masks vs the whole tile band
+    assert np.array_equal(out["tma"][0][:, :8], out["legacy"][0][:, :8])
+    for c in (8, 10, 12, 13, 14, 15):
+        assert relmax(out["tma"][0][:, c], out["legacy"][0][:, c]) < 1e-10
+    assert np.array_equal(out["tma"][0][:, 11], out["legacy"][0][:, 11])
+    assert relmax(out["tma"][1], out["legacy"][1]) < 1e-10
+    for n in out["tma"][2]:
+        assert relmax(out["tma"][2][n], out["legacy"][2][n]) < 1e-10
+    assert out["tma"][4] < 1e-9 and out["legacy"][4] < 1e-9

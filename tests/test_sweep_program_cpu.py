@@ -1,0 +1,139 @@
+"""Host logic of the TMA sweep (csrc/jk_sweep.cuh): the item list built by the library is interpreted here in NumPy --
+same algebra (Z-form recurrences with U = -L Linv, G = Linv^T Linv, V = -Linv^T L^T), same ring-slot / mbarrier-parity
+bookkeeping -- and checked against dense triangular solves.  No GPU needed: jk_sweep_program is host-only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import jacket_b200  # noqa: F401
+from jacket_b200 import _lib
+
+NB = 64
+RING = 5
+ROW_BEGIN, DIAG, ROW_END, NO_RING, INIT_RHS, OUT_FRAG, NO_OPERAND = 1, 2, 4, 8, 16, 32, 64
+
+
+def program(NT, bw, kx, backward):
+    lib = _lib.lib()
+    meta = np.zeros(3, dtype=np.int32)
+    n = lib.jk_sweep_program(NT, bw, kx, int(backward), None, 0, _lib.iptr(meta))
+    assert n > 0
+    items = np.zeros(6 * n, dtype=np.int32)
+    assert lib.jk_sweep_program(NT, bw, kx, int(backward), _lib.iptr(items), n, _lib.iptr(meta)) == n
+    return items.reshape(n, 6), meta
+
+
+def banded_spd(NT, bw, rng):
+    n = NT * NB
+    A = np.zeros((n, n))
+    hb = bw * NB - 7 if bw > 0 else NB - 1
+    for i in range(n):
+        lo = max(0, i - hb)
+        A[i, lo:i] = rng.standard_normal(i - lo) * 0.1
+    A = A + A.T + np.eye(n) * (2.0 + 0.2 * hb)
+    return A
+
+
+def tile(Lm, i, j):
+    return Lm[i * NB:(i + 1) * NB, j * NB:(j + 1) * NB]
+
+
+def run_program(items, meta, Lm, X, backward, known_rows=None):
+    """Interpret the item list on X ([NT*NB, nrhs], modified in place like the slab).  Returns tile products executed."""
+    NT = Lm.shape[0] // NB
+    Linv = [np.linalg.inv(tile(Lm, k, k)) for k in range(NT)]
+    ring_row = [None] * RING
+    ring_val = [None] * RING
+    fills = [0] * RING
+    pre_row, npre, ktop = (int(v) for v in meta)
+    for q in range(npre):
+        i = pre_row + q
+        slot = (ktop - i) % RING
+        ring_row[slot], ring_val[slot] = i, X[i * NB:(i + 1) * NB].copy()
+        fills[slot] += 1
+    acc = None
+    rhs = X[items[0][0] * NB:(items[0][0] + 1) * NB].copy() if items[0][2] & INIT_RHS else None
+    nprod = 0
+    for row, src, flags, xinfo, next_row, next_init in items:
+        if flags & ROW_BEGIN:
+            acc = rhs.copy() if flags & INIT_RHS else np.zeros((NB, X.shape[1]))
+        if flags & DIAG:
+            assert backward
+            acc += (Linv[row].T @ Linv[row]) @ X[row * NB:(row + 1) * NB]      # operand = Z_k from the slab
+            nprod += 1
+        elif not flags & NO_OPERAND:
+            slot, parity = xinfo & 0xFF, (xinfo >> 8) & 1
+            assert ring_row[slot] == src, (row, src, slot, ring_row)
+            assert (fills[slot] - 1) & 1 == parity, "mbarrier parity of the operand slot"
+            if backward:
+                A = -Linv[row].T @ tile(Lm, src, row).T
+            else:
+                A = -tile(Lm, row, src) @ Linv[src]
+            acc += A @ ring_val[slot]
+            nprod += 1
+        if flags & ROW_END:
+            if next_init:
+                rhs = X[next_row * NB:(next_row + 1) * NB].copy()
+            X[row * NB:(row + 1) * NB] = acc
+            if not flags & NO_RING:
+                oslot = (xinfo >> 16) & 0xFF
+                ring_row[oslot], ring_val[oslot] = row, acc.copy()
+                fills[oslot] += 1
+    return nprod
+
+
+@pytest.mark.parametrize("NT,bw", [(1, 0), (2, 1), (7, 2), (13, 4), (12, 3)])
+def test_plain_sweeps_solve_the_system(NT, bw):
+    rng = np.random.default_rng(NT * 10 + bw)
+    A = banded_spd(NT, bw, rng)
+    Lm = np.linalg.cholesky(A)
+    B = rng.standard_normal((NT * NB, 5))
+    X = B.copy()
+    f, mf = program(NT, bw, NT, False)
+    b, mb = program(NT, bw, NT, True)
+    run_program(f, mf, Lm, X, False)
+    # after the forward sweep the slab holds Z_k = L_kk Y_k
+    Y = np.linalg.solve(Lm, B)
+    for k in range(NT):
+        np.testing.assert_allclose(X[k * NB:(k + 1) * NB], tile(Lm, k, k) @ Y[k * NB:(k + 1) * NB], rtol=1e-9, atol=1e-11)
+    run_program(b, mb, Lm, X, True)
+    np.testing.assert_allclose(X, np.linalg.solve(A, B), rtol=1e-9, atol=1e-11)
+    # every row has exactly one ROW_BEGIN and one ROW_END, in processing order
+    for items, order in ((f, list(range(NT))), (b, list(range(NT - 1, -1, -1)))):
+        assert [r for r, _, fl, *_ in items if fl & ROW_BEGIN] == order
+        assert [r for r, _, fl, *_ in items if fl & ROW_END] == order
+
+
+@pytest.mark.parametrize("NT,bw,kx", [(9, 3, 6), (12, 4, 9), (10, 4, 4), (5, 2, 3)])
+def test_partial_forward_and_known_backward(NT, bw, kx):
+    """Second-chain semantics: forward rows >= kx only accumulate B_k - sum_{j<kx} L_kj Y_j; the backward sweep starts
+    below kx with rows >= kx known."""
+    rng = np.random.default_rng(100 * NT + kx)
+    A = banded_spd(NT, bw, rng)
+    Lm = np.linalg.cholesky(A)
+    B = rng.standard_normal((NT * NB, 3))
+    n1 = kx * NB
+    X = B.copy()
+    f, mf = program(NT, bw, kx, False)
+    run_program(f, mf, Lm, X, False)
+    Y1 = np.linalg.solve(Lm[:n1, :n1], B[:n1])
+    np.testing.assert_allclose(X[n1:], B[n1:] - Lm[n1:, :n1] @ Y1, rtol=1e-9, atol=1e-11)
+    assert all(fl & NO_RING for r, _, fl, *_ in f if fl & ROW_END and r >= kx)
+    # backward: take the exact solution of L^T x = y, give the rows >= kx, recover the rest from Z
+    Yfull = rng.standard_normal((NT * NB, 3))
+    Xtrue = np.linalg.solve(Lm.T, Yfull)
+    S = np.zeros_like(Yfull)
+    for k in range(kx):
+        S[k * NB:(k + 1) * NB] = tile(Lm, k, k) @ Yfull[k * NB:(k + 1) * NB]     # Z rows
+    S[n1:] = Xtrue[n1:]
+    b, mb = program(NT, bw, kx, True)
+    assert mb[0] == kx and mb[1] == min(bw, NT - kx)
+    run_program(b, mb, Lm, S, True)
+    np.testing.assert_allclose(S[:n1], Xtrue[:n1], rtol=1e-8, atol=1e-10)
+
+
+def test_program_rejects_wide_bands():
+    lib = _lib.lib()
+    assert lib.jk_sweep_program(8, 5, 8, 0, None, 0, None) < 0
+    assert lib.jk_sweep_program(0, 1, 0, 0, None, 0, None) < 0
