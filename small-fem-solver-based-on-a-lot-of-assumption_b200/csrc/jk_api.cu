@@ -29,7 +29,7 @@ struct jk_handle_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;        // side stream: the factorisation runs here, concurrently with the Morison stage
-    cudaEvent_t ev_fork = nullptr, ev_factor = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_factor_bwd = nullptr;   // ev_factor: forward sweeps may start; ev_factor_bwd: backward tile streams built too
     bool factor_inflight = false;
     std::string err;
     int64_t launches = 0;
@@ -171,6 +171,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi); }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_factor_bwd, cudaEventDisableTiming);
     h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
     h->h_xyz.assign(xyz, xyz + 3 * (size_t)n_nodes);
     h->h_conn.assign(conn, conn + 2 * (size_t)n_members);
@@ -239,6 +240,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_factor) cudaEventDestroy(h->ev_factor);
+    if (h->ev_factor_bwd) cudaEventDestroy(h->ev_factor_bwd);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JK_OK;
@@ -361,6 +363,10 @@ static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vect
         prog.push_back(make_uint4(0u, 0u, 0u, 0u));
     };
     auto slotinfo = [&](int seq) { return (seq % SW_RING) | (((seq / SW_RING) & 1) << 8); };
+    // a consumer warp has to wait on an operand row's mbarrier only the first time the program uses that row (program
+    // order = every warp's order, and a row solved earlier was waited on when the row after it was finished)
+    std::vector<char> waited(NT, 0);
+    auto need_wait = [&](int r) { if (waited[r]) return 0; waited[r] = 1; return SW_WAIT_X; };
     if (!backward) {
         pre_row = 0; npre = 0; ktop = 0;
         for (int k = 0; k < NT; ++k) {
@@ -370,8 +376,8 @@ static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vect
             const int out = (k % SW_RING) << 16;
             if (hi < lo) { push(k, k, SW_ROW_BEGIN | SW_INIT_RHS | SW_NO_OPERAND | end_flags, out, has_next ? k + 1 : 0, has_next ? 1 : 0); continue; }
             for (int j = lo; j <= hi; ++j) {
-                int flags = (j == lo ? (SW_ROW_BEGIN | SW_INIT_RHS) : 0) | (j == hi ? end_flags : 0);
-                push(k, j, flags, slotinfo(j) | out, has_next ? k + 1 : 0, (j == hi && has_next) ? 1 : 0);
+                int flags = (j == lo ? (SW_ROW_BEGIN | SW_INIT_RHS) : 0) | (j == hi ? end_flags : 0) | need_wait(j);
+                push(k, j, flags, slotinfo(j) | out, has_next ? k + 1 : 0, (j == lo && has_next) ? 1 : 0);   // next row's RHS is fetched at ROW_BEGIN
             }
         }
     } else {
@@ -382,7 +388,7 @@ static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vect
             const int hi = std::min(NT - 1, std::min(k + bw, ktop));
             const int out = ((ktop - k) % SW_RING) << 16;
             push(k, k, SW_ROW_BEGIN | SW_DIAG | (hi < k + 1 ? SW_ROW_END : 0), out, 0, 0);
-            for (int i = hi; i >= k + 1; --i) push(k, i, (i == k + 1 ? SW_ROW_END : 0), slotinfo(ktop - i) | out, 0, 0);
+            for (int i = hi; i >= k + 1; --i) push(k, i, (i == k + 1 ? SW_ROW_END : 0) | need_wait(i), slotinfo(ktop - i) | out, 0, 0);
         }
     }
 }
@@ -582,7 +588,7 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     if (!(E > 0) || !(G > 0)) JK_FAIL(h, JK_EINVAL, "jk_assemble: E and G must be positive");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
-    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0)); h->factor_inflight = false; }
+    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0)); h->factor_inflight = false; }
     h->E = E; h->G = G;
     tic(h, JK_T_ASSEMBLE);
     k_member_setup<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, h->d_xyz, h->d_conn, h->d_sec, h->d_secp, JK_SEC_NPROP, E, G, h->d_mc, h->d_Ke, h->d_Kl);
@@ -596,6 +602,17 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     }
     toc(h, JK_T_ASSEMBLE);
     h->assembled = true; h->factored = false;
+    return JK_OK;
+}
+
+static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d) {
+    if (!h->tma_sweep) return JK_OK;
+    for (int c = 0; c < h->n_chains; ++c) {
+        auto& w = h->ch[c].sw[d];
+        if (w.n_items == 0) continue;
+        k_sweep_build<<<w.n_items, 256, SWB_SMEM, s>>>(w.d_prog, w.d_stream, h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, d);
+        LAUNCH_CHECK(h);
+    }
     return JK_OK;
 }
 
@@ -655,14 +672,9 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
     k_tile_inverse<<<c0.NT, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw);
     LAUNCH_CHECK(h);
     if (h->n_chains == 2) { k_tile_inverse<<<c1.kS, 256, INVERSE_SMEM, s>>>(c1.d_tiles, c1.d_Linv, c1.bw); LAUNCH_CHECK(h); }
-    if (h->tma_sweep)
-        for (int c = 0; c < h->n_chains; ++c)
-            for (int d = 0; d < 2; ++d) {
-                auto& w = h->ch[c].sw[d];
-                if (w.n_items == 0) continue;
-                k_sweep_build<<<w.n_items, 256, SWB_SMEM, s>>>(w.d_prog, w.d_stream, h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, d);
-                LAUNCH_CHECK(h);
-            }
+    // tile streams of the forward sweeps; the factor timer stops here (this is what the forward sweeps wait for)
+    int rc = launch_sweep_build(h, s, 0);
+    if (rc != JK_OK) return rc;
     toc(h, JK_T_FACTOR, s);
     return JK_OK;
 }
@@ -687,6 +699,9 @@ extern "C" int jk_factor(jk_handle_t h) {
     cudaSetDevice(h->device);
     int rc = launch_factor(h, h->stream);
     if (rc != JK_OK) return rc;
+    if ((rc = launch_sweep_build(h, h->stream, 1)) != JK_OK) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_factor_bwd, h->stream));
     h->assembled = false;       // the tile storage now holds L
     h->factored = true;
     h->factor_inflight = true;
@@ -706,6 +721,9 @@ extern "C" int jk_factor_begin(jk_handle_t h) {
     int rc = launch_factor(h, h->stream2);
     if (rc != JK_OK) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream2));
+    // the backward tile streams are only needed after the forward sweeps: built behind the event, they overlap them
+    if ((rc = launch_sweep_build(h, h->stream2, 1)) != JK_OK) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_factor_bwd, h->stream2));
     h->assembled = false;
     h->factored = true;
     h->factor_inflight = true;
@@ -911,6 +929,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         }
         sweep(0, 0); LAUNCH_CHECK(h);
         toc(h, JK_T_SOLVE_FWD);
+        if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0));
         tic(h, JK_T_SOLVE_BWD);
         sweep(0, 1); LAUNCH_CHECK(h);
         if (h->n_chains == 2) {
@@ -929,8 +948,8 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
                 fprintf(stderr, "[jk sweep profile] chain %d %s: %d items\n", q / 2, q % 2 ? "backward" : "forward", h->ch[q / 2].sw[q % 2].n_items);
                 for (int w = 0; w < 8; ++w) {
                     const long long* p = hp + q * 64 + w * 8;
-                    fprintf(stderr, "   warp %d: total %lld | wait tile %lld | wait operand %lld | mma loop %lld | row store %lld | k-groups %lld (x2 DMMA pairs) | items %lld\n",
-                            w, p[6], p[0], p[1], p[2], p[3], p[4], p[5]);
+                    fprintf(stderr, "   warp %d: total %lld | wait tile %lld | row begin %lld | wait operand %lld | mma loop %lld | row store %lld | DMMAs %lld | items %lld\n",
+                            w, p[6], p[0], p[7], p[1], p[2], p[3], p[4], p[5]);
                 }
             }
         }
@@ -1316,7 +1335,7 @@ extern "C" int jk_solver_stats(jk_handle_t h, double* out) {
     if (!h->factored) JK_FAIL(h, JK_ESTATE, "jk_solver_stats: factor first");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
-    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0)); }
+    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0)); }
     unsigned long long* d_cnt = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&d_cnt, sizeof(unsigned long long)));
     CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));

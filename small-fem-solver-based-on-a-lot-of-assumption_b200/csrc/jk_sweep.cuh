@@ -30,6 +30,13 @@
 
 namespace jk {
 
+// experiment switches (variants are built as separate libraries and selected with JK_LIB; see tools/ab_bench.sh).
+// Measured and dropped: descriptors read from global by the consumers, a test_wait probe of the next tile, a
+// find-first-set walk of sparse masks, 4 stages (all within +-2 % or slower than this configuration).
+#ifndef JK_SW_RBN
+#define JK_SW_RBN 2        // 8-row blocks per consumer warp: 2 (x two 8-column blocks) or 4 (x one).  4 x 1 balances the schedulers
+                           // exactly but needs predicated row blocks in the forward sweeps; measured 4 % slower overall
+#endif
 #ifndef JK_SW_STAGES
 #define JK_SW_STAGES 3
 #endif
@@ -50,10 +57,11 @@ constexpr int SW_NO_RING = 8;               // ROW_END: row is not needed by lat
 constexpr int SW_INIT_RHS = 16;             // ROW_BEGIN: accumulators start from the right-hand side rows (row-major)
 constexpr int SW_OUT_FRAG = 32;             // ROW_END: store the row to the slab in fragment order (forward Z)
 constexpr int SW_NO_OPERAND = 64;           // placeholder item of a row without any tile (accumulators pass through)
+constexpr int SW_WAIT_X = 128;              // first use of the operand row by this sweep: wait on its mbarrier (later uses need not)
 
 // One item = 3 x uint4 in the program array:
 //   [0] = {row, src, flags, xinfo}   xinfo: bits 0-7 operand ring slot, bit 8 its mbarrier parity, bits 16-23 output slot
-//   [1] = {next_row, next_init, 0, 0}   (valid on ROW_END items: right-hand side rows to prefetch before the row is published)
+//   [1] = {next_row, next_init, 0, 0}   (ROW_BEGIN items of forward sweeps: right-hand side rows to prefetch for the next row)
 //   [2] = 8 x 16-bit k-group masks (written by k_sweep_build)
 constexpr int SW_ITEM_U4 = 3;
 
@@ -82,6 +90,12 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {      // non-blocking probe
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a broken pipeline traps (the launch fails with an error) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned spins = 0;
@@ -101,14 +115,15 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 // T is written in A-fragment order; the item's masks mark the (8-row block, 4-column group) cells with a non-zero.
 // Structural zeros of L are exact zeros (the envelope is never filled), so the test is exact.
 // ----------------------------------------------------------------------------------------------
-constexpr int SWB_LD = NB + 1;
-constexpr size_t SWB_SMEM = (size_t)2 * NB * SWB_LD * sizeof(double);
+constexpr int SWB_KC = 16;                 // K chunk: small shared-memory footprint, so build CTAs fit beside a sweep CTA on an SM
+constexpr int SWB_PLD = SWB_KC + 1, SWB_QLD = NB + 1;
+constexpr size_t SWB_SMEM = (size_t)(NB * SWB_PLD + SWB_KC * SWB_QLD) * sizeof(double);
 __global__ void __launch_bounds__(256) k_sweep_build(uint4* __restrict__ prog, double* __restrict__ stream,
                                                      const double* __restrict__ tiles, const double* __restrict__ Linv,
                                                      int bw, int backward) {
     extern __shared__ __align__(16) double smem[];
-    double* Ps = smem;                    // P[r][m]
-    double* Qs = smem + NB * SWB_LD;      // Q[m][c]
+    double* Ps = smem;                    // P[r][m - m0]   (NB x SWB_KC)
+    double* Qs = smem + NB * SWB_PLD;     // Q[m - m0][c]   (SWB_KC x NB)
     __shared__ unsigned msk[8];
     const int n = blockIdx.x, tid = threadIdx.x;
     const uint4 it = prog[(size_t)n * SW_ITEM_U4];
@@ -126,29 +141,36 @@ __global__ void __launch_bounds__(256) k_sweep_build(uint4* __restrict__ prog, d
     if (!backward) { ps = tiles + tile_off(row, src, bw); tp = false; qs = Linv + (size_t)src * SW_TILE; tq = false; sgn = -1.0; }
     else if (flags & SW_DIAG) { ps = Linv + (size_t)row * SW_TILE; tp = true; qs = ps; tq = false; sgn = 1.0; }
     else { ps = Linv + (size_t)row * SW_TILE; tp = true; qs = tiles + tile_off(src, row, bw); tq = true; sgn = -1.0; }
-    for (int idx = tid; idx < SW_TILE; idx += 256) {
-        const int a = idx / NB, b = idx % NB;
-        const double pv = ps[idx], qv = qs[idx];
-        if (tp) Ps[b * SWB_LD + a] = pv; else Ps[a * SWB_LD + b] = pv;
-        if (tq) Qs[b * SWB_LD + a] = qv; else Qs[a * SWB_LD + b] = qv;
-    }
-    __syncthreads();
     const int ty = tid / 16, tx = tid % 16;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    for (int m = 0; m < NB; ++m) {
-        double p[4], q[4];
+    for (int m0 = 0; m0 < NB; m0 += SWB_KC) {
+        __syncthreads();
+        // P[r][m] = tp ? ps[m][r] : ps[r][m];  Q[m][c] = tq ? qs[c][m] : qs[m][c]   for m in [m0, m0 + KC)
+        for (int idx = tid; idx < NB * SWB_KC; idx += 256) {
+            int r, m;
+            if (tp) { m = idx / NB; r = idx % NB; Ps[r * SWB_PLD + m] = ps[(m0 + m) * NB + r]; }
+            else { r = idx / SWB_KC; m = idx % SWB_KC; Ps[r * SWB_PLD + m] = ps[r * NB + m0 + m]; }
+            int c;
+            if (tq) { c = idx / SWB_KC; m = idx % SWB_KC; Qs[m * SWB_QLD + c] = qs[c * NB + m0 + m]; }
+            else { m = idx / NB; c = idx % NB; Qs[m * SWB_QLD + c] = qs[(m0 + m) * NB + c]; }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int m = 0; m < SWB_KC; ++m) {
+            double p[4], q[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = Ps[(4 * ty + i) * SWB_LD + m];
+            for (int i = 0; i < 4; ++i) p[i] = Ps[(4 * ty + i) * SWB_PLD + m];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = Qs[m * SWB_LD + tx + 16 * j];
+            for (int j = 0; j < 4; ++j) q[j] = Qs[m * SWB_QLD + tx + 16 * j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(p[i], q[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(p[i], q[j], acc[i][j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -165,35 +187,104 @@ __global__ void __launch_bounds__(256) k_sweep_build(uint4* __restrict__ prog, d
 }
 
 // Inner products of one item for one consumer warp: acc[a][b] += A(row block a) * X(column block b) over the k-groups.
-// R0 / R1: which of the warp's two row blocks take part.  All offsets are compile-time constants.
-template <bool R0, bool R1>
-__device__ __forceinline__ void sweep_mma_full(double (&acc)[2][2][2], const double* __restrict__ a0p, const double* __restrict__ a1p,
-                                               const double* __restrict__ bp) {
-    double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0}, b0[2], b1[2];
-    if (R0) a0[0] = a0p[0];
-    if (R1) a1[0] = a1p[0];
-    b0[0] = bp[0]; b1[0] = bp[32];
+// ap[a] / bp point at this lane's element of the first fragment; all further offsets are compile-time constants.
+constexpr int SW_RBN = JK_SW_RBN, SW_CBN = 4 / JK_SW_RBN;
+
+// every row block of the warp is either dense or empty (act[a], warp-uniform): register-double-buffered, fully unrolled
+template <bool ALL>
+__device__ __forceinline__ void sweep_mma_dense(double (&acc)[SW_RBN][SW_CBN][2], const double* const (&ap)[SW_RBN], const bool (&act)[SW_RBN],
+                                                const double* __restrict__ bp) {
+    double af[2][SW_RBN], bf[2][SW_CBN];
+#pragma unroll
+    for (int a = 0; a < SW_RBN; ++a) { af[0][a] = 0.0; af[1][a] = 0.0; if (ALL || act[a]) af[0][a] = ap[a][0]; }
+#pragma unroll
+    for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * 32];
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {
         const int cur = k4 & 1, nxt = cur ^ 1;
         if (k4 + 1 < 16) {      // fragments of the next k-group before the DMMAs of this one
-            if (R0) a0[nxt] = a0p[(k4 + 1) * 32];
-            if (R1) a1[nxt] = a1p[(k4 + 1) * 32];
-            b0[nxt] = bp[(k4 + 1) * 128]; b1[nxt] = bp[(k4 + 1) * 128 + 32];
+#pragma unroll
+            for (int a = 0; a < SW_RBN; ++a) if (ALL || act[a]) af[nxt][a] = ap[a][(k4 + 1) * 32];
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
         }
-        if (R0) { dmma(acc[0][0][0], acc[0][0][1], a0[cur], b0[cur]); dmma(acc[0][1][0], acc[0][1][1], a0[cur], b1[cur]); }
-        if (R1) { dmma(acc[1][0][0], acc[1][0][1], a1[cur], b0[cur]); dmma(acc[1][1][0], acc[1][1][1], a1[cur], b1[cur]); }
+#pragma unroll
+        for (int a = 0; a < SW_RBN; ++a)
+            if (ALL || act[a]) {
+#pragma unroll
+                for (int b = 0; b < SW_CBN; ++b) dmma(acc[a][b][0], acc[a][b][1], af[cur][a], bf[cur][b]);
+            }
     }
 }
-template <bool R0, bool R1>
-__device__ __forceinline__ void sweep_mma_masked(double (&acc)[2][2][2], const double* __restrict__ a0p, const double* __restrict__ a1p,
-                                                 const double* __restrict__ bp, unsigned mask) {
+// general masks: unrolled, one warp-uniform branch per k-group and row block
+__device__ __forceinline__ void sweep_mma_masked(double (&acc)[SW_RBN][SW_CBN][2], const double* const (&ap)[SW_RBN], const unsigned (&m)[SW_RBN],
+                                                 const double* __restrict__ bp) {
+    unsigned mu = 0u;
+#pragma unroll
+    for (int a = 0; a < SW_RBN; ++a) mu |= m[a];
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {
-        if (mask & (1u << k4)) {      // warp-uniform
-            const double b0 = bp[k4 * 128], b1 = bp[k4 * 128 + 32];
-            if (R0) { const double a = a0p[k4 * 32]; dmma(acc[0][0][0], acc[0][0][1], a, b0); dmma(acc[0][1][0], acc[0][1][1], a, b1); }
-            if (R1) { const double a = a1p[k4 * 32]; dmma(acc[1][0][0], acc[1][0][1], a, b0); dmma(acc[1][1][0], acc[1][1][1], a, b1); }
+        if (mu & (1u << k4)) {
+            double bf[SW_CBN];
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) bf[b] = bp[k4 * 128 + b * 32];
+#pragma unroll
+            for (int a = 0; a < SW_RBN; ++a)
+                if (m[a] & (1u << k4)) {
+                    const double af = ap[a][k4 * 32];
+#pragma unroll
+                    for (int b = 0; b < SW_CBN; ++b) dmma(acc[a][b][0], acc[a][b][1], af, bf[b]);
+                }
+        }
+    }
+}
+
+// all row blocks of the warp share one sparse mask (backward tiles: the mask is a column pattern): one branch per k-group
+__device__ __forceinline__ void sweep_mma_uniform(double (&acc)[SW_RBN][SW_CBN][2], const double* const (&ap)[SW_RBN], unsigned mask,
+                                                  const double* __restrict__ bp) {
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+        if (mask & (1u << k4)) {
+            double af[SW_RBN], bf[SW_CBN];
+#pragma unroll
+            for (int a = 0; a < SW_RBN; ++a) af[a] = ap[a][k4 * 32];
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) bf[b] = bp[k4 * 128 + b * 32];
+#pragma unroll
+            for (int a = 0; a < SW_RBN; ++a)
+#pragma unroll
+                for (int b = 0; b < SW_CBN; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+}
+// one row block on its own (masks differ between the warp's row blocks): dense -> double-buffered, sparse -> branch per k-group
+template <int A>
+__device__ __forceinline__ void sweep_mma_single(double (&acc)[SW_RBN][SW_CBN][2], const double* __restrict__ ap, unsigned mask,
+                                                 const double* __restrict__ bp) {
+    if (mask == 0xffffu) {
+        double af[2], bf[2][SW_CBN];
+        af[0] = ap[0];
+#pragma unroll
+        for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * 32];
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+            const int cur = k4 & 1, nxt = cur ^ 1;
+            if (k4 + 1 < 16) {
+                af[nxt] = ap[(k4 + 1) * 32];
+#pragma unroll
+                for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+            }
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) dmma(acc[A][b][0], acc[A][b][1], af[cur], bf[cur][b]);
+        }
+    } else if (mask) {
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+            if (mask & (1u << k4)) {
+                const double af = ap[k4 * 32];
+#pragma unroll
+                for (int b = 0; b < SW_CBN; ++b) dmma(acc[A][b][0], acc[A][b][1], af, bp[k4 * 128 + b * 32]);
+            }
         }
     }
 }
@@ -210,7 +301,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     double* As = reinterpret_cast<double*>(sw_smem);                 // [SW_STAGES][SW_TILE]   A tiles, fragment order
     double* Bs = As + SW_STAGES * SW_TILE;                           // [SW_XTILE]             Z_k of the backward diagonal item
     double* Xr = Bs + SW_XTILE;                                      // [SW_RING][SW_XTILE]    newest solved tiles, fragment order
-    uint4* Ds = reinterpret_cast<uint4*>(Xr + SW_RING * SW_XTILE);   // [SW_STAGES][SW_ITEM_U4] item descriptors
+    uint4* Ds = reinterpret_cast<uint4*>(Xr + SW_RING * SW_XTILE);   // [SW_STAGES][SW_ITEM_U4] item descriptors, staged by the producer
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ds + SW_STAGES * SW_ITEM_U4);
     const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + SW_STAGES), bar_x = smem_u32(bars + 2 * SW_STAGES),
                    bar_bfull = smem_u32(bars + 2 * SW_STAGES + SW_RING), bar_bempty = smem_u32(bars + 2 * SW_STAGES + SW_RING + 1);
@@ -219,7 +310,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
 
     if (tid == 0) {
         for (int s = 0; s < SW_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, SW_CONSUMER_WARPS); }
-        for (int s = 0; s < SW_RING; ++s) mbar_init(bar_x + 8 * s, SW_CONSUMERS);
+        for (int s = 0; s < SW_RING; ++s) mbar_init(bar_x + 8 * s, SW_CONSUMER_WARPS);
         mbar_init(bar_bfull, 1);
         mbar_init(bar_bempty, SW_CONSUMER_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -258,35 +349,39 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     }
 
     // ----------------------------------- consumer warps -----------------------------------
+    // Warp w owns SW_RBN row blocks x SW_CBN column blocks of the 64 x 32 result tile.  With 4 x 1 the two warps of a
+    // scheduler (w, w + 4) cover all eight row blocks of one column block, so every scheduler has the same DMMA count
+    // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
-    const int p = warp & 3, h = warp >> 2;
-    const int mb0 = p, mb1 = 7 - p;               // row blocks of this warp (warps w and w+4 share a scheduler and the row pair)
-    const int nt0 = 2 * h;                        // column blocks nt0, nt0 + 1
+    int rbs[SW_RBN], cb0;
+    if (SW_RBN == 4) { cb0 = warp & 3; for (int a = 0; a < 4; ++a) rbs[a] = 2 * a + (warp >> 2); }
+    else { cb0 = 2 * (warp >> 2); rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
     // known rows of a backward sweep that starts below the top (second chain: separator solution): row-major -> ring
     for (int q = 0; q < npre; ++q) {
         const int i = pre_row + q, slot = (ktop - i) % SW_RING;
         const double* g = Xslab + (size_t)i * SW_XTILE;
         double* dst = Xr + slot * SW_XTILE;
         for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[sw_x_index(e / SLAB, e % SLAB)] = g[e];
-        mbar_arrive(bar_x + 8 * slot);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x + 8 * slot);
     }
     // this lane's elements of a 64 x 32 tile: rows 8*mb + fr, columns 8*nt + 2*fk + {0, 1}
     auto rm_off = [&](int mb, int nt) { return (8 * mb + fr) * SLAB + 8 * nt + 2 * fk; };                       // row-major, double2
     auto fx_off = [&](int mb, int nt, int e) { return ((2 * mb + (fr >> 2)) * 4 + nt) * 32 + (2 * fk + e) * 4 + (fr & 3); };   // fragment order
-
-    double acc[2][2][2], rhs[2][2][2];
+    double acc[SW_RBN][SW_CBN][2], rhs[SW_RBN][SW_CBN][2];
+    auto load_rhs = [&](int r) {
+        const double* g = Xslab + (size_t)r * SW_XTILE;
+#pragma unroll
+        for (int a = 0; a < SW_RBN; ++a)
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) {
+                const double2 v = *reinterpret_cast<const double2*>(g + rm_off(rbs[a], cb0 + b));
+                rhs[a][b][0] = v.x; rhs[a][b][1] = v.y;
+            }
+    };
     {   // right-hand side rows of the first tile row (forward sweeps)
         const uint4 f0 = prog[0];
-        if (n_items > 0 && ((int)f0.z & SW_INIT_RHS)) {
-            const double* g = Xslab + (size_t)(int)f0.x * SW_XTILE;
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const double2 v = *reinterpret_cast<const double2*>(g + rm_off(a ? mb1 : mb0, nt0 + b));
-                    rhs[a][b][0] = v.x; rhs[a][b][1] = v.y;
-                }
-        }
+        if (n_items > 0 && ((int)f0.z & SW_INIT_RHS)) load_rhs((int)f0.x);
     }
     consumer_bar_sync();    // nobody stores a row before every consumer holds its first right-hand side
     int ndiag = 0;
@@ -302,74 +397,75 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         const int row = (int)d0.x, flags = (int)d0.z, xinfo = (int)d0.w;
         if (flags & SW_ROW_BEGIN) {
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+            for (int a = 0; a < SW_RBN; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < SW_CBN; ++b) {
                     acc[a][b][0] = (flags & SW_INIT_RHS) ? rhs[a][b][0] : 0.0;
                     acc[a][b][1] = (flags & SW_INIT_RHS) ? rhs[a][b][1] : 0.0;
                 }
+            // right-hand side of the NEXT row, a whole row ahead (HBM latency).  It must be issued before this row is
+            // published: after that another warp may overwrite that block with Z in fragment order.
+            if ((int)d1.y) load_rhs((int)d1.x);
         }
+        if (profiling) { t0 = clock64(); pc[7] += t0 - t1; t1 = t0; }
         const double* xb = Bs;
         if (flags & SW_DIAG) {
             mbar_wait(bar_bfull, (unsigned)ndiag & 1u);
         } else if (!(flags & SW_NO_OPERAND)) {
             const int slot = xinfo & 0xff;
-            mbar_wait(bar_x + 8 * slot, (unsigned)(xinfo >> 8) & 1u);
+            if (flags & SW_WAIT_X) mbar_wait(bar_x + 8 * slot, (unsigned)(xinfo >> 8) & 1u);
             xb = Xr + slot * SW_XTILE;
         }
         if (profiling) { t0 = clock64(); pc[1] += t0 - t1; }
-        // masks of this warp's two row blocks
-        const unsigned w0 = mb0 < 2 ? mk.x : (mb0 < 4 ? mk.y : (mb0 < 6 ? mk.z : mk.w));
-        const unsigned w1 = mb1 < 2 ? mk.x : (mb1 < 4 ? mk.y : (mb1 < 6 ? mk.z : mk.w));
-        const unsigned m0 = (w0 >> (16 * (mb0 & 1))) & 0xffffu, m1 = (w1 >> (16 * (mb1 & 1))) & 0xffffu;
-        const double* a0p = As + s * SW_TILE + (mb0 * 16) * 32 + lane;
-        const double* a1p = As + s * SW_TILE + (mb1 * 16) * 32 + lane;
-        const double* bp = xb + nt0 * 32 + lane;
-        if (!(flags & SW_NO_OPERAND)) {
-            // warp-uniform dispatch: dense row blocks run the unrolled, register-double-buffered loop; sparse ones the
-            // unrolled loop with one uniform branch per k-group
-            if (m0 == m1) {
-                if (m0 == 0xffffu) sweep_mma_full<true, true>(acc, a0p, a1p, bp);
-                else if (m0) sweep_mma_masked<true, true>(acc, a0p, a1p, bp, m0);
-            } else {
-                if (m0 == 0xffffu) sweep_mma_full<true, false>(acc, a0p, a1p, bp);
-                else if (m0) sweep_mma_masked<true, false>(acc, a0p, a1p, bp, m0);
-                if (m1 == 0xffffu) sweep_mma_full<false, true>(acc, a0p, a1p, bp);
-                else if (m1) sweep_mma_masked<false, true>(acc, a0p, a1p, bp, m1);
-            }
+        // masks of this warp's row blocks
+        const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
+        unsigned m[SW_RBN];
+        bool act[SW_RBN], all_dense = true, dense_or_empty = true, any = false, all_equal = true;
+        const double* ap[SW_RBN];
+#pragma unroll
+        for (int a = 0; a < SW_RBN; ++a) {
+            const int rb = rbs[a];
+            const unsigned w = rb < 2 ? mw[0] : (rb < 4 ? mw[1] : (rb < 6 ? mw[2] : mw[3]));
+            m[a] = (w >> (16 * (rb & 1))) & 0xffffu;
+            act[a] = m[a] == 0xffffu;
+            all_dense = all_dense && act[a];
+            dense_or_empty = dense_or_empty && (act[a] || m[a] == 0u);
+            any = any || m[a] != 0u;
+            all_equal = all_equal && m[a] == m[0];
+            ap[a] = As + s * SW_TILE + (rb * 16) * 32 + lane;
+        }
+        const double* bp = xb + cb0 * 32 + lane;
+        if (any && !(flags & SW_NO_OPERAND)) {
+            if (all_dense) sweep_mma_dense<true>(acc, ap, act, bp);
+            else if (all_equal) sweep_mma_uniform(acc, ap, m[0], bp);
+            else if (SW_RBN == 2) { sweep_mma_single<0>(acc, ap[0], m[0], bp); sweep_mma_single<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp); }
+            else if (dense_or_empty) sweep_mma_dense<false>(acc, ap, act, bp);
+            else sweep_mma_masked(acc, ap, m, bp);
         }
         __syncwarp();
-        if (profiling) { t1 = clock64(); pc[2] += t1 - t0; pc[4] += __popc(m0) + __popc(m1); pc[5] += 1; }
+        if (profiling) {
+            t1 = clock64(); pc[2] += t1 - t0; pc[5] += 1;
+            for (int a = 0; a < SW_RBN; ++a) pc[4] += __popc(m[a]) * SW_CBN;
+        }
         if (lane == 0) {
             mbar_arrive(bar_empty + 8 * s);
             if (flags & SW_DIAG) mbar_arrive(bar_bempty);
         }
         if (flags & SW_DIAG) ++ndiag;
         if (flags & SW_ROW_END) {
-            // right-hand side of the next row first: once this row is published another warp may overwrite that block
-            if ((int)d1.y) {
-                const double* g = Xslab + (size_t)(int)d1.x * SW_XTILE;
-#pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        const double2 v = *reinterpret_cast<const double2*>(g + rm_off(a ? mb1 : mb0, nt0 + b));
-                        rhs[a][b][0] = v.x; rhs[a][b][1] = v.y;
-                    }
-            }
             double* g = Xslab + (size_t)row * SW_XTILE;
             const int oslot = (xinfo >> 16) & 0xff;
             double* xr = Xr + oslot * SW_XTILE;
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+            for (int a = 0; a < SW_RBN; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const int mb = a ? mb1 : mb0, nt = nt0 + b;
+                for (int b = 0; b < SW_CBN; ++b) {
+                    const int mb = rbs[a], nt = cb0 + b;
                     if (flags & SW_OUT_FRAG) { g[fx_off(mb, nt, 0)] = acc[a][b][0]; g[fx_off(mb, nt, 1)] = acc[a][b][1]; }
                     else *reinterpret_cast<double2*>(g + rm_off(mb, nt)) = make_double2(acc[a][b][0], acc[a][b][1]);
                     if (!(flags & SW_NO_RING)) { xr[fx_off(mb, nt, 0)] = acc[a][b][0]; xr[fx_off(mb, nt, 1)] = acc[a][b][1]; }
                 }
-            if (!(flags & SW_NO_RING)) mbar_arrive(bar_x + 8 * oslot);
+            if (!(flags & SW_NO_RING)) { __syncwarp(); if (lane == 0) mbar_arrive(bar_x + 8 * oslot); }
             if (profiling) { t0 = clock64(); pc[3] += t0 - t1; }
         }
     }

@@ -11,7 +11,7 @@ from jacket_b200 import _lib
 
 NB = 64
 RING = 5
-ROW_BEGIN, DIAG, ROW_END, NO_RING, INIT_RHS, OUT_FRAG, NO_OPERAND = 1, 2, 4, 8, 16, 32, 64
+ROW_BEGIN, DIAG, ROW_END, NO_RING, INIT_RHS, OUT_FRAG, NO_OPERAND, WAIT_X = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def program(NT, bw, kx, backward):
@@ -53,11 +53,16 @@ def run_program(items, meta, Lm, X, backward, known_rows=None):
         ring_row[slot], ring_val[slot] = i, X[i * NB:(i + 1) * NB].copy()
         fills[slot] += 1
     acc = None
+    waited = set()      # operand rows some earlier item of the program already waited on
     rhs = X[items[0][0] * NB:(items[0][0] + 1) * NB].copy() if items[0][2] & INIT_RHS else None
     nprod = 0
     for row, src, flags, xinfo, next_row, next_init in items:
         if flags & ROW_BEGIN:
             acc = rhs.copy() if flags & INIT_RHS else np.zeros((NB, X.shape[1]))
+            if next_init:      # the next row's right-hand side is fetched a whole row ahead, before this row is stored
+                rhs = X[next_row * NB:(next_row + 1) * NB].copy()
+        else:
+            assert not next_init
         if flags & DIAG:
             assert backward
             acc += (Linv[row].T @ Linv[row]) @ X[row * NB:(row + 1) * NB]      # operand = Z_k from the slab
@@ -65,7 +70,11 @@ def run_program(items, meta, Lm, X, backward, known_rows=None):
         elif not flags & NO_OPERAND:
             slot, parity = xinfo & 0xFF, (xinfo >> 8) & 1
             assert ring_row[slot] == src, (row, src, slot, ring_row)
-            assert (fills[slot] - 1) & 1 == parity, "mbarrier parity of the operand slot"
+            if flags & WAIT_X:
+                assert (fills[slot] - 1) & 1 == parity, "mbarrier parity of the operand slot"
+                waited.add(src)
+            else:
+                assert src in waited, "operand row used without a wait must have been waited on earlier"
             if backward:
                 A = -Linv[row].T @ tile(Lm, src, row).T
             else:
@@ -73,8 +82,6 @@ def run_program(items, meta, Lm, X, backward, known_rows=None):
             acc += A @ ring_val[slot]
             nprod += 1
         if flags & ROW_END:
-            if next_init:
-                rhs = X[next_row * NB:(next_row + 1) * NB].copy()
             X[row * NB:(row + 1) * NB] = acc
             if not flags & NO_RING:
                 oslot = (xinfo >> 16) & 0xFF
