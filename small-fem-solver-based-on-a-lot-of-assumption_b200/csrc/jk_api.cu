@@ -862,7 +862,7 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
             k_morison_fourier<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, Nh, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, h->d_four, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
         }
     } else {
-        size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + 2) + MCHUNK * 8 + 2 * h->ng) * sizeof(double);
+        size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng) * sizeof(double);
         if (details) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details);
@@ -946,7 +946,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
             for (int q = 0; q < 4; ++q) {
                 if (h->ch[q / 2].sw[q % 2].n_items == 0 || q / 2 >= h->n_chains) continue;
                 fprintf(stderr, "[jk sweep profile] chain %d %s: %d items\n", q / 2, q % 2 ? "backward" : "forward", h->ch[q / 2].sw[q % 2].n_items);
-                for (int w = 0; w < 8; ++w) {
+                for (int w = 0; w < 8; ++w) {   // first eight consumer warps
                     const long long* p = hp + q * 64 + w * 8;
                     fprintf(stderr, "   warp %d: total %lld | wait tile %lld | row begin %lld | wait operand %lld | mma loop %lld | row store %lld | DMMAs %lld | items %lld\n",
                             w, p[6], p[0], p[7], p[1], p[2], p[3], p[4], p[5]);

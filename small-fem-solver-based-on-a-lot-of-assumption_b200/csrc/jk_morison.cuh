@@ -77,6 +77,127 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 //   totpart[chunk][9][ldP] chunk partial sums of drag / inertia / (drag+inertia) in member order
 //   details[m][4][ldP]     optional drag_kN, inertia_kN, total_kN, submerged_length (GUI.py:668-674)
 // ----------------------------------------------------------------------------------------------
+#ifndef JK_MORISON_SSUM
+#define JK_MORISON_SSUM 1
+#endif
+#if JK_MORISON_SSUM
+// Scalar-sum form.  With w^ = wave heading, c = current vector, z^ = vertical and e = member axis, the velocity and
+// acceleration of GUI.py:573-588 are U = uw w^ + c + w z^ and A = du w^ + dw z^, so their components normal to the
+// member (GUI.py:641-642) are U_perp = uw p1 + p0 + w p3 and A_perp = du p1 + dw p3 with the per-member vectors
+// p1 = w^ - (w^.e) e, p0 = c - (c.e) e, p3 = z^ - e_z e, and |U_perp|^2 = U.U - (U.e)^2.  The Gauss sums of
+// GUI.py:648-659 then only need the SCALARS sum(kd), sum(kd uw), sum(kd w), sum(ci du), sum(ci dw) and their
+// s-weighted twins; the 3-vectors are formed once per member.  ~30 % fewer FP64 instructions per point than the
+// component form (morison_point), same results to rounding (1e-15 relative).
+template <bool DETAILS>
+__global__ void __launch_bounds__(PH_TPB)
+k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
+               const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
+               WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
+               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int MS = 16;                                  // per-member constants
+    double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
+    double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][MS]: we ce e2 L | p1[3] p0[3] p3[3] | cD cI
+    double* s_g = s_m + MCHUNK * MS;                       // s[G], w[G]
+    double* s_c = s_g + 2 * G;                             // [MCHUNK][G][3]: cD L w_g, cI L w_g, s_g cI L w_g
+    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
+    int nm = min(MCHUNK, M - m0);
+    for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        const double* c = mc + (size_t)(m0 + i) * MC_STRIDE;
+        const double e0 = c[MC_E], e1 = c[MC_E + 1], e2 = c[MC_E + 2];
+        const double we = fma(wv.sin_w, e1, wv.cos_w * e0), ce = fma(wv.uc_sin_c, e1, wv.uc_cos_c * e0);
+        double* o = s_m + MS * i;
+        o[0] = we; o[1] = ce; o[2] = e2; o[3] = c[MC_L];
+        o[4] = fma(-we, e0, wv.cos_w); o[5] = fma(-we, e1, wv.sin_w); o[6] = -we * e2;            // p1
+        o[7] = fma(-ce, e0, wv.uc_cos_c); o[8] = fma(-ce, e1, wv.uc_sin_c); o[9] = -ce * e2;      // p0
+        o[10] = -e2 * e0; o[11] = -e2 * e1; o[12] = fma(-e2, e2, 1.0);                            // p3
+        o[13] = cD0 * c[MC_D];                             // 0.5*rho*Cd*D      (GUI.py:649)
+        o[14] = cI0 * c[MC_ACROSS];                        // rho*Cm*A_cross    (GUI.py:652)
+    }
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_g[i] = gsw[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nm * G; i += blockDim.x) {
+        const int mm = i / G, g = i % G;
+        const double Lw = s_m[MS * mm + 3] * s_g[G + g];
+        const double cil = s_m[MS * mm + 14] * Lw;
+        s_c[3 * i] = s_m[MS * mm + 13] * Lw; s_c[3 * i + 1] = cil; s_c[3 * i + 2] = s_g[g] * cil;
+    }
+    __syncthreads();
+
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ldP) return;
+    const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
+    const double wc2 = 2.0 * fma(wv.sin_w, wv.uc_sin_c, wv.cos_w * wv.uc_cos_c);       // 2 w^.c
+    const double cc = fma(wv.uc_sin_c, wv.uc_sin_c, wv.uc_cos_c * wv.uc_cos_c);        // c.c
+    double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
+
+    for (int mm = 0; mm < nm; ++mm) {
+        const double* cmem = s_m + MS * mm;
+        const double we = cmem[0], ce = cmem[1], e2 = cmem[2];
+        double Sd0 = 0, Sd1 = 0, Sd3 = 0, Td0 = 0, Td1 = 0, Td3 = 0, Si1 = 0, Si3 = 0, Ti1 = 0, Ti3 = 0;
+        double sub = 0.0;
+        const double* gpm = s_gp + mm * G * GP_STRIDE;
+        const double* cm = s_c + mm * G * 3;
+        for (int g = 0; g < G; ++g) {
+            const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1];
+            const double Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3], z = gpm[g * GP_STRIDE + 4];
+            // cos / sin of (k xw - omega t) at t and t + dt
+            const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
+            if (z > wv.a * c0) continue;                                       // dry at t (GUI.py:265, 292, 627)
+            const double c1 = fma(skx, sw1, ckx * cw1), s1 = fma(skx, cw1, -(ckx * sw1));
+            const bool wet1 = !(z > wv.a * c1);                                // GUI.py:269 at t + dt
+            const double u0 = fma(Cu, c0, wv.Uc), w0 = Cw * s0;                // GUI.py:279-281
+            const double u1 = wet1 ? fma(Cu, c1, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1 : 0.0;
+            const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;   // GUI.py:288
+            const double uw = u0 - wv.Uc;                                      // GUI.py:573
+            const double Ue = fma(w0, e2, fma(uw, we, ce));                    // U.e
+            const double UU = fma(w0, w0, fma(uw, uw + wc2, cc));              // U.U
+            const double mag = sqrt(fmax(fma(-Ue, Ue, UU), 0.0));              // |U_perp|  (GUI.py:647)
+            const double s = s_g[g];
+            const double kd = (mag > 1e-10) ? cm[3 * g] * mag : 0.0;           // GUI.py:648-651
+            const double skd = s * kd;
+            Sd0 += kd; Sd1 = fma(kd, uw, Sd1); Sd3 = fma(kd, w0, Sd3);
+            Td0 += skd; Td1 = fma(skd, uw, Td1); Td3 = fma(skd, w0, Td3);
+            const double cil = cm[3 * g + 1], scil = cm[3 * g + 2];
+            Si1 = fma(cil, du, Si1); Si3 = fma(cil, dw, Si3);
+            Ti1 = fma(scil, du, Ti1); Ti3 = fma(scil, dw, Ti3);
+            if (DETAILS) sub += cmem[3] * s_g[G + g];
+        }
+        const double T1 = Td1 + Ti1, T3 = Td3 + Ti3;
+        double md[3], mi[3];
+        size_t o = ((size_t)(m0 + mm) * 6) * ldP + p;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double p1 = cmem[4 + k], p0 = cmem[7 + k], p3 = cmem[10 + k];
+            md[k] = fma(p3, Sd3, fma(p0, Sd0, p1 * Sd1));
+            mi[k] = fma(p3, Si3, p1 * Si1);
+            const double F2 = fma(p3, T3, fma(p0, Td0, p1 * T1));
+            const double mt = md[k] + mi[k];
+            Fm[o + (size_t)k * ldP] = mt - F2;                                 // F1 = sum (1-s) f   (GUI.py:658)
+            Fm[o + (size_t)(3 + k) * ldP] = F2;                                // F2 = sum s f       (GUI.py:659)
+            td[k] += md[k]; ti[k] += mi[k]; tm[k] += mt;                        // GUI.py:664-666
+        }
+        if (DETAILS) {
+            size_t od = ((size_t)(m0 + mm) * 4) * ldP + p;
+            double mt0 = md[0] + mi[0], mt1 = md[1] + mi[1], mt2 = md[2] + mi[2];
+            details[od] = sqrt(md[0] * md[0] + md[1] * md[1] + md[2] * md[2]) / 1000.0;
+            details[od + ldP] = sqrt(mi[0] * mi[0] + mi[1] * mi[1] + mi[2] * mi[2]) / 1000.0;
+            details[od + 2 * (size_t)ldP] = sqrt(mt0 * mt0 + mt1 * mt1 + mt2 * mt2) / 1000.0;
+            details[od + 3 * (size_t)ldP] = sub;
+        }
+    }
+    size_t ot = ((size_t)chunk * 9) * ldP + p;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        totpart[ot + (size_t)k * ldP] = td[k];
+        totpart[ot + (size_t)(3 + k) * ldP] = ti[k];
+        totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
+    }
+}
+constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 16;   // doubles per member beside the Gauss tables (s_m)
+constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 3;     // doubles per Gauss point beside GP_STRIDE (s_c)
+#else
 template <bool DETAILS>
 __global__ void __launch_bounds__(PH_TPB)
 k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
@@ -161,6 +282,10 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
     }
 }
+
+constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 8;
+constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 2;
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Fourier-series kinematics (Stokes / Fenton form; wrapper semantics of the reference's raschii branch,

@@ -33,6 +33,9 @@ namespace jk {
 // experiment switches (variants are built as separate libraries and selected with JK_LIB; see tools/ab_bench.sh).
 // Measured and dropped: descriptors read from global by the consumers, a test_wait probe of the next tile, a
 // find-first-set walk of sparse masks, 4 stages (all within +-2 % or slower than this configuration).
+#ifndef JK_SW_WARPS
+#define JK_SW_WARPS 16     // consumer warps: 8 (four 8x8 result blocks each) or 16 (two each; four warps per scheduler)
+#endif
 #ifndef JK_SW_RBN
 #define JK_SW_RBN 2        // 8-row blocks per consumer warp: 2 (x two 8-column blocks) or 4 (x one).  4 x 1 balances the schedulers
                            // exactly but needs predicated row blocks in the forward sweeps; measured 4 % slower overall
@@ -43,7 +46,7 @@ namespace jk {
 constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1
 constexpr int SW_MAX_BW = SW_RING - 1;
-constexpr int SW_CONSUMER_WARPS = 8;
+constexpr int SW_CONSUMER_WARPS = JK_SW_WARPS;
 constexpr int SW_CONSUMERS = 32 * SW_CONSUMER_WARPS;
 constexpr int SW_THREADS = SW_CONSUMERS + 32;
 constexpr int SW_TILE = NB * NB;            // doubles per A tile
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(256) k_sweep_build(uint4* __restrict__ prog, d
 
 // Inner products of one item for one consumer warp: acc[a][b] += A(row block a) * X(column block b) over the k-groups.
 // ap[a] / bp point at this lane's element of the first fragment; all further offsets are compile-time constants.
-constexpr int SW_RBN = JK_SW_RBN, SW_CBN = 4 / JK_SW_RBN;
+constexpr int SW_RBN = (JK_SW_WARPS == 16) ? 1 : JK_SW_RBN, SW_CBN = (32 / JK_SW_WARPS) / SW_RBN;
 
 // every row block of the warp is either dense or empty (act[a], warp-uniform): register-double-buffered, fully unrolled
 template <bool ALL>
@@ -354,7 +357,8 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
     int rbs[SW_RBN], cb0;
-    if (SW_RBN == 4) { cb0 = warp & 3; for (int a = 0; a < 4; ++a) rbs[a] = 2 * a + (warp >> 2); }
+    if (SW_CONSUMER_WARPS == 16) { cb0 = 2 * (warp >> 3); rbs[0] = ((warp >> 2) & 1) ? 7 - (warp & 3) : (warp & 3); }   // scheduler s: row blocks s, 7 - s
+    else if (SW_RBN == 4) { cb0 = warp & 3; for (int a = 0; a < SW_RBN; ++a) rbs[a] = 2 * a + (warp >> 2); }
     else { cb0 = 2 * (warp >> 2); rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
     // known rows of a backward sweep that starts below the top (second chain: separator solution): row-major -> ring
     for (int q = 0; q < npre; ++q) {
@@ -438,7 +442,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         if (any && !(flags & SW_NO_OPERAND)) {
             if (all_dense) sweep_mma_dense<true>(acc, ap, act, bp);
             else if (all_equal) sweep_mma_uniform(acc, ap, m[0], bp);
-            else if (SW_RBN == 2) { sweep_mma_single<0>(acc, ap[0], m[0], bp); sweep_mma_single<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp); }
+            else if (SW_RBN <= 2) { sweep_mma_single<0>(acc, ap[0], m[0], bp); sweep_mma_single<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp); }
             else if (dense_or_empty) sweep_mma_dense<false>(acc, ap, act, bp);
             else sweep_mma_masked(acc, ap, m, bp);
         }
@@ -469,7 +473,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             if (profiling) { t0 = clock64(); pc[3] += t0 - t1; }
         }
     }
-    if (profiling && lane == 0) {
+    if (profiling && lane == 0 && warp < 8) {
         pc[6] = clock64() - t_begin;
         for (int i = 0; i < 8; ++i) prof[warp * 8 + i] = pc[i];
     }
