@@ -607,10 +607,13 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
 
 static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d) {
     if (!h->tma_sweep) return JK_OK;
-    for (int c = 0; c < h->n_chains; ++c) {
+    SweepBuildArgs a[2];
+    for (int c = 0; c < 2; ++c) {
         auto& w = h->ch[c].sw[d];
-        if (w.n_items == 0) continue;
-        k_sweep_build<<<w.n_items, 256, SWB_SMEM, s>>>(w.d_prog, w.d_stream, h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, d);
+        a[c] = SweepBuildArgs{w.d_prog, w.d_stream, h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, c < h->n_chains ? w.n_items : 0};
+    }
+    if (a[0].n_items + a[1].n_items > 0) {
+        k_sweep_build<<<a[0].n_items + a[1].n_items, 256, SWB_SMEM, s>>>(a[0], a[1], d);
         LAUNCH_CHECK(h);
     }
     return JK_OK;
@@ -669,9 +672,9 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
             }
         }
     }
-    k_tile_inverse<<<c0.NT, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw);
-    LAUNCH_CHECK(h);
-    if (h->n_chains == 2) { k_tile_inverse<<<c1.kS, 256, INVERSE_SMEM, s>>>(c1.d_tiles, c1.d_Linv, c1.bw); LAUNCH_CHECK(h); }
+    { const int n1 = h->n_chains == 2 ? c1.kS : 0;     // second chain: its separator rows are factored in the first chain
+      k_tile_inverse<<<c0.NT + n1, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw, c0.NT, c1.d_tiles, c1.d_Linv, c1.bw);
+      LAUNCH_CHECK(h); }
     // tile streams of the forward sweeps; the factor timer stops here (this is what the forward sweeps wait for)
     int rc = launch_sweep_build(h, s, 0);
     if (rc != JK_OK) return rc;

@@ -157,11 +157,16 @@ __global__ void __launch_bounds__(128) k_trailing_update(double* __restrict__ ti
 // The sweeps then apply diagonal blocks as DMMA products instead of scalar substitutions.
 // ----------------------------------------------------------------------------------------------
 constexpr size_t INVERSE_SMEM = (size_t)(2 * NB * (NB + 1)) * sizeof(double);
-__global__ void __launch_bounds__(256) k_tile_inverse(const double* __restrict__ tiles, double* __restrict__ Linv, int bw) {
+// Two chains in one launch: blocks [0, n0) invert the diagonal tiles of (tiles, Linv), blocks [n0, gridDim.x) those of
+// (tiles1, Linv1) -- the kernel is a latency chain of 64 steps per tile, so one wave for both chains costs what one costs.
+__global__ void __launch_bounds__(256) k_tile_inverse(const double* __restrict__ tiles, double* __restrict__ Linv, int bw, int n0,
+                                                      const double* __restrict__ tiles1, double* __restrict__ Linv1, int bw1) {
     extern __shared__ __align__(16) double smem[];
     double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem);
     double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem + NB * (NB + 1));
-    const int k = blockIdx.x, tid = threadIdx.x;
+    int k = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (k >= n0) { k -= n0; tiles = tiles1; Linv = Linv1; bw = bw1; }
     const double* g = tiles + tile_off(k, k, bw);
     for (int idx = tid; idx < NB * NB; idx += 256) {
         int r = idx / NB, c = idx % NB;

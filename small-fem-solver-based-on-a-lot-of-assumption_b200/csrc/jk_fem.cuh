@@ -10,6 +10,10 @@
 #pragma once
 #include "jk_common.cuh"
 
+#ifndef JK_POST_PREFETCH
+#define JK_POST_PREFETCH 0   // 1: next member's displacements in flight during this member's arithmetic (96 registers; measured 4 % slower)
+#endif
+
 namespace jk {
 
 // ----------------------------------------------------------------------------------------------
@@ -169,10 +173,7 @@ __device__ __forceinline__ void element_local_forces(const double* __restrict__ 
     Fl[3] = fma(-to, ul[9], to * ul[3]);
     Fl[4] = fma(k2y, ul[10], fma(k6yL, ul[8], fma(k4y, ul[4], -k6yL * ul[2])));
     Fl[5] = fma(k2z, ul[11], fma(-k6zL, ul[7], fma(k4z, ul[5], k6zL * ul[1])));
-    Fl[6] = fma(al, ul[6], -al * ul[0]);
-    Fl[7] = fma(-k6zL, ul[11], fma(k12z, ul[7], fma(-k6zL, ul[5], -k12z * ul[1])));
-    Fl[8] = fma(k6yL, ul[10], fma(k12y, ul[8], fma(k6yL, ul[4], -k12y * ul[2])));
-    Fl[9] = fma(to, ul[9], -to * ul[3]);
+    Fl[6] = -Fl[0]; Fl[7] = -Fl[1]; Fl[8] = -Fl[2]; Fl[9] = -Fl[3];   // bitwise what the mirrored products of GUI.py:406-421 give
     Fl[10] = fma(k4y, ul[10], fma(k6yL, ul[8], fma(k2y, ul[4], -k6yL * ul[2])));
     Fl[11] = fma(k4z, ul[11], fma(-k6zL, ul[7], fma(k2z, ul[5], k6zL * ul[1])));
 }
@@ -189,27 +190,27 @@ __device__ __forceinline__ void stress_point_coeffs(const double* __restrict__ c
     pt[2] = sqrt(fma(y, y, z * z)) * c[MC_IIX];
 }
 
-// 7 result fields of one member from its 12 local end forces (GUI.py:514-532)
+// 7 result fields of one member from its 12 local end forces (GUI.py:514-532).
+// Two exact identities keep the FP64 count down: (1) axial force, shears and torque of node 2 are the bitwise negatives
+// of node 1's (same products, opposite signs, GUI.py:406-421), so max(|n1|, |n2|) = |n1| for those rows; (2) the 8
+// stress points (GUI.py:139-145) lie on one circle in antipodal pairs, so tau is the same at all of them and
+// max_i sigma_i^2 = (|Fx/A| + max_{i<4} |Mz y_i/Iz + My z_i/Iy|)^2 -- 4 bending terms and one square root instead of 8
+// full evaluations (differences to the literal loop: rounding of cos/sin(theta + 180 deg), 1e-16 relative).
 __device__ __forceinline__ void member_row(const double* __restrict__ c, const double* __restrict__ pt, const double* Fl,
                                            double inv_fy, double* row) {
-    // node-1 forces carry the sign flip of GUI.py:428-429
-    double Fx = -Fl[0], Fy = -Fl[1], Fz = -Fl[2], Mx = -Fl[3], My = -Fl[4], Mz = -Fl[5];
-    double sFx = Fx * c[MC_IAX];
-    double tFy = Fy * c[MC_IAY], tFz = Fz * c[MC_IAZ];
-    double tS = fma(tFy, tFy, tFz * tFz);
-    double vm2max = 0.0;
+    // node-1 forces carry the sign flip of GUI.py:428-429 (irrelevant under the squares / absolute values below)
+    const double sFx = fabs(Fl[0] * c[MC_IAX]);
+    const double tFy = Fl[1] * c[MC_IAY], tFz = Fl[2] * c[MC_IAZ];
+    const double tM = Fl[3] * pt[2];
+    const double tau2 = fma(tM, tM, fma(tFy, tFy, tFz * tFz));
+    double bmax = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        double sig = fma(Mz, pt[3 * i], fma(My, pt[3 * i + 1], sFx));
-        double tM = Mx * pt[3 * i + 2];
-        double tau2 = fma(tM, tM, tS);
-        double vm2 = fma(3.0, tau2, sig * sig);
-        vm2max = fmax(vm2max, vm2);
-    }
-    double vm = sqrt(vm2max);
-    row[0] = fmax(fabs(Fl[0]), fabs(Fl[6])) * 1e-3;
-    row[1] = fmax(fabs(Fl[1]), fabs(Fl[7])) * 1e-3;
-    row[2] = fmax(fabs(Fl[2]), fabs(Fl[8])) * 1e-3;
+    for (int i = 0; i < 4; ++i) bmax = fmax(bmax, fabs(fma(Fl[5], pt[3 * i], Fl[4] * pt[3 * i + 1])));
+    const double sig = sFx + bmax;
+    const double vm = sqrt(fma(3.0, tau2, sig * sig));
+    row[0] = fabs(Fl[0]) * 1e-3;
+    row[1] = fabs(Fl[1]) * 1e-3;
+    row[2] = fabs(Fl[2]) * 1e-3;
     row[3] = fmax(fabs(Fl[4]), fabs(Fl[10])) * 1e-6;
     row[4] = fmax(fabs(Fl[5]), fabs(Fl[11])) * 1e-6;
     row[5] = vm;
@@ -247,15 +248,29 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
     if (p >= ldP) return;
     const size_t xbase = (size_t)(p / SLAB) * (size_t)n_pad * SLAB + (size_t)(p % SLAB);
     double best_u = -1.0, best_vm = 0.0; int best_m = 0;
-    for (int mm = 0; mm < nm; ++mm) {
-        const double* c = s_mc + mm * MC_STRIDE;
-        double ue[12], Fl[12], row[7];
-        int s1 = s_slot[2 * mm], s2 = s_slot[2 * mm + 1];
+    auto load_ue = [&](int mm, double* ue) {
+        const int s1 = s_slot[2 * mm], s2 = s_slot[2 * mm + 1];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             ue[k] = s1 >= 0 ? X[xbase + (size_t)(s1 + k) * SLAB] : 0.0;
             ue[6 + k] = s2 >= 0 ? X[xbase + (size_t)(s2 + k) * SLAB] : 0.0;
         }
+    };
+#if JK_POST_PREFETCH
+    double un[12];
+    load_ue(0, un);
+#endif
+    for (int mm = 0; mm < nm; ++mm) {
+        const double* c = s_mc + mm * MC_STRIDE;
+        double ue[12], Fl[12], row[7];
+#if JK_POST_PREFETCH
+        // the next member's displacements are requested before this member's arithmetic (L2 latency under ~150 FP64 ops)
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ue[k] = un[k];
+        if (mm + 1 < nm) load_ue(mm + 1, un);
+#else
+        load_ue(mm, ue);
+#endif
         element_local_forces(c, ue, Fl);
         member_row(c, s_pt + mm * 24, Fl, inv_fy, row);
         size_t o = ((size_t)(m0 + mm) * 7) * ldP + p;

@@ -36,6 +36,9 @@ namespace jk {
 #ifndef JK_SW_WARPS
 #define JK_SW_WARPS 16     // consumer warps: 8 (four 8x8 result blocks each) or 16 (two each; four warps per scheduler)
 #endif
+#ifndef JK_SW_W16_ROWPAIR
+#define JK_SW_W16_ROWPAIR 0   // 16 warps: 1 = each warp owns the row-block pair (s, 7 - s) x one column block; 0 = one row block x two column blocks
+#endif
 #ifndef JK_SW_RBN
 #define JK_SW_RBN 2        // 8-row blocks per consumer warp: 2 (x two 8-column blocks) or 4 (x one).  4 x 1 balances the schedulers
                            // exactly but needs predicated row blocks in the forward sweeps; measured 4 % slower overall
@@ -121,14 +124,21 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 constexpr int SWB_KC = 16;                 // K chunk: small shared-memory footprint, so build CTAs fit beside a sweep CTA on an SM
 constexpr int SWB_PLD = SWB_KC + 1, SWB_QLD = NB + 1;
 constexpr size_t SWB_SMEM = (size_t)(NB * SWB_PLD + SWB_KC * SWB_QLD) * sizeof(double);
-__global__ void __launch_bounds__(256) k_sweep_build(uint4* __restrict__ prog, double* __restrict__ stream,
-                                                     const double* __restrict__ tiles, const double* __restrict__ Linv,
-                                                     int bw, int backward) {
+struct SweepBuildArgs { uint4* prog; double* stream; const double* tiles; const double* Linv; int bw, n_items; };
+// blocks [0, a.n_items) build the stream of program a, the rest that of program b (both chains in one wave)
+__global__ void __launch_bounds__(256) k_sweep_build(SweepBuildArgs a, SweepBuildArgs b, int backward) {
     extern __shared__ __align__(16) double smem[];
     double* Ps = smem;                    // P[r][m - m0]   (NB x SWB_KC)
     double* Qs = smem + NB * SWB_PLD;     // Q[m - m0][c]   (SWB_KC x NB)
     __shared__ unsigned msk[8];
-    const int n = blockIdx.x, tid = threadIdx.x;
+    int n = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (n >= a.n_items) { n -= a.n_items; a = b; }
+    uint4* __restrict__ prog = a.prog;
+    double* __restrict__ stream = a.stream;
+    const double* __restrict__ tiles = a.tiles;
+    const double* __restrict__ Linv = a.Linv;
+    const int bw = a.bw;
     const uint4 it = prog[(size_t)n * SW_ITEM_U4];
     const int row = (int)it.x, src = (int)it.y, flags = (int)it.z;
     double* out = stream + (size_t)n * SW_TILE;
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(256) k_sweep_build(uint4* __restrict__ prog, d
 
 // Inner products of one item for one consumer warp: acc[a][b] += A(row block a) * X(column block b) over the k-groups.
 // ap[a] / bp point at this lane's element of the first fragment; all further offsets are compile-time constants.
-constexpr int SW_RBN = (JK_SW_WARPS == 16) ? 1 : JK_SW_RBN, SW_CBN = (32 / JK_SW_WARPS) / SW_RBN;
+constexpr int SW_RBN = (JK_SW_WARPS == 16 && JK_SW_RBN > 2) ? 1 : ((JK_SW_WARPS == 16 && JK_SW_RBN == 2 && !JK_SW_W16_ROWPAIR) ? 1 : JK_SW_RBN), SW_CBN = (32 / JK_SW_WARPS) / SW_RBN;
 
 // every row block of the warp is either dense or empty (act[a], warp-uniform): register-double-buffered, fully unrolled
 template <bool ALL>
@@ -357,7 +367,8 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
     int rbs[SW_RBN], cb0;
-    if (SW_CONSUMER_WARPS == 16) { cb0 = 2 * (warp >> 3); rbs[0] = ((warp >> 2) & 1) ? 7 - (warp & 3) : (warp & 3); }   // scheduler s: row blocks s, 7 - s
+    if (SW_CONSUMER_WARPS == 16 && SW_RBN == 2) { cb0 = warp >> 2; rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
+    else if (SW_CONSUMER_WARPS == 16) { cb0 = 2 * (warp >> 3); rbs[0] = ((warp >> 2) & 1) ? 7 - (warp & 3) : (warp & 3); }   // scheduler s: row blocks s, 7 - s
     else if (SW_RBN == 4) { cb0 = warp & 3; for (int a = 0; a < SW_RBN; ++a) rbs[a] = 2 * a + (warp >> 2); }
     else { cb0 = 2 * (warp >> 2); rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
     // known rows of a backward sweep that starts below the top (second chain: separator solution): row-major -> ring
