@@ -206,9 +206,11 @@ int jk_residual(jk_handle_t h, double* rel_residual);
 int jk_solver_stats(jk_handle_t h, double* out /* [4] */);
 /* Host-only introspection of the sweep item list (no device needed; used by the CPU tests): the program the TMA
  * sweep runs for a chain of n_tiles tile rows, tile half-bandwidth band_tiles, first partial / known tile row kx
- * (= n_tiles for a plain sweep).  items[6*i..] = row, src, flags, xinfo, next_row, next_init; meta[3] = first known
+ * (= n_tiles for a plain sweep), first_tile[n_tiles] (nullable) = first tile column of every tile row's envelope (tiles
+ * left of it are not visited; the tile next to the diagonal always is).  items[6*i..] = row, src, flags, xinfo, next_row, next_init; meta[3] = first known
  * row, known rows preloaded, top row of the ring numbering.  Returns the item count (items may be NULL to size). */
-int jk_sweep_program(int n_tiles, int band_tiles, int kx, int backward, int32_t* items, int cap_items, int32_t* meta);
+int jk_sweep_program(int n_tiles, int band_tiles, int kx, int backward, const int32_t* first_tile, int32_t* items, int cap_items,
+                     int32_t* meta);
 /* kernels launched by this handle since creation (bench "gpu_launches") */
 int64_t jk_launch_count(jk_handle_t h);
 void* jk_stream(jk_handle_t h);

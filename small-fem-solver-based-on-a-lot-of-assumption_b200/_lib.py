@@ -81,7 +81,7 @@ def _sig(lib):
     lib.jk_get_timings.argtypes = [H, _dp]
     lib.jk_residual.argtypes = [H, _dp]
     lib.jk_solver_stats.argtypes = [H, _dp]
-    lib.jk_sweep_program.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip]
+    lib.jk_sweep_program.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _ip]
     lib.jk_sweep_program.restype = C.c_int
     lib.jk_launch_count.argtypes = [H]
     lib.jk_launch_count.restype = C.c_int64

@@ -355,7 +355,10 @@ static void order_quality(int Nn, const std::vector<int>& conn, const std::vecto
 
 // Item list of one sweep of one chain (see jk_sweep.cuh).  kx = first partial (forward) / known (backward) tile row,
 // NT for a plain sweep.  Ring slots follow the processing order: seq(k) = k (forward) or ktop - k (backward).
-static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vector<uint4>& prog, int& pre_row, int& npre, int& ktop) {
+// jmin (nullable, [NT]): first tile column in which tile row k of the factor can hold a non-zero (row envelope of
+// the chain, no fill outside it): tiles left of it are dropped from the program.  The tile next to the diagonal is
+// always kept -- the last item of a row waiting on the row before it is what orders the ring and the slab updates.
+static void build_sweep_program(int NT, int bw, int kx, bool backward, const int* jmin, std::vector<uint4>& prog, int& pre_row, int& npre, int& ktop) {
     prog.clear();
     auto push = [&](int row, int src, int flags, int xinfo, int next_row, int next_init) {
         prog.push_back(make_uint4((unsigned)row, (unsigned)src, (unsigned)flags, (unsigned)xinfo));
@@ -363,6 +366,7 @@ static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vect
         prog.push_back(make_uint4(0u, 0u, 0u, 0u));
     };
     auto slotinfo = [&](int seq) { return (seq % SW_RING) | (((seq / SW_RING) & 1) << 8); };
+    auto first_col = [&](int k) { return jmin ? std::max(0, std::min(jmin[k], k)) : 0; };
     // a consumer warp has to wait on an operand row's mbarrier only the first time the program uses that row (program
     // order = every warp's order, and a row solved earlier was waited on when the row after it was finished)
     std::vector<char> waited(NT, 0);
@@ -370,11 +374,14 @@ static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vect
     if (!backward) {
         pre_row = 0; npre = 0; ktop = 0;
         for (int k = 0; k < NT; ++k) {
-            const int lo = std::max(0, k - bw), hi = std::min(k - 1, kx - 1);
             const bool partial = k >= kx, has_next = k + 1 < NT;
+            const int hi = std::min(k - 1, kx - 1);
+            int lo = std::max(std::max(0, k - bw), first_col(k));
+            if (!partial) lo = std::min(lo, k - 1);                 // always keep (k, k-1)
             const int end_flags = SW_ROW_END | (partial ? SW_NO_RING : SW_OUT_FRAG);
             const int out = (k % SW_RING) << 16;
-            if (hi < lo) { push(k, k, SW_ROW_BEGIN | SW_INIT_RHS | SW_NO_OPERAND | end_flags, out, has_next ? k + 1 : 0, has_next ? 1 : 0); continue; }
+            if (hi < lo || hi < 0) { push(k, k, SW_ROW_BEGIN | SW_INIT_RHS | SW_NO_OPERAND | end_flags, out, has_next ? k + 1 : 0, has_next ? 1 : 0); continue; }
+            lo = std::max(lo, 0);
             for (int j = lo; j <= hi; ++j) {
                 int flags = (j == lo ? (SW_ROW_BEGIN | SW_INIT_RHS) : 0) | (j == hi ? end_flags : 0) | need_wait(j);
                 push(k, j, flags, slotinfo(j) | out, has_next ? k + 1 : 0, (j == lo && has_next) ? 1 : 0);   // next row's RHS is fetched at ROW_BEGIN
@@ -388,9 +395,25 @@ static void build_sweep_program(int NT, int bw, int kx, bool backward, std::vect
             const int hi = std::min(NT - 1, std::min(k + bw, ktop));
             const int out = ((ktop - k) % SW_RING) << 16;
             push(k, k, SW_ROW_BEGIN | SW_DIAG | (hi < k + 1 ? SW_ROW_END : 0), out, 0, 0);
-            for (int i = hi; i >= k + 1; --i) push(k, i, (i == k + 1 ? SW_ROW_END : 0) | need_wait(i), slotinfo(ktop - i) | out, 0, 0);
+            for (int i = hi; i >= k + 1; --i) {
+                if (i != k + 1 && first_col(i) > k) continue;       // tile (i, k) lies left of row i's envelope
+                push(k, i, (i == k + 1 ? SW_ROW_END : 0) | need_wait(i), slotinfo(ktop - i) | out, 0, 0);
+            }
         }
     }
+}
+
+// First tile column of every tile row of a chain's factor.  node_first[s] = lowest chain slot coupled to slot s (<= s);
+// Cholesky fills the row envelope and nothing left of it.
+static std::vector<int> chain_tile_reach(int NT, int n_nodes_chain, const std::vector<int>& node_first) {
+    std::vector<int> jmin(NT);
+    for (int k = 0; k < NT; ++k) {
+        int reach = k * NB;                                        // padded rows: identity
+        const int n_lo = (k * NB) / 6, n_hi = std::min(n_nodes_chain - 1, (k * NB + NB - 1) / 6);
+        for (int nd = n_lo; nd <= n_hi; ++nd) reach = std::min(reach, 6 * node_first[nd]);
+        jmin[k] = reach / NB;
+    }
+    return jmin;
 }
 
 extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_nodes, int ordering, int solver) {
@@ -552,6 +575,23 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         CUDA_TRY(h, cudaMemcpyAsync(chn.d_blocks, blocks[c].data(), blocks[c].size() * sizeof(KBlock), cudaMemcpyHostToDevice, s));
         CUDA_TRY(h, cudaMemcpyAsync(chn.d_contrib, contribs[c].data(), contribs[c].size() * sizeof(int2), cudaMemcpyHostToDevice, s));
     }
+    // row envelope of each chain's factor at tile granularity (symbolic: no fill left of a row's first coupled slot;
+    // the separator block of the first chain is dense once the second chain's Schur complement is merged in)
+    std::vector<int> tile_reach[2];
+    for (int c = 0; c < h->n_chains; ++c) {
+        const std::vector<int>& sl = c == 0 ? slot0 : slot1;
+        const int nn = c == 0 ? nA + nS : nB + nS;
+        std::vector<int> node_first(nn);
+        for (int i = 0; i < nn; ++i) node_first[i] = i;
+        for (int m = 0; m < h->M; ++m) {
+            int s0 = sl[h->h_conn[2 * m]], s1 = sl[h->h_conn[2 * m + 1]];
+            if (s0 < 0 || s1 < 0) continue;
+            int hi = std::max(s0, s1), lo = std::min(s0, s1);
+            node_first[hi] = std::min(node_first[hi], lo);
+        }
+        if (h->n_chains == 2) { const int sep0 = c == 0 ? nA : nB; for (int i = sep0; i < nn; ++i) node_first[i] = std::min(node_first[i], sep0); }
+        tile_reach[c] = chain_tile_reach(h->ch[c].NT, nn, node_first);
+    }
     // sweep programs: the TMA pipeline keeps the last SW_RING solved tiles in shared memory, so it needs a narrow band
     h->tma_sweep = getenv("JK_SWEEP_LEGACY") == nullptr;
     for (int c = 0; c < h->n_chains; ++c) if (h->ch[c].bw > SW_MAX_BW) h->tma_sweep = false;
@@ -564,7 +604,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
             std::vector<uint4> prog;
             // the first chain sweeps all its rows (its separator rows are ordinary rows once the chains are merged);
             // the second chain's separator rows are partial (forward) / known (backward)
-            build_sweep_program(chn.NT, chn.bw, c == 0 ? chn.NT : chn.kS, d == 1, prog, w.pre_row, w.npre, w.ktop);
+            build_sweep_program(chn.NT, chn.bw, c == 0 ? chn.NT : chn.kS, d == 1, tile_reach[c].data(), prog, w.pre_row, w.npre, w.ktop);
             w.n_items = (int)prog.size() / SW_ITEM_U4;
             if (w.n_items == 0) continue;
             CUDA_TRY(h, dev_alloc(&w.d_prog, prog.size()));
@@ -1301,11 +1341,12 @@ extern "C" int jk_get_dims(jk_handle_t h, int32_t* out) {
     return JK_OK;
 }
 
-extern "C" int jk_sweep_program(int n_tiles, int band_tiles, int kx, int backward, int32_t* items, int cap_items, int32_t* meta) {
+extern "C" int jk_sweep_program(int n_tiles, int band_tiles, int kx, int backward, const int32_t* first_tile, int32_t* items, int cap_items,
+                                int32_t* meta) {
     if (n_tiles <= 0 || band_tiles < 0 || band_tiles > SW_MAX_BW || kx < 0 || kx > n_tiles) return JK_EINVAL;
     std::vector<uint4> prog;
     int pre_row = 0, npre = 0, ktop = 0;
-    build_sweep_program(n_tiles, band_tiles, kx, backward != 0, prog, pre_row, npre, ktop);
+    build_sweep_program(n_tiles, band_tiles, kx, backward != 0, first_tile, prog, pre_row, npre, ktop);
     const int n = (int)prog.size() / SW_ITEM_U4;
     if (meta) { meta[0] = pre_row; meta[1] = npre; meta[2] = ktop; }
     if (items) {

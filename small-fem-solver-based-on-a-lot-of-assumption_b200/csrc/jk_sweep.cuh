@@ -31,20 +31,21 @@
 namespace jk {
 
 // experiment switches (variants are built as separate libraries and selected with JK_LIB; see tools/ab_bench.sh).
-// Measured and dropped: descriptors read from global by the consumers, a test_wait probe of the next tile, a
-// find-first-set walk of sparse masks, 4 stages (all within +-2 % or slower than this configuration).
+// Measured and dropped (tools/ab_bench.sh, c4 workload): descriptors read from global by the consumers (-1 %), a
+// test_wait probe of the next tile before the products (-3 %), a find-first-set walk of sparse masks (-2 %), 8 warps
+// with 4 x 1 row blocks (-4 %).  Kept: 16 consumer warps (+3 % over 8), row-block pairs per warp and 4 stages (+1 %).
 #ifndef JK_SW_WARPS
 #define JK_SW_WARPS 16     // consumer warps: 8 (four 8x8 result blocks each) or 16 (two each; four warps per scheduler)
 #endif
 #ifndef JK_SW_W16_ROWPAIR
-#define JK_SW_W16_ROWPAIR 0   // 16 warps: 1 = each warp owns the row-block pair (s, 7 - s) x one column block; 0 = one row block x two column blocks
+#define JK_SW_W16_ROWPAIR 1   // 16 warps: 1 = each warp owns the row-block pair (s, 7 - s) x one column block; 0 = one row block x two column blocks
 #endif
 #ifndef JK_SW_RBN
 #define JK_SW_RBN 2        // 8-row blocks per consumer warp: 2 (x two 8-column blocks) or 4 (x one).  4 x 1 balances the schedulers
                            // exactly but needs predicated row blocks in the forward sweeps; measured 4 % slower overall
 #endif
 #ifndef JK_SW_STAGES
-#define JK_SW_STAGES 3
+#define JK_SW_STAGES 4
 #endif
 constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1

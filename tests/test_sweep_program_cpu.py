@@ -14,13 +14,14 @@ RING = 5
 ROW_BEGIN, DIAG, ROW_END, NO_RING, INIT_RHS, OUT_FRAG, NO_OPERAND, WAIT_X = 1, 2, 4, 8, 16, 32, 64, 128
 
 
-def program(NT, bw, kx, backward):
+def program(NT, bw, kx, backward, first_tile=None):
     lib = _lib.lib()
     meta = np.zeros(3, dtype=np.int32)
-    n = lib.jk_sweep_program(NT, bw, kx, int(backward), None, 0, _lib.iptr(meta))
+    ft = None if first_tile is None else np.ascontiguousarray(first_tile, dtype=np.int32)
+    n = lib.jk_sweep_program(NT, bw, kx, int(backward), _lib.iptr(ft), None, 0, _lib.iptr(meta))
     assert n > 0
     items = np.zeros(6 * n, dtype=np.int32)
-    assert lib.jk_sweep_program(NT, bw, kx, int(backward), _lib.iptr(items), n, _lib.iptr(meta)) == n
+    assert lib.jk_sweep_program(NT, bw, kx, int(backward), _lib.iptr(ft), _lib.iptr(items), n, _lib.iptr(meta)) == n
     return items.reshape(n, 6), meta
 
 
@@ -142,5 +143,69 @@ def test_partial_forward_and_known_backward(NT, bw, kx):
 
 def test_program_rejects_wide_bands():
     lib = _lib.lib()
-    assert lib.jk_sweep_program(8, 5, 8, 0, None, 0, None) < 0
-    assert lib.jk_sweep_program(0, 1, 0, 0, None, 0, None) < 0
+    assert lib.jk_sweep_program(8, 5, 8, 0, None, None, 0, None) < 0
+    assert lib.jk_sweep_program(0, 1, 0, 0, None, None, 0, None) < 0
+
+
+def ragged_spd(NT, bw, rng):
+    """SPD matrix whose row envelope varies from row to row (like a frame: some rows reach far back, most do not)."""
+    n = NT * NB
+    A = np.zeros((n, n))
+    hbmax = bw * NB - 7
+    for i in range(n):
+        reach = hbmax if (i // 6) % 5 == 0 else int(rng.integers(3, max(4, hbmax // 3)))
+        lo = max(0, i - reach)
+        A[i, lo:i] = rng.standard_normal(i - lo) * 0.1
+    A = A + A.T + np.eye(n) * (2.0 + 0.2 * hbmax)
+    return A
+
+
+def first_tiles(A):
+    n = A.shape[0]
+    first = np.array([np.flatnonzero(A[i, :i + 1])[0] for i in range(n)])
+    return np.array([first[k * NB:(k + 1) * NB].min() // NB for k in range(n // NB)], dtype=np.int32)
+
+
+@pytest.mark.parametrize("NT,bw,kx", [(11, 4, 11), (9, 3, 9), (12, 4, 8), (7, 2, 4)])
+def test_envelope_drops_empty_tiles_and_still_solves(NT, bw, kx):
+    """With the row envelope given, tiles left of it are not visited (fewer items) and the sweeps still solve the
+    system: Cholesky never fills outside the envelope."""
+    rng = np.random.default_rng(7 * NT + kx)
+    A = ragged_spd(NT, bw, rng)
+    # make some far tiles structurally empty: rows of every third tile row only reach one tile back
+    for k in range(2, NT, 3):
+        A[k * NB:(k + 1) * NB, :(k - 1) * NB] = 0.0
+        A[:(k - 1) * NB, k * NB:(k + 1) * NB] = 0.0
+    Lm = np.linalg.cholesky(A)
+    ft = first_tiles(A)
+    assert np.array_equal(first_tiles(np.where(np.abs(Lm) > 0, 1.0, 0.0)), ft)        # no fill left of the envelope
+    B = rng.standard_normal((NT * NB, 4))
+    f_all, _ = program(NT, bw, kx, False)
+    f, mf = program(NT, bw, kx, False, ft)
+    b_all, _ = program(NT, bw, kx, True)
+    b, mb = program(NT, bw, kx, True, ft)
+    assert len(f) < len(f_all) and len(b) < len(b_all)
+    # every normal row still ends on the tile next to the diagonal (the item that orders ring and slab updates)
+    for items, step in ((f, -1), (b, 1)):
+        for row, src, fl, *_ in items:
+            if fl & ROW_END and not fl & (NO_RING | NO_OPERAND) and not (fl & DIAG):
+                assert src == row + step
+    X = B.copy()
+    run_program(f, mf, Lm, X, False)
+    n1 = kx * NB
+    Y1 = np.linalg.solve(Lm[:n1, :n1], B[:n1])
+    for k in range(kx):
+        np.testing.assert_allclose(X[k * NB:(k + 1) * NB], tile(Lm, k, k) @ Y1[k * NB:(k + 1) * NB], rtol=1e-9, atol=1e-11)
+    if kx < NT:
+        np.testing.assert_allclose(X[n1:], B[n1:] - Lm[n1:, :n1] @ Y1, rtol=1e-9, atol=1e-11)
+        Xtrue = np.linalg.solve(Lm.T, rng.standard_normal((NT * NB, 4)))
+        Yfull = Lm.T @ Xtrue
+        S = np.zeros_like(Yfull)
+        for k in range(kx):
+            S[k * NB:(k + 1) * NB] = tile(Lm, k, k) @ Yfull[k * NB:(k + 1) * NB]
+        S[n1:] = Xtrue[n1:]
+        run_program(b, mb, Lm, S, True)
+        np.testing.assert_allclose(S[:n1], Xtrue[:n1], rtol=1e-8, atol=1e-10)
+    else:
+        run_program(b, mb, Lm, X, True)
+        np.testing.assert_allclose(X, np.linalg.solve(A, B), rtol=1e-9, atol=1e-11)
