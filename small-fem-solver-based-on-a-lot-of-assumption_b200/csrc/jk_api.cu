@@ -29,6 +29,7 @@ struct jk_handle_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;        // side stream: the factorisation runs here, concurrently with the Morison stage
+    cudaEvent_t ev_post_fork = nullptr, ev_post_join = nullptr;   // node-level post kernels run beside the member post on the side stream
     cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_factor_bwd = nullptr;   // ev_factor: forward sweeps may start; ev_factor_bwd: backward tile streams built too
     bool factor_inflight = false;
     std::string err;
@@ -172,6 +173,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_factor_bwd, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_post_join, cudaEventDisableTiming);
     h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
     h->h_xyz.assign(xyz, xyz + 3 * (size_t)n_nodes);
     h->h_conn.assign(conn, conn + 2 * (size_t)n_members);
@@ -241,6 +244,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_factor) cudaEventDestroy(h->ev_factor);
     if (h->ev_factor_bwd) cudaEventDestroy(h->ev_factor_bwd);
+    if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
+    if (h->ev_post_join) cudaEventDestroy(h->ev_post_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JK_OK;
@@ -1022,17 +1027,23 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     toc(h, JK_T_SOLVE_BWD);
     }
     tic(h, JK_T_POST);
+    // the two small node-level kernels (max translation, reactions) only read the solution: they run on the side stream
+    // beside the member post-processing
+    cudaStream_t s2 = h->stream2 ? h->stream2 : s;
+    if (s2 != s) { CUDA_TRY(h, cudaEventRecord(h->ev_post_fork, s)); CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_post_fork, 0)); }
+    dim3 gn(ceil_div(h->Nn, NCHUNK), ceil_div(ldP, PH_TPB));
+    k_node_post<<<gn, PH_TPB, 0, s2>>>(h->Nn, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_part_disp, h->d_part_node);
+    LAUNCH_CHECK(h);
+    dim3 gr(ceil_div(ldP, PH_TPB), h->n_fixed);
+    k_node_residual<<<gr, PH_TPB, 0, s2>>>(h->n_fixed, h->d_fixed_nodes, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn,
+                                           h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Ffix, h->d_react);
+    LAUNCH_CHECK(h);
+    if (s2 != s) CUDA_TRY(h, cudaEventRecord(h->ev_post_join, s2));
     dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, PH_TPB));
     k_member_post<<<gm, PH_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
                                         h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
     LAUNCH_CHECK(h);
-    dim3 gn(ceil_div(h->Nn, NCHUNK), ceil_div(ldP, PH_TPB));
-    k_node_post<<<gn, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_part_disp, h->d_part_node);
-    LAUNCH_CHECK(h);
-    dim3 gr(ceil_div(ldP, PH_TPB), h->n_fixed);
-    k_node_residual<<<gr, PH_TPB, 0, s>>>(h->n_fixed, h->d_fixed_nodes, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn,
-                                          h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Ffix, h->d_react);
-    LAUNCH_CHECK(h);
+    if (s2 != s) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_post_join, 0));
     toc(h, JK_T_POST);
     return JK_OK;
 }

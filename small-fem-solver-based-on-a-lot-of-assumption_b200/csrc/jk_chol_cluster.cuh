@@ -104,12 +104,14 @@ __device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, in
                 }
             }
             if (lane == 0) {
+                // 16-byte stores, lower triangle only (the entry just above the diagonal that a pair may cover gets 0;
+                // the rest of Dp's upper triangle is zeroed once by the caller): 40 stores instead of 100 on the chain
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j <= i) T[(c0 + i) * LS_LD + c0 + j] = d[i][j];
-                        Dp[i * DI_LD + j] = (j <= i) ? m[i][j] : 0.0;
+                    for (int j = 0; j <= i; j += 2) {
+                        *reinterpret_cast<double2*>(T + (c0 + i) * LS_LD + c0 + j) = make_double2(d[i][j], j + 1 <= i ? d[i][j + 1] : 0.0);
+                        *reinterpret_cast<double2*>(Dp + i * DI_LD + j) = make_double2(m[i][j], j + 1 <= i ? m[i][j + 1] : 0.0);
                     }
             }
         }
@@ -228,6 +230,8 @@ k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
         for (int q = tid; q < 512; q += CHOL_THREADS) { int b = q >> 6, r = (q >> 3) & 7, c = q & 7; Di[b * DI_BLK + r * DI_LD + c] = __ldcg(g + q); }
     };
 
+    for (int q = tid; q < 8 * DI_BLK; q += CHOL_THREADS) Di[q] = 0.0;    // potrf64_smem only writes the lower triangles
+    __syncthreads();
     if (cta == 0 && ch.k_begin < ch.k_end) {                 // prologue: potrf(k_begin)
         load_tile_async(Cs, tiles + tile_off(ch.k_begin, ch.k_begin, bw), tid, CHOL_THREADS);
         cp_async_commit(); cp_async_wait<0>();
