@@ -496,6 +496,8 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
     double sw0, cw0, sw1, cw1;
     { double tt = t[cc]; sincos(om * tt, &sw0, &cw0); sincos(om * (tt + wv.dt), &sw1, &cw1); }
     double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
+    const double wc2 = 2.0 * fma(sw, wv.uc_sin_c, cw * wv.uc_cos_c);                   // 2 w^.c for this state's heading
+    const double ucuc = fma(wv.uc_sin_c, wv.uc_sin_c, wv.uc_cos_c * wv.uc_cos_c);      // c.c
 
     for (int sub = 0; sub < nm; sub += ENS_EM) {
         const int nsub = min(ENS_EM, nm - sub);
@@ -524,30 +526,45 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
             const int mm = sub + ms;
             const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
             const double cDL = s_m[8 * mm + 3] * s_m[8 * mm + 5], cIL = s_m[8 * mm + 4] * s_m[8 * mm + 5];
-            MemberAcc A = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            // scalar-sum form (see k_morison_airy); the wave heading differs per sea state, so w^.e and p1 are per thread
+            const double we = fma(sw, e1, cw * e0), ce = fma(wv.uc_sin_c, e1, wv.uc_cos_c * e0);
+            double Sd0 = 0, Sd1 = 0, Sd3 = 0, Td0 = 0, Td1 = 0, Td3 = 0, Si1 = 0, Si3 = 0, Ti1 = 0, Ti3 = 0;
             for (int g = 0; g < G; ++g) {
                 const double* q = s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4;
                 const double ckx = q[0], skx = q[1], Cu = q[2], Cw = q[3], z = s_z[ms * G + g];
                 const double c0v = fma(skx, sw0, ckx * cw0), s0v = fma(skx, cw0, -(ckx * sw0));
-                const double eta0 = a * c0v;
-                if (z > eta0) continue;
+                if (z > a * c0v) continue;
                 const double c1v = fma(skx, sw1, ckx * cw1), s1v = fma(skx, cw1, -(ckx * sw1));
                 const bool wet1 = !(z > a * c1v);
                 const double u0 = fma(Cu, c0v, wv.Uc), w0 = Cw * s0v;
                 const double u1 = wet1 ? fma(Cu, c1v, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1v : 0.0;
                 const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;
-                const double uwo = u0 - wv.Uc;
-                const double wg = s_g[G + g];
-                morison_point(A, fma(uwo, cw, wv.uc_cos_c), fma(uwo, sw, wv.uc_sin_c), w0, du * cw, du * sw, dw,
-                              e0, e1, e2, cDL * wg, cIL * wg, s_g[g]);
+                const double uw = u0 - wv.Uc;
+                const double wg = s_g[G + g], sg = s_g[g];
+                const double Ue = fma(w0, e2, fma(uw, we, ce));
+                const double UU = fma(w0, w0, fma(uw, uw + wc2, ucuc));
+                const double mag = sqrt(fmax(fma(-Ue, Ue, UU), 0.0));
+                const double kd = (mag > 1e-10) ? (cDL * wg) * mag : 0.0;
+                const double skd = sg * kd, cil = cIL * wg, scil = sg * cil;
+                Sd0 += kd; Sd1 = fma(kd, uw, Sd1); Sd3 = fma(kd, w0, Sd3);
+                Td0 += skd; Td1 = fma(skd, uw, Td1); Td3 = fma(skd, w0, Td3);
+                Si1 = fma(cil, du, Si1); Si3 = fma(cil, dw, Si3);
+                Ti1 = fma(scil, du, Ti1); Ti3 = fma(scil, dw, Ti3);
             }
+            const double p1[3] = {fma(-we, e0, cw), fma(-we, e1, sw), -we * e2};
+            const double p0[3] = {fma(-ce, e0, wv.uc_cos_c), fma(-ce, e1, wv.uc_sin_c), -ce * e2};
+            const double p3[3] = {-e2 * e0, -e2 * e1, fma(-e2, e2, 1.0)};
+            const double T1 = Td1 + Ti1, T3 = Td3 + Ti3;
             size_t o = ((size_t)(m0 + mm) * 6) * ldC + cidx;
 #pragma unroll
             for (int kq = 0; kq < 3; ++kq) {
-                const double mt = A.md[kq] + A.mi[kq];
-                Fm[o + (size_t)kq * ldC] = mt - A.F2[kq];
-                Fm[o + (size_t)(3 + kq) * ldC] = A.F2[kq];
-                td[kq] += A.md[kq]; ti[kq] += A.mi[kq]; tm[kq] += mt;
+                const double md = fma(p3[kq], Sd3, fma(p0[kq], Sd0, p1[kq] * Sd1));
+                const double mi = fma(p3[kq], Si3, p1[kq] * Si1);
+                const double F2 = fma(p3[kq], T3, fma(p0[kq], Td0, p1[kq] * T1));
+                const double mt = md + mi;
+                Fm[o + (size_t)kq * ldC] = mt - F2;
+                Fm[o + (size_t)(3 + kq) * ldC] = F2;
+                td[kq] += md; ti[kq] += mi; tm[kq] += mt;
             }
         }
     }
