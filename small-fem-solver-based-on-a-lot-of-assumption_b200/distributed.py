@@ -104,13 +104,24 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
     import torch.distributed as dist
     lo, hi = shard_bounds(n_total, world_size, rank)
     P = hi - lo
+    host_table = host_crit = None
     if t_dev is not None:
         engine.phase_scan_dev(P, t_dev, fy)
     else:
         if t_host is None:
             t_host, _ = shard_times(wave.T, n_total, world_size, rank)
-        engine.phase_scan(t_host, fy)
+        host_table, host_crit = engine.phase_scan(t_host, fy)       # already copies table + critical index to the host
     table, val, idx = device_views(engine, P)
+    if world_size == 1:
+        # nothing to exchange: no all-gather, no merge kernels, and the table is copied to the host at most once
+        if not host_results:
+            return dict(local_table=table, offset=lo, critical_value=val.reshape(()), critical_index=(idx + lo).reshape(()),
+                        table=table if gather_table else None)
+        if host_table is None:
+            host_table, host_crit = engine.read_table(P)
+        fill_phase_deg(host_table, wave.omega)
+        return dict(local_table=table, offset=lo, critical_value=float(host_table[host_crit, 2]), critical_index=int(host_crit) + lo,
+                    table=host_table if gather_table else None)
     stream = torch.cuda.ExternalStream(engine.stream(), device=f"cuda:{engine.device}")
     with torch.cuda.stream(stream):
         cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=host_results)

@@ -399,3 +399,29 @@ def test_tma_sweep_matches_legacy_sweep(legs, bays, single_chain):
     for n in out["tma"][2]:
         assert relmax(out["tma"][2][n], out["legacy"][2][n]) < 1e-10
     assert out["tma"][4] < 1e-9 and out["legacy"][4] < 1e-9
+
+
+def test_single_rank_sharded_scan_paths_agree():
+    """world_size 1: the host path (one table copy, no merge kernels) and the resident path (device views only) of
+    sharded_phase_scan return the same table and critical phase as the plain phase scan."""
+    import torch
+    import jacket_b200 as jb
+    from jacket_b200.distributed import shard_times, sharded_phase_scan
+    ap = jb.AnalysisParams(wave_model="Airy")
+    nodes, members, fixed, top = jb.generate_jacket(6, 9)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    wave = _wave(jb, ap)
+    P = 96
+    ref = jb.phase_scan(st, wave, P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+    eng = ref.engine
+    t_host, lo = shard_times(wave.T, P, 1, 0)
+    a = sharded_phase_scan(eng, wave, P, ap.fy, t_host=t_host)
+    assert lo == 0 and a["critical_index"] == ref.critical_index and isinstance(a["critical_index"], int)
+    assert np.array_equal(a["table"], ref.table)
+    assert a["critical_value"] == ref.table[ref.critical_index, 2]
+    t_dev = torch.as_tensor(t_host, device=f"cuda:{eng.device}")
+    b = sharded_phase_scan(eng, wave, P, ap.fy, t_dev=t_dev.data_ptr(), host_results=False)
+    torch.cuda.synchronize()
+    assert int(b["critical_index"]) == ref.critical_index and float(b["critical_value"]) == ref.table[ref.critical_index, 2]
+    got = b["table"].cpu().numpy()
+    assert np.array_equal(got[:, 2:], ref.table[:, 2:]) and np.array_equal(got[:, 0], ref.table[:, 0])
