@@ -269,14 +269,14 @@ static void free_graph(int Nn, const std::vector<int>& conn, const std::vector<c
 // Cuthill-McKee from a root SET (in the given order) over the nodes with allowed[v] != 0 that are not yet visited;
 // neighbours are queued by increasing degree.  Appends to out and marks visited.
 static void cm_from(const std::vector<std::vector<int>>& nb, const std::vector<int>& roots, const std::vector<char>& allowed,
-                    std::vector<char>& visited, std::vector<int>& out) {
+                    std::vector<char>& visited, std::vector<int>& out, std::vector<int>* level = nullptr) {
     std::queue<int> q;
-    for (int r : roots) if (allowed[r] && !visited[r]) { visited[r] = 1; q.push(r); }
+    for (int r : roots) if (allowed[r] && !visited[r]) { visited[r] = 1; q.push(r); if (level) (*level)[r] = 0; }
     std::vector<int> nx;
     while (!q.empty()) {
         int u = q.front(); q.pop(); out.push_back(u);
         nx.clear();
-        for (int v : nb[u]) if (allowed[v] && !visited[v]) { visited[v] = 1; nx.push_back(v); }
+        for (int v : nb[u]) if (allowed[v] && !visited[v]) { visited[v] = 1; nx.push_back(v); if (level) (*level)[v] = (*level)[u] + 1; }
         std::sort(nx.begin(), nx.end(), [&](int a, int b) { return nb[a].size() != nb[b].size() ? nb[a].size() < nb[b].size() : a < b; });
         for (int v : nx) q.push(v);
     }
@@ -323,7 +323,8 @@ static void rcm_order(int Nn, const std::vector<std::vector<int>>& nb, const std
 // reverse Cuthill-McKee rooted at the SET of free nodes attached to a support: for a tower the level sets are then the
 // horizontal frames, which gives the minimum bandwidth (a single root makes slanted, wider fronts)
 static void rcm_order_from_supports(int Nn, const std::vector<int>& conn, const std::vector<std::vector<int>>& nb,
-                                    const std::vector<char>& is_fixed, std::vector<int>& order) {
+                                    const std::vector<char>& is_fixed, std::vector<int>& order, std::vector<int>* cm_out = nullptr,
+                                    std::vector<int>* level_out = nullptr) {
     std::vector<char> visited(Nn, 0), allowed(Nn, 0), is_root(Nn, 0);
     for (int i = 0; i < Nn; ++i) allowed[i] = !is_fixed[i];
     int M = (int)conn.size() / 2;
@@ -335,10 +336,57 @@ static void rcm_order_from_supports(int Nn, const std::vector<int>& conn, const 
     std::vector<int> roots;
     for (int i = 0; i < Nn; ++i) if (is_root[i]) roots.push_back(i);
     std::sort(roots.begin(), roots.end(), [&](int a, int b) { return nb[a].size() != nb[b].size() ? nb[a].size() < nb[b].size() : a < b; });
-    std::vector<int> cm;
-    cm_from(nb, roots, allowed, visited, cm);
-    for (int i = 0; i < Nn; ++i) if (allowed[i] && !visited[i]) cm_from(nb, {i}, allowed, visited, cm);   // parts not tied to a support
+    std::vector<int> cm, level(Nn, 0);
+    cm_from(nb, roots, allowed, visited, cm, &level);
+    for (int i = 0; i < Nn; ++i) if (allowed[i] && !visited[i]) cm_from(nb, {i}, allowed, visited, cm, &level);   // parts not tied to a support
     order.assign(cm.rbegin(), cm.rend());
+    if (cm_out) *cm_out = cm;
+    if (level_out) *level_out = level;
+}
+
+// A Cuthill-McKee order with its BFS levels kept contiguous but every level re-sorted by node degree (ascending or
+// descending, ties in CM order).  In a frame the degree separates node families (jacket: brace hinges 4, leg joints 8)
+// whose rows reach back differently far; grouping them makes the 8-row blocks of the sweep masks homogeneous.
+static std::vector<int> regroup_levels_by_degree(const std::vector<int>& cm, const std::vector<int>& level,
+                                                 const std::vector<std::vector<int>>& nb, bool ascending) {
+    std::vector<int> idx(cm.size());
+    for (size_t i = 0; i < cm.size(); ++i) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        const int la = level[cm[a]], lb = level[cm[b]];
+        if (la != lb) return la < lb;
+        const size_t da = nb[cm[a]].size(), db = nb[cm[b]].size();
+        if (da != db) return ascending ? da < db : da > db;
+        return a < b;
+    });
+    std::vector<int> out(cm.size());
+    for (size_t i = 0; i < cm.size(); ++i) out[i] = cm[idx[i]];
+    return out;
+}
+
+// What the triangular sweeps pay for an elimination order (one chain): 64x64 tile products per tile row, counted at the
+// granularity of the zero-block masks -- forward tiles are dense in every 8-row block that reaches them, backward tiles
+// in every 4-row group (jk_sweep.cuh).  Envelope-based (no fill left of a row's first coupled node).
+static double sweep_cost(int Nn, const std::vector<int>& conn, const std::vector<int>& order) {
+    const int n = (int)order.size();
+    std::vector<int> pos(Nn, -1), first(n);
+    for (int i = 0; i < n; ++i) { pos[order[i]] = i; first[i] = i; }
+    const int M = (int)conn.size() / 2;
+    for (int m = 0; m < M; ++m) {
+        int a = pos[conn[2 * m]], b = pos[conn[2 * m + 1]];
+        if (a < 0 || b < 0) continue;
+        int hi = std::max(a, b), lo = std::min(a, b);
+        first[hi] = std::min(first[hi], lo);
+    }
+    const int ndof = 6 * n;
+    double cost = 0.0;
+    auto reach_tile = [&](int r0, int r1) {          // first tile column touched by DOF rows [r0, r1)
+        int f = r0;
+        for (int nd = r0 / 6; nd <= (std::min(r1, ndof) - 1) / 6; ++nd) f = std::min(f, 6 * first[nd]);
+        return f / NB;
+    };
+    for (int r0 = 0; r0 < ndof; r0 += 8) cost += std::max(0, r0 / NB - reach_tile(r0, r0 + 8)) / 8.0;
+    for (int r0 = 0; r0 < ndof; r0 += 4) cost += std::max(0, r0 / NB - reach_tile(r0, r0 + 4)) / 16.0;
+    return cost;
 }
 
 // node half-bandwidth and envelope size (sum of row widths) of an ordering
@@ -440,14 +488,27 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         // two candidates: single-root RCM and RCM rooted at the support-adjacent set; keep the narrower band (then the
         // smaller envelope)
         free_graph(h->Nn, h->h_conn, is_fixed, nbr);
-        std::vector<int> o1, o2;
+        std::vector<int> o1, o2, cm2, lev2;
         rcm_order(h->Nn, nbr, is_fixed, o1);
-        rcm_order_from_supports(h->Nn, h->h_conn, nbr, is_fixed, o2);
+        rcm_order_from_supports(h->Nn, h->h_conn, nbr, is_fixed, o2, &cm2, &lev2);
         int hb1 = 0, hb2 = 0; long long pr1 = 0, pr2 = 0;
         order_quality(h->Nn, h->h_conn, o1, hb1, pr1);
         order_quality(h->Nn, h->h_conn, o2, hb2, pr2);
         const bool second = getenv("JK_RCM_SINGLE_ROOT") == nullptr && o2.size() == o1.size() && (hb2 < hb1 || (hb2 == hb1 && pr2 < pr1));
         h->h_free_nodes.swap(second ? o2 : o1);
+        if (second && getenv("JK_NO_LEVEL_REGROUP") == nullptr) {
+            // third / fourth candidate: same level structure, every level sorted by degree.  Kept when the band does not
+            // widen and the sweeps get cheaper (more non-zeros in L, but fewer mask blocks to multiply).
+            double best = sweep_cost(h->Nn, h->h_conn, h->h_free_nodes);
+            for (int asc = 0; asc < 2; ++asc) {
+                std::vector<int> g = regroup_levels_by_degree(cm2, lev2, nbr, asc == 1);
+                std::vector<int> cand(g.rbegin(), g.rend());
+                int hbc = 0; long long prc = 0;
+                order_quality(h->Nn, h->h_conn, cand, hbc, prc);
+                const double c = sweep_cost(h->Nn, h->h_conn, cand);
+                if (hbc <= hb2 && c < 0.98 * best) { best = c; h->h_free_nodes.swap(cand); }
+            }
+        }
     }
     else { h->h_free_nodes.clear(); for (int i = 0; i < h->Nn; ++i) if (!is_fixed[i]) h->h_free_nodes.push_back(i); }
     if ((int)h->h_free_nodes.size() != h->n_free_nodes) JK_FAIL(h, JK_EINVAL, "jk_set_supports: internal ordering error");
@@ -482,15 +543,25 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         for (int i = nA; i < nA + nS; ++i)
             for (int v : nbr[h->h_free_nodes[i]]) if (inB[v] && !visited[v]) { visited[v] = 1; roots.push_back(v); }
         for (int v : roots) visited[v] = 0;
-        cm_from(nbr, roots, inB, visited, cm);
+        std::vector<int> levB(h->Nn, 0);
+        cm_from(nbr, roots, inB, visited, cm, &levB);
         if ((int)cm.size() == nB) {
-            std::vector<int> trial(h->h_free_nodes);
-            std::copy(cm.begin(), cm.end(), trial.begin() + nA + nS);
-            int hb_old = 0, hb_new = 0; long long pr_old = 0, pr_new = 0;
-            std::vector<int> rev_old(h->h_free_nodes.rbegin(), h->h_free_nodes.rbegin() + nB + nS), rev_new(trial.rbegin(), trial.rbegin() + nB + nS);
+            int hb_old = 0; long long pr_old = 0;
+            std::vector<int> rev_old(h->h_free_nodes.rbegin(), h->h_free_nodes.rbegin() + nB + nS);
             order_quality(h->Nn, h->h_conn, rev_old, hb_old, pr_old);
-            order_quality(h->Nn, h->h_conn, rev_new, hb_new, pr_new);
-            if (hb_new <= hb_old && pr_new < pr_old) { h->h_free_nodes.swap(trial); for (int i = 0; i < N; ++i) pos[h->h_free_nodes[i]] = i; }
+            double best = sweep_cost(h->Nn, h->h_conn, rev_old);
+            std::vector<int> best_order;
+            for (int variant = 0; variant < (getenv("JK_NO_LEVEL_REGROUP") ? 1 : 3); ++variant) {
+                std::vector<int> g = variant == 0 ? cm : regroup_levels_by_degree(cm, levB, nbr, variant == 1);
+                std::vector<int> trial(h->h_free_nodes);
+                std::copy(g.begin(), g.end(), trial.begin() + nA + nS);
+                std::vector<int> rev_new(trial.rbegin(), trial.rbegin() + nB + nS);
+                int hb_new = 0; long long pr_new = 0;
+                order_quality(h->Nn, h->h_conn, rev_new, hb_new, pr_new);
+                const double c = sweep_cost(h->Nn, h->h_conn, rev_new);
+                if (hb_new <= hb_old && c < best) { best = c; best_order.swap(trial); }
+            }
+            if (!best_order.empty()) { h->h_free_nodes.swap(best_order); for (int i = 0; i < N; ++i) pos[h->h_free_nodes[i]] = i; }
         }
     }
     // local slot of every free node in its chain(s): chain 0 = [A; S] in order, chain 1 = [rev(B); rev(S)]
