@@ -29,6 +29,9 @@ struct jk_handle_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;        // side stream: the factorisation runs here, concurrently with the Morison stage
+    cudaStream_t stream3 = nullptr;        // load gather of one phase block while the Morison kernel works on the next
+    cudaEvent_t ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_gather = nullptr;
+    bool gather_inflight = false;
     cudaEvent_t ev_post_fork = nullptr, ev_post_join = nullptr;   // node-level post kernels run beside the member post on the side stream
     cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_factor_bwd = nullptr;   // ev_factor: forward sweeps may start; ev_factor_bwd: backward tile streams built too
     bool factor_inflight = false;
@@ -173,6 +176,9 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_factor_bwd, cudaEventDisableTiming);
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, hi); }
+    for (auto& e : h->ev_part) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_join, cudaEventDisableTiming);
     h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
@@ -244,6 +250,9 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_factor) cudaEventDestroy(h->ev_factor);
     if (h->ev_factor_bwd) cudaEventDestroy(h->ev_factor_bwd);
+    if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
+    for (auto& e : h->ev_part) if (e) cudaEventDestroy(e);
+    if (h->ev_gather) cudaEventDestroy(h->ev_gather);
     if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
     if (h->ev_post_join) cudaEventDestroy(h->ev_post_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -348,7 +357,7 @@ static void rcm_order_from_supports(int Nn, const std::vector<int>& conn, const 
 // descending, ties in CM order).  In a frame the degree separates node families (jacket: brace hinges 4, leg joints 8)
 // whose rows reach back differently far; grouping them makes the 8-row blocks of the sweep masks homogeneous.
 static std::vector<int> regroup_levels_by_degree(const std::vector<int>& cm, const std::vector<int>& level,
-                                                 const std::vector<std::vector<int>>& nb, bool ascending) {
+                                                 const std::vector<std::vector<int>>& nb, bool ascending, bool reverse_ties = false) {
     std::vector<int> idx(cm.size());
     for (size_t i = 0; i < cm.size(); ++i) idx[i] = (int)i;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
@@ -356,7 +365,7 @@ static std::vector<int> regroup_levels_by_degree(const std::vector<int>& cm, con
         if (la != lb) return la < lb;
         const size_t da = nb[cm[a]].size(), db = nb[cm[b]].size();
         if (da != db) return ascending ? da < db : da > db;
-        return a < b;
+        return reverse_ties ? a > b : a < b;
     });
     std::vector<int> out(cm.size());
     for (size_t i = 0; i < cm.size(); ++i) out[i] = cm[idx[i]];
@@ -497,11 +506,11 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         const bool second = getenv("JK_RCM_SINGLE_ROOT") == nullptr && o2.size() == o1.size() && (hb2 < hb1 || (hb2 == hb1 && pr2 < pr1));
         h->h_free_nodes.swap(second ? o2 : o1);
         if (second && getenv("JK_NO_LEVEL_REGROUP") == nullptr) {
-            // third / fourth candidate: same level structure, every level sorted by degree.  Kept when the band does not
+            // further candidates: same level structure, every level sorted by degree (either way, ties either way).  Kept when the band does not
             // widen and the sweeps get cheaper (more non-zeros in L, but fewer mask blocks to multiply).
             double best = sweep_cost(h->Nn, h->h_conn, h->h_free_nodes);
-            for (int asc = 0; asc < 2; ++asc) {
-                std::vector<int> g = regroup_levels_by_degree(cm2, lev2, nbr, asc == 1);
+            for (int v = 0; v < 4; ++v) {
+                std::vector<int> g = regroup_levels_by_degree(cm2, lev2, nbr, (v & 1) != 0, (v & 2) != 0);
                 std::vector<int> cand(g.rbegin(), g.rend());
                 int hbc = 0; long long prc = 0;
                 order_quality(h->Nn, h->h_conn, cand, hbc, prc);
@@ -551,8 +560,8 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
             order_quality(h->Nn, h->h_conn, rev_old, hb_old, pr_old);
             double best = sweep_cost(h->Nn, h->h_conn, rev_old);
             std::vector<int> best_order;
-            for (int variant = 0; variant < (getenv("JK_NO_LEVEL_REGROUP") ? 1 : 3); ++variant) {
-                std::vector<int> g = variant == 0 ? cm : regroup_levels_by_degree(cm, levB, nbr, variant == 1);
+            for (int variant = 0; variant < (getenv("JK_NO_LEVEL_REGROUP") ? 1 : 5); ++variant) {
+                std::vector<int> g = variant == 0 ? cm : regroup_levels_by_degree(cm, levB, nbr, ((variant - 1) & 1) != 0, ((variant - 1) & 2) != 0);
                 std::vector<int> trial(h->h_free_nodes);
                 std::copy(g.begin(), g.end(), trial.begin() + nA + nS);
                 std::vector<int> rev_new(trial.rbegin(), trial.rbegin() + nB + nS);
@@ -948,7 +957,7 @@ static WaveAiry launch_wave(jk_handle_t h) {
 }
 
 // Morison stage for the phases already in d_t: trig tables, Gauss-point tables (once per wave), K1
-static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
+static int run_morison(jk_handle_t h, int P, int ldP, bool details, int gather_parts = 1) {
     cudaStream_t s = h->stream;
     WaveAiry w = launch_wave(h);
     tic(h, JK_T_WAVE_SETUP);
@@ -984,10 +993,20 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
         size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng) * sizeof(double);
         if (details) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details);
+            k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);
         } else {
+            // Phase blocks: the load gather of block b (HBM-bound, side stream) runs under the Morison kernel of block b+1
+            // (FP64-bound).  gather_parts > 1 only when the caller gathers afterwards (scan_core).
             CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_morison_airy<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
+            const int nbx = (int)grid.x, parts = std::max(1, std::min(gather_parts, nbx));
+            for (int b = 0; b < parts; ++b) {
+                const int x0 = (int)((long long)nbx * b / parts), x1 = (int)((long long)nbx * (b + 1) / parts);
+                if (x1 <= x0) continue;
+                k_morison_airy<false><<<dim3(x1 - x0, grid.y), PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0,
+                                                                                 h->d_Fm, h->d_totpart, nullptr, x0 * PH_TPB);
+                if (b + 1 < parts) LAUNCH_CHECK(h);            // the last launch is counted by the common check below
+                if (parts > 1) CUDA_TRY(h, cudaEventRecord(h->ev_part[b], s));
+            }
         }
     }
     LAUNCH_CHECK(h);
@@ -1124,14 +1143,39 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
     cudaStream_t s = h->stream;
     int rc;
     if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
-    if ((rc = run_morison(h, P, ldP, false)) != JK_OK) return rc;
+    const int nbx = ceil_div(ldP, PH_TPB);
+    // Experiment (JK_GATHER_OVERLAP=1), off by default: Morison in four phase blocks with the load gather of block b on
+    // a side stream under the Morison kernel of block b+1.  Measured on c4: the gather's blocks displace Morison blocks
+    // and slow the concurrent factorisation (Morison 2.49 -> 2.97 ms, factor 2.88 -> 3.16 ms) -- more than the 0.4 ms
+    // of gather it hides, with full-size or throttled (JK_GATHER_ROWS) gather grids alike.
+    const bool split = fem && h->wave_kind == 0 && h->stream3 && nbx >= 8 && getenv("JK_GATHER_OVERLAP") != nullptr;
+    const int parts = split ? 4 : 1;
+    if ((rc = run_morison(h, P, ldP, false, parts)) != JK_OK) return rc;
     if (fem) {
-        tic(h, JK_T_RHS);
-        dim3 g(ceil_div(ldP, PH_TPB), h->Nn);
-        k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
-                                         h->d_X, h->d_Ffix, nullptr);
-        LAUNCH_CHECK(h);
-        toc(h, JK_T_RHS);
+        if (parts == 1) {
+            tic(h, JK_T_RHS);
+            dim3 g(nbx, h->Nn);
+            k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
+                                             h->d_X, h->d_Ffix, nullptr);
+            LAUNCH_CHECK(h);
+            toc(h, JK_T_RHS);
+        } else {
+            cudaStream_t s3 = h->stream3;
+            // throttled: a few long-running blocks (each walks Nn / gather_rows nodes) instead of one block per node, so
+            // that the gather streams from HBM beside the FP64-bound Morison kernel without displacing its blocks
+            static const int gather_rows = getenv("JK_GATHER_ROWS") ? atoi(getenv("JK_GATHER_ROWS")) : 32;
+            for (int b = 0; b < parts; ++b) {
+                const int x0 = (int)((long long)nbx * b / parts), x1 = (int)((long long)nbx * (b + 1) / parts);
+                CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_part[b], 0));
+                if (b == parts - 1) tic(h, JK_T_RHS, s3);       // the timer shows the exposed part: the gather of the last phase block
+                k_rhs_gather<<<dim3(x1 - x0, std::min(h->Nn, gather_rows)), PH_TPB, 0, s3>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
+                                                                      h->d_X, h->d_Ffix, nullptr, nullptr, nullptr, 0, 1, 0, x0 * PH_TPB);
+                LAUNCH_CHECK(h);
+            }
+            toc(h, JK_T_RHS, s3);
+            CUDA_TRY(h, cudaEventRecord(h->ev_gather, s3));
+            CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_gather, 0));
+        }
         if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
     }
     if ((rc = reduce_and_argmax(h, P, ldP, true, fem)) != JK_OK) return rc;

@@ -53,69 +53,77 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 // d' = d11 - d10^2 / d00 needs only the reciprocal), the column scaling by 1/sqrt(d) happens off the
 // chain.  Then one DMMA phase solves the rows below against the block inverse and one DMMA phase applies
 // the rank-8 update to the trailing block.
+// 8x8 diagonal block p of T (already carrying the updates of the panels before it): factor it in registers (every lane
+// of the calling warp holds the same values, no communication), write L_pp back and its inverse to Dp.
+__device__ __forceinline__ void potrf8_warp(double* __restrict__ T, double* __restrict__ Dp, int c0, int* __restrict__ info, int pivot_base, int lane) {
+    double d[8][8], m[8][8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) d[i][j] = T[(c0 + i) * LS_LD + c0 + j];
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double dc = d[c][c];
+        if (!(dc > 0.0)) { if (!bad && lane == 0) atomicCAS(info, 0, pivot_base + c0 + c + 1); bad = true; dc = 1.0; }
+        const double inv = fast_rcp(dc);
+        rs[c] = fast_rsqrt(dc);
+        double t[8];
+#pragma unroll
+        for (int i = c + 1; i < 8; ++i) t[i] = d[i][c] * inv;
+#pragma unroll
+        for (int j = c + 1; j < 8; ++j)
+#pragma unroll
+            for (int i = j; i < 8; ++i) {
+                if (i == j && j == c + 1) d[i][j] = fma(-(d[i][c] * d[i][c]), inv, d[i][j]);   // next pivot: shortest chain
+                else d[i][j] = fma(-d[i][c], t[j], d[i][j]);
+            }
+        d[c][c] = dc;
+    }
+    // L = Ltilde D^(1/2): scale the columns off the pivot chain
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int i = c + 1; i < 8; ++i) d[i][c] *= rs[c];
+        d[c][c] *= rs[c];
+    }
+    // M = L^-1 (lower) by forward substitution, 1/L_jj = rs_j
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        m[j][j] = rs[j];
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int kk = j; kk < i; ++kk) sacc = fma(d[i][kk], m[kk][j], sacc);
+            m[i][j] = -sacc * rs[i];
+        }
+    }
+    if (lane == 0) {
+        // 16-byte stores, lower triangle only (the entry just above the diagonal that a pair may cover gets 0;
+        // the rest of Dp's upper triangle is zeroed once by the caller): 40 stores instead of 100 on the chain
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; j += 2) {
+                *reinterpret_cast<double2*>(T + (c0 + i) * LS_LD + c0 + j) = make_double2(d[i][j], j + 1 <= i ? d[i][j + 1] : 0.0);
+                *reinterpret_cast<double2*>(Dp + i * DI_LD + j) = make_double2(m[i][j], j + 1 <= i ? m[i][j + 1] : 0.0);
+            }
+    }
+}
+
+// Eight 8-column panels with LOOKAHEAD inside the tile: after the rows below panel p are solved, warp 0 alone applies
+// the rank-8 update to the next diagonal block and factors it at once, while warps 1-7 apply the update to the rest of
+// the trailing block.  The chain per panel is  8x8 factor -> barrier -> rows-below solve (DMMA) -> barrier;  the
+// trailing update is off it.
 __device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, int* __restrict__ info, int pivot_base) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
+    if (warp == 0) potrf8_warp(T, Di, 0, info, pivot_base, lane);
     for (int p = 0; p < 8; ++p) {
         const int c0 = 8 * p;
         double* Dp = Di + p * DI_BLK;
-        if (warp == 0) {
-            double d[8][8], m[8][8], rs[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) d[i][j] = T[(c0 + i) * LS_LD + c0 + j];
-            bool bad = false;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                double dc = d[c][c];
-                if (!(dc > 0.0)) { if (!bad && lane == 0) atomicCAS(info, 0, pivot_base + c0 + c + 1); bad = true; dc = 1.0; }
-                const double inv = fast_rcp(dc);
-                rs[c] = fast_rsqrt(dc);
-                double t[8];
-#pragma unroll
-                for (int i = c + 1; i < 8; ++i) t[i] = d[i][c] * inv;
-#pragma unroll
-                for (int j = c + 1; j < 8; ++j)
-#pragma unroll
-                    for (int i = j; i < 8; ++i) {
-                        if (i == j && j == c + 1) d[i][j] = fma(-(d[i][c] * d[i][c]), inv, d[i][j]);   // next pivot: shortest chain
-                        else d[i][j] = fma(-d[i][c], t[j], d[i][j]);
-                    }
-                d[c][c] = dc;
-            }
-            // L = Ltilde D^(1/2): scale the columns off the pivot chain
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-#pragma unroll
-                for (int i = c + 1; i < 8; ++i) d[i][c] *= rs[c];
-                d[c][c] *= rs[c];
-            }
-            // M = L^-1 (lower) by forward substitution, 1/L_jj = rs_j
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                m[j][j] = rs[j];
-#pragma unroll
-                for (int i = j + 1; i < 8; ++i) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int kk = j; kk < i; ++kk) sacc = fma(d[i][kk], m[kk][j], sacc);
-                    m[i][j] = -sacc * rs[i];
-                }
-            }
-            if (lane == 0) {
-                // 16-byte stores, lower triangle only (the entry just above the diagonal that a pair may cover gets 0;
-                // the rest of Dp's upper triangle is zeroed once by the caller): 40 stores instead of 100 on the chain
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j <= i; j += 2) {
-                        *reinterpret_cast<double2*>(T + (c0 + i) * LS_LD + c0 + j) = make_double2(d[i][j], j + 1 <= i ? d[i][j + 1] : 0.0);
-                        *reinterpret_cast<double2*>(Dp + i * DI_LD + j) = make_double2(m[i][j], j + 1 <= i ? m[i][j + 1] : 0.0);
-                    }
-            }
-        }
-        __syncthreads();
+        __syncthreads();                                    // L_pp, its inverse and every update of panel p-1 are in place
         const int nmt = 7 - p;                              // 8-row tiles below the diagonal block
         if (nmt == 0) break;
         // ---- rows below: X = A * M^T (in place), one 8-row tile per warp ----
@@ -130,9 +138,10 @@ __device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, in
             T[(row0 + fr) * LS_LD + c0 + 2 * fk + 1] = x1;
         }
         __syncthreads();
-        // ---- trailing block: C(mi,nj) -= X_mi X_nj^T for the lower triangle of 8x8 tiles ----
+        // ---- trailing block: C(mi,nj) -= X_mi X_nj^T for the lower triangle of 8x8 tiles.  Tile 0 = the next diagonal
+        //      block: warp 0 takes it and goes straight on to factor it; the other warps share the rest. ----
         const int ntile = nmt * (nmt + 1) / 2;
-        for (int t = warp; t < ntile; t += CHOL_THREADS / 32) {
+        auto update_tile = [&](int t) {
             int mi = 0;
             while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
             const int nj = t - mi * (mi + 1) / 2;
@@ -143,8 +152,14 @@ __device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, in
             for (int k4 = 0; k4 < 2; ++k4)
                 dmma(c0v, c1v, -T[(ri + fr) * LS_LD + c0 + 4 * k4 + fk], T[(rj + fr) * LS_LD + c0 + 4 * k4 + fk]);
             cp[0] = c0v; cp[1] = c1v;
+        };
+        if (warp == 0) {
+            update_tile(0);
+            __syncwarp();
+            potrf8_warp(T, Di + (p + 1) * DI_BLK, c0 + 8, info, pivot_base, lane);
+        } else {
+            for (int t = warp; t < ntile; t += CHOL_THREADS / 32 - 1) update_tile(t);
         }
-        __syncthreads();
     }
 }
 

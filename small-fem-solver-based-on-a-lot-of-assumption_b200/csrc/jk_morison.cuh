@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(PH_TPB)
 k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
                const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
                WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
-               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details) {
+               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details, int p_off /* first phase of this launch */) {
     extern __shared__ __align__(16) double smem[];
     constexpr int MS = 16;                                  // per-member constants
     double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
@@ -125,7 +125,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     }
     __syncthreads();
 
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = p_off + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ldP) return;
     const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
     const double wc2 = 2.0 * fma(wv.sin_w, wv.uc_sin_c, wv.cos_w * wv.uc_cos_c);       // 2 w^.c
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(PH_TPB)
 k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
                const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
                WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
-               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details) {
+               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details, int p_off /* first phase of this launch */) {
     extern __shared__ __align__(16) double smem[];
     double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
     double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][8]: e0 e1 e2 cD cI L
@@ -228,7 +228,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     }
     __syncthreads();
 
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = p_off + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ldP) return;
     const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
     double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
@@ -600,10 +600,12 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
              const int* __restrict__ adj, const int* __restrict__ node2slot, const double* __restrict__ Fstatic,
              double* __restrict__ B, double* __restrict__ Ffix, double* __restrict__ nodal /* [Nn*3] single phase or null */,
              const double* __restrict__ Fdir = nullptr /* ensemble: [2][6*Nn] loads that follow the wave heading */,
-             const double* __restrict__ st = nullptr, int S = 0, int n_phase = 1, int C = 0) {
-    int node = blockIdx.y;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= Nn || p >= ldP) return;
+             const double* __restrict__ st = nullptr, int S = 0, int n_phase = 1, int C = 0, int p_off = 0 /* first phase of this launch */) {
+    int p = p_off + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ldP) return;
+    // grid.y = Nn: one node per block row; a smaller grid.y makes every block walk several nodes (throttled launch that
+    // runs beside the Morison kernel without taking its SM slots)
+    for (int node = blockIdx.y; node < Nn; node += gridDim.y) {
     double f[3] = {0, 0, 0};
     double fdir[6] = {0, 0, 0, 0, 0, 0};
     if (Fdir) {   // interface shear is applied along the wave direction of the case's sea state (GUI.py:1967-1971)
@@ -620,19 +622,20 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
     if (nodal && p == 0) { nodal[3 * node] = f[0]; nodal[3 * node + 1] = f[1]; nodal[3 * node + 2] = f[2]; }
     int s = node2slot[node];
     if (s >= 0) {
-        if (!B) return;
+        if (!B) continue;
         size_t o = rhs_off(s, p, n_pad);
 #pragma unroll
         for (int c = 0; c < 3; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + fdir[c] + f[c];
 #pragma unroll
         for (int c = 3; c < 6; ++c) B[o + (size_t)c * SLAB] = Fstatic[6 * node + c] + fdir[c];
     } else {
-        if (!Ffix) return;
+        if (!Ffix) continue;
         int fi = -1 - s;
 #pragma unroll
         for (int c = 0; c < 3; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + fdir[c] + f[c];
 #pragma unroll
         for (int c = 3; c < 6; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + fdir[c];
+    }
     }
 }
 
