@@ -990,7 +990,7 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details, int gather_p
             k_morison_fourier<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, Nh, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, h->d_four, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
         }
     } else {
-        size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng) * sizeof(double);
+        size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng + 1) * sizeof(double);
         if (details) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);

@@ -53,8 +53,8 @@ constexpr int MC_IIX = 40;
 constexpr int MC_IAY = 41;
 constexpr int MC_IAZ = 42;
 
-// Gauss-point table row (Airy): cos(k x_w), sin(k x_w), Cu, Cw, z
-constexpr int GP_STRIDE = 5;
+// Gauss-point table row (Airy): cos(k x_w), sin(k x_w), Cu, Cw, z, pad  (three 16-byte shared-memory loads)
+constexpr int GP_STRIDE = 6;
 
 // ----------------------------------------------------------------------------------------------
 // Addressing helpers

@@ -58,6 +58,7 @@ __global__ void k_gauss_setup_airy(int M, int G, const double* __restrict__ xyz,
     o[2] = wv.a * wv.omega * cosh(kz) / shkd;                                 // GUI.py:279
     o[3] = wv.a * wv.omega * sinh(kz) / shkd;                                 // GUI.py:280
     o[4] = z;
+    o[5] = 0.0;
 }
 
 // per phase: cos/sin(omega t), cos/sin(omega (t + dt)) -> trig[4][ldP]; padded phases repeat the last t
@@ -99,7 +100,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
     double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][MS]: we ce e2 L | p1[3] p0[3] p3[3] | cD cI
     double* s_g = s_m + MCHUNK * MS;                       // s[G], w[G]
-    double* s_c = s_g + 2 * G;                             // [MCHUNK][G][3]: cD L w_g, cI L w_g, s_g cI L w_g
+    double* s_c = s_g + 2 * G + ((2 * G) & 1);             // [MCHUNK][G][4]: cD L w_g, cI L w_g, s_g cI L w_g, s_g (16-byte aligned)
     int chunk = blockIdx.y, m0 = chunk * MCHUNK;
     int nm = min(MCHUNK, M - m0);
     for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
@@ -121,7 +122,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         const int mm = i / G, g = i % G;
         const double Lw = s_m[MS * mm + 3] * s_g[G + g];
         const double cil = s_m[MS * mm + 14] * Lw;
-        s_c[3 * i] = s_m[MS * mm + 13] * Lw; s_c[3 * i + 1] = cil; s_c[3 * i + 2] = s_g[g] * cil;
+        s_c[4 * i] = s_m[MS * mm + 13] * Lw; s_c[4 * i + 1] = cil; s_c[4 * i + 2] = s_g[g] * cil; s_c[4 * i + 3] = s_g[g];
     }
     __syncthreads();
 
@@ -138,10 +139,10 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         double Sd0 = 0, Sd1 = 0, Sd3 = 0, Td0 = 0, Td1 = 0, Td3 = 0, Si1 = 0, Si3 = 0, Ti1 = 0, Ti3 = 0;
         double sub = 0.0;
         const double* gpm = s_gp + mm * G * GP_STRIDE;
-        const double* cm = s_c + mm * G * 3;
+        const double* cm = s_c + mm * G * 4;
         for (int g = 0; g < G; ++g) {
-            const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1];
-            const double Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3], z = gpm[g * GP_STRIDE + 4];
+            const double2 g01 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE), g23 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE + 2);
+            const double ckx = g01.x, skx = g01.y, Cu = g23.x, Cw = g23.y, z = gpm[g * GP_STRIDE + 4];
             // cos / sin of (k xw - omega t) at t and t + dt
             const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
             if (z > wv.a * c0) continue;                                       // dry at t (GUI.py:265, 292, 627)
@@ -153,13 +154,20 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
             const double uw = u0 - wv.Uc;                                      // GUI.py:573
             const double Ue = fma(w0, e2, fma(uw, we, ce));                    // U.e
             const double UU = fma(w0, w0, fma(uw, uw + wc2, cc));              // U.U
-            const double mag = sqrt(fmax(fma(-Ue, Ue, UU), 0.0));              // |U_perp|  (GUI.py:647)
-            const double s = s_g[g];
-            const double kd = (mag > 1e-10) ? cm[3 * g] * mag : 0.0;           // GUI.py:648-651
+            // |U_perp| (GUI.py:647) by the hardware reciprocal-square-root seed and one Newton step: 6e-14 relative, far
+            // inside the 1e-9 contract, half the instructions of the IEEE sqrt.  |U_perp| > 1e-10 <=> m2 > 1e-20.
+            const double m2 = fma(-Ue, Ue, UU);
+            double ry;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ry) : "d"(m2));
+            const double t0 = m2 * ry;
+            const double mag = fma(0.5 * t0, fma(-t0, ry, 1.0), t0);
+            const double2 c01 = *reinterpret_cast<const double2*>(cm + 4 * g), c23 = *reinterpret_cast<const double2*>(cm + 4 * g + 2);
+            const double s = c23.y;
+            const double kd = (m2 > 1e-20) ? c01.x * mag : 0.0;                // GUI.py:648-651
             const double skd = s * kd;
             Sd0 += kd; Sd1 = fma(kd, uw, Sd1); Sd3 = fma(kd, w0, Sd3);
             Td0 += skd; Td1 = fma(skd, uw, Td1); Td3 = fma(skd, w0, Td3);
-            const double cil = cm[3 * g + 1], scil = cm[3 * g + 2];
+            const double cil = c01.y, scil = c23.x;
             Si1 = fma(cil, du, Si1); Si3 = fma(cil, dw, Si3);
             Ti1 = fma(scil, du, Ti1); Ti3 = fma(scil, dw, Ti3);
             if (DETAILS) sub += cmem[3] * s_g[G + g];
@@ -196,7 +204,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     }
 }
 constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 16;   // doubles per member beside the Gauss tables (s_m)
-constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 3;     // doubles per Gauss point beside GP_STRIDE (s_c)
+constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 4;     // doubles per Gauss point beside GP_STRIDE (s_c)
 #else
 template <bool DETAILS>
 __global__ void __launch_bounds__(PH_TPB)
