@@ -20,6 +20,9 @@
 
 namespace jk {
 
+#ifndef JK_TRSM_UNROLL
+#define JK_TRSM_UNROLL 1      // fully unrolled panel TRSM: the independent block updates of a step overlap (factor 2.92 -> 2.79 ms)
+#endif
 constexpr int CHOL_CLUSTER = 8;
 constexpr int CHOL_THREADS = 256;
 constexpr int DI_LD = 12;                                   // row stride of an 8x8 inverse block in smem (== 12 mod 16: conflict-free)
@@ -176,7 +179,11 @@ __device__ __forceinline__ void trsm64_warp(double* __restrict__ As, const doubl
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     double* arow = As + (8 * warp + fr) * LS_LD;
+#if JK_TRSM_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int b = 0; b < 8; ++b) {
         double x0 = 0.0, x1 = 0.0;
 #pragma unroll
@@ -185,6 +192,9 @@ __device__ __forceinline__ void trsm64_warp(double* __restrict__ As, const doubl
         arow[8 * b + 2 * fk] = x0; arow[8 * b + 2 * fk + 1] = x1;
         __syncwarp();
         const double a0 = -arow[8 * b + fk], a1 = -arow[8 * b + 4 + fk];
+#if JK_TRSM_UNROLL
+#pragma unroll
+#endif
         for (int b2 = b + 1; b2 < 8; ++b2) {
             double* cp = arow + 8 * b2 + 2 * fk;
             double c0v = cp[0], c1v = cp[1];
