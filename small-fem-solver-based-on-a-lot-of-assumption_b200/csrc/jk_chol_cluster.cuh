@@ -81,6 +81,14 @@ __device__ __forceinline__ void potrf8_warp(double* __restrict__ T, double* __re
                 if (i == j && j == c + 1) d[i][j] = fma(-(d[i][c] * d[i][c]), inv, d[i][j]);   // next pivot: shortest chain
                 else d[i][j] = fma(-d[i][c], t[j], d[i][j]);
             }
+        // the same row operations applied to the identity give Ltilde^-1 (product of the elimination matrices): the
+        // inverse is complete one FMA after the last pivot instead of a 28-FMA substitution chain afterwards
+#pragma unroll
+        for (int i = c + 1; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < c; ++j) m[i][j] = fma(-t[i], m[c][j], m[i][j]);
+            m[i][c] = -t[i];
+        }
         d[c][c] = dc;
     }
     // L = Ltilde D^(1/2): scale the columns off the pivot chain
@@ -90,17 +98,12 @@ __device__ __forceinline__ void potrf8_warp(double* __restrict__ T, double* __re
         for (int i = c + 1; i < 8; ++i) d[i][c] *= rs[c];
         d[c][c] *= rs[c];
     }
-    // M = L^-1 (lower) by forward substitution, 1/L_jj = rs_j
+    // M = L^-1 = D^(-1/2) Ltilde^-1: scale the rows, 1/L_ii = rs_i
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        m[j][j] = rs[j];
+    for (int i = 0; i < 8; ++i) {
 #pragma unroll
-        for (int i = j + 1; i < 8; ++i) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int kk = j; kk < i; ++kk) sacc = fma(d[i][kk], m[kk][j], sacc);
-            m[i][j] = -sacc * rs[i];
-        }
+        for (int j = 0; j < i; ++j) m[i][j] *= rs[i];
+        m[i][i] = rs[i];
     }
     if (lane == 0) {
         // 16-byte stores, lower triangle only (the entry just above the diagonal that a pair may cover gets 0;
