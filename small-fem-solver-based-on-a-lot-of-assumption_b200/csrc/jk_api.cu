@@ -221,6 +221,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, cudaFuncSetAttribute(k_trailing_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_panel_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_tile_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INVERSE_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_tile_inverse_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INVERSE_BLOCKED_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_band_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_CLUSTER_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
@@ -798,7 +799,11 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
         }
     }
     { const int n1 = h->n_chains == 2 ? c1.kS : 0;     // second chain: its separator rows are factored in the first chain
-      k_tile_inverse<<<c0.NT + n1, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw, c0.NT, c1.d_tiles, c1.d_Linv, c1.bw);
+      if (use_cluster && getenv("JK_INVERSE_LEGACY") == nullptr)     // the cluster kernel left the 8x8 block inverses in d_dinv
+          k_tile_inverse_blocked<<<c0.NT + n1, 256, INVERSE_BLOCKED_SMEM, s>>>(c0.d_tiles, c0.d_dinv, c0.d_Linv, c0.bw, 0, c0.NT,
+                                                                               c1.d_tiles, c1.d_dinv, c1.d_Linv, c1.bw);
+      else
+          k_tile_inverse<<<c0.NT + n1, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw, c0.NT, c1.d_tiles, c1.d_Linv, c1.bw);
       LAUNCH_CHECK(h); }
     // tile streams of the forward sweeps; the factor timer stops here (this is what the forward sweeps wait for)
     int rc = launch_sweep_build(h, s, 0);

@@ -189,6 +189,51 @@ __global__ void __launch_bounds__(256) k_tile_inverse(const double* __restrict__
     for (int idx = tid; idx < NB * NB; idx += 256) o[idx] = X[idx / NB][idx % NB];
 }
 
+// Blocked variant for tiles factored by the cluster kernel, which leaves the inverses of the eight 8x8 diagonal blocks
+// of every L_kk in dinv[k][8][8][8]: X = L^-1 by block forward substitution,
+//     X_bc = Dinv_b ( delta_bc I - sum_{e=c}^{b-1} L_be X_ec ),   b = 0..7, c <= b,
+// eight steps of two barriers each instead of 64 (5 us instead of 57 us on the tail of the factor stage).
+constexpr size_t INVERSE_BLOCKED_SMEM = (size_t)(2 * NB * (NB + 1) + 8 * NB) * sizeof(double);
+__global__ void __launch_bounds__(256) k_tile_inverse_blocked(const double* __restrict__ tiles, const double* __restrict__ dinv, double* __restrict__ Linv,
+                                                              int bw, int k_first, int n0, const double* __restrict__ tiles1,
+                                                              const double* __restrict__ dinv1, double* __restrict__ Linv1, int bw1) {
+    extern __shared__ __align__(16) double smem[];
+    double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem);
+    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem + NB * (NB + 1));
+    double (*T)[NB] = reinterpret_cast<double (*)[NB]>(smem + 2 * NB * (NB + 1));      // [8][NB] rows of the current block step
+    int k = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (k >= n0) { k -= n0; tiles = tiles1; dinv = dinv1; Linv = Linv1; bw = bw1; } else k += k_first;
+    const double* g = tiles + tile_off(k, k, bw);
+    const double* di = dinv + (size_t)k * 512;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        int r = idx / NB, c = idx % NB;
+        Ls[r][c] = (c <= r) ? g[idx] : 0.0;
+        X[r][c] = 0.0;
+    }
+    __syncthreads();
+    const int r8 = tid / 32, cq = tid % 32;                // row inside the block step, column (and column + 32)
+    for (int b = 0; b < 8; ++b) {
+        const int ncol = 8 * (b + 1);                      // columns 0 .. 8b+7 can be non-zero in block row b
+        const int r = 8 * b + r8;
+        for (int c = cq; c < ncol; c += 32) {
+            double acc = (c == r) ? 1.0 : 0.0;
+            for (int m = (c / 8) * 8; m < 8 * b; ++m) acc = fma(-Ls[r][m], X[m][c], acc);     // X[m][c] = 0 for m < 8*(c/8)
+            T[r8][c] = acc;
+        }
+        __syncthreads();
+        for (int c = cq; c < ncol; c += 32) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc = fma(di[b * 64 + r8 * 8 + q], T[q][c], acc);
+            X[r][c] = acc;
+        }
+        __syncthreads();
+    }
+    double* o = Linv + (size_t)k * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += 256) o[idx] = X[idx / NB][idx % NB];
+}
+
 // ----------------------------------------------------------------------------------------------
 // K4: triangular sweeps over one slab of SLAB right-hand sides per CTA (persistent over all tile rows).
 //
