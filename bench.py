@@ -431,6 +431,9 @@ def run_ours(args):
     ms_total, launches, out = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     stage = eng.timings()
+    if stage.get("solve_fwd2", -1.0) > 0:       # split factor: the forward sweeps run as two groups of launches around the factor join
+        stage["solve_fwd_first_parts"] = stage["solve_fwd"]
+        stage["solve_fwd"] = stage["solve_fwd"] + stage["solve_fwd2"]
     value = n_total * args.steps / (ms_total * 1e-3)
 
     e2e = None

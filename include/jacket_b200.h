@@ -88,7 +88,7 @@ typedef struct jk_handle_s* jk_handle_t;
 #define JK_SOLVER_DENSE      1   /* full lower triangle (the reference's dense K_ff, GUI.py:482) */
 
 /* stage timers returned by jk_get_timings (milliseconds, CUDA events on the handle's stream) */
-#define JK_NTIMERS          12
+#define JK_NTIMERS          13
 #define JK_T_ASSEMBLE        0
 #define JK_T_FACTOR          1
 #define JK_T_WAVE_SETUP      2
@@ -101,6 +101,7 @@ typedef struct jk_handle_s* jk_handle_t;
 #define JK_T_SCAN_TOTAL      9
 #define JK_T_H2D            10
 #define JK_T_D2H            11
+#define JK_T_SOLVE_FWD2     12   /* forward sweep launches issued after the factor join (split factor); -1 when not split */
 
 int         jk_version(void);
 const char* jk_last_error(jk_handle_t h);

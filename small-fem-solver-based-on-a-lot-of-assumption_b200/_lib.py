@@ -22,9 +22,9 @@ MEMBER_NCOL = 7
 DETAIL_NCOL = 4
 ORDER_NATURAL, ORDER_RCM = 0, 1
 SOLVER_BANDED, SOLVER_DENSE = 0, 1
-NTIMERS = 12
+NTIMERS = 13
 TIMER_NAMES = ("assemble", "factor", "wave_setup", "morison", "rhs", "solve_fwd", "solve_bwd",
-               "post", "reduce", "scan_total", "h2d", "d2h")
+               "post", "reduce", "scan_total", "h2d", "d2h", "solve_fwd2")
 TABLE_COLUMNS = ("t", "phase_deg", "total_kN", "drag_kN", "inertia_kN", "Fx_kN", "Fy_kN", "Fz_kN",
                  "max_disp_mm", "max_disp_node", "max_util", "max_util_member", "max_vm_MPa",
                  "sum_Rx", "sum_Ry", "sum_Rz")

@@ -33,6 +33,8 @@ struct jk_handle_s {
     cudaEvent_t ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_gather = nullptr;
     bool gather_inflight = false;
     cudaEvent_t ev_post_fork = nullptr, ev_post_join = nullptr;   // node-level post kernels run beside the member post on the side stream
+    cudaEvent_t ev_seg1 = nullptr, ev_fwd1 = nullptr;   // first factor segment done / its forward tile streams built
+    bool split_factor = false;
     cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_factor_bwd = nullptr;   // ev_factor: forward sweeps may start; ev_factor_bwd: backward tile streams built too
     bool factor_inflight = false;
     std::string err;
@@ -62,7 +64,10 @@ struct jk_handle_s {
         size_t tiles_elems = 0;
         // TMA sweep programs (jk_sweep.cuh): [0] forward, [1] backward.  Item list (host-built) + tile stream (built
         // from L after every factorisation by k_sweep_build)
-        struct Sweep { int n_items = 0, pre_row = 0, npre = 0, ktop = 0; uint4* d_prog = nullptr; double* d_stream = nullptr; } sw[2];
+        struct Sweep { int n_items = 0, pre_row = 0, npre = 0, ktop = 0; uint4* d_prog = nullptr; double* d_stream = nullptr;
+                       // forward programs can run as two launches: items [0, n_split) cover tile rows < k_split and only need
+                       // the factor's columns < k_split, so they start while the factorisation finishes the rest
+                       int n_split = 0, k_split = 0, npre2 = 0, xphase2 = 0; } sw[2];
     } ch[2];
     bool tma_sweep = false;   // narrow band: sweeps run as the TMA / mbarrier pipeline, otherwise the cp.async slab sweep
     int n_chains = 1, nS_nodes = 0;
@@ -179,6 +184,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, hi); }
     for (auto& e : h->ev_part) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_seg1, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_join, cudaEventDisableTiming);
     h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
@@ -254,6 +261,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
     for (auto& e : h->ev_part) if (e) cudaEventDestroy(e);
     if (h->ev_gather) cudaEventDestroy(h->ev_gather);
+    if (h->ev_seg1) cudaEventDestroy(h->ev_seg1);
+    if (h->ev_fwd1) cudaEventDestroy(h->ev_fwd1);
     if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
     if (h->ev_post_join) cudaEventDestroy(h->ev_post_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -681,6 +690,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     // sweep programs: the TMA pipeline keeps the last SW_RING solved tiles in shared memory, so it needs a narrow band
     h->tma_sweep = getenv("JK_SWEEP_LEGACY") == nullptr;
     for (int c = 0; c < h->n_chains; ++c) if (h->ch[c].bw > SW_MAX_BW) h->tma_sweep = false;
+    h->split_factor = false;
     for (int c = 0; c < 2; ++c)
         for (int d = 0; d < 2; ++d) {
             auto& w = h->ch[c].sw[d];
@@ -692,12 +702,28 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
             // the second chain's separator rows are partial (forward) / known (backward)
             build_sweep_program(chn.NT, chn.bw, c == 0 ? chn.NT : chn.kS, d == 1, tile_reach[c].data(), prog, w.pre_row, w.npre, w.ktop);
             w.n_items = (int)prog.size() / SW_ITEM_U4;
+            w.n_split = w.n_items; w.k_split = 0; w.npre2 = 0; w.xphase2 = 0;
+            if (d == 0 && w.n_items > 0) {
+                // split point: 80 % of the chain's own columns (the separator columns of the first chain come last anyway)
+                const int kS = chn.kS, k1 = (4 * kS) / 5;
+                if (k1 >= 2 * SW_RING && kS - k1 >= 4) {
+                    int n1 = 0;
+                    while (n1 < w.n_items && (int)prog[(size_t)n1 * SW_ITEM_U4].x < k1) ++n1;
+                    w.n_split = n1; w.k_split = k1; w.npre2 = std::min(chn.bw, k1);
+                    // slot s is next filled (preloaded or computed) by the first row r >= k1 - npre2 with r % R == s; the
+                    // item parities count fills from row 0, so the slot starts (r / R) & 1 phases ahead
+                    for (int r = k1 - w.npre2; r < k1 - w.npre2 + SW_RING; ++r) if ((r / SW_RING) & 1) w.xphase2 |= 1 << (r % SW_RING);
+                }
+            }
             if (w.n_items == 0) continue;
             CUDA_TRY(h, dev_alloc(&w.d_prog, prog.size()));
             CUDA_TRY(h, dev_alloc(&w.d_stream, (size_t)w.n_items * SW_TILE));
             CUDA_TRY(h, cudaMemcpyAsync(w.d_prog, prog.data(), prog.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
             CUDA_TRY(h, cudaStreamSynchronize(s));   // prog is a local
         }
+    // the factorisation runs in two segments (and the forward sweeps in two launches) when every chain has a split point
+    h->split_factor = h->tma_sweep && getenv("JK_NO_FACTOR_SPLIT") == nullptr;
+    for (int c = 0; c < h->n_chains; ++c) if (h->ch[c].sw[0].k_split == 0) h->split_factor = false;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_node2slot, h->h_node2slot.data(), (size_t)h->Nn * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -731,12 +757,15 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     return JK_OK;
 }
 
-static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d) {
+// part: 0 = whole program, 1 = items [0, n_split), 2 = items [n_split, n_items)   (forward programs of a split factor)
+static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d, int part = 0) {
     if (!h->tma_sweep) return JK_OK;
     SweepBuildArgs a[2];
     for (int c = 0; c < 2; ++c) {
         auto& w = h->ch[c].sw[d];
-        a[c] = SweepBuildArgs{w.d_prog, w.d_stream, h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, c < h->n_chains ? w.n_items : 0};
+        const int lo = part == 2 ? w.n_split : 0, hi = part == 1 ? w.n_split : w.n_items;
+        a[c] = SweepBuildArgs{w.d_prog ? w.d_prog + (size_t)lo * SW_ITEM_U4 : nullptr, w.d_stream ? w.d_stream + (size_t)lo * SW_TILE : nullptr,
+                              h->ch[c].d_tiles, h->ch[c].d_Linv, h->ch[c].bw, c < h->n_chains ? std::max(0, hi - lo) : 0};
     }
     if (a[0].n_items + a[1].n_items > 0) {
         k_sweep_build<<<a[0].n_items + a[1].n_items, 256, SWB_SMEM, s>>>(a[0], a[1], d);
@@ -746,7 +775,7 @@ static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d) {
 }
 
 // launches the factorisation on stream s (no host synchronisation)
-static int launch_factor(jk_handle_t h, cudaStream_t s) {
+static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nullptr) {
     tic(h, JK_T_FACTOR, s);
     CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), s));
     // narrow band: persistent cluster kernel(s) (latency chain); wide band / dense: per-column launches
@@ -757,6 +786,46 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
         const bool want_prof = getenv("JK_CHOL_PROFILE") != nullptr;
         if (want_prof) { CUDA_TRY(h, cudaMalloc((void**)&prof, (size_t)c0.NT * 8 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(prof, 0, (size_t)c0.NT * 8 * sizeof(long long), s)); }
         CholChain a{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, 0, c0.kS};
+        if (h->split_factor && s_side != nullptr) {
+            // Two segments.  After the first (80 % of each chain's columns) a side stream inverts those diagonal tiles and
+            // builds the forward tile streams of those rows, so the forward sweeps can start on them (run_fem) while this
+            // stream factors the rest, the separator, and builds the remaining streams.
+            auto& c1r = h->ch[h->n_chains == 2 ? 1 : 0];
+            const int k0 = c0.sw[0].k_split, k1 = c1r.sw[0].k_split;
+            CholChain a1{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, 0, k0}, a2{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, k0, c0.kS};
+            CholChain b1{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, 0, k1}, b2{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, k1, c1.kS};
+            const int ncl = h->n_chains == 2 ? 2 : 1;
+            k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a1, ncl == 2 ? b1 : a1, h->d_info, prof);
+            LAUNCH_CHECK(h);
+            CUDA_TRY(h, cudaEventRecord(h->ev_seg1, s));
+            CUDA_TRY(h, cudaStreamWaitEvent(s_side, h->ev_seg1, 0));
+            k_tile_inverse_blocked<<<k0 + (ncl == 2 ? k1 : 0), 256, INVERSE_BLOCKED_SMEM, s_side>>>(c0.d_tiles, c0.d_dinv, c0.d_Linv, c0.bw, 0, k0,
+                                                                                             c1.d_tiles, c1.d_dinv, c1.d_Linv, c1.bw, 0);
+            LAUNCH_CHECK(h);
+            int rc1 = launch_sweep_build(h, s_side, 0, 1);
+            if (rc1 != JK_OK) return rc1;
+            CUDA_TRY(h, cudaEventRecord(h->ev_fwd1, s_side));
+            k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a2, ncl == 2 ? b2 : a2, h->d_info, nullptr);
+            LAUNCH_CHECK(h);
+            if (ncl == 2) {
+                long long n = 36LL * h->nS_nodes * h->nS_nodes;
+                k_sep_merge_tiles<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c0.d_tiles, c0.bw, c0.kS, c1.d_tiles, c1.bw, c1.kS, h->nS_nodes);
+                LAUNCH_CHECK(h);
+                CholChain f{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, c0.kS, c0.NT};
+                k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(f, f, h->d_info, nullptr);
+                LAUNCH_CHECK(h);
+            }
+            const int n0b = c0.NT - k0, n1b = ncl == 2 ? c1.kS - k1 : 0;
+            k_tile_inverse_blocked<<<n0b + n1b, 256, INVERSE_BLOCKED_SMEM, s>>>(c0.d_tiles, c0.d_dinv, c0.d_Linv, c0.bw, k0, n0b,
+                                                                                c1.d_tiles, c1.d_dinv, c1.d_Linv, c1.bw, k1);
+            LAUNCH_CHECK(h);
+            int rc2 = launch_sweep_build(h, s, 0, 2);
+            if (rc2 != JK_OK) return rc2;
+            CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_fwd1, 0));      // the factor stage is complete when both branches are
+            toc(h, JK_T_FACTOR, s);
+            if (want_prof) { CUDA_TRY(h, cudaStreamSynchronize(s)); cudaFree(prof); }
+            return JK_OK;
+        }
         if (h->n_chains == 2) {
             // stage 1: both chains eliminate towards the separator, concurrently on two clusters
             CholChain b{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, 0, c1.kS};
@@ -801,7 +870,7 @@ static int launch_factor(jk_handle_t h, cudaStream_t s) {
     { const int n1 = h->n_chains == 2 ? c1.kS : 0;     // second chain: its separator rows are factored in the first chain
       if (use_cluster && getenv("JK_INVERSE_LEGACY") == nullptr)     // the cluster kernel left the 8x8 block inverses in d_dinv
           k_tile_inverse_blocked<<<c0.NT + n1, 256, INVERSE_BLOCKED_SMEM, s>>>(c0.d_tiles, c0.d_dinv, c0.d_Linv, c0.bw, 0, c0.NT,
-                                                                               c1.d_tiles, c1.d_dinv, c1.d_Linv, c1.bw);
+                                                                               c1.d_tiles, c1.d_dinv, c1.d_Linv, c1.bw, 0);
       else
           k_tile_inverse<<<c0.NT + n1, 256, INVERSE_SMEM, s>>>(c0.d_tiles, c0.d_Linv, c0.bw, c0.NT, c1.d_tiles, c1.d_Linv, c1.bw);
       LAUNCH_CHECK(h); }
@@ -833,6 +902,7 @@ extern "C" int jk_factor(jk_handle_t h) {
     int rc = launch_factor(h, h->stream);
     if (rc != JK_OK) return rc;
     if ((rc = launch_sweep_build(h, h->stream, 1)) != JK_OK) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fwd1, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->ev_factor_bwd, h->stream));
     h->assembled = false;       // the tile storage now holds L
@@ -851,7 +921,7 @@ extern "C" int jk_factor_begin(jk_handle_t h) {
     cudaSetDevice(h->device);
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-    int rc = launch_factor(h, h->stream2);
+    int rc = launch_factor(h, h->stream2, h->stream3);
     if (rc != JK_OK) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream2));
     // the backward tile streams are only needed after the forward sweeps: built behind the event, they overlap them
@@ -1047,31 +1117,48 @@ static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool f
 static int run_fem(jk_handle_t h, int ldP, double fy) {
     cudaStream_t s = h->stream;
     int nslab = ldP / SLAB;
-    if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0));   // join the side stream
+    if (h->factor_inflight && !h->tma_sweep) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0));   // join the side stream (the TMA path joins below)
     auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
     const int nS6 = 6 * h->nS_nodes;
     dim3 gsep(ceil_div(ldP, 128), std::max(1, nS6));
     static const bool sweep_prof = getenv("JK_SWEEP_PROFILE") != nullptr;
     long long* d_prof = nullptr;
     if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, 4 * 64 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, 4 * 64 * sizeof(long long), s)); }
-    auto sweep = [&](int c, int d) {
+    // part: 0 = whole program, 1 = items [0, n_split), 2 = the rest (continues from the rows part 1 left in the slab)
+    auto sweep = [&](int c, int d, int part = 0) {
         auto& chn = h->ch[c]; auto& w = chn.sw[d];
-        if (w.n_items > 0) k_sweep<<<nslab, SW_THREADS, SW_SMEM, s>>>(w.d_prog, w.d_stream, h->d_X, w.n_items, h->n_pad, chn.row0, w.pre_row, w.npre, w.ktop,
-                                                                      d_prof ? d_prof + (2 * c + d) * 64 : nullptr);
+        const int lo = part == 2 ? w.n_split : 0, hi = part == 1 ? w.n_split : w.n_items;
+        if (hi <= lo) return;
+        const bool cont = part == 2;
+        k_sweep<<<nslab, SW_THREADS, SW_SMEM, s>>>(w.d_prog + (size_t)lo * SW_ITEM_U4, w.d_stream + (size_t)lo * SW_TILE, h->d_X, hi - lo, h->n_pad, chn.row0,
+                                                   cont ? w.k_split - w.npre2 : w.pre_row, cont ? w.npre2 : w.npre, w.ktop, cont ? 1 : 0, cont ? w.xphase2 : 0,
+                                                   d_prof ? d_prof + (2 * c + d) * 64 : nullptr);
     };
     if (h->tma_sweep) {
         // same elimination-tree order as below; between its forward and backward sweep a chain's rows hold Z = L_kk Y_k
         // in fragment order (jk_sweep.cuh)
+        const bool split = h->split_factor && h->factor_inflight && c0.sw[0].n_split < c0.sw[0].n_items;
+        if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, split ? h->ev_fwd1 : h->ev_factor, 0));   // join the side stream(s)
         tic(h, JK_T_SOLVE_FWD);
-        if (h->n_chains == 2) {
+        if (h->n_chains == 2)
             CUDA_TRY(h, cudaMemset2DAsync(h->d_X + ((size_t)c1.row0 + (size_t)c1.kS * NB) * SLAB, (size_t)h->n_pad * SLAB * sizeof(double), 0,
                                           (size_t)(c1.NT - c1.kS) * NB * SLAB * sizeof(double), (size_t)nslab, s));
-            sweep(1, 0); LAUNCH_CHECK(h);
+        if (split) {
+            // rows below the split point of both chains only need the first factor segment: they run while the
+            // factorisation finishes (the chains do not depend on each other before the separator)
+            if (h->n_chains == 2) { sweep(1, 0, 1); LAUNCH_CHECK(h); }
+            sweep(0, 0, 1); LAUNCH_CHECK(h);
+            toc(h, JK_T_SOLVE_FWD);                           // first parts; the continuation is timed as SOLVE_FWD2
+            CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor, 0));
+            tic(h, JK_T_SOLVE_FWD2);
+            if (h->n_chains == 2) { sweep(1, 0, 2); LAUNCH_CHECK(h); }
+        } else if (h->n_chains == 2) { sweep(1, 0); LAUNCH_CHECK(h); }
+        if (h->n_chains == 2) {
             k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 0);
             LAUNCH_CHECK(h);
         }
-        sweep(0, 0); LAUNCH_CHECK(h);
-        toc(h, JK_T_SOLVE_FWD);
+        sweep(0, 0, split ? 2 : 0); LAUNCH_CHECK(h);
+        if (split) toc(h, JK_T_SOLVE_FWD2); else { toc(h, JK_T_SOLVE_FWD); h->ev_set[JK_T_SOLVE_FWD2] = false; }
         if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0));
         tic(h, JK_T_SOLVE_BWD);
         sweep(0, 1); LAUNCH_CHECK(h);

@@ -196,14 +196,14 @@ __global__ void __launch_bounds__(256) k_tile_inverse(const double* __restrict__
 constexpr size_t INVERSE_BLOCKED_SMEM = (size_t)(2 * NB * (NB + 1) + 8 * NB) * sizeof(double);
 __global__ void __launch_bounds__(256) k_tile_inverse_blocked(const double* __restrict__ tiles, const double* __restrict__ dinv, double* __restrict__ Linv,
                                                               int bw, int k_first, int n0, const double* __restrict__ tiles1,
-                                                              const double* __restrict__ dinv1, double* __restrict__ Linv1, int bw1) {
+                                                              const double* __restrict__ dinv1, double* __restrict__ Linv1, int bw1, int k_first1) {
     extern __shared__ __align__(16) double smem[];
     double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem);
     double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem + NB * (NB + 1));
     double (*T)[NB] = reinterpret_cast<double (*)[NB]>(smem + 2 * NB * (NB + 1));      // [8][NB] rows of the current block step
     int k = blockIdx.x;
     const int tid = threadIdx.x;
-    if (k >= n0) { k -= n0; tiles = tiles1; dinv = dinv1; Linv = Linv1; bw = bw1; } else k += k_first;
+    if (k >= n0) { k = k - n0 + k_first1; tiles = tiles1; dinv = dinv1; Linv = Linv1; bw = bw1; } else k += k_first;
     const double* g = tiles + tile_off(k, k, bw);
     const double* di = dinv + (size_t)k * 512;
     for (int idx = tid; idx < NB * NB; idx += 256) {

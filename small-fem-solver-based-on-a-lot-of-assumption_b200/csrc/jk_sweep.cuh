@@ -309,7 +309,11 @@ __device__ __forceinline__ void sweep_mma_single(double (&acc)[SW_RBN][SW_CBN][2
 __global__ void __launch_bounds__(SW_THREADS, 1)
 k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, double* __restrict__ X,
         int n_items, int n_pad /* rows of the whole slab */, int row0 /* first row of this chain in the slab */,
-        int pre_row /* first known tile row (backward, second chain) */, int npre /* known tile rows to preload */, int ktop,
+        int pre_row /* first known tile row */, int npre /* known tile rows to preload into the ring */, int ktop,
+        int pre_mode /* 0: backward, rows hold X row-major (second chain's separator solution), ring slot (ktop - row) % R;
+                        1: forward continuation, rows hold Z in fragment order, ring slot row % R */,
+        int xphase_bits /* bit s: ring slot s starts one mbarrier phase ahead (continuation of a program whose slot parities
+                           count from its first row) */,
         long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (JK_SWEEP_PROFILE) */) {
     extern __shared__ __align__(128) unsigned char sw_smem[];
     double* As = reinterpret_cast<double*>(sw_smem);                 // [SW_STAGES][SW_TILE]   A tiles, fragment order
@@ -372,12 +376,20 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     else if (SW_CONSUMER_WARPS == 16) { cb0 = 2 * (warp >> 3); rbs[0] = ((warp >> 2) & 1) ? 7 - (warp & 3) : (warp & 3); }   // scheduler s: row blocks s, 7 - s
     else if (SW_RBN == 4) { cb0 = warp & 3; for (int a = 0; a < SW_RBN; ++a) rbs[a] = 2 * a + (warp >> 2); }
     else { cb0 = 2 * (warp >> 2); rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
-    // known rows of a backward sweep that starts below the top (second chain: separator solution): row-major -> ring
+    // a program that continues another launch: bring the slots' mbarrier phases in step with the item parities
+    if (xphase_bits) {
+        if (lane == 0)
+            for (int sl = 0; sl < SW_RING; ++sl) if ((xphase_bits >> sl) & 1) mbar_arrive(bar_x + 8 * sl);
+        consumer_bar_sync();
+    }
+    // rows solved before this launch that its first rows need: the second chain's separator solution (backward,
+    // row-major) or the rows just before a forward continuation (Z, already in fragment order) -> ring
     for (int q = 0; q < npre; ++q) {
-        const int i = pre_row + q, slot = (ktop - i) % SW_RING;
+        const int i = pre_row + q, slot = (pre_mode ? i : ktop - i) % SW_RING;
         const double* g = Xslab + (size_t)i * SW_XTILE;
         double* dst = Xr + slot * SW_XTILE;
-        for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[sw_x_index(e / SLAB, e % SLAB)] = g[e];
+        if (pre_mode) { for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[e] = g[e]; }
+        else { for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[sw_x_index(e / SLAB, e % SLAB)] = g[e]; }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_x + 8 * slot);
     }

@@ -40,21 +40,34 @@ def tile(Lm, i, j):
     return Lm[i * NB:(i + 1) * NB, j * NB:(j + 1) * NB]
 
 
-def run_program(items, meta, Lm, X, backward, known_rows=None):
-    """Interpret the item list on X ([NT*NB, nrhs], modified in place like the slab).  Returns tile products executed."""
+def run_program(items, meta, Lm, X, backward, known_rows=None, forward_continuation=None):
+    """Interpret the item list on X ([NT*NB, nrhs], modified in place like the slab).  Returns tile products executed.
+    forward_continuation = (first_row, npre): the items continue a forward program from first_row in a NEW launch: the
+    npre rows before it are reloaded from the slab (they hold Z) and the slots' mbarrier phases are pre-advanced."""
     NT = Lm.shape[0] // NB
     Linv = [np.linalg.inv(tile(Lm, k, k)) for k in range(NT)]
     ring_row = [None] * RING
     ring_val = [None] * RING
     fills = [0] * RING
     pre_row, npre, ktop = (int(v) for v in meta)
-    for q in range(npre):
-        i = pre_row + q
-        slot = (ktop - i) % RING
-        ring_row[slot], ring_val[slot] = i, X[i * NB:(i + 1) * NB].copy()
-        fills[slot] += 1
-    acc = None
     waited = set()      # operand rows some earlier item of the program already waited on
+    if forward_continuation is not None:
+        k1, npre = forward_continuation
+        pre_row = k1 - npre
+        for r in range(pre_row, pre_row + RING):          # xphase bits of jk_set_supports
+            fills[r % RING] = (r // RING) & 1
+        for i in range(pre_row, k1):
+            slot = i % RING
+            ring_row[slot], ring_val[slot] = i, X[i * NB:(i + 1) * NB].copy()
+            fills[slot] += 1
+            waited.add(i)                                  # made visible by the consumers' barrier after the preload
+    else:
+        for q in range(npre):
+            i = pre_row + q
+            slot = (ktop - i) % RING
+            ring_row[slot], ring_val[slot] = i, X[i * NB:(i + 1) * NB].copy()
+            fills[slot] += 1
+    acc = None
     rhs = X[items[0][0] * NB:(items[0][0] + 1) * NB].copy() if items[0][2] & INIT_RHS else None
     nprod = 0
     for row, src, flags, xinfo, next_row, next_init in items:
@@ -209,3 +222,23 @@ def test_envelope_drops_empty_tiles_and_still_solves(NT, bw, kx):
     else:
         run_program(b, mb, Lm, X, True)
         np.testing.assert_allclose(X, np.linalg.solve(A, B), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("NT,bw,kx,k1", [(20, 4, 20, 16), (23, 3, 18, 14), (17, 4, 12, 11)])
+def test_forward_program_split_into_two_launches(NT, bw, kx, k1):
+    """Split factor: the forward items of tile rows < k1 run in one launch, the rest in a second one that reloads the
+    last band rows (Z) from the slab and pre-advances the ring slots' mbarrier phases.  Same result as one launch."""
+    rng = np.random.default_rng(31 * NT + k1)
+    A = banded_spd(NT, bw, rng)
+    Lm = np.linalg.cholesky(A)
+    B = rng.standard_normal((NT * NB, 3))
+    f, mf = program(NT, bw, kx, False)
+    X1 = B.copy()
+    run_program(f, mf, Lm, X1, False)
+    n1 = int(np.argmax(f[:, 0] >= k1))
+    assert 0 < n1 < len(f) and f[n1, 2] & ROW_BEGIN
+    X2 = B.copy()
+    run_program(f[:n1], mf, Lm, X2, False)
+    assert np.array_equal(X2[k1 * NB:], B[k1 * NB:])            # untouched rows still hold the right-hand side
+    run_program(f[n1:], mf, Lm, X2, False, forward_continuation=(k1, min(bw, k1)))
+    np.testing.assert_allclose(X2, X1, rtol=1e-12, atol=1e-13)
