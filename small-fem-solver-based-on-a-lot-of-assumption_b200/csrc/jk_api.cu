@@ -1221,8 +1221,8 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
                                            h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Ffix, h->d_react);
     LAUNCH_CHECK(h);
     if (s2 != s) CUDA_TRY(h, cudaEventRecord(h->ev_post_join, s2));
-    dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, PH_TPB));
-    k_member_post<<<gm, PH_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
+    dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, JK_POST_TPB));
+    k_member_post<<<gm, JK_POST_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
                                         h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
     LAUNCH_CHECK(h);
     if (s2 != s) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_post_join, 0));

@@ -10,6 +10,9 @@
 #pragma once
 #include "jk_common.cuh"
 
+#ifndef JK_POST_TPB
+#define JK_POST_TPB 128        // threads (= phases) per block of k_member_post (A/B switch: longer contiguous write runs)
+#endif
 #ifndef JK_POST_PREFETCH
 #define JK_POST_PREFETCH 0   // 1: next member's displacements in flight during this member's arithmetic (96 registers; measured 4 % slower)
 #endif
@@ -226,7 +229,7 @@ __device__ __forceinline__ double load_u(const double* __restrict__ X, const int
 // ----------------------------------------------------------------------------------------------
 // K5: block = 128 phases x MCHUNK members.  rows[m][7][ldP]; per-chunk running maxima.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PH_TPB)
+__global__ void __launch_bounds__(JK_POST_TPB)
 k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
               const int* __restrict__ conn, const double* __restrict__ mc, StressPts sp, double fy,
               double* __restrict__ rows, double* __restrict__ part_util, double* __restrict__ part_vm,

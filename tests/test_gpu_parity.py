@@ -425,3 +425,27 @@ def test_single_rank_sharded_scan_paths_agree():
     assert int(b["critical_index"]) == ref.critical_index and float(b["critical_value"]) == ref.table[ref.critical_index, 2]
     got = b["table"].cpu().numpy()
     assert np.array_equal(got[:, 2:], ref.table[:, 2:]) and np.array_equal(got[:, 0], ref.table[:, 0])
+
+
+def test_split_factor_is_bit_identical():
+    """Scheduling variant of the same arithmetic: the factorisation in two segments with the forward sweeps of the rows
+    below the split point started early (continuation launches reload the ring from the slab) vs everything in one
+    piece.  Same sums in the same order -> identical bits."""
+    import os
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    out = {}
+    for mode, env in (("default", {}), ("one_segment", {"JK_NO_FACTOR_SPLIT": "1"})):
+        os.environ.update(env)
+        try:
+            nodes, members, fixed, top = jb.generate_jacket(8, 40)
+            st = jb.build_structure(nodes, members, fixed, top, ap)
+            res = jb.phase_scan(st, _wave(jb, ap), 100, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+            out[mode] = (res.table.copy(), res.phase(37)["U"].copy(), res.engine.residual(), res.engine.dims())
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    assert out["default"][3]["n_chains"] == 2
+    assert np.array_equal(out["one_segment"][0], out["default"][0])
+    assert np.array_equal(out["one_segment"][1], out["default"][1])
+    assert out["default"][2] < 1e-9
