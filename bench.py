@@ -42,7 +42,7 @@ WORKLOADS = {
 FP64_PEAK_TFLOPS = 37.1    # measured on this pool (profiles/r01_fp64_peaks.json): DMMA m8n8k4 issue peak
 # dram read+write bytes per launch of the sweep kernels on c4 / 4096 phases, from the ncu --set full captures under profiles/
 SWEEP_TRAFFIC = {"k_slab_sweep": 1.31e9,      # profiles/r01b (legacy cp.async sweep)
-                 "k_sweep": 1.26e9}           # profiles/r01h: 2 kernel launches (both chains) per direction, 0.63 GB each
+                 "k_sweep": 1.21e9}           # profiles/r01j: forward 0.48+0.47+0.11+0.10 GB, backward 0.62+0.63 GB -> mean per direction
 
 
 def parse():
