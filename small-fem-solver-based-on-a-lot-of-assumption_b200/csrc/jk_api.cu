@@ -705,7 +705,12 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
             w.n_split = w.n_items; w.k_split = 0; w.npre2 = 0; w.xphase2 = 0;
             if (d == 0 && w.n_items > 0) {
                 // split point: 80 % of the chain's own columns (the separator columns of the first chain come last anyway)
-                const int kS = chn.kS, k1 = (4 * kS) / 5;
+                // 70 % of the chain's own columns: on c4 the first segment then ends well inside the Morison stage, so its
+                // inverse / stream-build kernels and the relaunch of the cluster kernel do not collide with the gather and
+                // the sweeps (60-80 % measure the same within 1 %; close to 90 % the second segment competes with the sweep
+                // CTAs for whole SMs and the step degrades badly)
+                static const int split_pct = getenv("JK_SPLIT_PCT") ? atoi(getenv("JK_SPLIT_PCT")) : 70;
+                const int kS = chn.kS, k1 = (int)((long long)split_pct * kS / 100);
                 if (k1 >= 2 * SW_RING && kS - k1 >= 4) {
                     int n1 = 0;
                     while (n1 < w.n_items && (int)prog[(size_t)n1 * SW_ITEM_U4].x < k1) ++n1;

@@ -278,7 +278,7 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
         member_row(c, s_pt + mm * 24, Fl, inv_fy, row);
         size_t o = ((size_t)(m0 + mm) * 7) * ldP + p;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) rows[o + (size_t)k * ldP] = row[k];
+        for (int k = 0; k < 7; ++k) __stcs(rows + o + (size_t)k * ldP, row[k]);      // write-once stream: keep the solution slab in L2
         if (row[6] > best_u) { best_u = row[6]; best_vm = row[5]; best_m = m0 + mm; }
     }
     size_t po = (size_t)chunk * ldP + p;
