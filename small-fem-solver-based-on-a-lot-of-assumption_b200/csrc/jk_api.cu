@@ -4,6 +4,8 @@
 // There is no CPU compute path: every jk_* numeric entry point launches kernels or fails.
 #include "../../include/jacket_b200.h"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -33,6 +35,9 @@ struct jk_handle_s {
     cudaEvent_t ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_gather = nullptr;
     bool gather_inflight = false;
     cudaEvent_t ev_post_fork = nullptr, ev_post_join = nullptr;   // node-level post kernels run beside the member post on the side stream
+    // start gate of the factor clusters (k_band_chol_cluster): device counter + cuStreamWaitValue32 on the main stream
+    unsigned* d_started = nullptr; unsigned started_target = 0;
+    CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     cudaEvent_t ev_seg1 = nullptr, ev_fwd1 = nullptr;   // first factor segment done / its forward tile streams built
     bool split_factor = false;
     cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_factor_bwd = nullptr;   // ev_factor: forward sweeps may start; ev_factor_bwd: backward tile streams built too
@@ -184,6 +189,14 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, hi); }
     for (auto& e : h->ev_part) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
+    if (getenv("JK_NO_START_GATE") == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn != nullptr
+            && cudaMalloc((void**)&h->d_started, sizeof(unsigned)) == cudaSuccess && cudaMemset(h->d_started, 0, sizeof(unsigned)) == cudaSuccess)
+            h->wait_value32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fn);
+        cudaGetLastError();
+    }
     cudaEventCreateWithFlags(&h->ev_seg1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
@@ -261,6 +274,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
     for (auto& e : h->ev_part) if (e) cudaEventDestroy(e);
     if (h->ev_gather) cudaEventDestroy(h->ev_gather);
+    if (h->d_started) cudaFree(h->d_started);
     if (h->ev_seg1) cudaEventDestroy(h->ev_seg1);
     if (h->ev_fwd1) cudaEventDestroy(h->ev_fwd1);
     if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
@@ -762,6 +776,8 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     return JK_OK;
 }
 
+__global__ void k_debug_spin(long long clocks) { const long long t0 = clock64(); while (clock64() - t0 < clocks) { } }
+
 // part: 0 = whole program, 1 = items [0, n_split), 2 = items [n_split, n_items)   (forward programs of a split factor)
 static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d, int part = 0) {
     if (!h->tma_sweep) return JK_OK;
@@ -791,6 +807,8 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
         const bool want_prof = getenv("JK_CHOL_PROFILE") != nullptr;
         if (want_prof) { CUDA_TRY(h, cudaMalloc((void**)&prof, (size_t)c0.NT * 8 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(prof, 0, (size_t)c0.NT * 8 * sizeof(long long), s)); }
         CholChain a{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, 0, c0.kS};
+        unsigned* gate = (s_side != nullptr && h->wait_value32) ? h->d_started : nullptr;   // asynchronous factorisation only
+        if (getenv("JK_DEBUG_FACTOR_DELAY")) k_debug_spin<<<1, 32, 0, s>>>(atoll(getenv("JK_DEBUG_FACTOR_DELAY")));   // test aid: lose the race on purpose
         if (h->split_factor && s_side != nullptr) {
             // Two segments.  After the first (80 % of each chain's columns) a side stream inverts those diagonal tiles and
             // builds the forward tile streams of those rows, so the forward sweeps can start on them (run_fem) while this
@@ -800,7 +818,8 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
             CholChain a1{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, 0, k0}, a2{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, k0, c0.kS};
             CholChain b1{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, 0, k1}, b2{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, k1, c1.kS};
             const int ncl = h->n_chains == 2 ? 2 : 1;
-            k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a1, ncl == 2 ? b1 : a1, h->d_info, prof);
+            k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a1, ncl == 2 ? b1 : a1, h->d_info, prof, gate);
+            if (gate) h->started_target += (unsigned)(ncl * CHOL_CLUSTER);
             LAUNCH_CHECK(h);
             CUDA_TRY(h, cudaEventRecord(h->ev_seg1, s));
             CUDA_TRY(h, cudaStreamWaitEvent(s_side, h->ev_seg1, 0));
@@ -834,7 +853,8 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
         if (h->n_chains == 2) {
             // stage 1: both chains eliminate towards the separator, concurrently on two clusters
             CholChain b{c1.d_tiles, c1.d_dinv, c1.NT, c1.bw, 0, c1.kS};
-            k_band_chol_cluster<<<2 * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a, b, h->d_info, prof);
+            k_band_chol_cluster<<<2 * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a, b, h->d_info, prof, gate);
+            if (gate) h->started_target += (unsigned)(2 * CHOL_CLUSTER);
             LAUNCH_CHECK(h);
             // stage 2: separator Schur complement = sum of both chains' trailing blocks
             long long n = 36LL * h->nS_nodes * h->nS_nodes;
@@ -845,7 +865,8 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
             k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(f, f, h->d_info, nullptr);
             LAUNCH_CHECK(h);
         } else {
-            k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a, a, h->d_info, prof);
+            k_band_chol_cluster<<<CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a, a, h->d_info, prof, gate);
+            if (gate) h->started_target += (unsigned)CHOL_CLUSTER;
             LAUNCH_CHECK(h);
         }
         if (want_prof) {   // debug aid: average clock deltas between the phase stamps of chain 0, CTA 0
@@ -926,8 +947,14 @@ extern "C" int jk_factor_begin(jk_handle_t h) {
     cudaSetDevice(h->device);
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    const unsigned target0 = h->started_target;
     int rc = launch_factor(h, h->stream2, h->stream3);
     if (rc != JK_OK) return rc;
+    if (h->wait_value32 && h->started_target != target0) {
+        // the main stream (Morison next) continues once every CTA of the first cluster launch is resident
+        if (h->wait_value32((CUstream)h->stream, (CUdeviceptr)h->d_started, (cuuint32_t)h->started_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            JK_FAIL(h, JK_ECUDA, "jk_factor_begin: cuStreamWaitValue32 failed");
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream2));
     // the backward tile streams are only needed after the forward sweeps: built behind the event, they overlap them
     if ((rc = launch_sweep_build(h, h->stream2, 1)) != JK_OK) return rc;

@@ -23,7 +23,10 @@ namespace jk {
 #ifndef JK_TRSM_UNROLL
 #define JK_TRSM_UNROLL 1      // fully unrolled panel TRSM: the independent block updates of a step overlap (factor 2.92 -> 2.79 ms)
 #endif
-constexpr int CHOL_CLUSTER = 8;
+#ifndef JK_CHOL_CLUSTER
+#define JK_CHOL_CLUSTER 8       // CTAs (SMs) per factorisation cluster
+#endif
+constexpr int CHOL_CLUSTER = JK_CHOL_CLUSTER;
 constexpr int CHOL_THREADS = 256;
 constexpr int DI_LD = 12;                                   // row stride of an 8x8 inverse block in smem (== 12 mod 16: conflict-free)
 constexpr int DI_BLK = 8 * DI_LD;
@@ -231,9 +234,14 @@ struct CholChain { double* tiles; double* dinv; int NT, bw, k_begin, k_end; };
 // from both ends at once (the second chain is the same matrix in reversed order), halving the pivot chain.
 __global__ void __cluster_dims__(CHOL_CLUSTER, 1, 1) __launch_bounds__(CHOL_THREADS, 1)
 k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
-                    long long* __restrict__ prof /* optional [NT][8] clock stamps of chain 0, CTA 0 (debug) */) {
+                    long long* __restrict__ prof /* optional [NT][8] clock stamps of chain 0, CTA 0 (debug) */,
+                    unsigned* __restrict__ started = nullptr /* optional: every CTA adds 1 as soon as it is resident */) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
+    // Start gate: the stream that launches the (SM-filling) Morison kernel waits on this counter, so that the factor
+    // clusters are resident first.  Otherwise the Morison grid can take every SM a moment earlier and the clusters -- which
+    // need eight nearly empty SMs of one GPC at the same time -- starve until it has run out of blocks (+2.7 ms per step).
+    if (started != nullptr && threadIdx.x == 0) { atomicAdd(started, 1u); __threadfence(); }
     const bool second = blockIdx.x >= CHOL_CLUSTER;
     const CholChain ch = second ? chain1 : chain0;
     double* __restrict__ tiles = ch.tiles;
