@@ -427,25 +427,42 @@ def test_single_rank_sharded_scan_paths_agree():
     assert np.array_equal(got[:, 2:], ref.table[:, 2:]) and np.array_equal(got[:, 0], ref.table[:, 0])
 
 
-def test_split_factor_is_bit_identical():
-    """Scheduling variant of the same arithmetic: the factorisation in two segments with the forward sweeps of the rows
-    below the split point started early (continuation launches reload the ring from the slab) vs everything in one
-    piece.  Same sums in the same order -> identical bits."""
+@pytest.mark.parametrize("legs,bays,single_chain", [(8, 40, False), (6, 60, True)])
+def test_split_factor_is_bit_identical(legs, bays, single_chain):
+    """Scheduling variants of the same arithmetic: the ASYNCHRONOUS factorisation in two segments, with the forward sweeps
+    of the rows below the split point started early and continuation launches that reload the ring from the slab, vs one
+    segment, vs the blocking factor.  Same sums in the same order -> identical bits."""
     import os
     import jacket_b200 as jb
     ap = jb.AnalysisParams(wave_model="Airy")
+    G = ap.E / (2 * (1 + ap.nu))
     out = {}
-    for mode, env in (("default", {}), ("one_segment", {"JK_NO_FACTOR_SPLIT": "1"})):
+    for mode, env in (("split", {}), ("one_segment", {"JK_NO_FACTOR_SPLIT": "1"}), ("no_gate", {"JK_NO_START_GATE": "1"})):
+        if single_chain:
+            env = dict(env, JK_SINGLE_CHAIN="1")
         os.environ.update(env)
         try:
-            nodes, members, fixed, top = jb.generate_jacket(8, 40)
+            nodes, members, fixed, top = jb.generate_jacket(legs, bays)
             st = jb.build_structure(nodes, members, fixed, top, ap)
-            res = jb.phase_scan(st, _wave(jb, ap), 100, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
-            out[mode] = (res.table.copy(), res.phase(37)["U"].copy(), res.engine.residual(), res.engine.dims())
+            ref = jb.phase_scan(st, _wave(jb, ap), 100, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)   # blocking factor
+            eng = ref.engine
+            tables = []
+            for _ in range(2):
+                eng.assemble(ap.E, G)
+                eng.factor(overlap=True)                      # jk_factor_begin: side streams, split when the chains are long enough
+                table, crit = eng.phase_scan(ref.table[:, 0].copy(), ap.fy)
+                assert crit == ref.critical_index
+                tables.append(table)
+            u = eng.fetch_phase(37)["U"].copy()
+            assert np.array_equal(tables[0], tables[1])
+            assert np.array_equal(tables[0][:, 2:], ref.table[:, 2:]), mode           # asynchronous == blocking
+            out[mode] = (tables[0], u, eng.residual(), eng.dims())
         finally:
             for k in env:
                 os.environ.pop(k, None)
-    assert out["default"][3]["n_chains"] == 2
-    assert np.array_equal(out["one_segment"][0], out["default"][0])
-    assert np.array_equal(out["one_segment"][1], out["default"][1])
-    assert out["default"][2] < 1e-9
+    assert out["split"][3]["n_chains"] == (1 if single_chain else 2)
+    assert out["split"][3]["n_tiles"] >= 28                   # long enough for the split to be active
+    for mode in ("one_segment", "no_gate"):
+        assert np.array_equal(out[mode][0], out["split"][0]), mode
+        assert np.array_equal(out[mode][1], out["split"][1]), mode
+    assert out["split"][2] < 1e-9
