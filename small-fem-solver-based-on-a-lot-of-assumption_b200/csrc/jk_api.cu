@@ -35,6 +35,9 @@ struct jk_handle_s {
     cudaEvent_t ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_gather = nullptr;
     bool gather_inflight = false;
     cudaEvent_t ev_post_fork = nullptr, ev_post_join = nullptr;   // node-level post kernels run beside the member post on the side stream
+    // pinned staging for the small per-scan host transfers (static load in, table + critical index + pivot flag out): one
+    // asynchronous copy each and a single synchronisation per scan instead of pageable copies with their own syncs
+    unsigned char* h_pin = nullptr; size_t pin_bytes = 0; cudaEvent_t ev_pin = nullptr; bool pin_busy = false;
     // start gate of the factor clusters (k_band_chol_cluster): device counter + cuStreamWaitValue32 on the main stream
     unsigned* d_started = nullptr; unsigned started_target = 0;
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -142,6 +145,16 @@ template <typename T>
 static void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+// pinned staging buffer of at least n bytes, free for reuse (the previous asynchronous copy out of it has finished)
+static unsigned char* pin_acquire(jk_handle_t h, size_t n) {
+    if (h->pin_busy) { cudaEventSynchronize(h->ev_pin); h->pin_busy = false; }
+    if (n > h->pin_bytes) {
+        if (h->h_pin) { cudaFreeHost(h->h_pin); h->h_pin = nullptr; h->pin_bytes = 0; }
+        if (cudaMallocHost((void**)&h->h_pin, n) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        h->pin_bytes = n;
+    }
+    return h->h_pin;
+}
 static void tic(jk_handle_t h, int id, cudaStream_t s = nullptr) { cudaEventRecord(h->ev0[id], s ? s : h->stream); }
 static void toc(jk_handle_t h, int id, cudaStream_t s = nullptr) { cudaEventRecord(h->ev1[id], s ? s : h->stream); h->ev_set[id] = true; }
 
@@ -197,6 +210,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
             h->wait_value32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fn);
         cudaGetLastError();
     }
+    cudaEventCreateWithFlags(&h->ev_pin, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_seg1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
@@ -274,6 +288,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
     for (auto& e : h->ev_part) if (e) cudaEventDestroy(e);
     if (h->ev_gather) cudaEventDestroy(h->ev_gather);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->ev_pin) cudaEventDestroy(h->ev_pin);
     if (h->d_started) cudaFree(h->d_started);
     if (h->ev_seg1) cudaEventDestroy(h->ev_seg1);
     if (h->ev_fwd1) cudaEventDestroy(h->ev_fwd1);
@@ -968,7 +984,15 @@ extern "C" int jk_factor_begin(jk_handle_t h) {
 extern "C" int jk_set_static_load(jk_handle_t h, const double* F) {
     if (!h || !F) return JK_EINVAL;
     cudaSetDevice(h->device);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_Fstatic, F, 6 * (size_t)h->Nn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const size_t nb = 6 * (size_t)h->Nn * sizeof(double);
+    if (unsigned char* pin = pin_acquire(h, nb)) {
+        memcpy(pin, F, nb);                                   // the caller's buffer is free again when this returns
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_Fstatic, pin, nb, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_pin, h->stream));
+        h->pin_busy = true;
+        return JK_OK;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_Fstatic, F, nb, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return JK_OK;
 }
@@ -1320,6 +1344,31 @@ extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* criti
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     long long idx = -1;
+    const size_t tb = table ? (size_t)P * JK_TABLE_NCOL * sizeof(double) : 0;
+    if (unsigned char* pin = pin_acquire(h, tb + 16)) {
+        // table, critical index and the factorisation's pivot flag in one pinned buffer, one synchronisation
+        if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0));   // d_info is final behind this event
+        tic(h, JK_T_D2H);
+        if (table) CUDA_TRY(h, cudaMemcpyAsync(pin, h->d_table, tb, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(pin + tb, h->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(pin + tb + 8, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+        toc(h, JK_T_D2H);
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        if (table) memcpy(table, pin, tb);
+        memcpy(&idx, pin + tb, sizeof(long long));
+        int info = 0;
+        memcpy(&info, pin + tb + 8, sizeof(int));
+        if (critical) *critical = (int64_t)idx;
+        if (h->factor_inflight) {
+            h->factor_inflight = false;
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream2));
+            if (info != 0) {
+                h->factored = false;
+                JK_FAIL(h, JK_ENOTSPD, "K_ff is not positive definite (pivot %d <= 0): structure is a mechanism or badly supported", info - 1);
+            }
+        }
+        return JK_OK;
+    }
     tic(h, JK_T_D2H);
     if (table) CUDA_TRY(h, cudaMemcpyAsync(table, h->d_table, (size_t)P * JK_TABLE_NCOL * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(&idx, h->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, s));
