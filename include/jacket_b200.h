@@ -158,7 +158,9 @@ int jk_morison_single(jk_handle_t h, double t, double* nodal_forces, double* tot
 
 /* The whole hot path for P phases: Morison -> RHS -> two triangular sweeps ->
  * reactions / member forces / utilisation -> per-phase table -> critical phase.
- * Full per-phase results stay in HBM; fetch rows with jk_fetch_phase. */
+ * Full per-phase results stay in HBM; fetch rows with jk_fetch_phase.
+ * With table == NULL and critical == NULL the call only queues the work (host times in, nothing read back, no
+ * synchronisation): read the results later with jk_read_table or on the device through jk_table_dev. */
 int jk_phase_scan(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical);
 /* Same, but nothing is copied: t_dev[P] is already in HBM and the table stays
  * there (jk_read_table copies it out).  Asynchronous on the handle's stream. */

@@ -38,6 +38,7 @@ struct jk_handle_s {
     // pinned staging for the small per-scan host transfers (static load in, table + critical index + pivot flag out): one
     // asynchronous copy each and a single synchronisation per scan instead of pageable copies with their own syncs
     unsigned char* h_pin = nullptr; size_t pin_bytes = 0; cudaEvent_t ev_pin = nullptr; bool pin_busy = false;
+    double* h_pin_t = nullptr; size_t pin_t_elems = 0; cudaEvent_t ev_pin_t = nullptr; bool pin_t_busy = false;   // phase times in
     // start gate of the factor clusters (k_band_chol_cluster): device counter + cuStreamWaitValue32 on the main stream
     unsigned* d_started = nullptr; unsigned started_target = 0;
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -211,6 +212,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
         cudaGetLastError();
     }
     cudaEventCreateWithFlags(&h->ev_pin, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_pin_t, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_seg1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
@@ -289,6 +291,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     for (auto& e : h->ev_part) if (e) cudaEventDestroy(e);
     if (h->ev_gather) cudaEventDestroy(h->ev_gather);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->h_pin_t) cudaFreeHost(h->h_pin_t);
+    if (h->ev_pin_t) cudaEventDestroy(h->ev_pin_t);
     if (h->ev_pin) cudaEventDestroy(h->ev_pin);
     if (h->d_started) cudaFree(h->d_started);
     if (h->ev_seg1) cudaEventDestroy(h->ev_seg1);
@@ -1386,10 +1390,23 @@ static int scan_host(jk_handle_t h, int P, const double* t, double fy, double* t
     if ((rc = ensure_buffers(h, P, fem, false)) != JK_OK) return rc;
     tic(h, JK_T_SCAN_TOTAL);
     tic(h, JK_T_H2D);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->pin_t_busy) { cudaEventSynchronize(h->ev_pin_t); h->pin_t_busy = false; }
+    if ((size_t)P > h->pin_t_elems) {
+        if (h->h_pin_t) { cudaFreeHost(h->h_pin_t); h->h_pin_t = nullptr; h->pin_t_elems = 0; }
+        if (cudaMallocHost((void**)&h->h_pin_t, (size_t)P * sizeof(double)) == cudaSuccess) h->pin_t_elems = (size_t)P; else cudaGetLastError();
+    }
+    if (h->h_pin_t) {
+        memcpy(h->h_pin_t, t, (size_t)P * sizeof(double));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_t, h->h_pin_t, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_pin_t, h->stream));
+        h->pin_t_busy = true;
+    } else {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
     toc(h, JK_T_H2D);
     if ((rc = scan_core(h, P, fy, fem)) != JK_OK) return rc;
     toc(h, JK_T_SCAN_TOTAL);
+    if (!table && !critical) return JK_OK;      // asynchronous form: the results stay in HBM (jk_read_table / jk_table_dev)
     return jk_read_table(h, P, table, critical);
 }
 

@@ -81,6 +81,9 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 #ifndef JK_MORISON_SSUM
 #define JK_MORISON_SSUM 1
 #endif
+#ifndef JK_MORISON_SUBFAST
+#define JK_MORISON_SUBFAST 1      // drag-only point loop + closed-form inertia sums for members below the lowest trough
+#endif
 #if JK_MORISON_SSUM
 // Scalar-sum form.  With w^ = wave heading, c = current vector, z^ = vertical and e = member axis, the velocity and
 // acceleration of GUI.py:573-588 are U = uw w^ + c + w z^ and A = du w^ + dw z^, so their components normal to the
@@ -101,6 +104,9 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
     double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][MS]: we ce e2 L | p1[3] p0[3] p3[3] | cD cI
     double* s_g = s_m + MCHUNK * MS;                       // s[G], w[G]
     double* s_c = s_g + 2 * G + ((2 * G) & 1);             // [MCHUNK][G][4]: cD L w_g, cI L w_g, s_g cI L w_g, s_g (16-byte aligned)
+#if JK_MORISON_SUBFAST
+    double* s_i = s_c + MCHUNK * G * 4;                    // [MCHUNK][8]: inertia sums of an always-submerged member (below)
+#endif
     int chunk = blockIdx.y, m0 = chunk * MCHUNK;
     int nm = min(MCHUNK, M - m0);
     for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
@@ -125,10 +131,40 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         s_c[4 * i] = s_m[MS * mm + 13] * Lw; s_c[4 * i + 1] = cil; s_c[4 * i + 2] = s_g[g] * cil; s_c[4 * i + 3] = s_g[g];
     }
     __syncthreads();
+#if JK_MORISON_SUBFAST
+    // Members that lie below the lowest trough (every Gauss point z <= -|a|: never dry, neither at t nor at t + dt) take
+    // a shorter point loop.  Their finite-difference acceleration is linear in the per-phase differences
+    //   du = Cu (ckx dcw + skx dsw),  dw = Cw (skx dcw - ckx dsw),   dcw = (cos w(t+dt) - cos wt)/dt,  dsw likewise,
+    // so the inertia Gauss sums sum(ci du), sum(ci dw) and their s-weighted twins collapse to 8 per-member constants
+    // times (dcw, dsw): the point loop keeps only the (non-linear) drag term.  Same value to rounding (1e-13 relative
+    // through the 1/dt amplification, like the direct form); the summation order is fixed, so results stay deterministic.
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        const double* gpm = s_gp + i * G * GP_STRIDE;
+        const double* cm = s_c + i * G * 4;
+        double I[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double zmax = -1e300;
+        for (int g = 0; g < G; ++g) {
+            const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1], Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3];
+            const double cil = cm[4 * g + 1], scil = cm[4 * g + 2];
+            zmax = fmax(zmax, gpm[g * GP_STRIDE + 4]);
+            I[0] = fma(cil * Cu, ckx, I[0]); I[1] = fma(cil * Cu, skx, I[1]);
+            I[2] = fma(cil * Cw, skx, I[2]); I[3] = fma(cil * Cw, ckx, I[3]);
+            I[4] = fma(scil * Cu, ckx, I[4]); I[5] = fma(scil * Cu, skx, I[5]);
+            I[6] = fma(scil * Cw, skx, I[6]); I[7] = fma(scil * Cw, ckx, I[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_i[8 * i + k] = I[k];
+        s_m[MS * i + 15] = (zmax <= -fabs(wv.a) * (1.0 + 1e-9)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+#endif
 
     int p = p_off + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ldP) return;
     const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
+#if JK_MORISON_SUBFAST
+    const double dcw = (cw1 - cw0) * wv.inv_dt, dsw = (sw1 - sw0) * wv.inv_dt;
+#endif
     const double wc2 = 2.0 * fma(wv.sin_w, wv.uc_sin_c, wv.cos_w * wv.uc_cos_c);       // 2 w^.c
     const double cc = fma(wv.uc_sin_c, wv.uc_sin_c, wv.uc_cos_c * wv.uc_cos_c);        // c.c
     double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
@@ -140,6 +176,33 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         double sub = 0.0;
         const double* gpm = s_gp + mm * G * GP_STRIDE;
         const double* cm = s_c + mm * G * 4;
+#if JK_MORISON_SUBFAST
+        const bool submerged = cmem[15] != 0.0;            // block-uniform: no divergence
+        if (submerged) {
+            for (int g = 0; g < G; ++g) {
+                const double2 g01 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE), g23 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE + 2);
+                const double ckx = g01.x, skx = g01.y;
+                const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
+                const double uw = g23.x * c0, w0 = g23.y * s0;                     // GUI.py:279-281, 573 (u - U_c)
+                const double Ue = fma(w0, e2, fma(uw, we, ce));
+                const double UU = fma(w0, w0, fma(uw, uw + wc2, cc));
+                const double m2 = fma(-Ue, Ue, UU);
+                double ry;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ry) : "d"(m2));
+                const double t0 = m2 * ry;
+                const double mag = fma(0.5 * t0, fma(-t0, ry, 1.0), t0);
+                const double cdl = cm[4 * g], s = cm[4 * g + 3];
+                const double kd = (m2 > 1e-20) ? cdl * mag : 0.0;                  // GUI.py:648-651
+                const double skd = s * kd;
+                Sd0 += kd; Sd1 = fma(kd, uw, Sd1); Sd3 = fma(kd, w0, Sd3);
+                Td0 += skd; Td1 = fma(skd, uw, Td1); Td3 = fma(skd, w0, Td3);
+                if (DETAILS) sub += cmem[3] * s_g[G + g];
+            }
+            const double* ci = s_i + 8 * mm;
+            Si1 = fma(ci[1], dsw, ci[0] * dcw); Si3 = fma(-ci[3], dsw, ci[2] * dcw);
+            Ti1 = fma(ci[5], dsw, ci[4] * dcw); Ti3 = fma(-ci[7], dsw, ci[6] * dcw);
+        } else
+#endif
         for (int g = 0; g < G; ++g) {
             const double2 g01 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE), g23 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE + 2);
             const double ckx = g01.x, skx = g01.y, Cu = g23.x, Cw = g23.y, z = gpm[g * GP_STRIDE + 4];
@@ -203,7 +266,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
     }
 }
-constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 16;   // doubles per member beside the Gauss tables (s_m)
+constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 16 + 8 * JK_MORISON_SUBFAST;   // doubles per member beside the Gauss tables (s_m, s_i)
 constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 4;     // doubles per Gauss point beside GP_STRIDE (s_c)
 #else
 template <bool DETAILS>
@@ -551,8 +614,12 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
                 const double wg = s_g[G + g], sg = s_g[g];
                 const double Ue = fma(w0, e2, fma(uw, we, ce));
                 const double UU = fma(w0, w0, fma(uw, uw + wc2, ucuc));
-                const double mag = sqrt(fmax(fma(-Ue, Ue, UU), 0.0));
-                const double kd = (mag > 1e-10) ? (cDL * wg) * mag : 0.0;
+                const double m2 = fma(-Ue, Ue, UU);                               // |U_perp|^2; rsqrt seed + one Newton step as in k_morison_airy
+                double ry;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ry) : "d"(m2));
+                const double t0 = m2 * ry;
+                const double mag = fma(0.5 * t0, fma(-t0, ry, 1.0), t0);
+                const double kd = (m2 > 1e-20) ? (cDL * wg) * mag : 0.0;
                 const double skd = sg * kd, cil = cIL * wg, scil = sg * cil;
                 Sd0 += kd; Sd1 = fma(kd, uw, Sd1); Sd3 = fma(kd, w0, Sd3);
                 Td0 += skd; Td1 = fma(skd, uw, Td1); Td3 = fma(skd, w0, Td3);

@@ -110,7 +110,10 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
     else:
         if t_host is None:
             t_host, _ = shard_times(wave.T, n_total, world_size, rank)
-        host_table, host_crit = engine.phase_scan(t_host, fy)       # already copies table + critical index to the host
+        if world_size == 1:
+            host_table, host_crit = engine.phase_scan(t_host, fy)   # already copies table + critical index to the host
+        else:
+            engine.phase_scan_begin(t_host, fy)                     # the local table is only needed on the device
     table, val, idx = device_views(engine, P)
     if world_size == 1:
         # nothing to exchange: no all-gather, no merge kernels, and the table is copied to the host at most once
@@ -124,24 +127,55 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
                     table=host_table if gather_table else None)
     stream = torch.cuda.ExternalStream(engine.stream(), device=f"cuda:{engine.device}")
     with torch.cuda.stream(stream):
-        cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=host_results)
+        if not host_results:
+            cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=False)
+            full = _allgather_table(table, n_total, world_size, P, group) if gather_table else None
+            return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
+        # host results: both all-gathers are queued behind the scan, their outputs go to ONE pinned staging buffer with
+        # asynchronous copies, and the only host synchronisation of the step is the library's own (read_critical, which
+        # also surfaces a failed factorisation)
+        pair = torch.stack([val.reshape(()), (idx + lo).reshape(()).to(torch.float64)])
+        pairs = torch.empty(world_size * 2, dtype=torch.float64, device=pair.device)
+        dist.all_gather_into_tensor(pairs, pair, group=group)
+        n_tab = n_total * L.TABLE_NCOL if gather_table else 0
+        pin = _pinned(world_size * 2 + n_tab)
+        pin[:world_size * 2].copy_(pairs, non_blocking=True)
+        if gather_table:
+            buf = _allgather_table(table, n_total, world_size, P, group)
+            pin[world_size * 2:].copy_(buf.reshape(-1), non_blocking=True)
+        engine.read_critical(P)
+        host = pin.numpy()
+        hp = host[:world_size * 2].reshape(world_size, 2)
+        cval, cidx = merge_critical(hp[:, 0], hp[:, 1].astype(np.int64))
         full = None
         if gather_table:
-            if world_size > 1:
-                sizes = [shard_bounds(n_total, world_size, r) for r in range(world_size)]
-                if all(h - l == P for l, h in sizes):
-                    buf = torch.empty(n_total * L.TABLE_NCOL, dtype=torch.float64, device=table.device)
-                    dist.all_gather_into_tensor(buf, table.contiguous().reshape(-1), group=group)
-                    buf = buf.reshape(n_total, L.TABLE_NCOL)
-                else:
-                    parts = [torch.empty((h - l, L.TABLE_NCOL), dtype=torch.float64, device=table.device) for l, h in sizes]
-                    dist.all_gather(parts, table.contiguous(), group=group)
-                    buf = torch.cat(parts)
-            else:
-                buf = table
-            if host_results:
-                full = buf.cpu().numpy()
-                fill_phase_deg(full, wave.omega)
-            else:
-                full = buf
+            full = host[world_size * 2:].reshape(n_total, L.TABLE_NCOL).copy()     # the staging buffer is reused by the next scan
+            fill_phase_deg(full, wave.omega)
     return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
+
+
+_PINNED = {}
+
+
+def _pinned(n):
+    """Reusable page-locked float64 staging buffer of at least n elements (one per process)."""
+    import torch
+    buf = _PINNED.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)
+        _PINNED["buf"] = buf
+    return buf[:n]
+
+
+def _allgather_table(table, n_total, world_size, P, group=None):
+    """All-gather the ranks' [P_r,16] tables into one [n_total,16] device tensor (NCCL, on the current stream)."""
+    import torch
+    import torch.distributed as dist
+    sizes = [shard_bounds(n_total, world_size, r) for r in range(world_size)]
+    if all(h - l == P for l, h in sizes):
+        buf = torch.empty(n_total * L.TABLE_NCOL, dtype=torch.float64, device=table.device)
+        dist.all_gather_into_tensor(buf, table.contiguous().reshape(-1), group=group)
+        return buf.reshape(n_total, L.TABLE_NCOL)
+    parts = [torch.empty((h - l, L.TABLE_NCOL), dtype=torch.float64, device=table.device) for l, h in sizes]
+    dist.all_gather(parts, table.contiguous(), group=group)
+    return torch.cat(parts)

@@ -137,6 +137,18 @@ class Engine:
         self._ck(self.lib.jk_phase_scan(self.h, t.shape[0], L.dptr(t), float(fy), L.dptr(table), C.byref(crit)))
         return table, int(crit.value)
 
+    def phase_scan_begin(self, t, fy):
+        """Queue a scan with host times and return without reading anything back (results: read_table / device views)."""
+        t = L.f64(t).reshape(-1)
+        self._ck(self.lib.jk_phase_scan(self.h, t.shape[0], L.dptr(t), float(fy), None, None))
+        return t.shape[0]
+
+    def read_critical(self, P):
+        """Synchronise with the last scan and return its local critical index (also surfaces a failed factorisation)."""
+        crit = C.c_int64(-1)
+        self._ck(self.lib.jk_read_table(self.h, P, None, C.byref(crit)))
+        return int(crit.value)
+
     def phase_scan_dev(self, P, t_dev_ptr, fy):
         self._ck(self.lib.jk_phase_scan_dev(self.h, int(P), C.c_void_p(t_dev_ptr), float(fy)))
 
