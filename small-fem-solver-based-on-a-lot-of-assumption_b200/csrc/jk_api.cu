@@ -41,6 +41,7 @@ struct jk_handle_s {
     double* h_pin_t = nullptr; size_t pin_t_elems = 0; cudaEvent_t ev_pin_t = nullptr; bool pin_t_busy = false;   // phase times in
     // start gate of the factor clusters (k_band_chol_cluster): device counter + cuStreamWaitValue32 on the main stream
     unsigned* d_started = nullptr; unsigned started_target = 0;
+    unsigned gate2_target = 0; bool gate2_armed = false;   // second factor segment resident (awaited before the first forward parts)
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     cudaEvent_t ev_seg1 = nullptr, ev_fwd1 = nullptr;   // first factor segment done / its forward tile streams built
     bool split_factor = false;
@@ -818,6 +819,7 @@ static int launch_sweep_build(jk_handle_t h, cudaStream_t s, int d, int part = 0
 // launches the factorisation on stream s (no host synchronisation)
 static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nullptr) {
     tic(h, JK_T_FACTOR, s);
+    h->gate2_armed = false;
     CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), s));
     // narrow band: persistent cluster kernel(s) (latency chain); wide band / dense: per-column launches
     const bool use_cluster = (h->factor_path == 0) && (h->bw <= 16);
@@ -849,8 +851,15 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
             int rc1 = launch_sweep_build(h, s_side, 0, 1);
             if (rc1 != JK_OK) return rc1;
             CUDA_TRY(h, cudaEventRecord(h->ev_fwd1, s_side));
-            k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a2, ncl == 2 ? b2 : a2, h->d_info, nullptr);
+            // second start gate: run_fem launches the first forward parts (one 200 KB CTA per SM on 128 SMs) only once these
+            // clusters are resident.  With the Morison + load stage as short as the first segment the sweeps otherwise win
+            // the race now and then, the clusters find no GPC with eight free SMs until both parts are through and the step
+            // grows by ~1 ms (seen as 5.5 vs 6.7 ms per step between runs).
+            static const bool gate2_on = getenv("JK_NO_START_GATE2") == nullptr;
+            k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a2, ncl == 2 ? b2 : a2, h->d_info, nullptr, gate2_on ? gate : nullptr);
             LAUNCH_CHECK(h);
+            h->gate2_armed = false;
+            if (gate && gate2_on) { h->gate2_target = h->started_target + (unsigned)(ncl * CHOL_CLUSTER); h->gate2_armed = true; }
             if (ncl == 2) {
                 long long n = 36LL * h->nS_nodes * h->nS_nodes;
                 k_sep_merge_tiles<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c0.d_tiles, c0.bw, c0.kS, c1.d_tiles, c1.bw, c1.kS, h->nS_nodes);
@@ -975,6 +984,7 @@ extern "C" int jk_factor_begin(jk_handle_t h) {
         if (h->wait_value32((CUstream)h->stream, (CUdeviceptr)h->d_started, (cuuint32_t)h->started_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
             JK_FAIL(h, JK_ECUDA, "jk_factor_begin: cuStreamWaitValue32 failed");
     }
+    if (h->gate2_armed) h->started_target = h->gate2_target;     // the counter also counts the second segment's CTAs
     CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream2));
     // the backward tile streams are only needed after the forward sweeps: built behind the event, they overlap them
     if ((rc = launch_sweep_build(h, h->stream2, 1)) != JK_OK) return rc;
@@ -1206,6 +1216,11 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         if (split) {
             // rows below the split point of both chains only need the first factor segment: they run while the
             // factorisation finishes (the chains do not depend on each other before the separator)
+            if (h->gate2_armed) {                            // ... once the second segment's clusters hold their SMs
+                h->gate2_armed = false;
+                if (h->wait_value32((CUstream)s, (CUdeviceptr)h->d_started, (cuuint32_t)h->gate2_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                    JK_FAIL(h, JK_ECUDA, "run_fem: cuStreamWaitValue32 failed");
+            }
             if (h->n_chains == 2) { sweep(1, 0, 1); LAUNCH_CHECK(h); }
             sweep(0, 0, 1); LAUNCH_CHECK(h);
             toc(h, JK_T_SOLVE_FWD);                           // first parts; the continuation is timed as SOLVE_FWD2
@@ -1539,7 +1554,7 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     tic(h, JK_T_MORISON);
     {
         dim3 grid(ceil_div(ldC, PH_TPB), ceil_div(h->M, MCHUNK));
-        size_t smem = ((size_t)ENS_MAXS * ENS_EM * h->ng * 4 + ENS_EM * h->ng + MCHUNK * 8 + 2 * h->ng) * sizeof(double);
+        size_t smem = ens_smem_doubles(h->ng, n_phase) * sizeof(double);
         CUDA_TRY(h, cudaFuncSetAttribute(k_morison_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_morison_ensemble<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, C, ldC, n_states, n_phase, h->d_xyz, h->d_conn, h->d_mc, h->d_gsw,
                                                       h->d_states, h->d_t, w, 0.5 * h->rho * h->Cd, h->rho * h->Cm, h->d_Fm, h->d_totpart);

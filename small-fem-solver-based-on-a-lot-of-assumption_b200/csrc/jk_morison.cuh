@@ -538,15 +538,23 @@ k_morison_fourier(int M, int G, int Nh, int ldP, const double* __restrict__ gp, 
 constexpr int ENS_EM = 8;        // members per table refill
 constexpr int ENS_MAXS = 17;     // states a 128-case block may touch (n_phase >= 8)
 
+__host__ __device__ inline int ens_max_states(int n_phase) { return min(ENS_MAXS, (PH_TPB + n_phase - 2) / n_phase + 1); }
+__host__ __device__ inline size_t ens_smem_doubles(int G, int n_phase) {
+    return (size_t)ens_max_states(n_phase) * ENS_EM * (G * 4 + 8) + ENS_EM * G + ENS_EM + MCHUNK * 8 + 2 * G;
+}
+
 __global__ void __launch_bounds__(PH_TPB)
 k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const double* __restrict__ xyz, const int* __restrict__ conn,
                    const double* __restrict__ mc, const double* __restrict__ gsw, const double* __restrict__ st,
                    const double* __restrict__ t, WaveAiry wv, double cD0, double cI0,
                    double* __restrict__ Fm, double* __restrict__ totpart) {
     extern __shared__ __align__(16) double smem[];
-    double* s_tab = smem;                                   // [ENS_MAXS][ENS_EM][G][4]
-    double* s_z = s_tab + ENS_MAXS * ENS_EM * G * 4;        // [ENS_EM][G]
-    double* s_m = s_z + ENS_EM * G;                         // [MCHUNK][8]
+    const int maxs = ens_max_states(n_phase);               // states a 128-case block may touch
+    double* s_tab = smem;                                   // [maxs][ENS_EM][G][4]
+    double* s_ci = s_tab + maxs * ENS_EM * G * 4;           // [maxs][ENS_EM][8] inertia sums of always-submerged members
+    double* s_z = s_ci + maxs * ENS_EM * 8;                 // [ENS_EM][G]
+    double* s_flag = s_z + ENS_EM * G;                      // [ENS_EM] 1 = below the lowest trough of every state of this block
+    double* s_m = s_flag + ENS_EM;                          // [MCHUNK][8]
     double* s_g = s_m + MCHUNK * 8;                         // s[G], w[G]
     const int chunk = blockIdx.y, m0 = chunk * MCHUNK;
     const int nm = min(MCHUNK, M - m0);
@@ -569,6 +577,9 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
     double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
     const double wc2 = 2.0 * fma(sw, wv.uc_sin_c, cw * wv.uc_cos_c);                   // 2 w^.c for this state's heading
     const double ucuc = fma(wv.uc_sin_c, wv.uc_sin_c, wv.uc_cos_c * wv.uc_cos_c);      // c.c
+    const double dcw = (cw1 - cw0) * wv.inv_dt, dsw = (sw1 - sw0) * wv.inv_dt;          // see the submerged path of k_morison_airy
+    double amax = 0.0;                                                                  // largest amplitude among the block's states
+    for (int s_i = 0; s_i < ns; ++s_i) amax = fmax(amax, fabs(st[s_first + s_i]));
 
     for (int sub = 0; sub < nm; sub += ENS_EM) {
         const int nsub = min(ENS_EM, nm - sub);
@@ -592,6 +603,27 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
             if (s_i == 0) s_z[mm * G + g] = z;
         }
         __syncthreads();
+        // closed-form inertia sums per (state, member) and the block-uniform submerged flag per member
+        for (int e = threadIdx.x; e < ns * nsub; e += blockDim.x) {
+            const int s_i = e / nsub, mm = e % nsub;
+            const double cIL = s_m[8 * (sub + mm) + 4] * s_m[8 * (sub + mm) + 5];
+            const double* q = s_tab + (size_t)(s_i * ENS_EM + mm) * G * 4;
+            double I[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double zmax = -1e300;
+            for (int g = 0; g < G; ++g) {
+                const double ckx = q[4 * g], skx = q[4 * g + 1], Cu = q[4 * g + 2], Cw = q[4 * g + 3];
+                const double cil = cIL * s_g[G + g], scil = s_g[g] * cil;
+                zmax = fmax(zmax, s_z[mm * G + g]);
+                I[0] = fma(cil * Cu, ckx, I[0]); I[1] = fma(cil * Cu, skx, I[1]);
+                I[2] = fma(cil * Cw, skx, I[2]); I[3] = fma(cil * Cw, ckx, I[3]);
+                I[4] = fma(scil * Cu, ckx, I[4]); I[5] = fma(scil * Cu, skx, I[5]);
+                I[6] = fma(scil * Cw, skx, I[6]); I[7] = fma(scil * Cw, ckx, I[7]);
+            }
+#pragma unroll
+            for (int kq = 0; kq < 8; ++kq) s_ci[(size_t)(s_i * ENS_EM + mm) * 8 + kq] = I[kq];
+            if (s_i == 0) s_flag[mm] = (zmax <= -amax * (1.0 + 1e-9)) ? 1.0 : 0.0;
+        }
+        __syncthreads();
         if (!live) continue;
         for (int ms = 0; ms < nsub; ++ms) {
             const int mm = sub + ms;
@@ -600,6 +632,28 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
             // scalar-sum form (see k_morison_airy); the wave heading differs per sea state, so w^.e and p1 are per thread
             const double we = fma(sw, e1, cw * e0), ce = fma(wv.uc_sin_c, e1, wv.uc_cos_c * e0);
             double Sd0 = 0, Sd1 = 0, Sd3 = 0, Td0 = 0, Td1 = 0, Td3 = 0, Si1 = 0, Si3 = 0, Ti1 = 0, Ti3 = 0;
+            if (s_flag[ms] != 0.0) {                       // block-uniform: drag-only point loop, inertia in closed form
+                for (int g = 0; g < G; ++g) {
+                    const double2 q01 = *reinterpret_cast<const double2*>(s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4);
+                    const double2 q23 = *reinterpret_cast<const double2*>(s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4 + 2);
+                    const double c0v = fma(q01.y, sw0, q01.x * cw0), s0v = fma(q01.y, cw0, -(q01.x * sw0));
+                    const double uw = q23.x * c0v, w0 = q23.y * s0v;
+                    const double Ue = fma(w0, e2, fma(uw, we, ce));
+                    const double UU = fma(w0, w0, fma(uw, uw + wc2, ucuc));
+                    const double m2 = fma(-Ue, Ue, UU);
+                    double ry;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ry) : "d"(m2));
+                    const double t0 = m2 * ry;
+                    const double mag = fma(0.5 * t0, fma(-t0, ry, 1.0), t0);
+                    const double kd = (m2 > 1e-20) ? (cDL * s_g[G + g]) * mag : 0.0;
+                    const double skd = s_g[g] * kd;
+                    Sd0 += kd; Sd1 = fma(kd, uw, Sd1); Sd3 = fma(kd, w0, Sd3);
+                    Td0 += skd; Td1 = fma(skd, uw, Td1); Td3 = fma(skd, w0, Td3);
+                }
+                const double* ci = s_ci + (size_t)(sl * ENS_EM + ms) * 8;
+                Si1 = fma(ci[1], dsw, ci[0] * dcw); Si3 = fma(-ci[3], dsw, ci[2] * dcw);
+                Ti1 = fma(ci[5], dsw, ci[4] * dcw); Ti3 = fma(-ci[7], dsw, ci[6] * dcw);
+            } else
             for (int g = 0; g < G; ++g) {
                 const double* q = s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4;
                 const double ckx = q[0], skx = q[1], Cu = q[2], Cw = q[3], z = s_z[ms * G + g];

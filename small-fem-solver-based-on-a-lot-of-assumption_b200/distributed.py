@@ -131,19 +131,23 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
             cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=False)
             full = _allgather_table(table, n_total, world_size, P, group) if gather_table else None
             return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
-        # host results: both all-gathers are queued behind the scan, their outputs go to ONE pinned staging buffer with
-        # asynchronous copies, and the only host synchronisation of the step is the library's own (read_critical, which
-        # also surfaces a failed factorisation)
+        # host results: both all-gathers are queued behind the scan and their outputs go to ONE pinned staging buffer with
+        # asynchronous copies.  The copies run on a torch-owned stream behind the engine's: the pinned block then only
+        # remembers a stream that outlives the engine (freeing it after jk_destroy would otherwise touch a dead stream).
         pair = torch.stack([val.reshape(()), (idx + lo).reshape(()).to(torch.float64)])
         pairs = torch.empty(world_size * 2, dtype=torch.float64, device=pair.device)
         dist.all_gather_into_tensor(pairs, pair, group=group)
         n_tab = n_total * L.TABLE_NCOL if gather_table else 0
         pin = _pinned(world_size * 2 + n_tab)
-        pin[:world_size * 2].copy_(pairs, non_blocking=True)
-        if gather_table:
-            buf = _allgather_table(table, n_total, world_size, P, group)
-            pin[world_size * 2:].copy_(buf.reshape(-1), non_blocking=True)
-        engine.read_critical(P)
+        buf = _allgather_table(table, n_total, world_size, P, group) if gather_table else None
+        cs = _copy_stream(pair.device)
+        cs.wait_stream(stream)
+        with torch.cuda.stream(cs):
+            pin[:world_size * 2].copy_(pairs, non_blocking=True)
+            if gather_table:
+                pin[world_size * 2:].copy_(buf.reshape(-1), non_blocking=True)
+        engine.read_critical(P)          # synchronises the engine's stream; also surfaces a failed factorisation
+        cs.synchronize()                 # the copies (and with them the temporaries) are done before anything is freed
         host = pin.numpy()
         hp = host[:world_size * 2].reshape(world_size, 2)
         cval, cidx = merge_critical(hp[:, 0], hp[:, 1].astype(np.int64))
@@ -155,6 +159,16 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
 
 
 _PINNED = {}
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One torch-owned copy stream per device."""
+    import torch
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
 
 
 def _pinned(n):

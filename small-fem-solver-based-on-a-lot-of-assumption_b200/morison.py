@@ -18,8 +18,18 @@ def phase_times(T, n_steps):
 
 def fill_phase_deg(table, omega):
     """Column 1 of the table, bit-identical to GUI.py:697-698."""
-    table[:, 1] = np.degrees(omega * table[:, 0]) % 360
+    table[:, 1] = mod360(np.degrees(omega * table[:, 0]))
     return table
+
+
+def mod360(x):
+    """``x % 360`` for float arrays, bit-identical (C fmod, then +360 where the remainder is negative -- what Python's and
+    NumPy's float ``%`` do) but twice as fast as NumPy's generic divmod loop."""
+    r = np.fmod(x, 360.0)
+    neg = r < 0
+    if neg.any():
+        r[neg] += 360.0
+    return r
 
 
 class MorisonCalculator:

@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, q):
+    try:
+        _run(rank, world, port, q)
+    except Exception:                     # the parent prints the child's traceback instead of a bare exit code
+        import traceback
+        q.put((rank, "ERR", traceback.format_exc()))
+        raise
+
+
+def _run(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     sys.path.insert(0, ROOT)
     import torch
@@ -52,6 +61,8 @@ def test_nccl_world2_sharded_scan_matches_unsharded():
     for pr in procs:
         pr.start()
     res = [q.get(timeout=300) for _ in procs]
+    for r in res:
+        assert r[1] != "ERR", r[2]
     for pr in procs:
         pr.join(timeout=120)
         assert pr.exitcode == 0
