@@ -41,6 +41,10 @@ struct jk_handle_s {
     double* h_pin_t = nullptr; size_t pin_t_elems = 0; cudaEvent_t ev_pin_t = nullptr; bool pin_t_busy = false;   // phase times in
     // start gate of the factor clusters (k_band_chol_cluster): device counter + cuStreamWaitValue32 on the main stream
     unsigned* d_started = nullptr; unsigned started_target = 0;
+    // early member post: chunks whose members only touch chain-0 / separator nodes are post-processed on a side stream
+    // while the second chain's backward sweep runs (HBM-bound work on the SMs the sweep leaves idle)
+    int* d_post_chunks = nullptr; int n_post_early = 0, n_post_late = 0, n_sm = 0;
+    cudaEvent_t ev_bwd0 = nullptr, ev_post_early = nullptr;
     unsigned gate2_target = 0; bool gate2_armed = false;   // second factor segment resident (awaited before the first forward parts)
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     cudaEvent_t ev_seg1 = nullptr, ev_fwd1 = nullptr;   // first factor segment done / its forward tile streams built
@@ -194,6 +198,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     jk_handle_t h = new jk_handle_s();
     h->device = device;
     cudaSetDevice(device);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; JK_FAIL((jk_handle_t)nullptr, JK_ECUDA, "jk_create: cudaStreamCreate failed"); } h->own_stream = true; }
     for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); h->ev_set[i] = false; }
@@ -216,6 +221,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     cudaEventCreateWithFlags(&h->ev_pin_t, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_seg1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_bwd0, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_post_early, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_join, cudaEventDisableTiming);
     h->Nn = n_nodes; h->M = n_members; h->nsec = n_sec;
@@ -298,6 +305,9 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->d_started) cudaFree(h->d_started);
     if (h->ev_seg1) cudaEventDestroy(h->ev_seg1);
     if (h->ev_fwd1) cudaEventDestroy(h->ev_fwd1);
+    if (h->ev_bwd0) cudaEventDestroy(h->ev_bwd0);
+    if (h->ev_post_early) cudaEventDestroy(h->ev_post_early);
+    dev_free(h->d_post_chunks);
     if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
     if (h->ev_post_join) cudaEventDestroy(h->ev_post_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -633,6 +643,24 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     for (int i = 0; i < N; ++i) {
         int node = h->h_free_nodes[i];
         h->h_node2slot[node] = (i < nA + nS) ? 6 * slot0[node] : c1.row0 + 6 * slot1[node];
+    }
+
+    // member chunks of the post-processing kernel: "early" = every member's nodes are solved once the first chain's
+    // backward sweep is through (A and S nodes live in chain 0's rows, fixed nodes have no rows), "late" = the rest
+    {
+        const int n_mchunk = ceil_div(h->M, MCHUNK);
+        std::vector<int> early, late;
+        for (int ch = 0; ch < n_mchunk; ++ch) {
+            bool e = h->n_chains == 2;
+            for (int m = ch * MCHUNK; e && m < std::min(h->M, (ch + 1) * MCHUNK); ++m)
+                for (int q = 0; q < 2; ++q) { const int sl = h->h_node2slot[h->h_conn[2 * m + q]]; if (sl >= c1.row0) e = false; }
+            (e ? early : late).push_back(ch);
+        }
+        h->n_post_early = (int)early.size(); h->n_post_late = (int)late.size();
+        early.insert(early.end(), late.begin(), late.end());
+        dev_free(h->d_post_chunks);
+        CUDA_TRY(h, dev_alloc(&h->d_post_chunks, early.size()));
+        CUDA_TRY(h, cudaMemcpy(h->d_post_chunks, early.data(), early.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
 
     // 6x6 block lists with contributions in member order (deterministic assembly), one list per chain.
@@ -1195,15 +1223,22 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     long long* d_prof = nullptr;
     if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, 4 * 64 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, 4 * 64 * sizeof(long long), s)); }
     // part: 0 = whole program, 1 = items [0, n_split), 2 = the rest (continues from the rows part 1 left in the slab)
-    auto sweep = [&](int c, int d, int part = 0) {
+    auto sweep = [&](int c, int d, int part = 0, unsigned* started = nullptr) {
         auto& chn = h->ch[c]; auto& w = chn.sw[d];
         const int lo = part == 2 ? w.n_split : 0, hi = part == 1 ? w.n_split : w.n_items;
-        if (hi <= lo) return;
+        if (hi <= lo) return false;
         const bool cont = part == 2;
         k_sweep<<<nslab, SW_THREADS, SW_SMEM, s>>>(w.d_prog + (size_t)lo * SW_ITEM_U4, w.d_stream + (size_t)lo * SW_TILE, h->d_X, hi - lo, h->n_pad, chn.row0,
                                                    cont ? w.k_split - w.npre2 : w.pre_row, cont ? w.npre2 : w.npre, w.ktop, cont ? 1 : 0, cont ? w.xphase2 : 0,
-                                                   d_prof ? d_prof + (2 * c + d) * 64 : nullptr);
+                                                   d_prof ? d_prof + (2 * c + d) * 64 : nullptr, started);
+        return true;
     };
+    // Early member post (see d_post_chunks): only when the backward sweep of the second chain leaves SMs idle (one CTA per
+    // SM, fewer slabs than SMs) -- the post blocks are released once every sweep CTA is resident (same counter as the
+    // factor's start gates), so they can only take what the sweep does not use.
+    static const bool post_overlap_on = getenv("JK_NO_POST_OVERLAP") == nullptr;
+    bool post_early = false;
+    dim3 gm_all(ceil_div(h->M, MCHUNK), ceil_div(ldP, JK_POST_TPB));
     if (h->tma_sweep) {
         // same elimination-tree order as below; between its forward and backward sweep a chain's rows hold Z = L_kk Y_k
         // in fragment order (jk_sweep.cuh)
@@ -1238,9 +1273,23 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         tic(h, JK_T_SOLVE_BWD);
         sweep(0, 1); LAUNCH_CHECK(h);
         if (h->n_chains == 2) {
+            const bool overlap = post_overlap_on && h->wait_value32 && h->stream3 && h->d_started && h->n_post_early >= 8 && nslab + 2 <= h->n_sm;
+            if (overlap) CUDA_TRY(h, cudaEventRecord(h->ev_bwd0, s));
             k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 1);
             LAUNCH_CHECK(h);
-            sweep(1, 1); LAUNCH_CHECK(h);
+            const bool launched = sweep(1, 1, 0, overlap ? h->d_started : nullptr); LAUNCH_CHECK(h);
+            if (overlap && launched) {
+                h->started_target += (unsigned)nslab;
+                cudaStream_t s3 = h->stream3;
+                CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_bwd0, 0));
+                if (h->wait_value32((CUstream)s3, (CUdeviceptr)h->d_started, (cuuint32_t)h->started_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                    JK_FAIL(h, JK_ECUDA, "run_fem: cuStreamWaitValue32 failed");
+                k_member_post<<<dim3(h->n_post_early, gm_all.y), JK_POST_TPB, 0, s3>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
+                                                                                   h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, h->d_post_chunks);
+                LAUNCH_CHECK(h);
+                CUDA_TRY(h, cudaEventRecord(h->ev_post_early, s3));
+                post_early = true;
+            }
         }
         toc(h, JK_T_SOLVE_BWD);
         if (d_prof) {   // debug aid: where the consumer warps of CTA 0 spend their clocks
@@ -1296,10 +1345,18 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
                                            h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Ffix, h->d_react);
     LAUNCH_CHECK(h);
     if (s2 != s) CUDA_TRY(h, cudaEventRecord(h->ev_post_join, s2));
-    dim3 gm(ceil_div(h->M, MCHUNK), ceil_div(ldP, JK_POST_TPB));
-    k_member_post<<<gm, JK_POST_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
-                                        h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
-    LAUNCH_CHECK(h);
+    if (post_early) {
+        if (h->n_post_late > 0) {
+            k_member_post<<<dim3(h->n_post_late, gm_all.y), JK_POST_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
+                                                                              h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, h->d_post_chunks + h->n_post_early);
+            LAUNCH_CHECK(h);
+        }
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_post_early, 0));
+    } else {
+        k_member_post<<<gm_all, JK_POST_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
+                                                 h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
+        LAUNCH_CHECK(h);
+    }
     if (s2 != s) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_post_join, 0));
     toc(h, JK_T_POST);
     return JK_OK;

@@ -233,13 +233,13 @@ __global__ void __launch_bounds__(JK_POST_TPB)
 k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
               const int* __restrict__ conn, const double* __restrict__ mc, StressPts sp, double fy,
               double* __restrict__ rows, double* __restrict__ part_util, double* __restrict__ part_vm,
-              int* __restrict__ part_mem) {
+              int* __restrict__ part_mem, const int* __restrict__ chunk_list = nullptr /* nullable: member chunks of this launch */) {
     __shared__ double s_mc[MCHUNK * MC_STRIDE];
     __shared__ int s_slot[MCHUNK * 2];
     __shared__ double s_pt[MCHUNK * 24];
     // chunk index is the FAST grid dimension: the blocks in flight share one or two 128-phase tiles, whose slice of
     // the solution (n x 128 doubles = 20 MB at c4) stays L2-resident while every member chunk re-reads its nodes
-    int chunk = blockIdx.x, m0 = chunk * MCHUNK;
+    int chunk = chunk_list ? chunk_list[blockIdx.x] : (int)blockIdx.x, m0 = chunk * MCHUNK;
     int nm = min(MCHUNK, M - m0);
     for (int i = threadIdx.x; i < nm * MC_STRIDE; i += blockDim.x) s_mc[i] = mc[(size_t)m0 * MC_STRIDE + i];
     for (int i = threadIdx.x; i < nm * 2; i += blockDim.x) s_slot[i] = node2slot[conn[2 * m0 + i]];

@@ -314,8 +314,10 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
                         1: forward continuation, rows hold Z in fragment order, ring slot row % R */,
         int xphase_bits /* bit s: ring slot s starts one mbarrier phase ahead (continuation of a program whose slot parities
                            count from its first row) */,
-        long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (JK_SWEEP_PROFILE) */) {
+        long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (JK_SWEEP_PROFILE) */,
+        unsigned* __restrict__ started = nullptr /* nullable: every CTA adds 1 as soon as it is resident (gate of the early member post) */) {
     extern __shared__ __align__(128) unsigned char sw_smem[];
+    if (started != nullptr && threadIdx.x == 0) { atomicAdd(started, 1u); __threadfence(); }
     double* As = reinterpret_cast<double*>(sw_smem);                 // [SW_STAGES][SW_TILE]   A tiles, fragment order
     double* Bs = As + SW_STAGES * SW_TILE;                           // [SW_XTILE]             Z_k of the backward diagonal item
     double* Xr = Bs + SW_XTILE;                                      // [SW_RING][SW_XTILE]    newest solved tiles, fragment order
