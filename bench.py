@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="phases in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--per-step", action="store_true", help="debug: print every timed step's duration (ms) to stderr")
     return ap.parse_args()
 
 
@@ -412,12 +413,18 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count()
+        marks = []
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(steps):
                 out = fn()
+                if args.per_step:
+                    marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record(stream)
             e1.record(stream)
         barrier()
+        if marks:
+            ts = [e0.elapsed_time(m) for m in marks]
+            print(f"[rank {rank}] step ms:", " ".join(f"{b - a:.2f}" for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -463,9 +470,21 @@ def run_ours(args):
         nnzL = sst["nnz_L"]
         sweep_flops_alg = 2.0 * nnzL * P
         nnz_band = n * (hb + 1) - hb * (hb + 1) // 2       # previous rounds' convention: every entry inside the DOF band
+        # Morison: members whose Gauss points all lie below the lowest trough take the drag-only loop (25 FP64 instructions
+        # per point, SASS count), the others the general loop (44 per wet point): executed FP64 instruction rate against
+        # the pipe's issue peak (half the FMA flop peak); the SURVEY figure (170 flop per point) is kept as "achieved"
+        xyz_b, conn_b = st.pack()[0], st.pack()[1]
+        zmax = np.maximum(xyz_b[conn_b[:, 0], 2], xyz_b[conn_b[:, 1], 2])
+        f_sub = float(np.mean(zmax <= -abs(p.H / 2.0) * (1.0 + 1e-9)))
+        mor_instr = (25.0 * f_sub + 44.0 * (1.0 - f_sub)) * G15 * M * P
         kernels = {
             "morison": {"ms": stage["morison"], "bound": "fp64", "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS,
-                        "achieved": 170.0 * G15 * M * P / (stage["morison"] * 1e-3) * 1e-12},
+                        "achieved": 170.0 * G15 * M * P / (stage["morison"] * 1e-3) * 1e-12,
+                        "submerged_member_fraction": f_sub,
+                        "executed_fp64_tinstr_per_s": mor_instr / (stage["morison"] * 1e-3) * 1e-12,
+                        "frac_executed": mor_instr / (stage["morison"] * 1e-3) * 1e-12 / (FP64_PEAK_TFLOPS / 2.0),
+                        "note": "achieved = SURVEY convention (170 flop per Gauss point, sincos = 40): the kernel executes far fewer, "
+                                "so frac exceeds 1; frac_executed = FP64 instructions issued (upper bound: dry points skip) / issue peak"},
             "solve_fwd": {"ms": stage["solve_fwd"], "bound": "tensor", "unit": "TFLOP/s", "peak": FP64_PEAK_TFLOPS,
                           "achieved": sweep_flops_alg / (stage["solve_fwd"] * 1e-3) * 1e-12,
                           "executed": sweep_flops_exec / (stage["solve_fwd"] * 1e-3) * 1e-12},
