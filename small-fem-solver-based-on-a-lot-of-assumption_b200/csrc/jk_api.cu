@@ -44,7 +44,7 @@ struct jk_handle_s {
     // early member post: chunks whose members only touch chain-0 / separator nodes are post-processed on a side stream
     // while the second chain's backward sweep runs (HBM-bound work on the SMs the sweep leaves idle)
     int* d_post_chunks = nullptr; int n_post_early = 0, n_post_late = 0, n_sm = 0;
-    cudaEvent_t ev_bwd0 = nullptr, ev_post_early = nullptr;
+    cudaEvent_t ev_bwd0 = nullptr, ev_post_early = nullptr, ev_mor = nullptr, ev_tot = nullptr;
     unsigned gate2_target = 0; bool gate2_armed = false;   // second factor segment resident (awaited before the first forward parts)
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     cudaEvent_t ev_seg1 = nullptr, ev_fwd1 = nullptr;   // first factor segment done / its forward tile streams built
@@ -222,6 +222,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     cudaEventCreateWithFlags(&h->ev_seg1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_bwd0, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_mor, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_tot, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_early, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_join, cudaEventDisableTiming);
@@ -306,6 +308,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->ev_seg1) cudaEventDestroy(h->ev_seg1);
     if (h->ev_fwd1) cudaEventDestroy(h->ev_fwd1);
     if (h->ev_bwd0) cudaEventDestroy(h->ev_bwd0);
+    if (h->ev_mor) cudaEventDestroy(h->ev_mor);
+    if (h->ev_tot) cudaEventDestroy(h->ev_tot);
     if (h->ev_post_early) cudaEventDestroy(h->ev_post_early);
     dev_free(h->d_post_chunks);
     if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
@@ -1196,14 +1200,28 @@ static int ensure_member_consts(jk_handle_t h) {
     return JK_OK;
 }
 
-static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool fem) {
+// Morison columns of the table (t, totals) on a side stream right after the Morison kernel: 3/4 of the reduction's reads
+// leave the tail of the scan.  The caller joins ev_tot before reduce_and_argmax(..., totals_done = true).
+static int reduce_totals_early(jk_handle_t h, int P, int ldP) {
+    cudaStream_t s = h->stream, s3 = h->stream3;
+    CUDA_TRY(h, cudaEventRecord(h->ev_mor, s));
+    CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_mor, 0));
+    k_phase_reduce<<<ceil_div(P, 32), 32 * RED_GROUPS, 0, s3>>>(P, ldP, h->d_t, ceil_div(h->M, MCHUNK), h->d_totpart, 0, nullptr, nullptr, nullptr,
+                                                      0, nullptr, nullptr, 0, nullptr, h->d_table, JK_TABLE_NCOL, 1);
+    LAUNCH_CHECK(h);
+    CUDA_TRY(h, cudaEventRecord(h->ev_tot, s3));
+    return JK_OK;
+}
+
+static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool fem, bool totals_done = false) {
     cudaStream_t s = h->stream;
+    if (totals_done) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_tot, 0));
     tic(h, JK_T_REDUCE);
     int n_mchunk = ceil_div(h->M, MCHUNK), n_nchunk = ceil_div(h->Nn, NCHUNK);
-    k_phase_reduce<<<ceil_div(P, 32), 32 * RED_GROUPS, 0, s>>>(P, ldP, h->d_t, n_mchunk, morison ? h->d_totpart : nullptr,
+    k_phase_reduce<<<ceil_div(P, 32), 32 * RED_GROUPS, 0, s>>>(P, ldP, h->d_t, n_mchunk, (morison && !totals_done) ? h->d_totpart : nullptr,
                                                      n_mchunk, fem ? h->d_part_util : nullptr, h->d_part_vm, h->d_part_mem,
                                                      n_nchunk, fem ? h->d_part_disp : nullptr, h->d_part_node,
-                                                     h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL);
+                                                     h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL, totals_done ? 0 : 1);
     LAUNCH_CHECK(h);
     k_argmax<<<1, 1024, 0, s>>>(P, h->d_table, JK_TABLE_NCOL, morison ? JK_COL_TOTAL_KN : JK_COL_MAX_UTIL, h->d_argval, h->d_argidx);
     LAUNCH_CHECK(h);
@@ -1375,6 +1393,9 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
     const bool split = fem && h->wave_kind == 0 && h->stream3 && nbx >= 8 && getenv("JK_GATHER_OVERLAP") != nullptr;
     const int parts = split ? 4 : 1;
     if ((rc = run_morison(h, P, ldP, false, parts)) != JK_OK) return rc;
+    static const bool early_totals_on = getenv("JK_NO_EARLY_TOTALS") == nullptr;
+    const bool totals_early = fem && early_totals_on && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
+    if (totals_early && (rc = reduce_totals_early(h, P, ldP)) != JK_OK) return rc;
     if (fem) {
         if (parts == 1) {
             tic(h, JK_T_RHS);
@@ -1402,7 +1423,7 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
         }
         if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
     }
-    if ((rc = reduce_and_argmax(h, P, ldP, true, fem)) != JK_OK) return rc;
+    if ((rc = reduce_and_argmax(h, P, ldP, true, fem, totals_early)) != JK_OK) return rc;
     h->lastP = P; h->last_ldP = ldP; h->last_morison = true; h->last_fem = fem; h->last_fy = fy;
     return JK_OK;
 }

@@ -799,7 +799,7 @@ k_phase_reduce(int P, int ldP, const double* __restrict__ t,
                const int* __restrict__ part_mem,
                int n_nchunk, const double* __restrict__ part_disp, const int* __restrict__ part_node,
                int n_fixed, const double* __restrict__ react,
-               double* __restrict__ table, int ncol) {
+               double* __restrict__ table, int ncol, int init_row = 1 /* 0: the row already holds t and the Morison totals (earlier launch) */) {
     __shared__ double s_sum[RED_GROUPS][9][32];
     __shared__ double s_val[RED_GROUPS][3][32];
     __shared__ int s_idx[RED_GROUPS][2][32];
@@ -839,8 +839,10 @@ k_phase_reduce(int P, int ldP, const double* __restrict__ t,
     __syncthreads();
     if (g != 0 || !live) return;
     double* row = table + (size_t)p * ncol;
-    for (int c = 0; c < ncol; ++c) row[c] = 0.0;
-    row[0] = t[p];
+    if (init_row) {
+        for (int c = 0; c < ncol; ++c) row[c] = 0.0;
+        row[0] = t[p];
+    }
     if (totpart) {
         double v[9];
 #pragma unroll
