@@ -11,7 +11,10 @@ namespace jk {
 constexpr int NB   = 64;    // solver tile edge (DOFs); K_ff and L live as NB x NB row-major tiles
 constexpr int SLAB = 32;    // right-hand sides (phases) per solver slab
 constexpr int PH_TPB = 128; // threads per block of the phase-parallel kernels (one thread = one phase)
-constexpr int MCHUNK = 32;  // members per block of the Morison / member-post kernels
+#ifndef JK_MCHUNK
+#define JK_MCHUNK 32
+#endif
+constexpr int MCHUNK = JK_MCHUNK;  // members per block of the Morison / member-post kernels (A/B switch)
 constexpr int NCHUNK = 64;  // nodes per block of the node-post kernel
 
 // member constant row (structure of the row is fixed; one row per member, AoS so a block can stage
