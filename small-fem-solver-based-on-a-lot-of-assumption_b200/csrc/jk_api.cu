@@ -44,6 +44,7 @@ struct jk_handle_s {
     // early member post: chunks whose members only touch chain-0 / separator nodes are post-processed on a side stream
     // while the second chain's backward sweep runs (HBM-bound work on the SMs the sweep leaves idle)
     int* d_post_chunks = nullptr; int n_post_early = 0, n_post_late = 0, n_sm = 0;
+    bool gate2_on = true, post_overlap_on = true, early_totals_on = true;   // A/B switches read at jk_create (JK_NO_START_GATE2, JK_NO_POST_OVERLAP, JK_NO_EARLY_TOTALS)
     cudaEvent_t ev_bwd0 = nullptr, ev_post_early = nullptr, ev_mor = nullptr, ev_tot = nullptr;
     unsigned gate2_target = 0; bool gate2_armed = false;   // second factor segment resident (awaited before the first forward parts)
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -199,6 +200,9 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     h->device = device;
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
+    h->gate2_on = getenv("JK_NO_START_GATE2") == nullptr;
+    h->post_overlap_on = getenv("JK_NO_POST_OVERLAP") == nullptr;
+    h->early_totals_on = getenv("JK_NO_EARLY_TOTALS") == nullptr;
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; JK_FAIL((jk_handle_t)nullptr, JK_ECUDA, "jk_create: cudaStreamCreate failed"); } h->own_stream = true; }
     for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); h->ev_set[i] = false; }
@@ -887,7 +891,7 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
             // clusters are resident.  With the Morison + load stage as short as the first segment the sweeps otherwise win
             // the race now and then, the clusters find no GPC with eight free SMs until both parts are through and the step
             // grows by ~1 ms (seen as 5.5 vs 6.7 ms per step between runs).
-            static const bool gate2_on = getenv("JK_NO_START_GATE2") == nullptr;
+            const bool gate2_on = h->gate2_on;
             k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a2, ncl == 2 ? b2 : a2, h->d_info, nullptr, gate2_on ? gate : nullptr);
             LAUNCH_CHECK(h);
             h->gate2_armed = false;
@@ -1254,7 +1258,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     // Early member post (see d_post_chunks): only when the backward sweep of the second chain leaves SMs idle (one CTA per
     // SM, fewer slabs than SMs) -- the post blocks are released once every sweep CTA is resident (same counter as the
     // factor's start gates), so they can only take what the sweep does not use.
-    static const bool post_overlap_on = getenv("JK_NO_POST_OVERLAP") == nullptr;
+    const bool post_overlap_on = h->post_overlap_on;
     bool post_early = false;
     dim3 gm_all(ceil_div(h->M, MCHUNK), ceil_div(ldP, JK_POST_TPB));
     if (h->tma_sweep) {
@@ -1393,8 +1397,7 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
     const bool split = fem && h->wave_kind == 0 && h->stream3 && nbx >= 8 && getenv("JK_GATHER_OVERLAP") != nullptr;
     const int parts = split ? 4 : 1;
     if ((rc = run_morison(h, P, ldP, false, parts)) != JK_OK) return rc;
-    static const bool early_totals_on = getenv("JK_NO_EARLY_TOTALS") == nullptr;
-    const bool totals_early = fem && early_totals_on && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
+    const bool totals_early = fem && h->early_totals_on && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
     if (totals_early && (rc = reduce_totals_early(h, P, ldP)) != JK_OK) return rc;
     if (fem) {
         if (parts == 1) {

@@ -466,3 +466,46 @@ def test_split_factor_is_bit_identical(legs, bays, single_chain):
         assert np.array_equal(out[mode][0], out["split"][0]), mode
         assert np.array_equal(out[mode][1], out["split"][1]), mode
     assert out["split"][2] < 1e-9
+
+
+def test_overlap_switches_are_bit_identical():
+    """Scheduling-only features of the asynchronous scan (second start gate, early member post beside the second chain's
+    backward sweep, Morison totals reduced on a side stream) against the same engine built with each switched off:
+    identical table, displacements and member rows -- the arithmetic per member chunk and per phase is the same."""
+    import os
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    G = ap.E / (2 * (1 + ap.nu))
+    out = {}
+    variants = (("default", {}), ("no_post_overlap", {"JK_NO_POST_OVERLAP": "1"}), ("no_early_totals", {"JK_NO_EARLY_TOTALS": "1"}),
+                ("no_gate2", {"JK_NO_START_GATE2": "1"}), ("none", {"JK_NO_POST_OVERLAP": "1", "JK_NO_EARLY_TOTALS": "1", "JK_NO_START_GATE2": "1"}))
+    for mode, env in variants:
+        os.environ.update(env)
+        try:
+            nodes, members, fixed, top = jb.generate_jacket(8, 40)            # two chains, 61 member chunks, long enough for the split
+            st = jb.build_structure(nodes, members, fixed, top, ap)
+            eng = jb.Engine(st)                                               # the switches are read when the handle is created
+            st._engine = eng
+            t = jb.phase_times(_wave(jb, ap).T, 256)
+            eng.set_supports(st.indices(fixed))
+            eng.set_static_load(jb.static_load(st, ap))
+            eng.set_wave(_wave(jb, ap))
+            eng.set_morison(np.deg2rad(90 - ap.wave_dir), np.deg2rad(90 - ap.current_dir), ap.rho_water, ap.Cd, ap.Cm, 15)
+            tables = []
+            for _ in range(2):
+                eng.assemble(ap.E, G)
+                eng.factor(overlap=True)
+                table, crit = eng.phase_scan(t, ap.fy)
+                tables.append((table, crit))
+            assert np.array_equal(tables[0][0], tables[1][0]) and tables[0][1] == tables[1][1]
+            ph = eng.fetch_phase(201)
+            # stored member rows (written by the early and the late post launches): utilisation of every 7th member, all phases
+            cols = np.stack([eng.member_column(m, 6, 256) for m in range(0, st.n_members, 7)])
+            out[mode] = (tables[0][0], tables[0][1], ph["U"].copy(), cols, ph["reactions"].copy(), eng.dims())
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    assert out["default"][5]["n_chains"] == 2
+    for mode, _ in variants[1:]:
+        for i in range(5):
+            assert np.array_equal(out[mode][i], out["default"][i]), (mode, i)
