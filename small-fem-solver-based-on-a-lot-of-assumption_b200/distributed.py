@@ -51,10 +51,15 @@ def device_views(engine, P):
     """torch views (no copy) of the table [P,16], the critical value [1] and index [1] of the last scan."""
     import torch
     lib = engine.lib
+    ptrs = (lib.jk_table_dev(engine.h), lib.jk_critical_value_dev(engine.h), lib.jk_critical_index_dev(engine.h), P)
+    cached = engine.__dict__.get("_dev_views")
+    if cached is not None and cached[0] == ptrs:          # the library's buffers only move when they grow
+        return cached[1]
     dev = f"cuda:{engine.device}"
-    table = torch.as_tensor(_DevArray(lib.jk_table_dev(engine.h), (P, L.TABLE_NCOL), "<f8"), device=dev)
-    val = torch.as_tensor(_DevArray(lib.jk_critical_value_dev(engine.h), (1,), "<f8"), device=dev)
-    idx = torch.as_tensor(_DevArray(lib.jk_critical_index_dev(engine.h), (1,), "<i8"), device=dev)
+    table = torch.as_tensor(_DevArray(ptrs[0], (P, L.TABLE_NCOL), "<f8"), device=dev)
+    val = torch.as_tensor(_DevArray(ptrs[1], (1,), "<f8"), device=dev)
+    idx = torch.as_tensor(_DevArray(ptrs[2], (1,), "<i8"), device=dev)
+    engine.__dict__["_dev_views"] = (ptrs, (table, val, idx))
     return table, val, idx
 
 

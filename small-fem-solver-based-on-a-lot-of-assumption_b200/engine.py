@@ -49,6 +49,7 @@ class Engine:
         self.fixed_idx = None
 
     def close(self):
+        self.__dict__.pop("_dev_views", None)            # torch views of library-owned device buffers (distributed.device_views)
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.jk_destroy(self.h)
             self.h = C.c_void_p()
@@ -132,7 +133,7 @@ class Engine:
 
     def phase_scan(self, t, fy):
         t = L.f64(t).reshape(-1)
-        table = np.zeros((t.shape[0], L.TABLE_NCOL))
+        table = np.empty((t.shape[0], L.TABLE_NCOL))     # the library overwrites every entry
         crit = C.c_int64(-1)
         self._ck(self.lib.jk_phase_scan(self.h, t.shape[0], L.dptr(t), float(fy), L.dptr(table), C.byref(crit)))
         return table, int(crit.value)
