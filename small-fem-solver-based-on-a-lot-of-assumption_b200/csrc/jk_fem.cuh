@@ -10,6 +10,9 @@
 #pragma once
 #include "jk_common.cuh"
 
+#ifndef JK_POST_PACKED
+#define JK_POST_PACKED 1      // per-member constants of k_member_post in one packed shared-memory row read with 16-byte loads
+#endif
 #ifndef JK_POST_TPB
 #define JK_POST_TPB 128        // threads (= phases) per block of k_member_post (A/B switch: longer contiguous write runs)
 #endif
@@ -220,6 +223,64 @@ __device__ __forceinline__ void member_row(const double* __restrict__ c, const d
     row[6] = vm * inv_fy;
 }
 
+// Packed per-member constants of k_member_post (one 256-byte shared-memory row, read with sixteen 16-byte loads):
+//   0-8 R | 9 alpha | 10 tors | 11 k12z 12 k6zL 13 k4z 14 k2z | 15 k12y 16 k6yL 17 k4y 18 k2y | 19 1/A 20 1/Ay 21 1/Az |
+//   22 R_o/Ix | 23 pad | 24+2i, 25+2i: y_i/Iz, z_i/Iy of stress points i = 0..3
+// The two functions below are element_local_forces / member_row with these indices: same operations in the same order,
+// so the stored rows stay bit-identical to k_member_post_single's.
+constexpr int PK_STRIDE = 32;
+__device__ __forceinline__ void pack_member_consts(const double* __restrict__ c, const StressPts& sp, double* __restrict__ pk) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) pk[i] = c[MC_R + i];
+    pk[9] = c[MC_ALPHA]; pk[10] = c[MC_TORS];
+    pk[11] = c[MC_K12Z]; pk[12] = c[MC_K6ZL]; pk[13] = c[MC_K4Z]; pk[14] = c[MC_K2Z];
+    pk[15] = c[MC_K12Y]; pk[16] = c[MC_K6YL]; pk[17] = c[MC_K4Y]; pk[18] = c[MC_K2Y];
+    pk[19] = c[MC_IAX]; pk[20] = c[MC_IAY]; pk[21] = c[MC_IAZ];
+    double pt[3];
+    stress_point_coeffs(c, sp, 0, pt);
+    pk[22] = pt[2]; pk[23] = 0.0; pk[24] = pt[0]; pk[25] = pt[1];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { stress_point_coeffs(c, sp, i, pt); pk[24 + 2 * i] = pt[0]; pk[25 + 2 * i] = pt[1]; }
+}
+__device__ __forceinline__ void element_local_forces_pk(const double* pk, const double* ue, double* Fl) {
+    double ul[12];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            ul[3 * a + i] = fma(pk[3 * i + 2], ue[3 * a + 2], fma(pk[3 * i + 1], ue[3 * a + 1], pk[3 * i] * ue[3 * a]));
+    const double al = pk[9], to = pk[10];
+    const double k12z = pk[11], k6zL = pk[12], k4z = pk[13], k2z = pk[14];
+    const double k12y = pk[15], k6yL = pk[16], k4y = pk[17], k2y = pk[18];
+    Fl[0] = fma(-al, ul[6], al * ul[0]);
+    Fl[1] = fma(k6zL, ul[11], fma(-k12z, ul[7], fma(k6zL, ul[5], k12z * ul[1])));
+    Fl[2] = fma(-k6yL, ul[10], fma(-k12y, ul[8], fma(-k6yL, ul[4], k12y * ul[2])));
+    Fl[3] = fma(-to, ul[9], to * ul[3]);
+    Fl[4] = fma(k2y, ul[10], fma(k6yL, ul[8], fma(k4y, ul[4], -k6yL * ul[2])));
+    Fl[5] = fma(k2z, ul[11], fma(-k6zL, ul[7], fma(k4z, ul[5], k6zL * ul[1])));
+    Fl[6] = -Fl[0]; Fl[7] = -Fl[1]; Fl[8] = -Fl[2]; Fl[9] = -Fl[3];
+    Fl[10] = fma(k4y, ul[10], fma(k6yL, ul[8], fma(k2y, ul[4], -k6yL * ul[2])));
+    Fl[11] = fma(k4z, ul[11], fma(-k6zL, ul[7], fma(k2z, ul[5], k6zL * ul[1])));
+}
+__device__ __forceinline__ void member_row_pk(const double* pk, const double* Fl, double inv_fy, double* row) {
+    const double sFx = fabs(Fl[0] * pk[19]);
+    const double tFy = Fl[1] * pk[20], tFz = Fl[2] * pk[21];
+    const double tM = Fl[3] * pk[22];
+    const double tau2 = fma(tM, tM, fma(tFy, tFy, tFz * tFz));
+    double bmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bmax = fmax(bmax, fabs(fma(Fl[5], pk[24 + 2 * i], Fl[4] * pk[25 + 2 * i])));
+    const double sig = sFx + bmax;
+    const double vm = sqrt(fma(3.0, tau2, sig * sig));
+    row[0] = fabs(Fl[0]) * 1e-3;
+    row[1] = fabs(Fl[1]) * 1e-3;
+    row[2] = fabs(Fl[2]) * 1e-3;
+    row[3] = fmax(fabs(Fl[4]), fabs(Fl[10])) * 1e-6;
+    row[4] = fmax(fabs(Fl[5]), fabs(Fl[11])) * 1e-6;
+    row[5] = vm;
+    row[6] = vm * inv_fy;
+}
+
 __device__ __forceinline__ double load_u(const double* __restrict__ X, const int* __restrict__ node2slot,
                                          int node, int comp, int p, int n_pad) {
     int s = node2slot[node];
@@ -236,7 +297,11 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
               int* __restrict__ part_mem, const int* __restrict__ chunk_list = nullptr /* nullable: member chunks of this launch */) {
     __shared__ double s_mc[MCHUNK * MC_STRIDE];
     __shared__ int s_slot[MCHUNK * 2];
+#if JK_POST_PACKED
+    __shared__ __align__(16) double s_pk[MCHUNK * PK_STRIDE];
+#else
     __shared__ double s_pt[MCHUNK * 24];
+#endif
     // chunk index is the FAST grid dimension: the blocks in flight share one or two 128-phase tiles, whose slice of
     // the solution (n x 128 doubles = 20 MB at c4) stays L2-resident while every member chunk re-reads its nodes
     int chunk = chunk_list ? chunk_list[blockIdx.x] : (int)blockIdx.x, m0 = chunk * MCHUNK;
@@ -244,7 +309,11 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
     for (int i = threadIdx.x; i < nm * MC_STRIDE; i += blockDim.x) s_mc[i] = mc[(size_t)m0 * MC_STRIDE + i];
     for (int i = threadIdx.x; i < nm * 2; i += blockDim.x) s_slot[i] = node2slot[conn[2 * m0 + i]];
     __syncthreads();
+#if JK_POST_PACKED
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) pack_member_consts(s_mc + i * MC_STRIDE, sp, s_pk + i * PK_STRIDE);
+#else
     for (int i = threadIdx.x; i < nm * 8; i += blockDim.x) stress_point_coeffs(s_mc + (i / 8) * MC_STRIDE, sp, i % 8, s_pt + 3 * i);
+#endif
     __syncthreads();
     const double inv_fy = 1.0 / fy;
     int p = blockIdx.y * blockDim.x + threadIdx.x;
@@ -264,7 +333,6 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
     load_ue(0, un);
 #endif
     for (int mm = 0; mm < nm; ++mm) {
-        const double* c = s_mc + mm * MC_STRIDE;
         double ue[12], Fl[12], row[7];
 #if JK_POST_PREFETCH
         // the next member's displacements are requested before this member's arithmetic (L2 latency under ~150 FP64 ops)
@@ -274,8 +342,20 @@ k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, co
 #else
         load_ue(mm, ue);
 #endif
+#if JK_POST_PACKED
+        double pk[PK_STRIDE];
+#pragma unroll
+        for (int q = 0; q < PK_STRIDE / 2; ++q) {
+            const double2 v = *reinterpret_cast<const double2*>(s_pk + mm * PK_STRIDE + 2 * q);
+            pk[2 * q] = v.x; pk[2 * q + 1] = v.y;
+        }
+        element_local_forces_pk(pk, ue, Fl);
+        member_row_pk(pk, Fl, inv_fy, row);
+#else
+        const double* c = s_mc + mm * MC_STRIDE;
         element_local_forces(c, ue, Fl);
         member_row(c, s_pt + mm * 24, Fl, inv_fy, row);
+#endif
         size_t o = ((size_t)(m0 + mm) * 7) * ldP + p;
 #pragma unroll
         for (int k = 0; k < 7; ++k) __stcs(rows + o + (size_t)k * ldP, row[k]);      // write-once stream: keep the solution slab in L2
