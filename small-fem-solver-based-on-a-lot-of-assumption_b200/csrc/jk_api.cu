@@ -1173,17 +1173,19 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details, int gather_p
     } else {
         size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng + 1) * sizeof(double);
         if (details) {
-            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_morison_airy<true><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);
+            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_morison_airy<true, 0><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);
         } else {
             // Phase blocks: the load gather of block b (HBM-bound, side stream) runs under the Morison kernel of block b+1
             // (FP64-bound).  gather_parts > 1 only when the caller gathers afterwards (scan_core).
-            CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // the default 15-point rule may have its own instantiation with fully unrolled point loops (-DJK_MORISON_G15=1)
+            auto kern = (JK_MORISON_G15 && h->ng == 15) ? k_morison_airy<false, 15> : k_morison_airy<false, 0>;
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int nbx = (int)grid.x, parts = std::max(1, std::min(gather_parts, nbx));
             for (int b = 0; b < parts; ++b) {
                 const int x0 = (int)((long long)nbx * b / parts), x1 = (int)((long long)nbx * (b + 1) / parts);
                 if (x1 <= x0) continue;
-                k_morison_airy<false><<<dim3(x1 - x0, grid.y), PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0,
+                kern<<<dim3(x1 - x0, grid.y), PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0,
                                                                                  h->d_Fm, h->d_totpart, nullptr, x0 * PH_TPB);
                 if (b + 1 < parts) LAUNCH_CHECK(h);            // the last launch is counted by the common check below
                 if (parts > 1) CUDA_TRY(h, cudaEventRecord(h->ev_part[b], s));

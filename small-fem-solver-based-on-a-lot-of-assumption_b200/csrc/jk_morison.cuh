@@ -81,6 +81,9 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 #ifndef JK_MORISON_SSUM
 #define JK_MORISON_SSUM 1
 #endif
+#ifndef JK_MORISON_G15
+#define JK_MORISON_G15 1          // the default 15-point rule gets its own instantiation with fully unrolled point loops (0: runtime loop only)
+#endif
 #ifndef JK_MORISON_SUBFAST
 #define JK_MORISON_SUBFAST 1      // drag-only point loop + closed-form inertia sums for members below the lowest trough
 #endif
@@ -92,13 +95,14 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 // GUI.py:648-659 then only need the SCALARS sum(kd), sum(kd uw), sum(kd w), sum(ci du), sum(ci dw) and their
 // s-weighted twins; the 3-vectors are formed once per member.  ~30 % fewer FP64 instructions per point than the
 // component form (morison_point), same results to rounding (1e-15 relative).
-template <bool DETAILS>
+template <bool DETAILS, int GT /* compile-time Gauss point count (fully unrolled point loops) or 0 */>
 __global__ void __launch_bounds__(PH_TPB)
-k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
+k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
                const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
                WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
                double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details, int p_off /* first phase of this launch */) {
     extern __shared__ __align__(16) double smem[];
+    const int G = GT > 0 ? GT : G_rt;
     constexpr int MS = 16;                                  // per-member constants
     double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
     double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][MS]: we ce e2 L | p1[3] p0[3] p3[3] | cD cI
@@ -143,6 +147,9 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
         const double* cm = s_c + i * G * 4;
         double I[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         double zmax = -1e300;
+#if JK_MORISON_G15
+#pragma unroll
+#endif
         for (int g = 0; g < G; ++g) {
             const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1], Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3];
             const double cil = cm[4 * g + 1], scil = cm[4 * g + 2];
@@ -179,6 +186,9 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
 #if JK_MORISON_SUBFAST
         const bool submerged = cmem[15] != 0.0;            // block-uniform: no divergence
         if (submerged) {
+#if JK_MORISON_G15
+#pragma unroll
+#endif
             for (int g = 0; g < G; ++g) {
                 const double2 g01 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE), g23 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE + 2);
                 const double ckx = g01.x, skx = g01.y;
@@ -202,6 +212,9 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
             Si1 = fma(ci[1], dsw, ci[0] * dcw); Si3 = fma(-ci[3], dsw, ci[2] * dcw);
             Ti1 = fma(ci[5], dsw, ci[4] * dcw); Ti3 = fma(-ci[7], dsw, ci[6] * dcw);
         } else
+#endif
+#if JK_MORISON_G15
+#pragma unroll
 #endif
         for (int g = 0; g < G; ++g) {
             const double2 g01 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE), g23 = *reinterpret_cast<const double2*>(gpm + g * GP_STRIDE + 2);
@@ -269,7 +282,7 @@ k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const doubl
 constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 16 + 8 * JK_MORISON_SUBFAST;   // doubles per member beside the Gauss tables (s_m, s_i)
 constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 4;     // doubles per Gauss point beside GP_STRIDE (s_c)
 #else
-template <bool DETAILS>
+template <bool DETAILS, int GT /* unused in the component form */>
 __global__ void __launch_bounds__(PH_TPB)
 k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
                const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
