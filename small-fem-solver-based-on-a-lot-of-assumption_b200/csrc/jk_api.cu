@@ -1638,8 +1638,9 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     {
         dim3 grid(ceil_div(ldC, PH_TPB), ceil_div(h->M, MCHUNK));
         size_t smem = ens_smem_doubles(h->ng, n_phase) * sizeof(double);
-        CUDA_TRY(h, cudaFuncSetAttribute(k_morison_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_morison_ensemble<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, C, ldC, n_states, n_phase, h->d_xyz, h->d_conn, h->d_mc, h->d_gsw,
+        auto kern = (JK_ENSEMBLE_G15 && h->ng == 15) ? k_morison_ensemble<15> : k_morison_ensemble<0>;
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, C, ldC, n_states, n_phase, h->d_xyz, h->d_conn, h->d_mc, h->d_gsw,
                                                       h->d_states, h->d_t, w, 0.5 * h->rho * h->Cd, h->rho * h->Cm, h->d_Fm, h->d_totpart);
         LAUNCH_CHECK(h);
     }

@@ -556,12 +556,17 @@ __host__ __device__ inline size_t ens_smem_doubles(int G, int n_phase) {
     return (size_t)ens_max_states(n_phase) * ENS_EM * (G * 4 + 8) + ENS_EM * G + ENS_EM + MCHUNK * 8 + 2 * G;
 }
 
+#ifndef JK_ENSEMBLE_G15
+#define JK_ENSEMBLE_G15 0         // 1: own instantiation of the ensemble kernel for the 15-point rule, point loops fully unrolled (A/B)
+#endif
+template <int GT /* compile-time Gauss point count or 0 */>
 __global__ void __launch_bounds__(PH_TPB)
-k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const double* __restrict__ xyz, const int* __restrict__ conn,
+k_morison_ensemble(int M, int G_rt, int C, int ldC, int S, int n_phase, const double* __restrict__ xyz, const int* __restrict__ conn,
                    const double* __restrict__ mc, const double* __restrict__ gsw, const double* __restrict__ st,
                    const double* __restrict__ t, WaveAiry wv, double cD0, double cI0,
                    double* __restrict__ Fm, double* __restrict__ totpart) {
     extern __shared__ __align__(16) double smem[];
+    const int G = GT > 0 ? GT : G_rt;
     const int maxs = ens_max_states(n_phase);               // states a 128-case block may touch
     double* s_tab = smem;                                   // [maxs][ENS_EM][G][4]
     double* s_ci = s_tab + maxs * ENS_EM * G * 4;           // [maxs][ENS_EM][8] inertia sums of always-submerged members
@@ -646,6 +651,9 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
             const double we = fma(sw, e1, cw * e0), ce = fma(wv.uc_sin_c, e1, wv.uc_cos_c * e0);
             double Sd0 = 0, Sd1 = 0, Sd3 = 0, Td0 = 0, Td1 = 0, Td3 = 0, Si1 = 0, Si3 = 0, Ti1 = 0, Ti3 = 0;
             if (s_flag[ms] != 0.0) {                       // block-uniform: drag-only point loop, inertia in closed form
+#if JK_ENSEMBLE_G15
+#pragma unroll
+#endif
                 for (int g = 0; g < G; ++g) {
                     const double2 q01 = *reinterpret_cast<const double2*>(s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4);
                     const double2 q23 = *reinterpret_cast<const double2*>(s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4 + 2);
@@ -667,6 +675,9 @@ k_morison_ensemble(int M, int G, int C, int ldC, int S, int n_phase, const doubl
                 Si1 = fma(ci[1], dsw, ci[0] * dcw); Si3 = fma(-ci[3], dsw, ci[2] * dcw);
                 Ti1 = fma(ci[5], dsw, ci[4] * dcw); Ti3 = fma(-ci[7], dsw, ci[6] * dcw);
             } else
+#if JK_ENSEMBLE_G15
+#pragma unroll
+#endif
             for (int g = 0; g < G; ++g) {
                 const double* q = s_tab + ((size_t)(sl * ENS_EM + ms) * G + g) * 4;
                 const double ckx = q[0], skx = q[1], Cu = q[2], Cw = q[3], z = s_z[ms * G + g];
