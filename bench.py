@@ -48,8 +48,8 @@ SWEEP_TRAFFIC = {"k_slab_sweep": 1.31e9,      # profiles/r01b (legacy cp.async s
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)     # 20 x 5.4 ms: long enough for a few clock samples and to average host jitter
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4_jacket10k", choices=list(WORKLOADS))
     ap.add_argument("--phases", type=int, default=0, help="phases per GPU (default: workload's)")
