@@ -72,7 +72,7 @@ DET_KEYS = ("drag_kN", "inertia_kN", "total_kN", "submerged_length")
 PH_KEYS = ("t", "phase_deg", "total_kN", "drag_kN", "inertia_kN", "Fx_kN", "Fy_kN", "Fz_kN")
 
 
-def make_case(ref, name, nodes, members, fixed, top, p, scans, fem_phases_of, n_fem_phases):
+def make_case(ref, name, nodes, members, fixed, top, p, scans, fem_phases_of, n_fem_phases, store_elements=True):
     t0 = time.time()
     leg = ref.TubularSection(p["D_leg"], p["t_leg"], "Leg", p["rho_steel"])
     brace = ref.TubularSection(p["D_brace"], p["t_brace"], "Brace", p["rho_steel"])
@@ -108,9 +108,10 @@ def make_case(ref, name, nodes, members, fixed, top, p, scans, fem_phases_of, n_
             out["fem_t0_rows"] = np.array([[row[k] for k in ROW_KEYS] for row in rows])
             out["fem_t0_length_m"] = np.array([row["length_m"] for row in rows])
             out["K_global"] = fem.K_global.copy() if fem.n_dof <= 200 else np.zeros(0)
-            out["Ke"] = np.array([e.K_global for e in fem.elements])
-            out["Kl"] = np.array([e.K_local for e in fem.elements])
-            out["T3"] = np.array([e.T[:3, :3] for e in fem.elements])
+            if store_elements:   # 2.3 MB each at 2k members: the small cases pin the element matrices
+                out["Ke"] = np.array([e.K_global for e in fem.elements])
+                out["Kl"] = np.array([e.K_local for e in fem.elements])
+                out["T3"] = np.array([e.T[:3, :3] for e in fem.elements])
     # Morison scans
     for n_steps in scans:
         res = mor.find_critical_phase(n_steps=n_steps)
@@ -145,6 +146,12 @@ def main():
     sys.path.insert(0, ROOT)
     import jacket_b200 as jb   # only for the synthetic input geometry of the gen* cases (host code, no GPU)
 
+    if "--only-large" in sys.argv:
+        sys.argv.append("--large")
+        nodes, members, fixed, top = jb.generate_jacket(8, 41)
+        make_case(ref, "gen8x41_airy", nodes, members, fixed, top, dict(GUI_DEFAULTS), scans=(4, 16), fem_phases_of=16, n_fem_phases=3,
+                  store_elements=False)
+        return
     # case 1: the reference's own default model with the GUI defaults (BASELINE configs[0], [1] on the pinned Airy path)
     nodes, members, fixed, top = ref.create_default_3leg_jacket(47.0)
     make_case(ref, "default3_airy", nodes, members, fixed, top, dict(GUI_DEFAULTS), scans=(36, 360),
@@ -163,6 +170,13 @@ def main():
              F_axial=9000.0, F_shear=700.0, D_leg=1500.0, t_leg=50.0, D_brace=600.0, t_brace=20.0)
     nodes, members, fixed, top = jb.generate_jacket(5, 6, r_bottom=22.0, r_top=9.0, z_bottom=-50.0, z_top=14.0)
     make_case(ref, "gen5x6_airy", nodes, members, fixed, top, p, scans=(16,), fem_phases_of=16, n_fem_phases=8)
+
+    # case 4 (`--large`): BASELINE configs[2]/[4] geometry -- 8 legs x 41 bays, 1,976 members, 3,936 free DOF -- with the GUI
+    # defaults; a 4- and a 16-phase Morison scan and 3 per-phase FEM solves by the reference (about 1.5 minutes of its Python loops)
+    if "--large" in sys.argv:
+        nodes, members, fixed, top = jb.generate_jacket(8, 41)
+        make_case(ref, "gen8x41_airy", nodes, members, fixed, top, dict(GUI_DEFAULTS), scans=(4, 16), fem_phases_of=16, n_fem_phases=3,
+                  store_elements=False)
 
 
 if __name__ == "__main__":

@@ -128,8 +128,20 @@ def test_run_analysis_vs_reference(golden):
 
 def test_phase_scan_vs_reference(golden):
     """The hot path: Morison + FEM for every phase; rows of the phases the reference was replayed at."""
+    _check_phase_scan_vs_reference(golden[1], 1e-10)
+
+
+def test_phase_scan_vs_reference_c3_size():
+    """Same check on the BASELINE configs[2] / [4] geometry (8 legs x 41 bays: 1,976 members, 3,936 free DOF) against vectors
+    the reference's own classes produced (tests/golden/make_golden.py --large): 16-phase Morison scan, three per-phase FEM
+    cases.  The reference solves with LU, this path with a banded Cholesky factor: they agree to ~1e-11 here (CPU estimate
+    with LAPACK potrf: 7e-12 on U), the bar stays 1e-9."""
+    from conftest import load_golden
+    _check_phase_scan_vs_reference(load_golden("gen8x41_airy"), 1e-9)
+
+
+def _check_phase_scan_vs_reference(g, residual_bound):
     import jacket_b200 as jb
-    _, g = golden
     st, ap = product_structure(g)
     P = int(g["phasefem_P"])
     res = jb.phase_scan(st, _wave(jb, ap), P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
@@ -163,7 +175,7 @@ def test_phase_scan_vs_reference(golden):
     worst = int(np.argmax(g["phasefem_rows"][0][:, 6]))
     series = res.member_series(worst, "utilization")
     assert relmax(series[g["phasefem_idx"]], g["phasefem_rows"][:, worst, 6]) < TOL
-    assert res.engine.residual() < 1e-10
+    assert res.engine.residual() < residual_bound
 
 
 def test_mid_size_vs_oracle():

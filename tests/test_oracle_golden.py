@@ -130,3 +130,45 @@ def test_equilibrium_invariant(golden):
     # loads on the fixed nodes are part of F and also appear (negated) in R = K U - F
     total = applied + R[:, :, :3].sum(axis=1)
     assert np.max(np.abs(total)) / np.max(np.abs(applied)) < 1e-9
+
+
+def test_c3_size_jacket_against_the_reference():
+    """BASELINE configs[2] / [4] geometry (8 legs x 41 bays: 1,976 members, 3,936 free DOF): Morison at two times, a 4- and a 16-phase
+    scan, the t = 0 FEM case and three per-phase FEM cases computed by the reference's own classes
+    (tests/golden/make_golden.py --large) against the oracle.  Element matrices are not stored for this case."""
+    from conftest import load_golden
+    g = load_golden("gen8x41_airy")
+    p = golden_params(g)
+    m = oracle_model(g)
+    assert g["conn"].shape == (1976, 2) and g["xyz"].shape == (664, 3)
+    w = _wave(p)
+    assert abs(w.k - g["wave_k"]) < 1e-15 and abs(w.omega - g["wave_omega"]) < 1e-15
+    for tag in ("t0", "t1"):
+        out = orc.morison_phases(m, w, np.array([float(g[f"mor_{tag}_t"])]), **_mor_kw(p))
+        assert relmax(out["nodal_forces"][0], g[f"mor_{tag}_nodal"]) < TIGHT
+        totals = np.concatenate([out["total_drag"][0], out["total_inertia"][0], out["total_morison"][0]])
+        assert relmax(totals, g[f"mor_{tag}_totals"]) < TIGHT
+    for n in (4, 16):
+        tn = orc.phase_times(p["T"], n)
+        tab, crit = orc.phase_table(orc.morison_phases(m, w, tn, **_mor_kw(p)), tn, w.omega)
+        assert crit == int(g[f"scan{n}_critical"])
+        assert np.array_equal(tab[:, :2], g[f"scan{n}_table"][:, :2]) and relmax(tab[:, 2:], g[f"scan{n}_table"][:, 2:]) < TIGHT
+    fem = orc.FEM(m, p["E"], p["nu"])
+    F = _fem_inputs(g, p, fem, g["mor_t0_nodal"][None])
+    assert relmax(F[0], g["fem_t0_F"]) < 1e-14
+    U = fem.solve(F)
+    assert relmax(U[0], g["fem_t0_U"]) < 1e-9                 # two LU factorisations of a 3,936 x 3,936 system
+    assert relmax(fem.reactions(U, F)[0], g["fem_t0_reactions"]) < 1e-9
+    mf = fem.member_forces(U, p["fy"])
+    for c, k in enumerate(("Fx_max_kN", "Fy_max_kN", "Fz_max_kN", "My_max_kNm", "Mz_max_kNm", "von_mises_max_MPa", "utilization")):
+        assert relmax(mf[k][0], g["fem_t0_rows"][:, c]) < 1e-9
+    P = int(g["phasefem_P"])
+    t = orc.phase_times(p["T"], P)[g["phasefem_idx"]]
+    res = orc.phase_scan(m, w, t, E=p["E"], nu=p["nu"], fy=p["fy"], F_axial_kN=p["F_axial"], F_shear_kN=p["F_shear"],
+                         M_moment_kNm=p["M_moment"], M_torsion_kNm=p["M_torsion"], self_weight=str(p["self_weight_mode"]),
+                         custom_sw_tonnes=p["custom_sw"], fem=fem, **_mor_kw(p))
+    assert relmax(res["F"], g["phasefem_F"]) < 1e-14
+    for i in range(len(t)):
+        assert relmax(res["U"][i], g["phasefem_U"][i]) < 1e-9
+        assert relmax(res["reactions"][i], g["phasefem_reactions"][i]) < 1e-9
+        assert relmax(res["members"]["utilization"][i], g["phasefem_rows"][i][:, 6]) < 1e-9
