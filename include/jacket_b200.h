@@ -106,6 +106,27 @@ typedef struct jk_handle_s* jk_handle_t;
 int         jk_version(void);
 const char* jk_last_error(jk_handle_t h);
 
+/* Documented run-time options of a handle (the library never reads the environment).  Defaults in brackets.
+ * Scheduling switches -- every setting produces bit-identical results (tests/test_gpu_parity.py):
+ *   start_gate [1]          the main stream waits until the factor clusters are resident (asynchronous factorisation)
+ *   start_gate2 [1]         the first forward sweep parts wait until the second factor segment is resident
+ *   post_overlap [1]        member post of first-chain chunks beside the second chain's backward sweep
+ *   early_totals [1]        Morison columns of the table reduced on a side stream behind the Morison kernel
+ *   cuda_graph [1]          jk_phase_scan_dev replays the resident scan as a captured CUDA graph
+ *   fused_loads [1]         the Morison kernel lumps member end forces into nodal loads itself (0: member forces are
+ *                           written to HBM and gathered by a second kernel; same sums in the same order)
+ *   sweep_slab [0]          right-hand sides per triangular-sweep CTA: 0 = chosen so that the CTAs fill the SMs, 8, 16, 32
+ * Ordering / storage switches, read by the next jk_set_supports (results agree to rounding, the reference's run_analysis
+ * has no counterpart: GUI.py:481-490 is a dense LU):
+ *   two_chains [1]  factor_split [1]  split_pct [70]  level_regroup [1]  support_rooted_rcm [1]  tma_sweep [1]
+ *   blocked_inverse [1]
+ * Debug aids: profile_chol [0], profile_sweep [0] (clock breakdowns on stderr), debug_factor_delay [0] (clocks).
+ * jk_option_count / jk_option_name enumerate the keys. */
+int         jk_set_option(jk_handle_t h, const char* key, int value);
+int         jk_get_option(jk_handle_t h, const char* key, int* value);
+int         jk_option_count(void);
+const char* jk_option_name(int index);
+
 /* Replaces CustomJacketStructure (GUI.py:302-354) as the geometry carrier:
  * xyz[n_nodes*3] (m, z = 0 at MWL), conn[n_members*2] node indices,
  * sec_id[n_members] rows of sec_props[n_sec*JK_SEC_NPROP].
@@ -155,6 +176,11 @@ int jk_morison_scan(jk_handle_t h, int P, const double* t, double* table, int64_
  * nodal_forces[n_nodes*3], totals[9] = drag xyz, inertia xyz, morison xyz (N),
  * details[n_members*JK_DETAIL_NCOL]; any output may be NULL. */
 int jk_morison_single(jk_handle_t h, double t, double* nodal_forces, double* totals, double* details);
+
+/* MorisonCalculator.get_kinematics_3d (GUI.py:559-589, with RaschiiWave.get_kinematics GUI.py:290-296 inside) for n
+ * points xyz[n*3] at time t, evaluated by the device functions of the Morison kernels:
+ * out[n*10] = u_wave v_wave w_wave u_current v_current du_dt dv_dt dw_dt submerged(0/1) eta. */
+int jk_kinematics_points(jk_handle_t h, int n, const double* xyz, double t, double* out);
 
 /* The whole hot path for P phases: Morison -> RHS -> two triangular sweeps ->
  * reactions / member forces / utilisation -> per-phase table -> critical phase.

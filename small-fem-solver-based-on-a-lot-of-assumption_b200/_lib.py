@@ -55,6 +55,12 @@ def _sig(lib):
     lib.jk_version.restype = C.c_int
     lib.jk_last_error.restype = C.c_char_p
     lib.jk_last_error.argtypes = [H]
+    lib.jk_set_option.argtypes = [H, C.c_char_p, C.c_int]
+    lib.jk_get_option.argtypes = [H, C.c_char_p, C.POINTER(C.c_int)]
+    lib.jk_option_count.restype = C.c_int
+    lib.jk_option_name.argtypes = [C.c_int]
+    lib.jk_option_name.restype = C.c_char_p
+    lib.jk_kinematics_points.argtypes = [H, C.c_int, _dp, C.c_double, _dp]
     lib.jk_create.argtypes = [C.c_int, C.c_void_p, C.c_int, _dp, C.c_int, _ip, _ip, C.c_int, _dp, C.POINTER(H)]
     lib.jk_destroy.argtypes = [H]
     lib.jk_set_supports.argtypes = [H, C.c_int, _ip, C.c_int, C.c_int]
@@ -94,7 +100,7 @@ def _sig(lib):
                  "jk_set_wave_airy", "jk_set_wave_fourier", "jk_set_morison", "jk_morison_scan", "jk_morison_single",
                  "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_ensemble_scan", "jk_fetch_phase",
                  "jk_fetch_member_column", "jk_get_dims", "jk_get_order", "jk_get_K", "jk_get_elements",
-                 "jk_get_timings", "jk_residual", "jk_solver_stats"):
+                 "jk_get_timings", "jk_residual", "jk_solver_stats", "jk_set_option", "jk_get_option", "jk_kinematics_points"):
         getattr(lib, name).restype = C.c_int
 
 

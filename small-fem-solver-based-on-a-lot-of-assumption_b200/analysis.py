@@ -146,7 +146,8 @@ def run_analysis(nodes, members, fixed_nodes, top_nodes, params: AnalysisParams 
         fem.apply_nodal_force(name, fv)
     apply_self_weight(fem.F_global, structure, p.self_weight_mode, p.custom_sw)
     fem.apply_boundary_conditions(structure.get_bottom_nodes())
-    U = fem.solve(fy=p.fy)
+    fem._fy = float(p.fy)          # yield stress of the device-side utilisation (the reference passes fy to get_member_internal_forces only)
+    U = fem.solve()
     reactions = fem.get_reactions()
     internal_forces = fem.get_member_internal_forces(p.fy)
     max_util = max(m["utilization"] for m in internal_forces)
@@ -168,6 +169,11 @@ class PhaseScanResult:
     fy: float
     engine: object = field(repr=False, default=None)
     columns: tuple = L.TABLE_COLUMNS
+    generation: int = -1           # engine generation the resident rows belong to (a later scan on the same structure overwrites them)
+
+    def _resident(self):
+        if self.generation >= 0:
+            self.engine.check_generation(self.generation, "PhaseScanResult")
 
     @property
     def n_phases(self):
@@ -191,6 +197,7 @@ class PhaseScanResult:
 
     def phase(self, i, end_forces=False):
         """Full results of phase i in the reference's shapes: U, reactions{node: [6]}, internal_forces[list of dict]."""
+        self._resident()
         got = self.engine.fetch_phase(i, U=True, reactions=True, rows=True, end_forces=end_forces, nodal=True)
         st = self.structure
         reactions = {st.node_list[int(n)]: got["reactions"][k].copy() for k, n in enumerate(self.engine.fixed_idx)}
@@ -202,6 +209,7 @@ class PhaseScanResult:
         return out
 
     def member_series(self, member, column="utilization"):
+        self._resident()
         mi = member if isinstance(member, int) else [m["name"] for m in self.structure.members].index(member)
         return self.engine.member_column(mi, L.MEMBER_COLUMNS.index(column), self.n_phases)
 
@@ -225,7 +233,7 @@ def phase_scan(structure, wave, n_steps=360, *, wave_direction=0.0, current_dire
     tt = phase_times(wave.T, n_steps) if t is None else np.asarray(t, dtype=np.float64)
     table, crit = eng.phase_scan(tt, fy)
     fill_phase_deg(table, wave.omega)
-    return PhaseScanResult(structure, wave, table, crit, fy, eng)
+    return PhaseScanResult(structure, wave, table, crit, fy, eng, generation=eng.generation)
 
 
 def phase_scan_from_params(nodes, members, fixed_nodes, top_nodes, params: AnalysisParams | None = None, n_steps=360):
@@ -252,6 +260,7 @@ class EnsembleResult:
     fy: float
     engine: object = field(repr=False, default=None)
     columns: tuple = L.TABLE_COLUMNS
+    generation: int = -1
 
     @property
     def n_states(self):
@@ -273,6 +282,8 @@ class EnsembleResult:
         return int(s), int(p)
 
     def case(self, state, phase, end_forces=False):
+        if self.generation >= 0:
+            self.engine.check_generation(self.generation, "EnsembleResult")
         got = self.engine.fetch_phase(int(state) * self.n_phase + int(phase), U=True, reactions=True, rows=True,
                                       end_forces=end_forces, nodal=True)
         st = self.structure
@@ -338,4 +349,4 @@ def ensemble_scan(structure, H, T, wave_dir, n_phase=16, *, d=50.0, U_c=0.0, cur
     t = np.arange(n_phase)[None, :] * T[:, None] / n_phase                           # (i*T)/n_steps, GUI.py:696, per state
     table, crit = eng.ensemble_scan(H / 2.0, k, omega, np.deg2rad(90.0 - wave_dir), t, fy, F_dir)
     table[:, :, 1] = mod360(np.degrees(omega[:, None] * table[:, :, 0]))
-    return EnsembleResult(structure, H, T, wave_dir, k, table, crit, fy, eng)
+    return EnsembleResult(structure, H, T, wave_dir, k, table, crit, fy, eng, generation=eng.generation)

@@ -26,14 +26,38 @@ using namespace jk;
 
 static thread_local std::string g_err;
 
+// Run-time options (jk_set_option / jk_get_option).  The library never reads the environment.
+enum JkOpt { OPT_START_GATE, OPT_START_GATE2, OPT_POST_OVERLAP, OPT_EARLY_TOTALS, OPT_FACTOR_SPLIT, OPT_SPLIT_PCT, OPT_TWO_CHAINS,
+             OPT_LEVEL_REGROUP, OPT_SUPPORT_ROOTED_RCM, OPT_TMA_SWEEP, OPT_BLOCKED_INVERSE, OPT_PROFILE_CHOL, OPT_PROFILE_SWEEP,
+             OPT_DEBUG_FACTOR_DELAY, OPT_SWEEP_SLAB, OPT_CUDA_GRAPH, OPT_FUSED_LOADS, OPT_COUNT };
+struct JkOptDesc { const char* key; int def, lo, hi; };
+static const JkOptDesc g_opts[OPT_COUNT] = {
+    {"start_gate", 1, 0, 1},            // main stream waits until the factor clusters are resident (asynchronous factorisation)
+    {"start_gate2", 1, 0, 1},           // first forward sweep parts wait until the second factor segment is resident
+    {"post_overlap", 1, 0, 1},          // member post of first-chain chunks beside the second chain's backward sweep
+    {"early_totals", 1, 0, 1},          // Morison columns of the table reduced on a side stream behind the Morison kernel
+    {"factor_split", 1, 0, 1},          // two factor segments, forward sweeps start on the first      [next jk_set_supports]
+    {"split_pct", 70, 10, 95},          // split point in % of a chain's columns                         [next jk_set_supports]
+    {"two_chains", 1, 0, 1},            // two-sided elimination                                         [next jk_set_supports]
+    {"level_regroup", 1, 0, 1},         // BFS levels re-sorted by node degree (block-cost ordering)      [next jk_set_supports]
+    {"support_rooted_rcm", 1, 0, 1},    // RCM rooted at the support-adjacent node set as a candidate    [next jk_set_supports]
+    {"tma_sweep", 1, 0, 1},             // TMA / mbarrier sweep pipeline (0: cp.async slab sweep)        [next jk_set_supports]
+    {"blocked_inverse", 1, 0, 1},       // diagonal-tile inverses from the factor's 8x8 block inverses
+    {"profile_chol", 0, 0, 1},          // debug: clock stamps of the cluster factorisation to stderr
+    {"profile_sweep", 0, 0, 1},         // debug: clock sums of the sweep warps to stderr
+    {"debug_factor_delay", 0, 0, 2000000000},   // test aid: spin this many clocks in front of the factorisation
+    {"sweep_slab", 0, 0, 32},           // right-hand sides per sweep CTA: 0 = auto (fill the SMs), 8, 16 or 32
+    {"cuda_graph", 1, 0, 1},            // replay the resident scan (jk_phase_scan_dev) as a captured CUDA graph
+    {"fused_loads", 1, 0, 1},           // Morison kernel lumps member end forces into nodal loads itself (no member-force round trip)
+};
+
 struct jk_handle_s {
+    int opt[OPT_COUNT];
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;        // side stream: the factorisation runs here, concurrently with the Morison stage
     cudaStream_t stream3 = nullptr;        // load gather of one phase block while the Morison kernel works on the next
-    cudaEvent_t ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_gather = nullptr;
-    bool gather_inflight = false;
     cudaEvent_t ev_post_fork = nullptr, ev_post_join = nullptr;   // node-level post kernels run beside the member post on the side stream
     // pinned staging for the small per-scan host transfers (static load in, table + critical index + pivot flag out): one
     // asynchronous copy each and a single synchronisation per scan instead of pageable copies with their own syncs
@@ -44,7 +68,6 @@ struct jk_handle_s {
     // early member post: chunks whose members only touch chain-0 / separator nodes are post-processed on a side stream
     // while the second chain's backward sweep runs (HBM-bound work on the SMs the sweep leaves idle)
     int* d_post_chunks = nullptr; int n_post_early = 0, n_post_late = 0, n_sm = 0;
-    bool gate2_on = true, post_overlap_on = true, early_totals_on = true;   // A/B switches read at jk_create (JK_NO_START_GATE2, JK_NO_POST_OVERLAP, JK_NO_EARLY_TOTALS)
     cudaEvent_t ev_bwd0 = nullptr, ev_post_early = nullptr, ev_mor = nullptr, ev_tot = nullptr;
     unsigned gate2_target = 0; bool gate2_armed = false;   // second factor segment resident (awaited before the first forward parts)
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -87,7 +110,8 @@ struct jk_handle_s {
     bool tma_sweep = false;   // narrow band: sweeps run as the TMA / mbarrier pipeline, otherwise the cp.async slab sweep
     int n_chains = 1, nS_nodes = 0;
     int factor_path = 0;   // 0 = auto (cluster kernel for narrow bands), 1 = per-column launches
-    int* d_info = nullptr;
+    int* d_info = nullptr;          // pivot flag of the factorisation in flight
+    int* d_info_sticky = nullptr;   // first non-zero pivot flag since it was last reported (survives re-assembly in a resident loop)
     bool assembled = false, factored = false;
     double E = 0, G = 0;
 
@@ -115,7 +139,7 @@ struct jk_handle_s {
     int *d_part_mem = nullptr, *d_part_node = nullptr;
     long long* d_argidx = nullptr;
     int lastP = 0, last_ldP = 0;
-    bool last_morison = false, last_fem = false;
+    bool last_morison = false, last_fem = false, last_fdir = false;
     double last_fy = 355.0;
 
     cudaEvent_t ev0[JK_NTIMERS], ev1[JK_NTIMERS];
@@ -174,6 +198,30 @@ extern "C" void* jk_table_dev(jk_handle_t h) { return h ? (void*)h->d_table : nu
 extern "C" void* jk_critical_value_dev(jk_handle_t h) { return h ? (void*)h->d_argval : nullptr; }
 extern "C" void* jk_critical_index_dev(jk_handle_t h) { return h ? (void*)h->d_argidx : nullptr; }
 
+static int find_option(const char* key) {
+    if (!key) return -1;
+    for (int i = 0; i < OPT_COUNT; ++i) if (strcmp(key, g_opts[i].key) == 0) return i;
+    return -1;
+}
+extern "C" int jk_set_option(jk_handle_t h, const char* key, int value) {
+    if (!h) return JK_EINVAL;
+    const int i = find_option(key);
+    if (i < 0) JK_FAIL(h, JK_EINVAL, "jk_set_option: unknown option '%s'", key ? key : "(null)");
+    if (value < g_opts[i].lo || value > g_opts[i].hi) JK_FAIL(h, JK_EINVAL, "jk_set_option: %s must be in %d..%d (got %d)", key, g_opts[i].lo, g_opts[i].hi, value);
+    if (i == OPT_SWEEP_SLAB && value != 0 && value != 8 && value != 16 && value != 32) JK_FAIL(h, JK_EINVAL, "jk_set_option: sweep_slab must be 0 (auto), 8, 16 or 32");
+    h->opt[i] = value;
+    return JK_OK;
+}
+extern "C" int jk_get_option(jk_handle_t h, const char* key, int* value) {
+    if (!h || !value) return JK_EINVAL;
+    const int i = find_option(key);
+    if (i < 0) JK_FAIL(h, JK_EINVAL, "jk_get_option: unknown option '%s'", key ? key : "(null)");
+    *value = h->opt[i];
+    return JK_OK;
+}
+extern "C" int jk_option_count(void) { return OPT_COUNT; }
+extern "C" const char* jk_option_name(int i) { return (i >= 0 && i < OPT_COUNT) ? g_opts[i].key : nullptr; }
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xyz, int n_members,
                          const int32_t* conn, const int32_t* sec_id, int n_sec, const double* sec_props,
@@ -200,9 +248,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     h->device = device;
     cudaSetDevice(device);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
-    h->gate2_on = getenv("JK_NO_START_GATE2") == nullptr;
-    h->post_overlap_on = getenv("JK_NO_POST_OVERLAP") == nullptr;
-    h->early_totals_on = getenv("JK_NO_EARLY_TOTALS") == nullptr;
+    for (int i = 0; i < OPT_COUNT; ++i) h->opt[i] = g_opts[i].def;
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; JK_FAIL((jk_handle_t)nullptr, JK_ECUDA, "jk_create: cudaStreamCreate failed"); } h->own_stream = true; }
     for (int i = 0; i < JK_NTIMERS; ++i) { cudaEventCreate(&h->ev0[i]); cudaEventCreate(&h->ev1[i]); h->ev_set[i] = false; }
@@ -211,9 +257,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     cudaEventCreateWithFlags(&h->ev_factor, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_factor_bwd, cudaEventDisableTiming);
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, hi); }
-    for (auto& e : h->ev_part) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
-    if (getenv("JK_NO_START_GATE") == nullptr) {
+    {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn != nullptr
@@ -256,6 +300,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, dev_alloc(&h->d_adj, 2 * (size_t)n_members));
     CUDA_TRY(h, dev_alloc(&h->d_Fstatic, 6 * (size_t)n_nodes));
     CUDA_TRY(h, dev_alloc(&h->d_info, 1));
+    CUDA_TRY(h, dev_alloc(&h->d_info_sticky, 1));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_info_sticky, 0, sizeof(int), h->stream));
     CUDA_TRY(h, dev_alloc(&h->d_argval, 1));
     CUDA_TRY(h, dev_alloc(&h->d_argidx, 1));
     CUDA_TRY(h, dev_alloc(&h->d_res, 2));
@@ -290,7 +336,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
     for (auto& c : h->ch) { dev_free(c.d_blocks); dev_free(c.d_contrib); dev_free(c.d_tiles); dev_free(c.d_Linv); dev_free(c.d_dinv);
                             for (auto& w : c.sw) { dev_free(w.d_prog); dev_free(w.d_stream); } }
-    dev_free(h->d_info);
+    dev_free(h->d_info); dev_free(h->d_info_sticky);
     dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four); dev_free(h->d_states); dev_free(h->d_state_crit);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
@@ -302,8 +348,6 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->ev_factor) cudaEventDestroy(h->ev_factor);
     if (h->ev_factor_bwd) cudaEventDestroy(h->ev_factor_bwd);
     if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
-    for (auto& e : h->ev_part) if (e) cudaEventDestroy(e);
-    if (h->ev_gather) cudaEventDestroy(h->ev_gather);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->h_pin_t) cudaFreeHost(h->h_pin_t);
     if (h->ev_pin_t) cudaEventDestroy(h->ev_pin_t);
@@ -566,9 +610,9 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         int hb1 = 0, hb2 = 0; long long pr1 = 0, pr2 = 0;
         order_quality(h->Nn, h->h_conn, o1, hb1, pr1);
         order_quality(h->Nn, h->h_conn, o2, hb2, pr2);
-        const bool second = getenv("JK_RCM_SINGLE_ROOT") == nullptr && o2.size() == o1.size() && (hb2 < hb1 || (hb2 == hb1 && pr2 < pr1));
+        const bool second = h->opt[OPT_SUPPORT_ROOTED_RCM] && o2.size() == o1.size() && (hb2 < hb1 || (hb2 == hb1 && pr2 < pr1));
         h->h_free_nodes.swap(second ? o2 : o1);
-        if (second && getenv("JK_NO_LEVEL_REGROUP") == nullptr) {
+        if (second && h->opt[OPT_LEVEL_REGROUP]) {
             // further candidates: same level structure, every level sorted by degree (either way, ties either way).  Kept when the band does not
             // widen and the sweeps get cheaper (more non-zeros in L, but fewer mask blocks to multiply).
             double best = sweep_cost(h->Nn, h->h_conn, h->h_free_nodes);
@@ -597,7 +641,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     // two chains when the band is narrow and long enough: |A|, |B| multiples of 32 nodes (= 3 tiles), separator >= hbn nodes
     int nA = N, nS = 0, nB = 0;
     h->n_chains = 1;
-    if (solver == JK_SOLVER_BANDED && getenv("JK_SINGLE_CHAIN") == nullptr && N - hbn >= 4 * 32 && 6 * hbn + 5 <= 12 * NB) {
+    if (solver == JK_SOLVER_BANDED && h->opt[OPT_TWO_CHAINS] && N - hbn >= 4 * 32 && 6 * hbn + 5 <= 12 * NB) {
         int avail = N - hbn;
         nA = 32 * (avail / 64);
         nB = 32 * ((avail - nA) / 32);
@@ -623,7 +667,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
             order_quality(h->Nn, h->h_conn, rev_old, hb_old, pr_old);
             double best = sweep_cost(h->Nn, h->h_conn, rev_old);
             std::vector<int> best_order;
-            for (int variant = 0; variant < (getenv("JK_NO_LEVEL_REGROUP") ? 1 : 5); ++variant) {
+            for (int variant = 0; variant < (h->opt[OPT_LEVEL_REGROUP] ? 5 : 1); ++variant) {
                 std::vector<int> g = variant == 0 ? cm : regroup_levels_by_degree(cm, levB, nbr, ((variant - 1) & 1) != 0, ((variant - 1) & 2) != 0);
                 std::vector<int> trial(h->h_free_nodes);
                 std::copy(g.begin(), g.end(), trial.begin() + nA + nS);
@@ -759,7 +803,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         tile_reach[c] = chain_tile_reach(h->ch[c].NT, nn, node_first);
     }
     // sweep programs: the TMA pipeline keeps the last SW_RING solved tiles in shared memory, so it needs a narrow band
-    h->tma_sweep = getenv("JK_SWEEP_LEGACY") == nullptr;
+    h->tma_sweep = h->opt[OPT_TMA_SWEEP] != 0;
     for (int c = 0; c < h->n_chains; ++c) if (h->ch[c].bw > SW_MAX_BW) h->tma_sweep = false;
     h->split_factor = false;
     for (int c = 0; c < 2; ++c)
@@ -780,7 +824,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
                 // inverse / stream-build kernels and the relaunch of the cluster kernel do not collide with the gather and
                 // the sweeps (60-80 % measure the same within 1 %; close to 90 % the second segment competes with the sweep
                 // CTAs for whole SMs and the step degrades badly)
-                static const int split_pct = getenv("JK_SPLIT_PCT") ? atoi(getenv("JK_SPLIT_PCT")) : 70;
+                const int split_pct = h->opt[OPT_SPLIT_PCT];
                 const int kS = chn.kS, k1 = (int)((long long)split_pct * kS / 100);
                 if (k1 >= 2 * SW_RING && kS - k1 >= 4) {
                     int n1 = 0;
@@ -798,15 +842,15 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
             CUDA_TRY(h, cudaStreamSynchronize(s));   // prog is a local
         }
     // the factorisation runs in two segments (and the forward sweeps in two launches) when every chain has a split point
-    h->split_factor = h->tma_sweep && getenv("JK_NO_FACTOR_SPLIT") == nullptr;
+    h->split_factor = h->tma_sweep && h->opt[OPT_FACTOR_SPLIT];
     for (int c = 0; c < h->n_chains; ++c) if (h->ch[c].sw[0].k_split == 0) h->split_factor = false;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_node2slot, h->h_node2slot.data(), (size_t)h->Nn * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     h->have_supports = true; h->assembled = false; h->factored = false;
-    // buffers sized by n_pad / n_fixed must be rebuilt
-    h->cap_ldP = 0;
+    // buffers sized by n_pad / n_fixed must be rebuilt; resident results no longer match the new row numbering
+    h->cap_ldP = 0; h->lastP = 0; h->last_fem = false;
     return JK_OK;
 }
 
@@ -830,8 +874,13 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     }
     toc(h, JK_T_ASSEMBLE);
     h->assembled = true; h->factored = false;
+    h->lastP = 0; h->last_fem = false;        // resident rows belong to the previous stiffness
     return JK_OK;
 }
+
+// end of a factorisation: latch a non-positive pivot into the sticky flag (reported by the next call that talks to the host;
+// the on-device argmax poisons the critical pair meanwhile)
+__global__ void k_latch_info(const int* __restrict__ info, int* __restrict__ sticky) { if (*info != 0 && *sticky == 0) *sticky = *info; }
 
 __global__ void k_debug_spin(long long clocks) { const long long t0 = clock64(); while (clock64() - t0 < clocks) { } }
 
@@ -862,11 +911,11 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
     auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
     if (use_cluster) {
         long long* prof = nullptr;
-        const bool want_prof = getenv("JK_CHOL_PROFILE") != nullptr;
+        const bool want_prof = h->opt[OPT_PROFILE_CHOL] != 0;
         if (want_prof) { CUDA_TRY(h, cudaMalloc((void**)&prof, (size_t)c0.NT * 8 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(prof, 0, (size_t)c0.NT * 8 * sizeof(long long), s)); }
         CholChain a{c0.d_tiles, c0.d_dinv, c0.NT, c0.bw, 0, c0.kS};
-        unsigned* gate = (s_side != nullptr && h->wait_value32) ? h->d_started : nullptr;   // asynchronous factorisation only
-        if (getenv("JK_DEBUG_FACTOR_DELAY")) k_debug_spin<<<1, 32, 0, s>>>(atoll(getenv("JK_DEBUG_FACTOR_DELAY")));   // test aid: lose the race on purpose
+        unsigned* gate = (s_side != nullptr && h->wait_value32 && h->opt[OPT_START_GATE]) ? h->d_started : nullptr;   // asynchronous factorisation only
+        if (h->opt[OPT_DEBUG_FACTOR_DELAY] > 0) k_debug_spin<<<1, 32, 0, s>>>((long long)h->opt[OPT_DEBUG_FACTOR_DELAY]);   // test aid: lose the race on purpose
         if (h->split_factor && s_side != nullptr) {
             // Two segments.  After the first (80 % of each chain's columns) a side stream inverts those diagonal tiles and
             // builds the forward tile streams of those rows, so the forward sweeps can start on them (run_fem) while this
@@ -891,7 +940,7 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
             // clusters are resident.  With the Morison + load stage as short as the first segment the sweeps otherwise win
             // the race now and then, the clusters find no GPC with eight free SMs until both parts are through and the step
             // grows by ~1 ms (seen as 5.5 vs 6.7 ms per step between runs).
-            const bool gate2_on = h->gate2_on;
+            const bool gate2_on = h->opt[OPT_START_GATE2] != 0;
             k_band_chol_cluster<<<ncl * CHOL_CLUSTER, CHOL_THREADS, CHOL_CLUSTER_SMEM, s>>>(a2, ncl == 2 ? b2 : a2, h->d_info, nullptr, gate2_on ? gate : nullptr);
             LAUNCH_CHECK(h);
             h->gate2_armed = false;
@@ -911,6 +960,8 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
             int rc2 = launch_sweep_build(h, s, 0, 2);
             if (rc2 != JK_OK) return rc2;
             CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_fwd1, 0));      // the factor stage is complete when both branches are
+            k_latch_info<<<1, 1, 0, s>>>(h->d_info, h->d_info_sticky);
+            LAUNCH_CHECK(h);
             toc(h, JK_T_FACTOR, s);
             if (want_prof) { CUDA_TRY(h, cudaStreamSynchronize(s)); cudaFree(prof); }
             return JK_OK;
@@ -959,7 +1010,7 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
         }
     }
     { const int n1 = h->n_chains == 2 ? c1.kS : 0;     // second chain: its separator rows are factored in the first chain
-      if (use_cluster && getenv("JK_INVERSE_LEGACY") == nullptr)     // the cluster kernel left the 8x8 block inverses in d_dinv
+      if (use_cluster && h->opt[OPT_BLOCKED_INVERSE])     // the cluster kernel left the 8x8 block inverses in d_dinv
           k_tile_inverse_blocked<<<c0.NT + n1, 256, INVERSE_BLOCKED_SMEM, s>>>(c0.d_tiles, c0.d_dinv, c0.d_Linv, c0.bw, 0, c0.NT,
                                                                                c1.d_tiles, c1.d_dinv, c1.d_Linv, c1.bw, 0);
       else
@@ -968,18 +1019,20 @@ static int launch_factor(jk_handle_t h, cudaStream_t s, cudaStream_t s_side = nu
     // tile streams of the forward sweeps; the factor timer stops here (this is what the forward sweeps wait for)
     int rc = launch_sweep_build(h, s, 0);
     if (rc != JK_OK) return rc;
+    k_latch_info<<<1, 1, 0, s>>>(h->d_info, h->d_info_sticky);
+    LAUNCH_CHECK(h);
     toc(h, JK_T_FACTOR, s);
     return JK_OK;
 }
 
 // host-side completion of an asynchronous factorisation: pivot check.  Call only after the streams were synchronised.
 static int finish_factor(jk_handle_t h) {
-    if (!h->factor_inflight) return JK_OK;
+    if (h->factor_inflight) CUDA_TRY(h, cudaStreamSynchronize(h->stream2));
     h->factor_inflight = false;
     int info = 0;
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream2));
-    CUDA_TRY(h, cudaMemcpy(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(&info, h->d_info_sticky, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) {
+        CUDA_TRY(h, cudaMemset(h->d_info_sticky, 0, sizeof(int)));
         h->factored = false;
         JK_FAIL(h, JK_ENOTSPD, "K_ff is not positive definite (pivot %d <= 0): structure is a mechanism or badly supported", info - 1);
     }
@@ -1138,7 +1191,7 @@ static WaveAiry launch_wave(jk_handle_t h) {
 }
 
 // Morison stage for the phases already in d_t: trig tables, Gauss-point tables (once per wave), K1
-static int run_morison(jk_handle_t h, int P, int ldP, bool details, int gather_parts = 1) {
+static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
     cudaStream_t s = h->stream;
     WaveAiry w = launch_wave(h);
     tic(h, JK_T_WAVE_SETUP);
@@ -1176,20 +1229,10 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details, int gather_p
             CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_morison_airy<true, 0><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);
         } else {
-            // Phase blocks: the load gather of block b (HBM-bound, side stream) runs under the Morison kernel of block b+1
-            // (FP64-bound).  gather_parts > 1 only when the caller gathers afterwards (scan_core).
             // the default 15-point rule may have its own instantiation with fully unrolled point loops (-DJK_MORISON_G15=1)
             auto kern = (JK_MORISON_G15 && h->ng == 15) ? k_morison_airy<false, 15> : k_morison_airy<false, 0>;
             CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int nbx = (int)grid.x, parts = std::max(1, std::min(gather_parts, nbx));
-            for (int b = 0; b < parts; ++b) {
-                const int x0 = (int)((long long)nbx * b / parts), x1 = (int)((long long)nbx * (b + 1) / parts);
-                if (x1 <= x0) continue;
-                kern<<<dim3(x1 - x0, grid.y), PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0,
-                                                                                 h->d_Fm, h->d_totpart, nullptr, x0 * PH_TPB);
-                if (b + 1 < parts) LAUNCH_CHECK(h);            // the last launch is counted by the common check below
-                if (parts > 1) CUDA_TRY(h, cudaEventRecord(h->ev_part[b], s));
-            }
+            kern<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr, 0);
         }
     }
     LAUNCH_CHECK(h);
@@ -1229,7 +1272,8 @@ static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool f
                                                      n_nchunk, fem ? h->d_part_disp : nullptr, h->d_part_node,
                                                      h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL, totals_done ? 0 : 1);
     LAUNCH_CHECK(h);
-    k_argmax<<<1, 1024, 0, s>>>(P, h->d_table, JK_TABLE_NCOL, morison ? JK_COL_TOTAL_KN : JK_COL_MAX_UTIL, h->d_argval, h->d_argidx);
+    k_argmax<<<1, 1024, 0, s>>>(P, h->d_table, JK_TABLE_NCOL, morison ? JK_COL_TOTAL_KN : JK_COL_MAX_UTIL, h->d_argval, h->d_argidx,
+                                fem ? h->d_info_sticky : nullptr);
     LAUNCH_CHECK(h);
     toc(h, JK_T_REDUCE);
     return JK_OK;
@@ -1243,7 +1287,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     auto& c0 = h->ch[0]; auto& c1 = h->ch[1];
     const int nS6 = 6 * h->nS_nodes;
     dim3 gsep(ceil_div(ldP, 128), std::max(1, nS6));
-    static const bool sweep_prof = getenv("JK_SWEEP_PROFILE") != nullptr;
+    const bool sweep_prof = h->opt[OPT_PROFILE_SWEEP] != 0;
     long long* d_prof = nullptr;
     if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, 4 * 64 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, 4 * 64 * sizeof(long long), s)); }
     // part: 0 = whole program, 1 = items [0, n_split), 2 = the rest (continues from the rows part 1 left in the slab)
@@ -1260,7 +1304,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     // Early member post (see d_post_chunks): only when the backward sweep of the second chain leaves SMs idle (one CTA per
     // SM, fewer slabs than SMs) -- the post blocks are released once every sweep CTA is resident (same counter as the
     // factor's start gates), so they can only take what the sweep does not use.
-    const bool post_overlap_on = h->post_overlap_on;
+    const bool post_overlap_on = h->opt[OPT_POST_OVERLAP] != 0;
     bool post_early = false;
     dim3 gm_all(ceil_div(h->M, MCHUNK), ceil_div(ldP, JK_POST_TPB));
     if (h->tma_sweep) {
@@ -1392,44 +1436,20 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
     int rc;
     if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
     const int nbx = ceil_div(ldP, PH_TPB);
-    // Experiment (JK_GATHER_OVERLAP=1), off by default: Morison in four phase blocks with the load gather of block b on
-    // a side stream under the Morison kernel of block b+1.  Measured on c4: the gather's blocks displace Morison blocks
-    // and slow the concurrent factorisation (Morison 2.49 -> 2.97 ms, factor 2.88 -> 3.16 ms) -- more than the 0.4 ms
-    // of gather it hides, with full-size or throttled (JK_GATHER_ROWS) gather grids alike.
-    const bool split = fem && h->wave_kind == 0 && h->stream3 && nbx >= 8 && getenv("JK_GATHER_OVERLAP") != nullptr;
-    const int parts = split ? 4 : 1;
-    if ((rc = run_morison(h, P, ldP, false, parts)) != JK_OK) return rc;
-    const bool totals_early = fem && h->early_totals_on && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
+    if ((rc = run_morison(h, P, ldP, false)) != JK_OK) return rc;
+    const bool totals_early = fem && h->opt[OPT_EARLY_TOTALS] && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
     if (totals_early && (rc = reduce_totals_early(h, P, ldP)) != JK_OK) return rc;
     if (fem) {
-        if (parts == 1) {
-            tic(h, JK_T_RHS);
-            dim3 g(nbx, h->Nn);
-            k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
-                                             h->d_X, h->d_Ffix, nullptr);
-            LAUNCH_CHECK(h);
-            toc(h, JK_T_RHS);
-        } else {
-            cudaStream_t s3 = h->stream3;
-            // throttled: a few long-running blocks (each walks Nn / gather_rows nodes) instead of one block per node, so
-            // that the gather streams from HBM beside the FP64-bound Morison kernel without displacing its blocks
-            static const int gather_rows = getenv("JK_GATHER_ROWS") ? atoi(getenv("JK_GATHER_ROWS")) : 32;
-            for (int b = 0; b < parts; ++b) {
-                const int x0 = (int)((long long)nbx * b / parts), x1 = (int)((long long)nbx * (b + 1) / parts);
-                CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_part[b], 0));
-                if (b == parts - 1) tic(h, JK_T_RHS, s3);       // the timer shows the exposed part: the gather of the last phase block
-                k_rhs_gather<<<dim3(x1 - x0, std::min(h->Nn, gather_rows)), PH_TPB, 0, s3>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
-                                                                      h->d_X, h->d_Ffix, nullptr, nullptr, nullptr, 0, 1, 0, x0 * PH_TPB);
-                LAUNCH_CHECK(h);
-            }
-            toc(h, JK_T_RHS, s3);
-            CUDA_TRY(h, cudaEventRecord(h->ev_gather, s3));
-            CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_gather, 0));
-        }
+        tic(h, JK_T_RHS);
+        dim3 g(nbx, std::min(h->Nn, 65535));
+        k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
+                                         h->d_X, h->d_Ffix, nullptr);
+        LAUNCH_CHECK(h);
+        toc(h, JK_T_RHS);
         if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
     }
     if ((rc = reduce_and_argmax(h, P, ldP, true, fem, totals_early)) != JK_OK) return rc;
-    h->lastP = P; h->last_ldP = ldP; h->last_morison = true; h->last_fem = fem; h->last_fy = fy;
+    h->lastP = P; h->last_ldP = ldP; h->last_morison = true; h->last_fem = fem; h->last_fy = fy; h->last_fdir = false;
     return JK_OK;
 }
 
@@ -1453,7 +1473,7 @@ extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* criti
         tic(h, JK_T_D2H);
         if (table) CUDA_TRY(h, cudaMemcpyAsync(pin, h->d_table, tb, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(h, cudaMemcpyAsync(pin + tb, h->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaMemcpyAsync(pin + tb + 8, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(pin + tb + 8, h->d_info_sticky, sizeof(int), cudaMemcpyDeviceToHost, s));
         toc(h, JK_T_D2H);
         CUDA_TRY(h, cudaStreamSynchronize(s));
         if (table) memcpy(table, pin, tb);
@@ -1461,10 +1481,10 @@ extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* criti
         int info = 0;
         memcpy(&info, pin + tb + 8, sizeof(int));
         if (critical) *critical = (int64_t)idx;
-        if (h->factor_inflight) {
-            h->factor_inflight = false;
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream2));
+        if (h->factor_inflight) { h->factor_inflight = false; CUDA_TRY(h, cudaStreamSynchronize(h->stream2)); }
+        {
             if (info != 0) {
+                CUDA_TRY(h, cudaMemset(h->d_info_sticky, 0, sizeof(int)));
                 h->factored = false;
                 JK_FAIL(h, JK_ENOTSPD, "K_ff is not positive definite (pivot %d <= 0): structure is a mechanism or badly supported", info - 1);
             }
@@ -1591,6 +1611,23 @@ extern "C" int jk_morison_single(jk_handle_t h, double t, double* nodal_forces, 
     return JK_OK;
 }
 
+extern "C" int jk_kinematics_points(jk_handle_t h, int n, const double* xyz, double t, double* out) {
+    if (!h) return JK_EINVAL;
+    if (n <= 0 || !xyz || !out) JK_FAIL(h, JK_EINVAL, "jk_kinematics_points: n must be positive, xyz and out non-NULL");
+    if (!h->have_wave || !h->have_morison) JK_FAIL(h, JK_ESTATE, "jk_kinematics_points: call jk_set_wave_* and jk_set_morison first");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    int rc;
+    if ((rc = ensure_tmp(h, 13 * (size_t)n)) != JK_OK) return rc;
+    double *d_xyz = h->d_tmp, *d_out = h->d_tmp + 3 * (size_t)n;
+    CUDA_TRY(h, cudaMemcpyAsync(d_xyz, xyz, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    k_kinematics_points<<<ceil_div(n, 128), 128, 0, s>>>(n, d_xyz, t, launch_wave(h), h->n_harm, h->wave_kind == 1 ? h->d_four : nullptr, d_out);
+    LAUNCH_CHECK(h);
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, 10 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return JK_OK;
+}
+
 // Sea-state ensemble: n_states Airy sea states x n_phase phases each = one batch of load cases on one factor.
 extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const double* a, const double* k, const double* omega,
                                 const double* theta_wave, const double* t, const double* F_dir, double fy, double* table,
@@ -1647,7 +1684,7 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     toc(h, JK_T_MORISON);
     tic(h, JK_T_RHS);
     {
-        dim3 g(ceil_div(ldC, PH_TPB), h->Nn);
+        dim3 g(ceil_div(ldC, PH_TPB), std::min(h->Nn, 65535));
         k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldC, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic, h->d_X, h->d_Ffix, nullptr,
                                          d_Fdir, h->d_states, n_states, n_phase, C);
         LAUNCH_CHECK(h);
@@ -1658,7 +1695,7 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     k_argmax_per_state<<<ceil_div(n_states, 128), 128, 0, s>>>(n_states, n_phase, h->d_table, JK_TABLE_NCOL, JK_COL_TOTAL_KN, h->d_state_crit);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SCAN_TOTAL);
-    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy;
+    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = F_dir != nullptr;
     tic(h, JK_T_D2H);
     if (table) CUDA_TRY(h, cudaMemcpyAsync(table, h->d_table, (size_t)C * JK_TABLE_NCOL * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<long long> crit(n_states);
@@ -1687,7 +1724,7 @@ extern "C" int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy) {
     toc(h, JK_T_H2D);
     CUDA_TRY(h, cudaMemsetAsync(h->d_t, 0, (size_t)ldP * sizeof(double), s));
     tic(h, JK_T_RHS);
-    dim3 g(ceil_div(ldP, PH_TPB), h->Nn);
+    dim3 g(ceil_div(ldP, PH_TPB), std::min(h->Nn, 65535));
     k_rhs_from_loads<<<g, PH_TPB, 0, s>>>(h->Nn, nrhs, ldP, h->n_pad, h->d_Fload, h->d_node2slot, h->d_X, h->d_Ffix);
     LAUNCH_CHECK(h);
     toc(h, JK_T_RHS);
@@ -1695,7 +1732,7 @@ extern "C" int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy) {
     if ((rc = reduce_and_argmax(h, nrhs, ldP, false, true)) != JK_OK) return rc;
     toc(h, JK_T_SCAN_TOTAL);
     CUDA_TRY(h, cudaStreamSynchronize(s));
-    h->lastP = nrhs; h->last_ldP = ldP; h->last_morison = false; h->last_fem = true; h->last_fy = fy;
+    h->lastP = nrhs; h->last_ldP = ldP; h->last_morison = false; h->last_fem = true; h->last_fy = fy; h->last_fdir = false;
     return finish_factor(h);
 }
 
@@ -1899,10 +1936,9 @@ k_free_residual(int n_free_nodes, const int* __restrict__ free_nodes, int P, int
                 const int* __restrict__ adj, const double* __restrict__ Ke, const double* __restrict__ Fstatic,
                 const double* __restrict__ Fm /* null: loads from Fload */, const double* __restrict__ Fload, int Nn,
                 unsigned long long* __restrict__ out /* [2]: max |r|, max |F| as double bits */) {
-    int sidx = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     double rmax = 0.0, fmaxv = 0.0;
-    if (sidx < n_free_nodes && p < P) {
+    for (int sidx = blockIdx.y; sidx < n_free_nodes && p < P; sidx += gridDim.y) {        // grid.y is capped at 65,535
         int node = free_nodes[sidx];
         double r[6] = {0, 0, 0, 0, 0, 0}, f[6];
         for (int c = 0; c < 6; ++c) f[c] = Fm ? Fstatic[6 * node + c] : Fload[(size_t)p * 6 * Nn + 6 * node + c];
@@ -1932,10 +1968,11 @@ k_free_residual(int n_free_nodes, const int* __restrict__ free_nodes, int P, int
 extern "C" int jk_residual(jk_handle_t h, double* rel) {
     if (!h || !rel) return JK_EINVAL;
     if (!h->last_fem || h->lastP <= 0) JK_FAIL(h, JK_ESTATE, "jk_residual: no FEM results are resident");
+    if (h->last_fdir) JK_FAIL(h, JK_ESTATE, "jk_residual: not available after an ensemble scan with heading-dependent loads (F_dir)");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     CUDA_TRY(h, cudaMemsetAsync(h->d_res, 0, 2 * sizeof(double), s));
-    dim3 g(ceil_div(h->lastP, PH_TPB), h->n_free_nodes);
+    dim3 g(ceil_div(h->lastP, PH_TPB), std::min(h->n_free_nodes, 65535));
     k_free_residual<<<g, PH_TPB, 0, s>>>(h->n_free_nodes, h->d_free_nodes, h->lastP, h->last_ldP, h->n_pad, h->d_X, h->d_node2slot,
                                          h->d_conn, h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Fstatic,
                                          h->last_morison ? h->d_Fm : nullptr, h->d_Fload, h->Nn, (unsigned long long*)h->d_res);

@@ -731,6 +731,63 @@ k_morison_ensemble(int M, int G_rt, int C, int ldC, int S, int n_phase, const do
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// MorisonCalculator.get_kinematics_3d (GUI.py:559-589) for arbitrary points at one time: the point form of what the
+// Morison kernels evaluate at the Gauss points (same split of the phase angle, same dry rule at t and t + dt, same
+// forward difference).  out[n][10] = u_wave v_wave w_wave u_current v_current du_dt dv_dt dw_dt submerged eta.
+// four == nullptr: Airy closed form; otherwise the Fourier series with the wrapper's clamp (GUI.py:272).
+// ----------------------------------------------------------------------------------------------
+__global__ void k_kinematics_points(int n, const double* __restrict__ xyz, double t, WaveAiry wv, int Nh,
+                                    const double* __restrict__ four, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const double xw = __dadd_rn(__dmul_rn(x, wv.cos_w), __dmul_rn(y, wv.sin_w));   // GUI.py:562
+    double skx, ckx, sw0, cw0, sw1, cw1;
+    sincos(wv.k * xw, &skx, &ckx);
+    sincos(wv.omega * t, &sw0, &cw0);
+    sincos(wv.omega * (t + wv.dt), &sw1, &cw1);
+    const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
+    const double c1 = fma(skx, sw1, ckx * cw1), s1 = fma(skx, cw1, -(ckx * sw1));
+    double eta0, eta1, u0 = 0.0, w0 = 0.0, u1 = 0.0, w1 = 0.0;
+    if (four == nullptr) {
+        eta0 = wv.a * c0; eta1 = wv.a * c1;                                     // GUI.py:265
+    } else {
+        eta0 = 0.0; eta1 = 0.0;
+        double a0 = c0, a0m = 1.0, a1 = c1, a1m = 1.0;
+        for (int j = 0; j < Nh; ++j) {
+            eta0 = fma(four[j], a0, eta0); eta1 = fma(four[j], a1, eta1);
+            const double n0 = fma(2.0 * c0, a0, -a0m), n1 = fma(2.0 * c1, a1, -a1m);
+            a0m = a0; a0 = n0; a1m = a1; a1 = n1;
+        }
+    }
+    double* o = out + (size_t)i * 10;
+    o[9] = eta0;
+    if (z > eta0) {                                                             // dry at t (GUI.py:292, 565-569)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) o[q] = 0.0;
+        return;
+    }
+    const bool wet1 = !(z > eta1);                                              // GUI.py:269 at t + dt
+    if (four == nullptr) {
+        const double shkd = sinh(wv.k * wv.d), kz = wv.k * (z + wv.d);
+        const double Cu = wv.a * wv.omega * cosh(kz) / shkd, Cw = wv.a * wv.omega * sinh(kz) / shkd;   // GUI.py:279-280
+        u0 = Cu * c0; w0 = Cw * s0; u1 = Cu * c1; w1 = Cw * s1;
+    } else {
+        const double zb = z + wv.d;                                             // clamp of GUI.py:272
+        fourier_uw_direct(Nh, four, wv.k, fmax(0.01, fmin(zb, wv.d + eta0 - 0.01)), c0, s0, u0, w0);
+        if (wet1) fourier_uw_direct(Nh, four, wv.k, fmax(0.01, fmin(zb, wv.d + eta1 - 0.01)), c1, s1, u1, w1);
+    }
+    u0 += wv.Uc;                                                                // GUI.py:281
+    u1 = wet1 ? u1 + wv.Uc : 0.0; w1 = wet1 ? w1 : 0.0;
+    const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;        // GUI.py:288
+    const double uw = u0 - wv.Uc;                                               // GUI.py:573
+    o[0] = uw * wv.cos_w; o[1] = uw * wv.sin_w; o[2] = w0;
+    o[3] = wv.uc_cos_c; o[4] = wv.uc_sin_c;                                     // U_c (cos, sin)(theta_c), GUI.py:582-583
+    o[5] = du * wv.cos_w; o[6] = du * wv.sin_w; o[7] = dw;
+    o[8] = 1.0;
+}
+
 // first index (within each sea state) of the maximum of table[:, col]; one thread per state
 __global__ void k_argmax_per_state(int S, int n_phase, const double* __restrict__ table, int ncol, int col, long long* __restrict__ out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -796,16 +853,17 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
 __global__ void __launch_bounds__(PH_TPB)
 k_rhs_from_loads(int Nn, int P, int ldP, int n_pad, const double* __restrict__ F, const int* __restrict__ node2slot,
                  double* __restrict__ B, double* __restrict__ Ffix) {
-    int node = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= Nn || p >= ldP) return;
+    if (p >= ldP) return;
     int pp = min(p, P - 1);
-    int s = node2slot[node];
+    for (int node = blockIdx.y; node < Nn; node += gridDim.y) {        // grid.y is capped at 65,535
+        int s = node2slot[node];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        double v = F[(size_t)pp * 6 * Nn + 6 * node + c];
-        if (s >= 0) B[rhs_off(s + c, p, n_pad)] = v;
-        else Ffix[(size_t)(6 * (-1 - s) + c) * ldP + p] = v;
+        for (int c = 0; c < 6; ++c) {
+            double v = F[(size_t)pp * 6 * Nn + 6 * node + c];
+            if (s >= 0) B[rhs_off(s + c, p, n_pad)] = v;
+            else Ffix[(size_t)(6 * (-1 - s) + c) * ldP + p] = v;
+        }
     }
 }
 
@@ -898,7 +956,7 @@ k_phase_reduce(int P, int ldP, const double* __restrict__ t,
 // K6: first index of the maximum of table[:, col] (Python max(key=...) semantics, GUI.py:717).
 // One block; per-thread strided scan, warp-shuffle reduce, then across warps.
 __global__ void k_argmax(int P, const double* __restrict__ table, int ncol, int col, double* __restrict__ out_val,
-                         long long* __restrict__ out_idx) {
+                         long long* __restrict__ out_idx, const int* __restrict__ poison = nullptr /* non-zero: the factor is unusable */) {
     double best = 0.0; long long bi = -1;
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         double v = table[(size_t)p * ncol + col];
@@ -927,7 +985,10 @@ __global__ void k_argmax(int P, const double* __restrict__ table, int ncol, int 
             long long oi = __shfl_down_sync(0xffffffffu, bi, off);
             if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
         }
-        if (lane == 0) { *out_val = best; *out_idx = bi; }
+        if (lane == 0) {
+            if (poison != nullptr && *poison != 0) { best = __longlong_as_double(0x7ff8000000000000LL); bi = -1; }   // NaN, no index
+            *out_val = best; *out_idx = bi;
+        }
     }
 }
 

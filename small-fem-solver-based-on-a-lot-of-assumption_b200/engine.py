@@ -22,7 +22,7 @@ def default_device():
 
 
 class Engine:
-    def __init__(self, structure, device=None, stream=None, ordering="rcm", solver="banded"):
+    def __init__(self, structure, device=None, stream=None, ordering="rcm", solver="banded", options=None):
         self.structure = structure
         self.lib = L.lib()
         self.device = default_device() if device is None else int(device)
@@ -40,6 +40,9 @@ class Engine:
                 self.lib.jk_destroy(self.h)
                 self.h = C.c_void_p()
             raise L.JacketError(rc, msg.decode() if msg else "")
+        self.options = dict(options or {})
+        for key, value in self.options.items():          # jk_set_option: documented switches of include/jacket_b200.h
+            self._ck(self.lib.jk_set_option(self.h, str(key).encode(), int(value)))
         self._fixed = None
         self._moduli = None
         self._factored = False
@@ -47,6 +50,10 @@ class Engine:
         self._wave_sig = None
         self._morison_sig = None
         self.fixed_idx = None
+        self._lengths = None
+        # Results live in HBM and are overwritten by the next scan / solve: every call that replaces or invalidates them
+        # bumps the generation, result objects remember theirs and fetches through a stale object raise (check_generation)
+        self.generation = 0
 
     def close(self):
         self.__dict__.pop("_dev_views", None)            # torch views of library-owned device buffers (distributed.device_views)
@@ -61,23 +68,48 @@ class Engine:
             pass
 
     def _ck(self, rc):
+        if rc == -4:                                  # JK_ENOTSPD: the factor is unusable
+            self._factored = False
         L.check(rc, self.h)
+
+    def _bump(self):
+        self.generation += 1
+        return self.generation
+
+    def check_generation(self, generation, who="result"):
+        if generation != self.generation:
+            raise L.JacketError(-5, f"{who} is stale: the engine's device buffers were overwritten by a later scan / solve / "
+                                    "re-assembly on the same structure (results are resident in HBM, one set per engine)")
+
+    # -- options (documented run-time switches of the library, jk_set_option) ----
+    def set_option(self, key, value):
+        self._ck(self.lib.jk_set_option(self.h, str(key).encode(), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int(0)
+        self._ck(self.lib.jk_get_option(self.h, str(key).encode(), C.byref(v)))
+        return int(v.value)
 
     # -- FEM side ---------------------------------------------------------------
     def set_supports(self, fixed_idx):
         fixed_idx = L.i32(fixed_idx)
+        _, first = np.unique(fixed_idx, return_index=True)         # the library drops repeated nodes, keeping first occurrences
+        fixed_idx = L.i32(fixed_idx[np.sort(first)])
         key = tuple(int(i) for i in fixed_idx)
         if key == self._fixed:
             return
+        self._bump()
         self._ck(self.lib.jk_set_supports(self.h, len(fixed_idx), L.iptr(fixed_idx), self.ordering, self.solver))
         self._fixed, self.fixed_idx = key, fixed_idx
         self._assembled_for = None
         self._factored = False
 
     def assemble(self, E, G):
+        self._bump()
         self._ck(self.lib.jk_assemble(self.h, float(E), float(G)))
         self._moduli = (float(E), float(G))
         self._factored = False
+        self._lengths = None
 
     def factor(self, overlap=False):
         """Blocked Cholesky.  overlap=True queues it on the side stream so the next scan's Morison stage runs
@@ -118,6 +150,7 @@ class Engine:
 
     # -- scans ------------------------------------------------------------------
     def morison_scan(self, t):
+        self._bump()
         t = L.f64(t).reshape(-1)
         table = np.zeros((t.shape[0], L.TABLE_NCOL))
         crit = C.c_int64(-1)
@@ -125,6 +158,7 @@ class Engine:
         return table, int(crit.value)
 
     def morison_single(self, t, want_details=True):
+        self._bump()
         nodal = np.zeros((self.n_nodes, 3))
         totals = np.zeros(9)
         details = np.zeros((self.n_members, L.DETAIL_NCOL)) if want_details else None
@@ -132,6 +166,7 @@ class Engine:
         return nodal, totals, details
 
     def phase_scan(self, t, fy):
+        self._bump()
         t = L.f64(t).reshape(-1)
         table = np.empty((t.shape[0], L.TABLE_NCOL))     # the library overwrites every entry
         crit = C.c_int64(-1)
@@ -139,6 +174,7 @@ class Engine:
         return table, int(crit.value)
 
     def phase_scan_begin(self, t, fy):
+        self._bump()
         """Queue a scan with host times and return without reading anything back (results: read_table / device views)."""
         t = L.f64(t).reshape(-1)
         self._ck(self.lib.jk_phase_scan(self.h, t.shape[0], L.dptr(t), float(fy), None, None))
@@ -151,6 +187,7 @@ class Engine:
         return int(crit.value)
 
     def phase_scan_dev(self, P, t_dev_ptr, fy):
+        self._bump()
         self._ck(self.lib.jk_phase_scan_dev(self.h, int(P), C.c_void_p(t_dev_ptr), float(fy)))
 
     def read_table(self, P):
@@ -160,6 +197,7 @@ class Engine:
         return table, int(crit.value)
 
     def ensemble_scan(self, a, k, omega, theta_wave, t, fy, F_dir=None):
+        self._bump()
         a, k, omega, theta_wave = (L.f64(v).reshape(-1) for v in (a, k, omega, theta_wave))
         S = a.shape[0]
         t = L.f64(t).reshape(S, -1)
@@ -172,6 +210,7 @@ class Engine:
         return table.reshape(S, n_phase, L.TABLE_NCOL), crit
 
     def solve(self, F, fy=355.0):
+        self._bump()
         F = L.f64(F).reshape(-1, 6 * self.n_nodes)
         self._ck(self.lib.jk_solve(self.h, F.shape[0], L.dptr(F), float(fy)))
 
@@ -217,6 +256,22 @@ class Engine:
         self._ck(self.lib.jk_get_elements(self.h, L.dptr(Ke), L.dptr(Kl), L.dptr(R), L.dptr(Ln)))
         return Ke, Kl, R, Ln
 
+    def member_lengths(self):
+        """Member lengths in m (cached: they only depend on the geometry)."""
+        if self._lengths is None:
+            Ln = np.zeros(self.n_members)
+            self._ck(self.lib.jk_get_elements(self.h, None, None, None, L.dptr(Ln)))
+            self._lengths = Ln
+        return self._lengths
+
+    def kinematics_points(self, xyz, t):
+        """MorisonCalculator.get_kinematics_3d (GUI.py:559-589) for many points at once, on the device: [n, 10] =
+        u_wave v_wave w_wave u_current v_current du_dt dv_dt dw_dt submerged eta."""
+        xyz = L.f64(xyz).reshape(-1, 3)
+        out = np.zeros((xyz.shape[0], 10))
+        self._ck(self.lib.jk_kinematics_points(self.h, xyz.shape[0], L.dptr(xyz), float(t), L.dptr(out)))
+        return out
+
     def timings(self):
         ms = np.zeros(L.NTIMERS)
         self._ck(self.lib.jk_get_timings(self.h, L.dptr(ms)))
@@ -242,9 +297,19 @@ class Engine:
 
 
 def get_engine(structure, **kw):
-    """The structure's engine, created on first use (one handle per structure and GPU)."""
+    """The structure's engine, created on first use (one handle per structure and GPU).  A different device, ordering or
+    solver storage than the existing engine's replaces it (earlier result objects then report themselves stale)."""
     eng = getattr(structure, "_engine", None)
-    if eng is None or (kw and any(getattr(eng, k, None) != v for k, v in kw.items() if k == "device")):
+    if eng is not None and kw:
+        want = dict(device=kw.get("device", eng.device),
+                    ordering={"rcm": L.ORDER_RCM, "natural": L.ORDER_NATURAL}[kw["ordering"]] if "ordering" in kw else eng.ordering,
+                    solver={"banded": L.SOLVER_BANDED, "dense": L.SOLVER_DENSE}[kw["solver"]] if "solver" in kw else eng.solver,
+                    options=dict(kw["options"] or {}) if "options" in kw else eng.options)
+        if any(getattr(eng, k) != v for k, v in want.items()):
+            eng._bump()
+            eng.close()
+            eng = None
+    if eng is None:
         eng = Engine(structure, **kw)
         structure._engine = eng
     return eng

@@ -48,6 +48,28 @@ class MorisonCalculator:
         eng.set_morison(self.theta_wave, self.theta_current, self.rho, self.Cd, self.Cm, n_gauss)
         return eng
 
+    def get_kinematics_3d(self, x, y, z, t):
+        """Wave and current velocity / wave acceleration at one point in global axes (GUI.py:559-589): the 2-D wave
+        solution acts along the wave heading, the current (taken out of the wave's u again) along its own heading."""
+        cw, sw = np.cos(self.theta_wave), np.sin(self.theta_wave)
+        plane = self.wave.get_kinematics(x * cw + y * sw, z, t)
+        if not plane["submerged"]:
+            return dict(u_wave=0, v_wave=0, w_wave=0, u_current=0, v_current=0, du_dt=0, dv_dt=0, dw_dt=0,
+                        submerged=False, eta=plane["eta"])
+        Uc = self.wave.U_c
+        along = plane["u"] - Uc
+        return dict(u_wave=along * cw, v_wave=along * sw, w_wave=plane["w"],
+                    u_current=Uc * np.cos(self.theta_current), v_current=Uc * np.sin(self.theta_current),
+                    du_dt=plane["du_dt"] * cw, dv_dt=plane["du_dt"] * sw, dw_dt=plane["dw_dt"],
+                    submerged=True, eta=plane["eta"])
+
+    KINEMATICS_COLUMNS = ("u_wave", "v_wave", "w_wave", "u_current", "v_current", "du_dt", "dv_dt", "dw_dt", "submerged", "eta")
+
+    def kinematics_points(self, points, t):
+        """get_kinematics_3d for an [n, 3] array of points at time t, evaluated on the GPU with the device functions of
+        the Morison kernels -> [n, 10] array (columns KINEMATICS_COLUMNS)."""
+        return self._engine().kinematics_points(points, t)
+
     def compute_all_morison_forces(self, t=0.0, n_gauss=15):
         eng = self._engine(n_gauss)
         nodal, totals, details = eng.morison_single(t, want_details=True)

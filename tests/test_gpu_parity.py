@@ -88,7 +88,8 @@ def test_fem_solver_facade_t0_vs_reference(golden, ordering, solver):
     import jacket_b200 as jb
     _, g = golden
     st, ap = product_structure(g)
-    fem = jb.FEMSolver(st, ap.E, ap.nu, ordering=ordering, solver=solver)
+    jb.get_engine(st, ordering=ordering, solver=solver)
+    fem = jb.FEMSolver(st, ap.E, ap.nu)
     fem.F_global[:] = g["fem_t0_F"]
     fem.apply_boundary_conditions(st.get_bottom_nodes())
     assert np.array_equal(np.sort(fem.fixed_dofs), np.sort((6 * g["fixed"][:, None] + np.arange(6)).ravel()))
@@ -279,7 +280,7 @@ def test_fourier_series_kinematics_vs_oracle(model, N, H):
     ap = jb.AnalysisParams(H=H, wave_model=model, N_harm=N, U_c=1.2, wave_dir=25.0, current_dir=70.0)
     nodes, members, fixed, top = jb.create_default_3leg_jacket()
     st = jb.build_structure(nodes, members, fixed, top, ap)
-    wave = jb.RaschiiWave(ap.H, ap.T, ap.d, ap.U_c, model, N, nonlinear=True)
+    wave = jb.RaschiiWave.with_own_fits(ap.H, ap.T, ap.d, ap.U_c, model, N)
     assert wave.kind == "fourier" and wave.actual_model == model
     P = 72
     res = jb.phase_scan(st, wave, P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
@@ -348,23 +349,18 @@ def test_sea_state_ensemble_vs_oracle(S, n_phase):
 
 def test_two_chain_factorisation_matches_single_chain():
     """The two-sided elimination (two chains + separator) and the plain single chain give the same solution."""
-    import os
     import jacket_b200 as jb
     ap = jb.AnalysisParams(wave_model="Airy")
     out = {}
     for mode in ("two", "single"):
-        if mode == "single":
-            os.environ["JK_SINGLE_CHAIN"] = "1"
-        try:
-            nodes, members, fixed, top = jb.generate_jacket(8, 30)
-            st = jb.build_structure(nodes, members, fixed, top, ap)
-            res = jb.phase_scan(st, _wave(jb, ap), 48, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
-            d = res.engine.dims()
-            out[mode] = (res.table.copy(), res.phase(5)["U"], res.phase(40)["reactions"], d, res.engine.residual())
-            order = res.engine.order()
-            assert sorted(order.tolist()) == sorted(st.indices([n for n in nodes if n not in fixed]).tolist())
-        finally:
-            os.environ.pop("JK_SINGLE_CHAIN", None)
+        nodes, members, fixed, top = jb.generate_jacket(8, 30)
+        st = jb.build_structure(nodes, members, fixed, top, ap)
+        jb.get_engine(st, options={"two_chains": 0} if mode == "single" else None)
+        res = jb.phase_scan(st, _wave(jb, ap), 48, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+        d = res.engine.dims()
+        out[mode] = (res.table.copy(), res.phase(5)["U"], res.phase(40)["reactions"], d, res.engine.residual())
+        order = res.engine.order()
+        assert sorted(order.tolist()) == sorted(st.indices([n for n in nodes if n not in fixed]).tolist())
     assert out["two"][3]["n_chains"] == 2 and out["single"][3]["n_chains"] == 1
     assert out["two"][3]["separator_nodes"] >= (out["two"][3]["dof_half_bandwidth"] - 5) // 6
     assert out["two"][0].shape == out["single"][0].shape
@@ -382,24 +378,16 @@ def test_two_chain_factorisation_matches_single_chain():
 def test_tma_sweep_matches_legacy_sweep(legs, bays, single_chain):
     """The TMA / mbarrier sweep pipeline (Z-form recurrences, zero-block masks) and the cp.async slab sweep solve the
     same systems; the pipeline executes fewer flops than the band holds."""
-    import os
     import jacket_b200 as jb
     ap = jb.AnalysisParams(wave_model="Airy")
     out = {}
     for mode in ("tma", "legacy"):
-        if mode == "legacy":
-            os.environ["JK_SWEEP_LEGACY"] = "1"
-        if single_chain:
-            os.environ["JK_SINGLE_CHAIN"] = "1"
-        try:
-            nodes, members, fixed, top = jb.generate_jacket(legs, bays)
-            st = jb.build_structure(nodes, members, fixed, top, ap)
-            res = jb.phase_scan(st, _wave(jb, ap), 70, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
-            out[mode] = (res.table.copy(), res.phase(3)["U"], res.phase(69)["reactions"], res.engine.solver_stats(), res.engine.residual(),
-                         res.engine.dims())
-        finally:
-            os.environ.pop("JK_SWEEP_LEGACY", None)
-            os.environ.pop("JK_SINGLE_CHAIN", None)
+        nodes, members, fixed, top = jb.generate_jacket(legs, bays)
+        st = jb.build_structure(nodes, members, fixed, top, ap)
+        jb.get_engine(st, options={"tma_sweep": 0 if mode == "legacy" else 1, "two_chains": 0 if single_chain else 1})
+        res = jb.phase_scan(st, _wave(jb, ap), 70, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)
+        out[mode] = (res.table.copy(), res.phase(3)["U"], res.phase(69)["reactions"], res.engine.solver_stats(), res.engine.residual(),
+                     res.engine.dims())
     st_t, st_l = out["tma"][3], out["legacy"][3]
     assert st_t["tma_sweep"] and not st_l["tma_sweep"]
     assert st_t["nnz_L"] == st_l["nnz_L"] > 0
@@ -445,37 +433,32 @@ def test_split_factor_is_bit_identical(legs, bays, single_chain):
     """Scheduling variants of the same arithmetic: the ASYNCHRONOUS factorisation in two segments, with the forward sweeps
     of the rows below the split point started early and continuation launches that reload the ring from the slab, vs one
     segment, vs the blocking factor.  Same sums in the same order -> identical bits."""
-    import os
     import jacket_b200 as jb
     ap = jb.AnalysisParams(wave_model="Airy")
     G = ap.E / (2 * (1 + ap.nu))
     out = {}
-    for mode, env in (("split", {}), ("one_segment", {"JK_NO_FACTOR_SPLIT": "1"}), ("no_gate", {"JK_NO_START_GATE": "1"})):
+    for mode, opts in (("split", {}), ("one_segment", {"factor_split": 0}), ("no_gate", {"start_gate": 0}), ("no_graph", {"cuda_graph": 0})):
         if single_chain:
-            env = dict(env, JK_SINGLE_CHAIN="1")
-        os.environ.update(env)
-        try:
-            nodes, members, fixed, top = jb.generate_jacket(legs, bays)
-            st = jb.build_structure(nodes, members, fixed, top, ap)
-            ref = jb.phase_scan(st, _wave(jb, ap), 100, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)   # blocking factor
-            eng = ref.engine
-            tables = []
-            for _ in range(2):
-                eng.assemble(ap.E, G)
-                eng.factor(overlap=True)                      # jk_factor_begin: side streams, split when the chains are long enough
-                table, crit = eng.phase_scan(ref.table[:, 0].copy(), ap.fy)
-                assert crit == ref.critical_index
-                tables.append(table)
-            u = eng.fetch_phase(37)["U"].copy()
-            assert np.array_equal(tables[0], tables[1])
-            assert np.array_equal(tables[0][:, 2:], ref.table[:, 2:]), mode           # asynchronous == blocking
-            out[mode] = (tables[0], u, eng.residual(), eng.dims())
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
+            opts = dict(opts, two_chains=0)
+        nodes, members, fixed, top = jb.generate_jacket(legs, bays)
+        st = jb.build_structure(nodes, members, fixed, top, ap)
+        jb.get_engine(st, options=opts)
+        ref = jb.phase_scan(st, _wave(jb, ap), 100, wave_direction=ap.wave_dir, current_direction=ap.current_dir, params=ap)   # blocking factor
+        eng = ref.engine
+        tables = []
+        for _ in range(2):
+            eng.assemble(ap.E, G)
+            eng.factor(overlap=True)                      # jk_factor_begin: side streams, split when the chains are long enough
+            table, crit = eng.phase_scan(ref.table[:, 0].copy(), ap.fy)
+            assert crit == ref.critical_index
+            tables.append(table)
+        u = eng.fetch_phase(37)["U"].copy()
+        assert np.array_equal(tables[0], tables[1])
+        assert np.array_equal(tables[0][:, 2:], ref.table[:, 2:]), mode           # asynchronous == blocking
+        out[mode] = (tables[0], u, eng.residual(), eng.dims())
     assert out["split"][3]["n_chains"] == (1 if single_chain else 2)
     assert out["split"][3]["n_tiles"] >= 28                   # long enough for the split to be active
-    for mode in ("one_segment", "no_gate"):
+    for mode in ("one_segment", "no_gate", "no_graph"):
         assert np.array_equal(out[mode][0], out["split"][0]), mode
         assert np.array_equal(out[mode][1], out["split"][1]), mode
     assert out["split"][2] < 1e-9
@@ -485,19 +468,18 @@ def test_overlap_switches_are_bit_identical():
     """Scheduling-only features of the asynchronous scan (second start gate, early member post beside the second chain's
     backward sweep, Morison totals reduced on a side stream) against the same engine built with each switched off:
     identical table, displacements and member rows -- the arithmetic per member chunk and per phase is the same."""
-    import os
     import jacket_b200 as jb
     ap = jb.AnalysisParams(wave_model="Airy")
     G = ap.E / (2 * (1 + ap.nu))
     out = {}
-    variants = (("default", {}), ("no_post_overlap", {"JK_NO_POST_OVERLAP": "1"}), ("no_early_totals", {"JK_NO_EARLY_TOTALS": "1"}),
-                ("no_gate2", {"JK_NO_START_GATE2": "1"}), ("none", {"JK_NO_POST_OVERLAP": "1", "JK_NO_EARLY_TOTALS": "1", "JK_NO_START_GATE2": "1"}))
-    for mode, env in variants:
-        os.environ.update(env)
-        try:
+    variants = (("default", {}), ("no_post_overlap", {"post_overlap": 0}), ("no_early_totals", {"early_totals": 0}),
+                ("no_gate2", {"start_gate2": 0}), ("unfused_loads", {"fused_loads": 0}), ("slab16", {"sweep_slab": 16}), ("slab8", {"sweep_slab": 8}),
+                ("none", {"post_overlap": 0, "early_totals": 0, "start_gate2": 0, "cuda_graph": 0, "fused_loads": 0, "sweep_slab": 32}))
+    for mode, opts in variants:
+        if True:
             nodes, members, fixed, top = jb.generate_jacket(8, 40)            # two chains, 61 member chunks, long enough for the split
             st = jb.build_structure(nodes, members, fixed, top, ap)
-            eng = jb.Engine(st)                                               # the switches are read when the handle is created
+            eng = jb.Engine(st, options=opts)
             st._engine = eng
             t = jb.phase_times(_wave(jb, ap).T, 256)
             eng.set_supports(st.indices(fixed))
@@ -515,9 +497,6 @@ def test_overlap_switches_are_bit_identical():
             # stored member rows (written by the early and the late post launches): utilisation of every 7th member, all phases
             cols = np.stack([eng.member_column(m, 6, 256) for m in range(0, st.n_members, 7)])
             out[mode] = (tables[0][0], tables[0][1], ph["U"].copy(), cols, ph["reactions"].copy(), eng.dims())
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
     assert out["default"][5]["n_chains"] == 2
     for mode, _ in variants[1:]:
         for i in range(5):

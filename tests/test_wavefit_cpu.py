@@ -58,7 +58,7 @@ def test_model_selection_thresholds():
 
 def test_raschiiwave_opt_in():
     import jacket_b200 as jb
-    w = jb.RaschiiWave(8.0, T, D, 1.0, "Stokes", 5, nonlinear=True)
+    w = jb.RaschiiWave.with_own_fits(8.0, T, D, 1.0, "Stokes", 5)
     assert w.kind == "fourier" and w.actual_model == "Stokes" and w.actual_N == 5 and len(w.wave.E) == 5
     assert w.omega == 2 * np.pi / T and w.L == 2 * np.pi / w.k
     w0 = jb.RaschiiWave(8.0, T, D, 1.0, "Stokes", 5)
