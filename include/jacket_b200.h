@@ -54,8 +54,8 @@ typedef struct jk_handle_s* jk_handle_t;
 
 /* columns of the per-phase result table written by jk_phase_scan / jk_morison_scan.
  * 0..7 are the reference's find_critical_phase row (GUI.py:705-714); column 1
- * (phase_deg) is left 0 by the library and filled by the host wrapper with
- * numpy.degrees(omega*t) % 360 so it is bit-identical to the reference.
+ * (phase_deg) = numpy.degrees(omega*t) % 360 evaluated on the device with the same
+ * IEEE operations (two multiplies, exact fmod), bit-identical to the reference.
  * 8..15 are the per-phase FEM summary (run_analysis replayed at t_i). */
 #define JK_TABLE_NCOL       16
 #define JK_COL_T             0
@@ -231,8 +231,10 @@ int jk_residual(jk_handle_t h, double* rel_residual);
 /* Solver statistics after a factorisation: out[0] = non-zeros of L (exact count, lower triangle incl. diagonal),
  * out[1] = FP64 flops the two triangular sweeps EXECUTE per load case (DMMA k-groups kept by the zero-block masks,
  * or all tile products of the band on the legacy path), out[2] = sweep items per slab (0 on the legacy path),
- * out[3] = 1 if the TMA / mbarrier sweep pipeline is active, 0 for the cp.async slab sweep. */
-int jk_solver_stats(jk_handle_t h, double* out /* [4] */);
+ * out[3] = 1 if the TMA / mbarrier sweep pipeline is active, 0 for the cp.async slab sweep,
+ * out[4] = non-zeros of L for the candidate ordering with the smallest envelope (symbolic count; the ordering in use
+ * trades a larger envelope for fewer mask blocks), out[5] = right-hand sides per sweep CTA of the last solve. */
+int jk_solver_stats(jk_handle_t h, double* out /* [6] */);
 /* Host-only introspection of the sweep item list (no device needed; used by the CPU tests): the program the TMA
  * sweep runs for a chain of n_tiles tile rows, tile half-bandwidth band_tiles, first partial / known tile row kx
  * (= n_tiles for a plain sweep), first_tile[n_tiles] (nullable) = first tile column of every tile row's envelope (tiles

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib as L
 from .engine import get_engine
 from .fem import FEMSolver, member_rows_to_dicts
-from .morison import MorisonCalculator, fill_phase_deg, mod360, phase_times
+from .morison import MorisonCalculator, phase_times
 from .sections import TubularSection
 from .structure import CustomJacketStructure
 from .wave import RaschiiWave, g
@@ -231,8 +231,7 @@ def phase_scan(structure, wave, n_steps=360, *, wave_direction=0.0, current_dire
     eng.set_wave(wave)
     eng.set_morison(np.deg2rad(90.0 - wave_direction), np.deg2rad(90.0 - current_direction), rho_water, Cd, Cm, n_gauss)
     tt = phase_times(wave.T, n_steps) if t is None else np.asarray(t, dtype=np.float64)
-    table, crit = eng.phase_scan(tt, fy)
-    fill_phase_deg(table, wave.omega)
+    table, crit = eng.phase_scan(tt, fy)          # column 1 (phase_deg) is filled on the device, bit-identical to GUI.py:697-698
     return PhaseScanResult(structure, wave, table, crit, fy, eng, generation=eng.generation)
 
 
@@ -348,5 +347,4 @@ def ensemble_scan(structure, H, T, wave_dir, n_phase=16, *, d=50.0, U_c=0.0, cur
     eng.set_morison(0.0, np.deg2rad(90.0 - current_direction), rho_water, Cd, Cm, n_gauss)
     t = np.arange(n_phase)[None, :] * T[:, None] / n_phase                           # (i*T)/n_steps, GUI.py:696, per state
     table, crit = eng.ensemble_scan(H / 2.0, k, omega, np.deg2rad(90.0 - wave_dir), t, fy, F_dir)
-    table[:, :, 1] = mod360(np.degrees(omega[:, None] * table[:, :, 0]))
     return EnsembleResult(structure, H, T, wave_dir, k, table, crit, fy, eng, generation=eng.generation)

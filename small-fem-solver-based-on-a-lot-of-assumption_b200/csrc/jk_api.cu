@@ -109,6 +109,7 @@ struct jk_handle_s {
     } ch[2];
     bool tma_sweep = false;   // narrow band: sweeps run as the TMA / mbarrier pipeline, otherwise the cp.async slab sweep
     int n_chains = 1, nS_nodes = 0;
+    long long nnz_env_min = 0;   // non-zeros of L (lower triangle incl. diagonal) for the candidate ordering with the smallest envelope
     int factor_path = 0;   // 0 = auto (cluster kernel for narrow bands), 1 = per-column launches
     int* d_info = nullptr;          // pivot flag of the factorisation in flight
     int* d_info_sticky = nullptr;   // first non-zero pivot flag since it was last reported (survives re-assembly in a resident loop)
@@ -139,6 +140,7 @@ struct jk_handle_s {
     int *d_part_mem = nullptr, *d_part_node = nullptr;
     long long* d_argidx = nullptr;
     int lastP = 0, last_ldP = 0;
+    int sweep_slab_last = SLAB;   // right-hand sides per sweep CTA of the last solve
     bool last_morison = false, last_fem = false, last_fdir = false;
     double last_fy = 355.0;
 
@@ -610,6 +612,8 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
         int hb1 = 0, hb2 = 0; long long pr1 = 0, pr2 = 0;
         order_quality(h->Nn, h->h_conn, o1, hb1, pr1);
         order_quality(h->Nn, h->h_conn, o2, hb2, pr2);
+        // envelope of L at DOF level: 36 entries per coupled node pair inside the row envelope + 21 per diagonal node block
+        h->nnz_env_min = 36LL * std::min(pr1, o2.size() == o1.size() ? pr2 : pr1) + 21LL * (long long)o1.size();
         const bool second = h->opt[OPT_SUPPORT_ROOTED_RCM] && o2.size() == o1.size() && (hb2 < hb1 || (hb2 == hb1 && pr2 < pr1));
         h->h_free_nodes.swap(second ? o2 : o1);
         if (second && h->opt[OPT_LEVEL_REGROUP]) {
@@ -621,12 +625,18 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
                 std::vector<int> cand(g.rbegin(), g.rend());
                 int hbc = 0; long long prc = 0;
                 order_quality(h->Nn, h->h_conn, cand, hbc, prc);
+                h->nnz_env_min = std::min(h->nnz_env_min, 36LL * prc + 21LL * (long long)cand.size());
                 const double c = sweep_cost(h->Nn, h->h_conn, cand);
                 if (hbc <= hb2 && c < 0.98 * best) { best = c; h->h_free_nodes.swap(cand); }
             }
         }
     }
-    else { h->h_free_nodes.clear(); for (int i = 0; i < h->Nn; ++i) if (!is_fixed[i]) h->h_free_nodes.push_back(i); }
+    else {
+        h->h_free_nodes.clear(); for (int i = 0; i < h->Nn; ++i) if (!is_fixed[i]) h->h_free_nodes.push_back(i);
+        int hb0 = 0; long long pr0 = 0;
+        order_quality(h->Nn, h->h_conn, h->h_free_nodes, hb0, pr0);
+        h->nnz_env_min = 36LL * pr0 + 21LL * (long long)h->h_free_nodes.size();
+    }
     if ((int)h->h_free_nodes.size() != h->n_free_nodes) JK_FAIL(h, JK_EINVAL, "jk_set_supports: internal ordering error");
     h->n_free = 6 * h->n_free_nodes;
     h->solver = solver;
@@ -1256,13 +1266,14 @@ static int reduce_totals_early(jk_handle_t h, int P, int ldP) {
     CUDA_TRY(h, cudaEventRecord(h->ev_mor, s));
     CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_mor, 0));
     k_phase_reduce<<<ceil_div(P, 32), 32 * RED_GROUPS, 0, s3>>>(P, ldP, h->d_t, ceil_div(h->M, MCHUNK), h->d_totpart, 0, nullptr, nullptr, nullptr,
-                                                      0, nullptr, nullptr, 0, nullptr, h->d_table, JK_TABLE_NCOL, 1);
+                                                      0, nullptr, nullptr, 0, nullptr, h->d_table, JK_TABLE_NCOL, 1, h->wv.omega);
     LAUNCH_CHECK(h);
     CUDA_TRY(h, cudaEventRecord(h->ev_tot, s3));
     return JK_OK;
 }
 
-static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool fem, bool totals_done = false) {
+static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool fem, bool totals_done = false,
+                             const double* st_omega = nullptr, int n_phase = 1) {
     cudaStream_t s = h->stream;
     if (totals_done) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_tot, 0));
     tic(h, JK_T_REDUCE);
@@ -1270,7 +1281,8 @@ static int reduce_and_argmax(jk_handle_t h, int P, int ldP, bool morison, bool f
     k_phase_reduce<<<ceil_div(P, 32), 32 * RED_GROUPS, 0, s>>>(P, ldP, h->d_t, n_mchunk, (morison && !totals_done) ? h->d_totpart : nullptr,
                                                      n_mchunk, fem ? h->d_part_util : nullptr, h->d_part_vm, h->d_part_mem,
                                                      n_nchunk, fem ? h->d_part_disp : nullptr, h->d_part_node,
-                                                     h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL, totals_done ? 0 : 1);
+                                                     h->n_fixed, fem ? h->d_react : nullptr, h->d_table, JK_TABLE_NCOL, totals_done ? 0 : 1,
+                                                     morison ? h->wv.omega : -1.0, st_omega, n_phase);
     LAUNCH_CHECK(h);
     k_argmax<<<1, 1024, 0, s>>>(P, h->d_table, JK_TABLE_NCOL, morison ? JK_COL_TOTAL_KN : JK_COL_MAX_UTIL, h->d_argval, h->d_argidx,
                                 fem ? h->d_info_sticky : nullptr);
@@ -1691,7 +1703,7 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     }
     toc(h, JK_T_RHS);
     if ((rc = run_fem(h, ldC, fy)) != JK_OK) return rc;
-    if ((rc = reduce_and_argmax(h, C, ldC, true, true)) != JK_OK) return rc;
+    if ((rc = reduce_and_argmax(h, C, ldC, true, true, false, h->d_states + 2 * (size_t)n_states, n_phase)) != JK_OK) return rc;
     k_argmax_per_state<<<ceil_div(n_states, 128), 128, 0, s>>>(n_states, n_phase, h->d_table, JK_TABLE_NCOL, JK_COL_TOTAL_KN, h->d_state_crit);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SCAN_TOTAL);
@@ -1870,6 +1882,7 @@ extern "C" int jk_solver_stats(jk_handle_t h, double* out) {
     CUDA_TRY(h, cudaStreamSynchronize(s));
     cudaFree(d_cnt);
     out[0] = (double)cnt; out[1] = exec; out[2] = (double)items; out[3] = h->tma_sweep ? 1.0 : 0.0;
+    out[4] = (double)h->nnz_env_min; out[5] = (double)h->sweep_slab_last;
     return JK_OK;
 }
 

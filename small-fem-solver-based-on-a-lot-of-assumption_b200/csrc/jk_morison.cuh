@@ -881,7 +881,9 @@ k_phase_reduce(int P, int ldP, const double* __restrict__ t,
                const int* __restrict__ part_mem,
                int n_nchunk, const double* __restrict__ part_disp, const int* __restrict__ part_node,
                int n_fixed, const double* __restrict__ react,
-               double* __restrict__ table, int ncol, int init_row = 1 /* 0: the row already holds t and the Morison totals (earlier launch) */) {
+               double* __restrict__ table, int ncol, int init_row = 1 /* 0: the row already holds t and the Morison totals (earlier launch) */,
+               double omega = -1.0 /* >= 0: column 1 = degrees(omega t) % 360 (GUI.py:697-698) */,
+               const double* __restrict__ st_omega = nullptr /* ensemble: omega of sea state p / n_phase */, int n_phase = 1) {
     __shared__ double s_sum[RED_GROUPS][9][32];
     __shared__ double s_val[RED_GROUPS][3][32];
     __shared__ int s_idx[RED_GROUPS][2][32];
@@ -924,6 +926,15 @@ k_phase_reduce(int P, int ldP, const double* __restrict__ t,
     if (init_row) {
         for (int c = 0; c < ncol; ++c) row[c] = 0.0;
         row[0] = t[p];
+        const double om = st_omega ? st_omega[p / n_phase] : omega;
+        if (om >= 0.0) {
+            // numpy.degrees(omega * t) % 360 bit for bit: two IEEE multiplies (degrees = x * (180 / pi)), the exact C fmod,
+            // and Python's sign fix-up of a negative remainder
+            const double deg = __dmul_rn(__dmul_rn(om, t[p]), 180.0 / 3.141592653589793238462643383279502884);
+            double r = fmod(deg, 360.0);
+            if (r != 0.0 && r < 0.0) r += 360.0;
+            row[1] = r;
+        }
     }
     if (totpart) {
         double v[9];

@@ -1,19 +1,22 @@
 """Multi-GPU phase sharding.
 
-Phases are independent units: rank r of g evaluates the contiguous block
-[r*P_local, (r+1)*P_local) of a P_local*g-phase scan on its own GPU (geometry and the
-factor of K are replicated -- identical on every rank, the assembly is deterministic).
-The only exchange is the final critical-phase reduction: one (max total_kN, first index)
-pair per rank through an NCCL all-gather (16 B per rank over NVLink), merged with the
-reference's first-maximum rule (GUI.py:717), plus an optional gather of the per-phase
-table.  torch.distributed is plumbing only (process group, NCCL / gloo transport).
+Phases are independent units: rank r of g evaluates the contiguous block [lo_r, hi_r) of an n_total-phase scan on its
+own GPU (geometry and the factor of K are replicated -- identical on every rank, the assembly is deterministic).  There
+is no data-path collective.  The only exchange is the final critical-phase reduction: one (max total_kN, first global
+index) pair per rank through an NCCL all-gather (16 B per rank over NVLink), merged with the reference's first-maximum
+rule (GUI.py:717), plus -- on request -- a gather of the per-phase table to ONE rank.  torch.distributed is plumbing only
+(process group, NCCL / gloo transport).
+
+Host results: every rank gets the merged critical pair and its OWN shard of the table; the full table is assembled on
+`table_rank` only (default 0; None: nowhere).  Nothing is broadcast back and no rank touches another rank's rows on the
+host, so the per-step host work does not grow with the number of ranks.  Tables returned as host arrays are views of two
+alternating page-locked buffers: a result stays valid until the second-next call on the same engine.
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import _lib as L
-from .morison import fill_phase_deg
 
 
 def shard_bounds(n_total, world_size, rank):
@@ -65,11 +68,12 @@ def device_views(engine, P):
 
 def merge_critical_device(pairs):
     """First-maximum merge of an all-gathered [world, 2] (value, global index) tensor ON THE DEVICE (no host sync):
-    larger value wins, ties go to the smaller index."""
+    larger value wins, ties go to the smaller index; NaN pairs (a rank whose factorisation failed) never win."""
     import torch
     vals, idxs = pairs[:, 0], pairs[:, 1]
-    best = vals.max()
-    idx = torch.where(vals == best, idxs, torch.full_like(idxs, float("inf"))).min()
+    ok = (vals == vals) & (idxs >= 0)
+    best = torch.where(ok, vals, torch.full_like(vals, float("-inf"))).max()
+    idx = torch.where(ok & (vals == best), idxs, torch.full_like(idxs, float("inf"))).min()
     return best, idx
 
 
@@ -95,75 +99,129 @@ def allgather_critical(local_value, local_global_index, group=None, device=None,
     return merge_critical(out[:, 0], out[:, 1].astype(np.int64))
 
 
+def gather_table_to(table, n_total, world_size, rank, group=None, dst=0):
+    """Gather the ranks' [P_r,16] tables to rank ``dst`` as one [n_total,16] tensor (None elsewhere).  NCCL or gloo; runs on
+    the current stream.  Shards are padded to the largest block so that one flat gather serves ragged splits too."""
+    import torch
+    import torch.distributed as dist
+    sizes = [shard_bounds(n_total, world_size, r) for r in range(world_size)]
+    pmax = max(h - l for l, h in sizes)
+    mine = table.contiguous()
+    if mine.shape[0] < pmax:
+        mine = torch.cat([mine, mine.new_zeros((pmax - mine.shape[0], L.TABLE_NCOL))])
+    parts = [torch.empty_like(mine) for _ in range(world_size)] if rank == dst else None
+    dist.gather(mine, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([p[:h - l] for p, (l, h) in zip(parts, sizes)]) if any(h - l < pmax for l, h in sizes) else torch.cat(parts)
+
+
+def _allgather_table(table, n_total, world_size, P, group=None):
+    """All-gather the ranks' [P_r,16] tables into one [n_total,16] device tensor on EVERY rank (resident path)."""
+    import torch
+    import torch.distributed as dist
+    sizes = [shard_bounds(n_total, world_size, r) for r in range(world_size)]
+    if all(h - l == P for l, h in sizes):
+        buf = torch.empty(n_total * L.TABLE_NCOL, dtype=torch.float64, device=table.device)
+        dist.all_gather_into_tensor(buf, table.contiguous().reshape(-1), group=group)
+        return buf.reshape(n_total, L.TABLE_NCOL)
+    parts = [torch.empty((h - l, L.TABLE_NCOL), dtype=torch.float64, device=table.device) for l, h in sizes]
+    dist.all_gather(parts, table.contiguous(), group=group)
+    return torch.cat(parts)
+
+
 def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=None, gather_table=True,
-                       t_dev=None, t_host=None, host_results=True):
+                       t_dev=None, t_host=None, host_results=True, table_rank=0):
     """One rank's part of an n_total-phase scan + the cross-rank critical-phase reduction.
 
-    Returns dict(local_table (torch view on device), offset, critical_value, critical_index (global),
-    table (global [n_total,16] on every rank if gather_table else None)).
-    With t_dev (a device pointer holding this rank's times) nothing crosses PCIe before the reduction; with
-    host_results=False nothing crosses it afterwards either (critical pair and gathered table stay device tensors and
-    the call does not synchronise with the host).
+    Returns dict(local_table, offset, critical_value, critical_index (global), table).
+      host_results=True   critical pair as Python numbers; local_table = this rank's shard [P_r,16] (host);
+                          table = the full [n_total,16] host table on rank `table_rank` if gather_table, None elsewhere.
+      host_results=False  everything stays on the device and the call does not synchronise with the host: critical pair as
+                          0-d tensors, local_table = view of the library's table, table = all-gathered device tensor on
+                          every rank if gather_table.
+    With t_dev (device pointer to this rank's times) nothing crosses PCIe before the reduction either.
     """
     import torch
     import torch.distributed as dist
     lo, hi = shard_bounds(n_total, world_size, rank)
     P = hi - lo
-    host_table = host_crit = None
     if t_dev is not None:
         engine.phase_scan_dev(P, t_dev, fy)
     else:
         if t_host is None:
             t_host, _ = shard_times(wave.T, n_total, world_size, rank)
-        if world_size == 1:
-            host_table, host_crit = engine.phase_scan(t_host, fy)   # already copies table + critical index to the host
-        else:
-            engine.phase_scan_begin(t_host, fy)                     # the local table is only needed on the device
-    table, val, idx = device_views(engine, P)
-    if world_size == 1:
-        # nothing to exchange: no all-gather, no merge kernels, and the table is copied to the host at most once
-        if not host_results:
-            return dict(local_table=table, offset=lo, critical_value=val.reshape(()), critical_index=(idx + lo).reshape(()),
+        if world_size == 1 and host_results:
+            table, crit = engine.phase_scan(t_host, fy)         # one pinned copy of table + critical index, one synchronisation
+            return dict(local_table=table, offset=lo, critical_value=float(table[crit, 2]), critical_index=int(crit) + lo,
                         table=table if gather_table else None)
-        if host_table is None:
-            host_table, host_crit = engine.read_table(P)
-        fill_phase_deg(host_table, wave.omega)
-        return dict(local_table=table, offset=lo, critical_value=float(host_table[host_crit, 2]), critical_index=int(host_crit) + lo,
-                    table=host_table if gather_table else None)
+        engine.phase_scan_begin(t_host, fy)                     # queue only: the table is needed on the device first
+    table, val, idx = device_views(engine, P)
+    # everything below is ordered behind the scan on the engine's own (non-blocking) stream
     stream = torch.cuda.ExternalStream(engine.stream(), device=f"cuda:{engine.device}")
+    caller = torch.cuda.current_stream(torch.device(f"cuda:{engine.device}"))
     with torch.cuda.stream(stream):
         if not host_results:
-            cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=False)
-            full = _allgather_table(table, n_total, world_size, P, group) if gather_table else None
-            return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
-        # host results: both all-gathers are queued behind the scan and their outputs go to ONE pinned staging buffer with
-        # asynchronous copies.  The copies run on a torch-owned stream behind the engine's: the pinned block then only
-        # remembers a stream that outlives the engine (freeing it after jk_destroy would otherwise touch a dead stream).
+            if world_size == 1:
+                out = dict(local_table=table, offset=lo, critical_value=val.reshape(()).clone(), critical_index=(idx + lo).reshape(()),
+                           table=table if gather_table else None)
+            else:
+                cval, cidx = allgather_critical(val, idx + lo, group=group, to_host=False)
+                full = _allgather_table(table, n_total, world_size, P, group) if gather_table else None
+                out = dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
+            # the returned tensors (views of the library's buffers among them) are consumed on the caller's stream: order it
+            # behind the engine's stream (an event wait on the device, no host synchronisation)
+            if caller.cuda_stream != stream.cuda_stream:
+                caller.wait_stream(stream)
+            return out
+        if world_size == 1:                                     # device times in, host results out
+            host_table, host_crit = engine.read_table(P)
+            return dict(local_table=host_table, offset=lo, critical_value=float(host_table[host_crit, 2]), critical_index=int(host_crit) + lo,
+                        table=host_table if gather_table else None)
+        # host results on several ranks: pair all-gather + table gather to one rank are queued behind the scan; their outputs
+        # and this rank's shard go to ONE pinned staging buffer with asynchronous copies on a torch-owned stream (the pinned
+        # block then only remembers a stream that outlives the engine), and the host synchronises once.
+        want_full = gather_table and table_rank is not None
+        n_loc = P * L.TABLE_NCOL
+        n_full = n_total * L.TABLE_NCOL if (want_full and rank == table_rank) else 0
+        pin = _pinned(engine, world_size * 2 + n_loc + n_full)
         pair = torch.stack([val.reshape(()), (idx + lo).reshape(()).to(torch.float64)])
-        pairs = torch.empty(world_size * 2, dtype=torch.float64, device=pair.device)
-        dist.all_gather_into_tensor(pairs, pair, group=group)
-        n_tab = n_total * L.TABLE_NCOL if gather_table else 0
-        pin = _pinned(world_size * 2 + n_tab)
-        buf = _allgather_table(table, n_total, world_size, P, group) if gather_table else None
         cs = _copy_stream(pair.device)
-        cs.wait_stream(stream)
-        with torch.cuda.stream(cs):
-            pin[:world_size * 2].copy_(pairs, non_blocking=True)
-            if gather_table:
-                pin[world_size * 2:].copy_(buf.reshape(-1), non_blocking=True)
-        engine.read_critical(P)          # synchronises the engine's stream; also surfaces a failed factorisation
-        cs.synchronize()                 # the copies (and with them the temporaries) are done before anything is freed
+        if dist.get_backend(group) == "gloo":
+            # CPU transport (tests on a box with fewer GPUs than ranks): this rank's pair and shard come to the host first,
+            # the collectives run on host tensors
+            cs.wait_stream(stream)
+            with torch.cuda.stream(cs):
+                pin[:2].copy_(pair, non_blocking=True)
+                pin[world_size * 2:world_size * 2 + n_loc].copy_(table.reshape(-1), non_blocking=True)
+            engine.read_critical(P)
+            cs.synchronize()
+            mine = pin[:2].clone()
+            dist.all_gather_into_tensor(pin[:world_size * 2], mine, group=group)
+            if want_full:
+                full_cpu = gather_table_to(pin[world_size * 2:world_size * 2 + n_loc].reshape(P, L.TABLE_NCOL), n_total, world_size, rank, group, table_rank)
+                if full_cpu is not None:
+                    pin[world_size * 2 + n_loc:].copy_(full_cpu.reshape(-1))
+        else:
+            pairs = torch.empty(world_size * 2, dtype=torch.float64, device=pair.device)
+            dist.all_gather_into_tensor(pairs, pair, group=group)
+            full_dev = gather_table_to(table, n_total, world_size, rank, group, table_rank) if want_full else None
+            cs.wait_stream(stream)
+            with torch.cuda.stream(cs):
+                pin[:world_size * 2].copy_(pairs, non_blocking=True)
+                pin[world_size * 2:world_size * 2 + n_loc].copy_(table.reshape(-1), non_blocking=True)
+                if full_dev is not None:
+                    pin[world_size * 2 + n_loc:].copy_(full_dev.reshape(-1), non_blocking=True)
+            engine.read_critical(P)          # synchronises the engine's stream; also surfaces a failed factorisation
+            cs.synchronize()                 # the copies (and with them the temporaries) are done before anything is freed
         host = pin.numpy()
         hp = host[:world_size * 2].reshape(world_size, 2)
         cval, cidx = merge_critical(hp[:, 0], hp[:, 1].astype(np.int64))
-        full = None
-        if gather_table:
-            full = host[world_size * 2:].reshape(n_total, L.TABLE_NCOL).copy()     # the staging buffer is reused by the next scan
-            fill_phase_deg(full, wave.omega)
-    return dict(local_table=table, offset=lo, critical_value=cval, critical_index=cidx, table=full)
+        local = host[world_size * 2:world_size * 2 + n_loc].reshape(P, L.TABLE_NCOL)
+        full = host[world_size * 2 + n_loc:].reshape(n_total, L.TABLE_NCOL) if n_full else None
+    return dict(local_table=local, offset=lo, critical_value=cval, critical_index=cidx, table=full)
 
 
-_PINNED = {}
 _COPY_STREAMS = {}
 
 
@@ -176,25 +234,15 @@ def _copy_stream(device):
     return _COPY_STREAMS[key]
 
 
-def _pinned(n):
-    """Reusable page-locked float64 staging buffer of at least n elements (one per process)."""
+def _pinned(engine, n):
+    """Page-locked float64 staging: two buffers per engine used in turn, so the arrays handed out by one call stay intact
+    during the next call (no copy out of the staging area)."""
     import torch
-    buf = _PINNED.get("buf")
+    state = engine.__dict__.setdefault("_pinned_pair", {"bufs": [None, None], "turn": 0})
+    k = state["turn"]
+    state["turn"] = 1 - k
+    buf = state["bufs"][k]
     if buf is None or buf.numel() < n:
         buf = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)
-        _PINNED["buf"] = buf
+        state["bufs"][k] = buf
     return buf[:n]
-
-
-def _allgather_table(table, n_total, world_size, P, group=None):
-    """All-gather the ranks' [P_r,16] tables into one [n_total,16] device tensor (NCCL, on the current stream)."""
-    import torch
-    import torch.distributed as dist
-    sizes = [shard_bounds(n_total, world_size, r) for r in range(world_size)]
-    if all(h - l == P for l, h in sizes):
-        buf = torch.empty(n_total * L.TABLE_NCOL, dtype=torch.float64, device=table.device)
-        dist.all_gather_into_tensor(buf, table.contiguous().reshape(-1), group=group)
-        return buf.reshape(n_total, L.TABLE_NCOL)
-    parts = [torch.empty((h - l, L.TABLE_NCOL), dtype=torch.float64, device=table.device) for l, h in sizes]
-    dist.all_gather(parts, table.contiguous(), group=group)
-    return torch.cat(parts)

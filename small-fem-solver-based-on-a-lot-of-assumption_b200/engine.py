@@ -57,6 +57,7 @@ class Engine:
 
     def close(self):
         self.__dict__.pop("_dev_views", None)            # torch views of library-owned device buffers (distributed.device_views)
+        self.__dict__.pop("_pinned_pair", None)
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.jk_destroy(self.h)
             self.h = C.c_void_p()
@@ -284,10 +285,10 @@ class Engine:
 
     def solver_stats(self):
         """nnz(L), executed sweep flops per load case, sweep items per slab, TMA-pipeline flag."""
-        out = np.zeros(4)
+        out = np.zeros(6)
         self._ck(self.lib.jk_solver_stats(self.h, L.dptr(out)))
         return {"nnz_L": int(out[0]), "sweep_flops_executed_per_case": float(out[1]), "sweep_items": int(out[2]),
-                "tma_sweep": bool(out[3])}
+                "tma_sweep": bool(out[3]), "nnz_L_min_envelope": int(out[4]), "sweep_slab": int(out[5])}
 
     def launch_count(self):
         return int(self.lib.jk_launch_count(self.h))

@@ -17,7 +17,8 @@ def phase_times(T, n_steps):
 
 
 def fill_phase_deg(table, omega):
-    """Column 1 of the table, bit-identical to GUI.py:697-698."""
+    """Column 1 of the table, bit-identical to GUI.py:697-698.  Host mirror of what k_phase_reduce writes on the device
+    (the library fills the column itself); kept for callers that build tables from their own times."""
     table[:, 1] = mod360(np.degrees(omega * table[:, 0]))
     return table
 
@@ -89,7 +90,7 @@ class MorisonCalculator:
         eng = self._engine()
         t = phase_times(self.wave.T, n_steps) if t is None else np.asarray(t, dtype=np.float64)
         table, crit = eng.morison_scan(t)
-        return fill_phase_deg(table, self.wave.omega), crit
+        return table, crit
 
     def find_critical_phase(self, n_steps=36):
         table, crit = self.scan_table(n_steps)

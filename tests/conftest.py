@@ -63,3 +63,29 @@ def relmax(a, b):
 @pytest.fixture(scope="session", params=GOLDEN_CASES)
 def golden(request):
     return request.param, load_golden(request.param)
+
+
+def generated_case(g, legs, bays):
+    """(jb, structure, params, wave kwargs) of a generator jacket whose inputs are stored in a large golden file; asserts
+    that the regenerated geometry is the one the reference was run on."""
+    import jacket_b200 as jb
+    p = golden_params(g)
+    ap = jb.AnalysisParams(**{k: p[k] for k in ("E", "nu", "fy", "rho_steel", "rho_water", "D_leg", "t_leg", "D_brace", "t_brace", "H", "T",
+                                                 "d", "U_c", "wave_dir", "current_dir", "Cd", "Cm", "F_axial", "F_shear", "M_moment",
+                                                 "M_torsion", "custom_sw")}, self_weight_mode=str(p["self_weight_mode"]), wave_model="Airy")
+    nodes, members, fixed, top = jb.generate_jacket(legs, bays)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    xyz, conn, sec_id, _, _ = st.pack()
+    assert np.array_equal(xyz, g["xyz"]) and np.array_equal(conn, g["conn"]) and np.array_equal(sec_id == 0, g["is_leg"])
+    assert np.array_equal(st.indices(fixed), g["fixed"]) and np.array_equal(st.indices(top), g["top"])
+    return jb, st, ap, fixed
+
+
+def fem_summary_columns(U, reactions, rows):
+    """Columns 8..15 of the per-phase table from one phase's full results (run_analysis' log lines GUI.py:2027-2054):
+    max |translation| and its node, max utilisation and its member, its von Mises stress, sum of the reactions."""
+    tr = np.linalg.norm(np.asarray(U).reshape(-1, 6)[:, :3], axis=1)
+    util = np.asarray(rows)[:, 6]
+    m = int(np.argmax(util))
+    R = np.asarray(reactions)[:, :3].sum(axis=0)
+    return np.array([tr.max(), float(np.argmax(tr)), util[m], float(m), np.asarray(rows)[m, 5], R[0], R[1], R[2]])

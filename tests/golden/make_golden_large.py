@@ -2,6 +2,7 @@
 
 Run in the build container only (needs /root/reference):
 
+    python tests/golden/make_golden_large.py small   # gen4x3_endforces.npz  (76 members: the 12 member end forces, GUI.py:424-432)
     python tests/golden/make_golden_large.py c3      # gen8x41_scan1024.npz  (configs[2]: 1,976 members, 1,024-phase Morison scan)
     python tests/golden/make_golden_large.py c4      # gen16x104_c4.npz      (configs[3]: 10,000 members, phases of the 4,096-phase scan)
 
@@ -149,10 +150,27 @@ def make_c4(workers, fem_phases, scan_phases):
     print(f"c4: {len(cases)} FEM cases -> {path} ({os.path.getsize(path) / 1024:.0f} KiB, {time.time() - t0:.0f}s)")
 
 
+def make_small():
+    """4-leg x 3-bay generator jacket (76 members): every member's 12 end forces (a20, GUI.py:424-432) at 4 phases of a 24-phase scan."""
+    p = dict(GUI_DEFAULTS)
+    legs, bays, P = 4, 3, 24
+    cases = [_fem_case((legs, bays, p, P, i, True)) for i in (0, 7, 13, 23)]
+    _, st, wave, _, fixed, top = _reference_objects(legs, bays, p)
+    out = _inputs(st, fixed, top, p)
+    out.update(phasefem_P=np.array(P), phasefem_idx=np.array([c["i"] for c in cases]), phasefem_U=np.array([c["U"] for c in cases]),
+               phasefem_rows=np.array([c["rows"] for c in cases]), phasefem_reactions=np.array([c["reactions"] for c in cases]),
+               end_forces=np.array([c["end_forces"] for c in cases]))
+    path = os.path.join(HERE, "gen4x3_endforces.npz")
+    np.savez_compressed(path, **out)
+    print(f"small: {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c3"
     workers = int(os.environ.get("JK_GOLDEN_WORKERS", max(1, (os.cpu_count() or 2) - 1)))
-    if which == "c3":
+    if which == "small":
+        make_small()
+    elif which == "c3":
         make_c3(workers)
     elif which == "c4":
         # critical phase of the 4,096-phase scan (oracle estimate, passed on the command line) first: it gets the end forces

@@ -1,0 +1,238 @@
+"""The CUDA path at BASELINE.json's named sizes against vectors produced by the reference's own classes
+(tests/golden/make_golden_large.py) and against the oracle:
+
+  configs[2]  8 legs x 41 bays, 1,976 members: every row of the reference's 1,024-phase Morison scan + critical index,
+              FEM of a dozen phases against the oracle (U, reactions, member rows, 12 end forces, table columns 8-15);
+  configs[3]  16 legs x 104 bays, 10,000 members / 19,968 free DOF, 4,096 phases: 70 reference rows of the Morison scan
+              (incl. the critical phase), the oracle's table for all 4,096 rows, 8 full FEM cases of the reference incl. end forces.
+
+Tolerance: 1e-9 (max|delta| / max|ref| per field per phase, SURVEY 7 hard part 3); critical index exact.  At configs[3] the
+reference's own LU output is up to 2e-8 away from the converged solution of its equations (tests/test_oracle_golden.py), so
+there the 1e-9 bar is asserted against that converged solution (oracle FEM.solve_refined) and the raw reference output is
+matched to its noise floor."""
+import numpy as np
+import pytest
+
+from conftest import fem_summary_columns, generated_case, golden_params, load_golden, relmax
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+LU_NOISE_C4 = 3e-8
+MEMBER_KEYS = ("Fx_max_kN", "Fy_max_kN", "Fz_max_kN", "My_max_kNm", "Mz_max_kNm", "von_mises_max_MPa", "utilization")
+
+
+def _oracle(g):
+    from oracle import jacket_oracle as orc
+    p = golden_params(g)
+    sections = [(p["D_leg"], p["t_leg"], p["rho_steel"]), (p["D_brace"], p["t_brace"], p["rho_steel"])]
+    model = orc.Model(g["xyz"], g["conn"], np.where(g["is_leg"], 0, 1), sections, g["fixed"], g["top"])
+    return orc, p, model, orc.AiryWave(p["H"], p["T"], p["d"], p["U_c"])
+
+
+def _scan(jb, st, ap, P):
+    wave = jb.RaschiiWave(ap.H, ap.T, ap.d, ap.U_c, "Airy")
+    return jb.phase_scan(st, wave, P, wave_direction=ap.wave_dir, current_direction=ap.current_dir, Cd=ap.Cd, Cm=ap.Cm,
+                         rho_water=ap.rho_water, E=ap.E, nu=ap.nu, fy=ap.fy, params=ap)
+
+
+def _check_phase(ph, row, U, R, mf, k, tol, fixed):
+    """One phase of the CUDA path against (U, reactions, member fields incl. end forces) of a CPU solution."""
+    assert relmax(ph["U"], U) < tol
+    assert relmax(np.array([ph["reactions"][n] for n in fixed]), R) < tol
+    rows = np.array([[r[key] for key in MEMBER_KEYS] for r in ph["internal_forces"]])
+    for j, key in enumerate(MEMBER_KEYS):
+        assert relmax(rows[:, j], mf[key][k]) < tol, key
+    for blk in (slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 12)):          # a20: forces / moments at node 1 / node 2
+        assert relmax(ph["end_forces"][:, blk], mf["end_forces"][k][:, blk]) < tol
+    want = fem_summary_columns(U, R, np.stack([mf[key][k] for key in MEMBER_KEYS], axis=1))
+    got = np.array([row[c] for c in ("max_disp_mm", "max_disp_node", "max_util", "max_util_member", "max_vm_MPa", "sum_Rx", "sum_Ry", "sum_Rz")])
+    assert got[1] == want[1] and got[3] == want[3]                              # governing node / member: exact
+    assert abs(got[0] - want[0]) < tol * want[0] and abs(got[2] - want[2]) < tol * want[2] and abs(got[4] - want[4]) < tol * want[4]
+    assert relmax(got[5:], want[5:]) < tol
+
+
+def test_c3_full_1024_phase_scan_vs_reference():
+    g = load_golden("gen8x41_scan1024")
+    jb, st, ap, fixed = generated_case(g, 8, 41)
+    wave = jb.RaschiiWave(ap.H, ap.T, ap.d, ap.U_c, "Airy")
+    mor = jb.MorisonCalculator(st, wave, ap.wave_dir, ap.current_dir, ap.Cd, ap.Cm, ap.rho_water)
+    table, crit = mor.scan_table(1024)                                          # find_critical_phase on the GPU (Morison only)
+    assert crit == int(g["scan1024_critical"]) == 1009
+    assert np.array_equal(table[:, :2], g["scan1024_table"][:, :2])             # t and phase_deg: bit-identical
+    for c in range(2, 8):
+        assert relmax(table[:, c], g["scan1024_table"][:, c]) < TOL
+    res = _scan(jb, st, ap, 1024)                                               # the whole hot path (Morison + FEM per phase)
+    assert res.critical_index == 1009 and np.array_equal(res.table[:, :8], table[:, :8])
+    # FEM of a dozen phases against the oracle (LU at 3,936 DOF is reproducible to ~1e-11)
+    orc, p, model, ow = _oracle(g)
+    idx = np.unique(np.r_[np.linspace(0, 1023, 11).astype(int), 1009])
+    t = orc.phase_times(p["T"], 1024)[idx]
+    ref = orc.phase_scan(model, ow, t, wave_direction=p["wave_dir"], current_direction=p["current_dir"], Cd=p["Cd"], Cm=p["Cm"],
+                         rho_water=p["rho_water"], E=p["E"], nu=p["nu"], fy=p["fy"], F_axial_kN=p["F_axial"], F_shear_kN=p["F_shear"],
+                         self_weight="calculated")
+    for k, i in enumerate(idx):
+        ph = res.phase(int(i), end_forces=True)
+        assert relmax(ph["nodal_forces"], ref["morison"]["nodal_forces"][k]) < TOL
+        _check_phase(ph, res.row(int(i)), ref["U"][k], ref["reactions"][k], ref["members"], k, TOL, fixed)
+
+
+@pytest.fixture(scope="module")
+def c4():
+    g = load_golden("gen16x104_c4")
+    jb, st, ap, fixed = generated_case(g, 16, 104)
+    res = _scan(jb, st, ap, 4096)
+    return g, jb, st, ap, fixed, res
+
+
+def test_c4_morison_table_and_critical_phase(c4):
+    """All 4,096 rows against the oracle's table (pinned to the reference on 70 of them, 2.7e-16), the 70 reference rows
+    directly, and the critical index."""
+    g, jb, st, ap, fixed, res = c4
+    fx = load_golden("c4_oracle_scan4096")
+    idx = g["scan4096_idx"]
+    assert res.critical_index == int(fx["critical"]) == 4044 == int(idx[np.argmax(g["scan4096_rows"][:, 2])])
+    assert np.array_equal(res.table[:, :2], fx["table"][:, :2])
+    for c in range(2, 8):
+        assert relmax(res.table[idx, c], g["scan4096_rows"][:, c]) < TOL
+        assert relmax(res.table[:, c], fx["table"][:, c]) < TOL
+    # the fixture is what the live oracle computes (spot check, 24 phases)
+    orc, p, model, ow = _oracle(g)
+    some = np.arange(7, 4096, 171)
+    t = orc.phase_times(p["T"], 4096)[some]
+    live = orc.phase_table(orc.morison_phases(model, ow, t, p["wave_dir"], p["current_dir"], p["Cd"], p["Cm"], p["rho_water"]), t, ow.omega)[0]
+    assert relmax(live, fx["table"][some]) < 1e-14
+
+
+def test_c4_fem_vs_reference_and_converged_oracle(c4):
+    """8 full FEM cases of the reference at 19,968 free DOF (incl. the critical phase): U, reactions, 7 member fields, 12 end
+    forces, table columns 8-15 -- within 1e-9 of the converged solution of the reference's equations, and within the
+    reference's own LU noise of its raw output."""
+    g, jb, st, ap, fixed, res = c4
+    orc, p, model, ow = _oracle(g)
+    fi = g["phasefem_idx"]
+    t = orc.phase_times(p["T"], 4096)[fi]
+    mor = orc.morison_phases(model, ow, t, p["wave_dir"], p["current_dir"], p["Cd"], p["Cm"], p["rho_water"])
+    fem = orc.FEM(model, p["E"], p["nu"])
+    inter, sw = fem.static_loads(p["wave_dir"], p["F_axial"], p["F_shear"], p["M_moment"], p["M_torsion"], str(p["self_weight_mode"]))
+    F = fem.load_matrix(mor["nodal_forces"], inter, sw)
+    U = fem.solve_refined(F, steps=2)
+    R, mf = fem.reactions(U, F), fem.member_forces(U, p["fy"])
+    worst_conv, worst_raw = 0.0, 0.0
+    for k, i in enumerate(fi):
+        ph = res.phase(int(i), end_forces=True)
+        assert relmax(ph["nodal_forces"], g["phasefem_nodal"][k]) < TOL                   # Morison nodal loads vs the reference
+        _check_phase(ph, res.row(int(i)), U[k], R[k], mf, k, TOL, fixed)                    # vs the converged solution: 1e-9
+        rows = np.array([[r[key] for key in MEMBER_KEYS] for r in ph["internal_forces"]])
+        raw = [relmax(ph["U"], g["phasefem_U"][k]), relmax(np.array([ph["reactions"][n] for n in fixed]), g["phasefem_reactions"][k])]
+        raw += [relmax(rows[:, j], g["phasefem_rows"][k][:, j]) for j in range(7)]
+        worst_raw = max(worst_raw, max(raw))
+        worst_conv = max(worst_conv, relmax(ph["U"], U[k]))
+        assert max(raw) < LU_NOISE_C4, (int(i), raw)                                        # vs the reference's raw LU output
+    for k, i in enumerate(g["endforce_idx"]):
+        ef = res.phase(int(i), end_forces=True)["end_forces"]
+        for blk in (slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 12)):
+            assert relmax(ef[:, blk], g["end_forces"][k][:, blk]) < LU_NOISE_C4
+    print(f"[c4 parity] worst U error vs converged solution {worst_conv:.2e}; worst field error vs the reference's raw LU output {worst_raw:.2e}")
+    # the solve on the GPU is closer to the converged solution than the reference's LU is
+    assert worst_conv < min(relmax(g["phasefem_U"][k], U[k]) for k in range(len(fi)))
+
+
+def test_end_forces_vs_reference_small():
+    """a20 (GUI.py:424-432): 12 end forces of every member, reference vectors of the 4 x 3 generator jacket."""
+    g = load_golden("gen4x3_endforces")
+    jb, st, ap, fixed = generated_case(g, 4, 3)
+    res = _scan(jb, st, ap, int(g["phasefem_P"]))
+    for k, i in enumerate(g["phasefem_idx"]):
+        ph = res.phase(int(i), end_forces=True)
+        assert relmax(ph["U"], g["phasefem_U"][k]) < TOL
+        for blk in (slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 12)):
+            assert relmax(ph["end_forces"][:, blk], g["end_forces"][k][:, blk]) < TOL
+        rows = np.array([[r[key] for key in MEMBER_KEYS] for r in ph["internal_forces"]])
+        assert relmax(rows, g["phasefem_rows"][k]) < TOL
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kinematics_points_on_device_vs_reference_and_host(tag):
+    """jk_kinematics_points (device functions of the Morison kernels) = MorisonCalculator.get_kinematics_3d (host scalar
+    code) = the reference's values, incl. the points that dry out within dt."""
+    import jacket_b200 as jb
+    g = {k[2:]: v for k, v in load_golden("kinematics_airy").items() if k.startswith(tag + "_")}
+    H, T, d, U_c, wave_dir, current_dir = g["params"]
+    nodes, members, fixed, top = jb.create_default_3leg_jacket()
+    st = jb.build_structure(nodes, members, fixed, top, jb.AnalysisParams())
+    wave = jb.RaschiiWave(H, T, d, U_c, "Airy", 10)
+    mor = jb.MorisonCalculator(st, wave, wave_dir, current_dir)
+    t = float(g["t"])
+    dev = mor.kinematics_points(g["points"], t)
+    assert dev.shape == g["kin3"].shape and np.array_equal(dev[:, 8], g["kin3"][:, 8])        # same points are wet
+    host = np.array([[float(mor.get_kinematics_3d(*pt, t)[c]) for c in mor.KINEMATICS_COLUMNS] for pt in g["points"]])
+    for c in range(10):
+        assert relmax(dev[:, c], g["kin3"][:, c]) < TOL, mor.KINEMATICS_COLUMNS[c]
+        assert relmax(dev[:, c], host[:, c]) < TOL, mor.KINEMATICS_COLUMNS[c]
+    # Fourier series form (own fits): device vs host scalar code
+    wf = jb.RaschiiWave.with_own_fits(8.0, 9.4, 50.0, 0.9, "Stokes", 5)
+    mf = jb.MorisonCalculator(st, wf, 20.0, 75.0)
+    pts = g["points"][::5]
+    dev = mf.kinematics_points(pts, 1.1)
+    host = np.array([[float(mf.get_kinematics_3d(*pt, 1.1)[c]) for c in mf.KINEMATICS_COLUMNS] for pt in pts])
+    assert np.array_equal(dev[:, 8], host[:, 8])
+    for c in range(10):
+        assert relmax(dev[:, c], host[:, c]) < 1e-8, mf.KINEMATICS_COLUMNS[c]       # 1/dt amplifies the series' rounding differences
+
+
+def test_beam_element_host_constructor_vs_device_elements():
+    """BeamElement3D built on its own (host) = the element k_member_setup builds on the device (FEMSolver.elements)."""
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams()
+    nodes, members, fixed, top = jb.generate_jacket(5, 4)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    fem = jb.FEMSolver(st, ap.E, ap.nu)
+    for m, el in zip(st.members, fem.elements):
+        host = jb.BeamElement3D(st.nodes[m["node1"]], st.nodes[m["node2"]], m["section"], fem.E, fem.G)
+        assert relmax(el.K_local, host.K_local) < 1e-14 and relmax(el.T, host.T) < 1e-14 and relmax(el.K_global, host.K_global) < 1e-13
+        assert abs(el.L - host.L) < 1e-14 * host.L
+
+
+def test_stale_results_are_refused():
+    """Results live in HBM, one set per engine: an older result object must not silently return a newer scan's rows."""
+    import jacket_b200 as jb
+    from jacket_b200 import JacketError
+    ap = jb.AnalysisParams(wave_model="Airy")
+    nodes, members, fixed, top = jb.generate_jacket(4, 4)
+    st = jb.build_structure(nodes, members, fixed, top, ap)
+    first = _scan(jb, st, ap, 24)
+    u = first.phase(3)["U"]
+    second = _scan(jb, st, ap, 40)
+    with pytest.raises(JacketError, match="stale"):
+        first.phase(3)
+    with pytest.raises(JacketError, match="stale"):
+        first.member_series(0)
+    assert second.phase(3)["U"].shape == u.shape
+    fem = jb.FEMSolver(st, ap.E, ap.nu)
+    fem.apply_boundary_conditions(st.get_bottom_nodes())
+    fem.F_global[2::6] = -1.0e4
+    fem.solve()
+    with pytest.raises(JacketError, match="stale"):
+        second.phase(0)
+    assert len(fem.get_reactions()) == len(fixed)
+    _scan(jb, st, ap, 8)
+    with pytest.raises(JacketError, match="stale"):
+        fem.get_reactions()
+
+
+def test_options_api():
+    import jacket_b200 as jb
+    from jacket_b200 import JacketError
+    nodes, members, fixed, top = jb.generate_jacket(4, 3)
+    st = jb.build_structure(nodes, members, fixed, top, jb.AnalysisParams())
+    eng = jb.Engine(st, options={"split_pct": 60, "two_chains": 0})
+    assert eng.get_option("split_pct") == 60 and eng.get_option("two_chains") == 0 and eng.get_option("start_gate") == 1
+    with pytest.raises(JacketError):
+        eng.set_option("no_such_switch", 1)
+    with pytest.raises(JacketError):
+        eng.set_option("split_pct", 400)
+    with pytest.raises(JacketError):
+        eng.set_option("sweep_slab", 12)
+    names = [eng.lib.jk_option_name(i).decode() for i in range(eng.lib.jk_option_count())]
+    assert "cuda_graph" in names and "fused_loads" in names and "sweep_slab" in names
+    eng.close()

@@ -3,10 +3,12 @@
 follows the reference's operation order."""
 import numpy as np
 
-from conftest import golden_params, oracle_model, relmax
+from conftest import golden_params, load_golden, oracle_model, relmax
 from oracle import jacket_oracle as orc
 
 TIGHT = 5e-13
+TOL = 1e-9          # the north star's bar (LU per case in the reference vs one LU for all cases in the oracle: ~1e-11)
+MEMBER_KEYS = ("Fx_max_kN", "Fy_max_kN", "Fz_max_kN", "My_max_kNm", "Mz_max_kNm", "von_mises_max_MPa", "utilization")
 
 
 def _wave(p):
@@ -172,3 +174,88 @@ def test_c3_size_jacket_against_the_reference():
         assert relmax(res["U"][i], g["phasefem_U"][i]) < 1e-9
         assert relmax(res["reactions"][i], g["phasefem_reactions"][i]) < 1e-9
         assert relmax(res["members"]["utilization"][i], g["phasefem_rows"][i][:, 6]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] / [3] at full size: vectors produced by the reference's own classes (tests/golden/make_golden_large.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _large_oracle_model(g):
+    from oracle import jacket_oracle as orc
+    p = golden_params(g)
+    sections = [(p["D_leg"], p["t_leg"], p["rho_steel"]), (p["D_brace"], p["t_brace"], p["rho_steel"])]
+    model = orc.Model(g["xyz"], g["conn"], np.where(g["is_leg"], 0, 1), sections, g["fixed"], g["top"])
+    return orc, p, model, orc.AiryWave(p["H"], p["T"], p["d"], p["U_c"])
+
+
+def test_oracle_full_1024_phase_scan_at_c3_size():
+    """configs[2]: every row of the reference's 1,024-phase Morison scan of the 1,976-member jacket, and its critical index."""
+    g = load_golden("gen8x41_scan1024")
+    orc, p, model, wave = _large_oracle_model(g)
+    t = orc.phase_times(p["T"], 1024)
+    mor = orc.morison_phases(model, wave, t, p["wave_dir"], p["current_dir"], p["Cd"], p["Cm"], p["rho_water"])
+    tab, crit = orc.phase_table(mor, t, wave.omega)
+    assert crit == int(g["scan1024_critical"]) == 1009
+    assert np.array_equal(tab[:, :2], g["scan1024_table"][:, :2])          # t and phase_deg: same expressions, same bits
+    for c in range(2, 8):
+        assert relmax(tab[:, c], g["scan1024_table"][:, c]) < 1e-13
+
+
+LU_NOISE_C4 = 3e-8   # measured: how far the reference's own LU results at 19,968 DOF are from the converged solution of its equations
+
+
+def test_oracle_at_c4_size_vs_reference():
+    """configs[3]: 70 rows of the 4,096-phase Morison scan (incl. the critical phase 4044 and its neighbours) and 8 full FEM
+    cases (U, reactions, member rows, 12 end forces) of the reference at 10,000 members / 19,968 free DOF; the committed
+    oracle table of all 4,096 phases (c4_oracle_scan4096.npz) agrees with the reference on those rows.
+
+    LU noise floor: at this size numpy.linalg.solve is only reproducible to ~2e-9 on U and ~8e-9 on the shear forces -- the
+    reference's per-case dgesv and the oracle's multi-right-hand-side dgesv (same algorithm, different blocking) differ by
+    that much, and BOTH are up to 7e-9 / 2e-8 away from the converged solution of the same equations (LU + iterative
+    refinement with 80-bit residuals, FEM.solve_refined; the relative residual drops from 4e-8 to 2e-11).  So at c4 the
+    1e-9 bar is asserted against the converged solution (the GPU path in tests/test_gpu_reference_sizes.py) and the raw
+    reference output is matched to its own noise, LU_NOISE_C4."""
+    g = load_golden("gen16x104_c4")
+    fx = load_golden("c4_oracle_scan4096")
+    idx = g["scan4096_idx"]
+    assert int(fx["critical"]) == 4044 and int(idx[np.argmax(g["scan4096_rows"][:, 2])]) == 4044
+    assert np.array_equal(fx["table"][idx, :2], g["scan4096_rows"][:, :2])
+    for c in range(2, 8):
+        assert relmax(fx["table"][idx, c], g["scan4096_rows"][:, c]) < 1e-13
+    orc, p, model, wave = _large_oracle_model(g)
+    fi = g["phasefem_idx"]
+    t = orc.phase_times(p["T"], 4096)[fi]
+    assert np.array_equal(t, g["phasefem_t"])
+    mor = orc.morison_phases(model, wave, t, p["wave_dir"], p["current_dir"], p["Cd"], p["Cm"], p["rho_water"])
+    assert relmax(mor["nodal_forces"], g["phasefem_nodal"]) < 1e-13
+    tot = np.concatenate([mor["total_drag"], mor["total_inertia"], mor["total_morison"]], axis=1)
+    assert relmax(tot, g["phasefem_totals"]) < 1e-13
+    fem = orc.FEM(model, p["E"], p["nu"])
+    inter, sw = fem.static_loads(p["wave_dir"], p["F_axial"], p["F_shear"], p["M_moment"], p["M_torsion"], str(p["self_weight_mode"]))
+    F = fem.load_matrix(mor["nodal_forces"], inter, sw)
+    U = fem.solve_refined(F, steps=2)
+    assert fem.refine_history[0] > 1e-9 and fem.refine_history[-1] < 1e-10       # plain LU leaves a 4e-8 residual; refinement removes it
+    R, mf = fem.reactions(U, F), fem.member_forces(U, p["fy"])
+    worst = 0.0
+    for k in range(len(fi)):
+        errs = [relmax(g["phasefem_U"][k], U[k]), relmax(g["phasefem_reactions"][k], R[k])]
+        errs += [relmax(g["phasefem_rows"][k][:, j], mf[key][k]) for j, key in enumerate(MEMBER_KEYS)]
+        worst = max(worst, max(errs))
+        assert max(errs) < LU_NOISE_C4, (int(fi[k]), errs)
+    assert worst > TOL                                  # ... and it IS noise above the 1e-9 bar: the reference cannot define 1e-9 here
+    for k, i in enumerate(g["endforce_idx"]):
+        kk = int(np.flatnonzero(fi == i)[0])
+        for blk in (slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 12)):      # forces and moments of node 1 / node 2
+            assert relmax(mf["end_forces"][kk][:, blk], g["end_forces"][k][:, blk]) < LU_NOISE_C4
+
+
+def test_oracle_end_forces_small_case():
+    """a20 (GUI.py:424-432): the 12 end forces of every member of the 4 x 3 generator jacket at 4 phases."""
+    g = load_golden("gen4x3_endforces")
+    orc, p, model, wave = _large_oracle_model(g)
+    t = orc.phase_times(p["T"], int(g["phasefem_P"]))[g["phasefem_idx"]]
+    res = orc.phase_scan(model, wave, t, wave_direction=p["wave_dir"], current_direction=p["current_dir"], Cd=p["Cd"], Cm=p["Cm"],
+                         rho_water=p["rho_water"], E=p["E"], nu=p["nu"], fy=p["fy"], F_axial_kN=p["F_axial"], F_shear_kN=p["F_shear"],
+                         self_weight="calculated")
+    assert relmax(res["U"], g["phasefem_U"]) < TOL
+    for blk in (slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 12)):
+        assert relmax(res["members"]["end_forces"][:, :, blk], g["end_forces"][:, :, blk]) < TOL
