@@ -87,6 +87,36 @@ __global__ void __launch_bounds__(256) k_dmma16816(double* out, int iters, doubl
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Are the FP64 FMA pipe and the DMMA path separate issue resources?  Even warps run the DFMA loop, odd warps the DMMA loop
+// (mode 0), or every warp interleaves both (mode 1).  If the aggregate exceeds either peak alone they overlap.
+__global__ void __launch_bounds__(256) k_mixed(double* out, int iters, double seed, int mode) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, cc = 1e-9;
+    double c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c[j] = 0.0;
+    double ma = seed + threadIdx.x * 1e-3, mb = 1.0 + threadIdx.x * 1e-4;
+    const bool do_fma = mode == 1 || ((threadIdx.x >> 5) & 1) == 0, do_mma = mode == 1 || ((threadIdx.x >> 5) & 1) == 1;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+        if (do_fma) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+                a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+            }
+        }
+        if (do_mma) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma884(c[2 * j], c[2 * j + 1], ma, mb);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += c[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static float time_ms(F launch, int reps) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -118,6 +148,14 @@ int main() {
         ms = time_ms([&] { k_dmma16816<<<grid, 256>>>(out, iters, 1.0); }, 5);
         flops = 2.0 * 2048 * 4 * iters * 8.0 * grid;
         printf(", \"dmma16816_tflops_bps%d\": %.2f", bps, flops / ms * 1e-9);
+    }
+    for (int mode = 0; mode < 2; ++mode) {
+        int grid = sms * 4, iters = 4096;
+        float ms = time_ms([&] { k_mixed<<<grid, 256>>>(out, iters, 1.0, mode); }, 5);
+        // per warp and iteration: 64 DFMA x 32 lanes (2048 FMA) and / or 8 DMMA x 256 FMA (2048 FMA)
+        double fma_warps = mode == 1 ? 8.0 : 4.0, mma_warps = mode == 1 ? 8.0 : 4.0;
+        double flops = 2.0 * 2048.0 * iters * (fma_warps + mma_warps) * grid;
+        printf(", \"mixed_dfma_dmma_tflops_mode%d\": %.2f", mode, flops / ms * 1e-9);
     }
     CK(cudaGetLastError());
     printf("}\n");
