@@ -61,17 +61,31 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 // the rank-8 update to the trailing block.
 // 8x8 diagonal block p of T (already carrying the updates of the panels before it): factor it in registers (every lane
 // of the calling warp holds the same values, no communication), write L_pp back and its inverse to Dp.
+// WANT_L / WANT_M: which of the two results this warp produces.  The pivot recurrence itself is cheap (about 150 of the ~400
+// FP64 instructions); two warps on different schedulers running it redundantly -- one finishing L_pp, the other the inverse --
+// halve the issue-bound time of the block (1,600 -> ~800 clocks) without any exchange between them.
+template <bool WANT_L, bool WANT_M>
 __device__ __forceinline__ void potrf8_warp(double* __restrict__ T, double* __restrict__ Dp, int c0, int* __restrict__ info, int pivot_base, int lane) {
     double d[8][8], m[8][8], rs[8];
+    constexpr bool PAIR_L = WANT_L && !WANT_M, PAIR_M = WANT_M && !WANT_L;
+    // A pair of warps works on the same block (one finishes L_pp, the other the inverse) and L_pp overwrites the block both
+    // read.  The inverse's warp reads it with volatile loads (which the compiler may not sink below the barrier instruction)
+    // and arrives on a named barrier at once; the L warp waits on that barrier just before its stores -- by then the other
+    // warp's loads are a thousand clocks old, so nobody ever blocks.  (Without the hand-shake about one factorisation in
+    // three met a "non-positive pivot": the compiler is free to read T late in a warp that never writes it.)
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) d[i][j] = T[(c0 + i) * LS_LD + c0 + j];
+        for (int j = 0; j <= i; ++j) {
+            if (PAIR_M) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(d[i][j]) : "r"((unsigned)__cvta_generic_to_shared(T + (c0 + i) * LS_LD + c0 + j)) : "memory");
+            else d[i][j] = T[(c0 + i) * LS_LD + c0 + j];
+        }
+    if (PAIR_M) asm volatile("bar.arrive 3, 64;\n" ::: "memory");
     bool bad = false;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         double dc = d[c][c];
-        if (!(dc > 0.0)) { if (!bad && lane == 0) atomicCAS(info, 0, pivot_base + c0 + c + 1); bad = true; dc = 1.0; }
+        if (!(dc > 0.0)) { if (WANT_L && !bad && lane == 0) atomicCAS(info, 0, pivot_base + c0 + c + 1); bad = true; dc = 1.0; }
         const double inv = fast_rcp(dc);
         rs[c] = fast_rsqrt(dc);
         double t[8];
@@ -86,39 +100,102 @@ __device__ __forceinline__ void potrf8_warp(double* __restrict__ T, double* __re
             }
         // the same row operations applied to the identity give Ltilde^-1 (product of the elimination matrices): the
         // inverse is complete one FMA after the last pivot instead of a 28-FMA substitution chain afterwards
+        if (WANT_M) {
 #pragma unroll
-        for (int i = c + 1; i < 8; ++i) {
+            for (int i = c + 1; i < 8; ++i) {
 #pragma unroll
-            for (int j = 0; j < c; ++j) m[i][j] = fma(-t[i], m[c][j], m[i][j]);
-            m[i][c] = -t[i];
+                for (int j = 0; j < c; ++j) m[i][j] = fma(-t[i], m[c][j], m[i][j]);
+                m[i][c] = -t[i];
+            }
         }
         d[c][c] = dc;
     }
-    // L = Ltilde D^(1/2): scale the columns off the pivot chain
+    if (WANT_L) {
+        // L = Ltilde D^(1/2): scale the columns off the pivot chain
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 8; ++c) {
 #pragma unroll
-        for (int i = c + 1; i < 8; ++i) d[i][c] *= rs[c];
-        d[c][c] *= rs[c];
+            for (int i = c + 1; i < 8; ++i) d[i][c] *= rs[c];
+            d[c][c] *= rs[c];
+        }
     }
-    // M = L^-1 = D^(-1/2) Ltilde^-1: scale the rows, 1/L_ii = rs_i
+    if (WANT_M) {
+        // M = L^-1 = D^(-1/2) Ltilde^-1: scale the rows, 1/L_ii = rs_i
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {
 #pragma unroll
-        for (int j = 0; j < i; ++j) m[i][j] *= rs[i];
-        m[i][i] = rs[i];
+            for (int j = 0; j < i; ++j) m[i][j] *= rs[i];
+            m[i][i] = rs[i];
+        }
     }
+    if (PAIR_L) asm volatile("bar.sync 3, 64;\n" ::: "memory");       // the partner has read the block (see above)
     if (lane == 0) {
         // 16-byte stores, lower triangle only (the entry just above the diagonal that a pair may cover gets 0;
-        // the rest of Dp's upper triangle is zeroed once by the caller): 40 stores instead of 100 on the chain
+        // the rest of Dp's upper triangle is zeroed once by the caller): 20 stores per result
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j <= i; j += 2) {
-                *reinterpret_cast<double2*>(T + (c0 + i) * LS_LD + c0 + j) = make_double2(d[i][j], j + 1 <= i ? d[i][j + 1] : 0.0);
-                *reinterpret_cast<double2*>(Dp + i * DI_LD + j) = make_double2(m[i][j], j + 1 <= i ? m[i][j + 1] : 0.0);
+                if (WANT_L) *reinterpret_cast<double2*>(T + (c0 + i) * LS_LD + c0 + j) = make_double2(d[i][j], j + 1 <= i ? d[i][j + 1] : 0.0);
+                if (WANT_M) *reinterpret_cast<double2*>(Dp + i * DI_LD + j) = make_double2(m[i][j], j + 1 <= i ? m[i][j + 1] : 0.0);
             }
     }
+}
+
+// The same 8x8 factorisation with the work DEALT OVER THE LANES instead of replicated in every lane: lane (r, q) = (lane / 4,
+// lane % 4) owns the two entries (r, 2q) and (r, 2q + 1) of the (symmetric, both triangles carried) block and of the
+// unit-lower inverse being accumulated -- the DMMA accumulator layout.  Per pivot a lane needs its row's multiplier
+// d[r][c], the pivot row entries d[c][2q..2q+1] and the inverse's row c: six register shuffles.  The replicated form issues
+// ~400 warp-wide FP64 instructions per block (two issue cycles each: 1,600 clocks measured, issue-bound); this one ~15 per
+// pivot, so the block costs its dependency chain  fma -> shuffle -> reciprocal  per pivot.  Same recurrences
+// (d' = d - (a b) / piv, LDL^T form, square roots off the chain); products are associated as (a b) * inv.
+__device__ __forceinline__ void potrf8_lanes(double* __restrict__ T, double* __restrict__ Dp, int c0, int* __restrict__ info, int pivot_base, int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r = lane >> 2, q = lane & 3, j0 = 2 * q, j1 = 2 * q + 1;
+    double d0 = T[(c0 + max(r, j0)) * LS_LD + c0 + min(r, j0)];
+    double d1 = T[(c0 + max(r, j1)) * LS_LD + c0 + min(r, j1)];
+    double m0 = 0.0, m1 = 0.0;                 // inverse of the unit-lower factor, strictly lower part
+    double rs_r = 0.0, rs_0 = 0.0, rs_1 = 0.0;  // 1 / sqrt(pivot) of row r and of columns j0, j1
+    int bad = -1;                               // first non-positive pivot (uniform over the lanes); no branches on the chain
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double piv = __shfl_sync(FULL, (c & 1) ? d1 : d0, 4 * c + (c >> 1));
+        // everything that does not need 1 / piv first: the shuffles and the products run under the reciprocal
+        const double a = __shfl_sync(FULL, (c & 1) ? d1 : d0, (lane & ~3) | (c >> 1));      // d[r][c]
+        const double b0 = __shfl_sync(FULL, d0, 4 * c + q), b1 = __shfl_sync(FULL, d1, 4 * c + q);   // d[c][j0], d[c][j1]
+        const double mc0 = __shfl_sync(FULL, m0, 4 * c + q), mc1 = __shfl_sync(FULL, m1, 4 * c + q); // m[c][j0], m[c][j1]
+        const bool neg = !(piv > 0.0);
+        bad = (neg && bad < 0) ? c : bad;
+        piv = neg ? 1.0 : piv;
+        const double inv = fast_rcp(piv);
+        const double ab0 = a * b0, ab1 = a * b1, am0 = a * mc0, am1 = a * mc1;
+        const double nd0 = fma(-ab0, inv, d0), nd1 = fma(-ab1, inv, d1);
+        const double nm0 = fma(-am0, inv, m0), nm1 = fma(-am1, inv, m1), ta = -(a * inv);
+        const bool below = r > c;
+        d0 = (below && j0 > c) ? nd0 : d0;
+        d1 = (below && j1 > c) ? nd1 : d1;
+        m0 = below ? ((j0 < c) ? nm0 : (j0 == c ? ta : m0)) : m0;
+        m1 = below ? ((j1 < c) ? nm1 : (j1 == c ? ta : m1)) : m1;
+        const double rs = fast_rsqrt(piv);
+        rs_r = (c == r) ? rs : rs_r; rs_0 = (c == j0) ? rs : rs_0; rs_1 = (c == j1) ? rs : rs_1;
+    }
+    if (bad >= 0 && lane == 0) atomicCAS(info, 0, pivot_base + c0 + bad + 1);
+    // L = Ltilde D^(1/2) (entry (r, j) holds d[r][j] as it stood at pivot j: scale by 1 / sqrt(piv_j)); M = D^(-1/2) Ltilde^-1
+    const double l0 = (j0 <= r) ? d0 * rs_0 : 0.0, l1 = (j1 <= r) ? d1 * rs_1 : 0.0;
+    const double i0 = (j0 < r) ? m0 * rs_r : (j0 == r ? rs_r : 0.0), i1 = (j1 < r) ? m1 * rs_r : (j1 == r ? rs_r : 0.0);
+    *reinterpret_cast<double2*>(T + (c0 + r) * LS_LD + c0 + j0) = make_double2(l0, l1);
+    *reinterpret_cast<double2*>(Dp + r * DI_LD + j0) = make_double2(i0, i1);
+}
+
+#ifndef JK_POTRF8_LANES
+#define JK_POTRF8_LANES 0      // 1: lane-distributed 8x8 pivot blocks (potrf8_lanes: measured no faster, 1,590 clocks -- the shuffles sit on the chain), 0: replicated in every lane
+#endif
+__device__ __forceinline__ void potrf8(double* __restrict__ T, double* __restrict__ Dp, int c0, int* __restrict__ info, int pivot_base, int lane) {
+#if JK_POTRF8_LANES
+    potrf8_lanes(T, Dp, c0, info, pivot_base, lane);
+#else
+    potrf8_warp<true, true>(T, Dp, c0, info, pivot_base, lane);
+#endif
 }
 
 // Eight 8-column panels with LOOKAHEAD inside the tile: after the rows below panel p are solved, warp 0 alone applies
@@ -128,7 +205,7 @@ __device__ __forceinline__ void potrf8_warp(double* __restrict__ T, double* __re
 __device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, int* __restrict__ info, int pivot_base) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
-    if (warp == 0) potrf8_warp(T, Di, 0, info, pivot_base, lane);
+    if (warp == 0) potrf8(T, Di, 0, info, pivot_base, lane);
     for (int p = 0; p < 8; ++p) {
         const int c0 = 8 * p;
         double* Dp = Di + p * DI_BLK;
@@ -165,11 +242,74 @@ __device__ void potrf64_smem(double* __restrict__ T, double* __restrict__ Di, in
         if (warp == 0) {
             update_tile(0);
             __syncwarp();
-            potrf8_warp(T, Di + (p + 1) * DI_BLK, c0 + 8, info, pivot_base, lane);
+            potrf8(T, Di + (p + 1) * DI_BLK, c0 + 8, info, pivot_base, lane);
         } else {
             for (int t = warp; t < ntile; t += CHOL_THREADS / 32 - 1) update_tile(t);
         }
     }
+}
+
+// potrf64_smem with the 8x8 pivot blocks factored by TWO warps at once (warp 0 -> L_pp, warp 1 -> its inverse; see
+// potrf8_warp): warp 0 applies the rank-8 update to the next diagonal block, the pair meets at a 64-thread named barrier and
+// both read the block; warps 2-7 share the rest of the trailing update.
+__device__ void potrf64_pipelined(double* __restrict__ T, double* __restrict__ Di, int* __restrict__ info, int pivot_base) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    if (warp == 0) potrf8_warp<true, false>(T, Di, 0, info, pivot_base, lane);
+    else if (warp == 1) potrf8_warp<false, true>(T, Di, 0, info, pivot_base, lane);
+    for (int p = 0; p < 8; ++p) {
+        const int c0 = 8 * p;
+        double* Dp = Di + p * DI_BLK;
+        __syncthreads();                                    // L_pp, its inverse and every update of panel p-1 are in place
+        const int nmt = 7 - p;                              // 8-row tiles below the diagonal block
+        if (nmt == 0) break;
+        if (warp < nmt) {                                   // rows below: X = A * M^T (in place), one 8-row tile per warp
+            const int row0 = c0 + 8 + 8 * warp;
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int k4 = 0; k4 < 2; ++k4)
+                dmma(x0, x1, T[(row0 + fr) * LS_LD + c0 + 4 * k4 + fk], Dp[fr * DI_LD + 4 * k4 + fk]);
+            __syncwarp();
+            T[(row0 + fr) * LS_LD + c0 + 2 * fk] = x0;
+            T[(row0 + fr) * LS_LD + c0 + 2 * fk + 1] = x1;
+        }
+        __syncthreads();
+        const int ntile = nmt * (nmt + 1) / 2;
+        auto update_tile = [&](int t) {
+            int mi = 0;
+            while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
+            const int nj = t - mi * (mi + 1) / 2;
+            const int ri = c0 + 8 + 8 * mi, rj = c0 + 8 + 8 * nj;
+            double* cp = T + (ri + fr) * LS_LD + rj + 2 * fk;
+            double c0v = cp[0], c1v = cp[1];
+#pragma unroll
+            for (int k4 = 0; k4 < 2; ++k4)
+                dmma(c0v, c1v, -T[(ri + fr) * LS_LD + c0 + 4 * k4 + fk], T[(rj + fr) * LS_LD + c0 + 4 * k4 + fk]);
+            cp[0] = c0v; cp[1] = c1v;
+        };
+        if (warp == 0) {
+            update_tile(0);
+            __syncwarp();
+            asm volatile("bar.sync 2, 64;\n" ::: "memory");          // the next diagonal block is final: hand it to warp 1 as well
+            potrf8_warp<true, false>(T, Di + (p + 1) * DI_BLK, c0 + 8, info, pivot_base, lane);
+        } else if (warp == 1) {
+            asm volatile("bar.sync 2, 64;\n" ::: "memory");
+            potrf8_warp<false, true>(T, Di + (p + 1) * DI_BLK, c0 + 8, info, pivot_base, lane);
+        } else {
+            for (int t = warp - 1; t < ntile; t += CHOL_THREADS / 32 - 2) update_tile(t);
+        }
+    }
+}
+
+#ifndef JK_POTRF_TWO_WARPS
+#define JK_POTRF_TWO_WARPS 1
+#endif
+__device__ __forceinline__ void potrf64(double* __restrict__ T, double* __restrict__ Di, int* __restrict__ info, int pivot_base) {
+#if JK_POTRF_TWO_WARPS
+    potrf64_pipelined(T, Di, info, pivot_base);
+#else
+    potrf64_smem(T, Di, info, pivot_base);
+#endif
 }
 
 __device__ __forceinline__ void store_tile(double* __restrict__ g, const double* __restrict__ T, int tid, int nthreads) {
@@ -210,6 +350,38 @@ __device__ __forceinline__ void trsm64_warp(double* __restrict__ As, const doubl
         }
         __syncwarp();
     }
+}
+
+// C (lower 8x8 tiles) -= A A^T for 64x64 tiles in shared memory, all 8 warps: row blocks paired (w, 7-w) per SM
+// sub-partition so that every scheduler issues the same number of DMMAs.  Ends with a CTA barrier.
+__device__ __forceinline__ void syrk64_lower(const double* __restrict__ As, double* __restrict__ Cs) {
+    // The 36 lower 8x8 tiles are dealt round-robin over the 8 warps (4 or 5 each, 80 DMMAs at most) instead of one row block per
+    // warp (16 ... 128 DMMAs): the warp with the longest list sets the time of this step of the critical chain
+    // (tools/chol_probe.cu: 5,100 -> 4,050 clocks; 8 warps can saturate the SM's DMMA pipe, 2,300 clocks, so what is left is
+    // operand-load latency).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int t = warp + 8 * q;                       // tile index in the row-major lower triangle
+        if (t >= 36) break;
+        int mi = 0;
+        while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
+        const int nj = t - mi * (mi + 1) / 2;
+        const double* ap = As + (8 * mi + fr) * LS_LD + fk;
+        const double* bp = As + (8 * nj + fr) * LS_LD + fk;
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two partial sums: even / odd k-groups
+#pragma unroll
+        for (int k4 = 0; k4 < NB / 4; k4 += 2) {
+            dmma(c0, c1, ap[4 * k4], bp[4 * k4]);
+            dmma(e0, e1, ap[4 * k4 + 4], bp[4 * k4 + 4]);
+        }
+        double2* cp = reinterpret_cast<double2*>(Cs + (8 * mi + fr) * LS_LD + 8 * nj + 2 * fk);
+        double2 v = *cp;
+        v.x -= c0 + e0; v.y -= c1 + e1;
+        *cp = v;
+    }
+    __syncthreads();
 }
 
 // acc(8 rows x 64 cols per warp) = As * Bs^T over the full 64-deep contraction
@@ -272,7 +444,7 @@ k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
         load_tile_async(Cs, tiles + tile_off(ch.k_begin, ch.k_begin, bw), tid, CHOL_THREADS);
         cp_async_commit(); cp_async_wait<0>();
         __syncthreads();
-        potrf64_smem(Cs, Di, info, ch.k_begin * NB);
+        potrf64(Cs, Di, info, ch.k_begin * NB);
         store_tile(tiles + tile_off(ch.k_begin, ch.k_begin, bw), Cs, tid, CHOL_THREADS);
         store_dinv(ch.k_begin);
     }
@@ -311,31 +483,11 @@ k_band_chol_cluster(CholChain chain0, CholChain chain1, int* __restrict__ info,
             }
             cluster_arrive();                                 // barrier A: L_{k+1,k} published
             if (w >= 1) {
-                // D_{k+1} -= L_{k+1,k} L_{k+1,k}^T, lower 8x8 tiles only; row blocks paired (w, 7-w) per SM sub-partition
-                const int rb = (warp < 4) ? warp : 11 - warp;
-                const double* ap = As + (8 * rb + fr) * LS_LD + fk;
-                const double* bp = As + fr * LS_LD + fk;
-                double acc[8][2];
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-#pragma unroll 2
-                for (int k4 = 0; k4 < NB / 4; ++k4) {
-                    const double av = ap[4 * k4];
-#pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
-                        if (nt <= rb) dmma(acc[nt][0], acc[nt][1], av, bp[nt * 8 * LS_LD + 4 * k4]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt)
-                    if (nt <= rb) {
-                        double* cp = Nx + (8 * rb + fr) * LS_LD + 8 * nt + 2 * fk;
-                        cp[0] -= acc[nt][0]; cp[1] -= acc[nt][1];
-                    }
-                __syncthreads();
+                syrk64_lower(As, Nx);                         // D_{k+1} -= L_{k+1,k} L_{k+1,k}^T
             }
             if (w >= 1 || factor_next) {
                 JK_STAMP(3);
-                if (factor_next) potrf64_smem(Nx, Di, info, (k + 1) * NB);
+                if (factor_next) potrf64(Nx, Di, info, (k + 1) * NB);
                 JK_STAMP(4);
                 store_tile(tiles + tile_off(k + 1, k + 1, bw), Nx, tid, CHOL_THREADS);
                 if (factor_next) store_dinv(k + 1);
