@@ -27,11 +27,12 @@ using namespace jk;
 static thread_local std::string g_err;
 
 // Run-time options (jk_set_option / jk_get_option).  The library never reads the environment.
-enum JkOpt { OPT_START_GATE, OPT_START_GATE2, OPT_POST_OVERLAP, OPT_EARLY_TOTALS, OPT_FACTOR_SPLIT, OPT_SPLIT_PCT, OPT_TWO_CHAINS,
+enum JkOpt { OPT_DEBUG_MORISON_SMEM_PAD, OPT_START_GATE, OPT_START_GATE2, OPT_POST_OVERLAP, OPT_EARLY_TOTALS, OPT_FACTOR_SPLIT, OPT_SPLIT_PCT, OPT_TWO_CHAINS,
              OPT_LEVEL_REGROUP, OPT_SUPPORT_ROOTED_RCM, OPT_TMA_SWEEP, OPT_BLOCKED_INVERSE, OPT_PROFILE_CHOL, OPT_PROFILE_SWEEP,
              OPT_DEBUG_FACTOR_DELAY, OPT_SWEEP_SLAB, OPT_CUDA_GRAPH, OPT_FUSED_LOADS, OPT_COUNT };
 struct JkOptDesc { const char* key; int def, lo, hi; };
 static const JkOptDesc g_opts[OPT_COUNT] = {
+    {"debug_morison_smem_pad", 0, 0, 160},  // experiment: extra KB of dynamic shared memory per Morison block (occupancy probe)
     {"start_gate", 1, 0, 1},            // main stream waits until the factor clusters are resident (asynchronous factorisation)
     {"start_gate2", 1, 0, 1},           // first forward sweep parts wait until the second factor segment is resident
     {"post_overlap", 1, 0, 1},          // member post of first-chain chunks beside the second chain's backward sweep
@@ -133,7 +134,7 @@ struct jk_handle_s {
     // scan buffers (capacity cap_ldP phases)
     int cap_ldP = 0;
     bool cap_details = false;
-    double *d_t = nullptr, *d_trig = nullptr, *d_Fm = nullptr, *d_X = nullptr, *d_Ffix = nullptr, *d_rows = nullptr;
+    double *d_t = nullptr, *d_trig = nullptr, *d_Fm = nullptr, *d_X = nullptr, *d_Z = nullptr, *d_Ffix = nullptr, *d_rows = nullptr;
     double *d_totpart = nullptr, *d_part_util = nullptr, *d_part_vm = nullptr, *d_part_disp = nullptr, *d_react = nullptr;
     double *d_table = nullptr, *d_details = nullptr, *d_Fload = nullptr, *d_argval = nullptr, *d_tmp = nullptr, *d_res = nullptr;
     size_t fload_elems = 0, tmp_elems = 0;
@@ -323,7 +324,9 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, cudaFuncSetAttribute(k_band_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_CLUSTER_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWB_SMEM));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     return JK_OK;
@@ -340,7 +343,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
                             for (auto& w : c.sw) { dev_free(w.d_prog); dev_free(w.d_stream); } }
     dev_free(h->d_info); dev_free(h->d_info_sticky);
     dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four); dev_free(h->d_states); dev_free(h->d_state_crit);
-    dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Ffix); dev_free(h->d_rows);
+    dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Z); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
     dev_free(h->d_table); dev_free(h->d_details); dev_free(h->d_Fload); dev_free(h->d_argval); dev_free(h->d_tmp); dev_free(h->d_res);
     dev_free(h->d_part_mem); dev_free(h->d_part_node); dev_free(h->d_argidx);
@@ -1173,6 +1176,7 @@ static int ensure_buffers(jk_handle_t h, int P, bool need_fem, bool need_details
         if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "supports not set");
         CUDA_TRY(h, dev_alloc(&h->d_X, (size_t)h->n_pad * l));
         CUDA_TRY(h, cudaMemsetAsync(h->d_X, 0, (size_t)h->n_pad * l * sizeof(double), h->stream));
+        if (h->tma_sweep) CUDA_TRY(h, dev_alloc(&h->d_Z, (size_t)h->n_pad * l));     // forward intermediate of the TMA sweeps (fragment order)
         CUDA_TRY(h, dev_alloc(&h->d_Ffix, (size_t)h->n_fixed * 6 * l));
         CUDA_TRY(h, dev_alloc(&h->d_react, (size_t)h->n_fixed * 6 * l));
         CUDA_TRY(h, dev_alloc(&h->d_rows, (size_t)h->M * JK_MEMBER_NCOL * l));
@@ -1234,7 +1238,8 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
             k_morison_fourier<false><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, Nh, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, h->d_four, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr);
         }
     } else {
-        size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng + 1) * sizeof(double);
+        size_t smem = ((size_t)MCHUNK * h->ng * (GP_STRIDE + MORISON_AIRY_SMEM_PER_POINT_EXTRA) + MCHUNK * MORISON_AIRY_SMEM_PER_MEMBER_EXTRA + 2 * h->ng + 1) * sizeof(double)
+                      + (size_t)h->opt[OPT_DEBUG_MORISON_SMEM_PAD] * 1024;
         if (details) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_morison_airy<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_morison_airy<true, 0><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);
@@ -1302,15 +1307,26 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     const bool sweep_prof = h->opt[OPT_PROFILE_SWEEP] != 0;
     long long* d_prof = nullptr;
     if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, 4 * 64 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, 4 * 64 * sizeof(long long), s)); }
+    // Right-hand sides per sweep CTA: a whole slab (32) when the slabs fill the GPU, otherwise half or a quarter of a slab per CTA
+    // (option sweep_slab = 32 / 16 / 8 forces it).  Few phases make a sweep a latency chain per CTA; narrower CTAs shorten it.
+    int ncb = 4;
+    if (h->opt[OPT_SWEEP_SLAB] > 0) ncb = h->opt[OPT_SWEEP_SLAB] / 8;
+    else if (2 * nslab <= h->n_sm) ncb = (4 * nslab <= h->n_sm + h->n_sm / 2) ? 1 : 2;
+    const int sweep_ctas = nslab * (4 / ncb);
+    h->sweep_slab_last = 8 * ncb;
     // part: 0 = whole program, 1 = items [0, n_split), 2 = the rest (continues from the rows part 1 left in the slab)
     auto sweep = [&](int c, int d, int part = 0, unsigned* started = nullptr) {
         auto& chn = h->ch[c]; auto& w = chn.sw[d];
         const int lo = part == 2 ? w.n_split : 0, hi = part == 1 ? w.n_split : w.n_items;
         if (hi <= lo) return false;
         const bool cont = part == 2;
-        k_sweep<<<nslab, SW_THREADS, SW_SMEM, s>>>(w.d_prog + (size_t)lo * SW_ITEM_U4, w.d_stream + (size_t)lo * SW_TILE, h->d_X, hi - lo, h->n_pad, chn.row0,
-                                                   cont ? w.k_split - w.npre2 : w.pre_row, cont ? w.npre2 : w.npre, w.ktop, cont ? 1 : 0, cont ? w.xphase2 : 0,
-                                                   d_prof ? d_prof + (2 * c + d) * 64 : nullptr, started);
+        const uint4* prog = w.d_prog + (size_t)lo * SW_ITEM_U4;
+        const double* strm = w.d_stream + (size_t)lo * SW_TILE;
+        const int pre_row = cont ? w.k_split - w.npre2 : w.pre_row, npre = cont ? w.npre2 : w.npre, xph = cont ? w.xphase2 : 0;
+        long long* pf = d_prof ? d_prof + (2 * c + d) * 64 : nullptr;
+        if (ncb == 4) k_sweep<4><<<sweep_ctas, sw_threads(4), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started);
+        else if (ncb == 2) k_sweep<2><<<sweep_ctas, sw_threads(2), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started);
+        else k_sweep<1><<<sweep_ctas, sw_threads(1), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started);
         return true;
     };
     // Early member post (see d_post_chunks): only when the backward sweep of the second chain leaves SMs idle (one CTA per
@@ -1353,13 +1369,13 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         tic(h, JK_T_SOLVE_BWD);
         sweep(0, 1); LAUNCH_CHECK(h);
         if (h->n_chains == 2) {
-            const bool overlap = post_overlap_on && h->wait_value32 && h->stream3 && h->d_started && h->n_post_early >= 8 && nslab + 2 <= h->n_sm;
+            const bool overlap = post_overlap_on && h->wait_value32 && h->stream3 && h->d_started && h->n_post_early >= 8 && sweep_ctas + 2 <= h->n_sm;
             if (overlap) CUDA_TRY(h, cudaEventRecord(h->ev_bwd0, s));
             k_sep_exchange<<<gsep, 128, 0, s>>>(h->d_X, h->n_pad, ldP, c0.row0 + c0.kS * NB, c1.row0 + c1.kS * NB, h->nS_nodes, 1);
             LAUNCH_CHECK(h);
             const bool launched = sweep(1, 1, 0, overlap ? h->d_started : nullptr); LAUNCH_CHECK(h);
             if (overlap && launched) {
-                h->started_target += (unsigned)nslab;
+                h->started_target += (unsigned)sweep_ctas;
                 cudaStream_t s3 = h->stream3;
                 CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_bwd0, 0));
                 if (h->wait_value32((CUstream)s3, (CUdeviceptr)h->d_started, (cuuint32_t)h->started_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)

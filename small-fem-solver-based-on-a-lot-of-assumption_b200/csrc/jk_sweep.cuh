@@ -30,29 +30,23 @@
 
 namespace jk {
 
-// experiment switches (variants are built as separate libraries and selected with JK_LIB; see tools/ab_bench.sh).
-// Measured and dropped (tools/ab_bench.sh, c4 workload): descriptors read from global by the consumers (-1 %), a
-// test_wait probe of the next tile before the products (-3 %), a find-first-set walk of sparse masks (-2 %), 8 warps
-// with 4 x 1 row blocks (-4 %).  Kept: 16 consumer warps (+3 % over 8), row-block pairs per warp and 4 stages (+1 %).
-#ifndef JK_SW_WARPS
-#define JK_SW_WARPS 16     // consumer warps: 8 (four 8x8 result blocks each) or 16 (two each; four warps per scheduler)
-#endif
-#ifndef JK_SW_W16_ROWPAIR
-#define JK_SW_W16_ROWPAIR 1   // 16 warps: 1 = each warp owns the row-block pair (s, 7 - s) x one column block; 0 = one row block x two column blocks
-#endif
-#ifndef JK_SW_RBN
-#define JK_SW_RBN 2        // 8-row blocks per consumer warp: 2 (x two 8-column blocks) or 4 (x one).  4 x 1 balances the schedulers
-                           // exactly but needs predicated row blocks in the forward sweeps; measured 4 % slower overall
-#endif
+// Measured and dropped (tools/ab_bench.sh, c4 workload): descriptors read from global by the consumers (-1 %), a test_wait
+// probe of the next tile before the products (-3 %), a find-first-set walk of sparse masks (-2 %), 8 warps with 4 x 1 row
+// blocks (-4 %), one row block x two column blocks per warp.  Kept: four consumer warps per 8-column block (16 for a whole
+// slab), each owning the row-block pair (s, 7 - s) so that triangular masks balance, and 4 stages.
+//
+// A CTA owns NCB of the four 8-column blocks of a slab (template parameter): 4 = the whole slab (16 consumer warps), 2 or 1
+// when there are fewer slabs than SMs (few phases: the sweeps are then a latency chain per CTA and more, narrower CTAs fill
+// the GPU).  CTAs that share a slab never touch each other's data: right-hand sides / solutions are row-major in X (own
+// columns), the forward sweep's intermediate Z lives in a SEPARATE array in fragment order (own column-block groups).
 #ifndef JK_SW_STAGES
 #define JK_SW_STAGES 4
 #endif
 constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1
 constexpr int SW_MAX_BW = SW_RING - 1;
-constexpr int SW_CONSUMER_WARPS = JK_SW_WARPS;
-constexpr int SW_CONSUMERS = 32 * SW_CONSUMER_WARPS;
-constexpr int SW_THREADS = SW_CONSUMERS + 32;
+constexpr int SW_MAX_CONSUMER_WARPS = 16;
+__host__ __device__ constexpr int sw_threads(int ncb) { return 128 * ncb + 32; }   // 4 consumer warps per column block + the producer warp
 constexpr int SW_TILE = NB * NB;            // doubles per A tile
 constexpr int SW_XTILE = NB * SLAB;         // doubles per X tile
 
@@ -112,7 +106,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;\n" :: "n"(SW_CONSUMERS) : "memory"); }
+template <int CONSUMERS>
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;\n" :: "n"(CONSUMERS) : "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // K3d: build the tile stream of one sweep program.  One CTA per item:
@@ -202,7 +197,7 @@ __global__ void __launch_bounds__(256) k_sweep_build(SweepBuildArgs a, SweepBuil
 
 // Inner products of one item for one consumer warp: acc[a][b] += A(row block a) * X(column block b) over the k-groups.
 // ap[a] / bp point at this lane's element of the first fragment; all further offsets are compile-time constants.
-constexpr int SW_RBN = (JK_SW_WARPS == 16 && JK_SW_RBN > 2) ? 1 : ((JK_SW_WARPS == 16 && JK_SW_RBN == 2 && !JK_SW_W16_ROWPAIR) ? 1 : JK_SW_RBN), SW_CBN = (32 / JK_SW_WARPS) / SW_RBN;
+constexpr int SW_RBN = 2, SW_CBN = 1;     // per consumer warp: the row-block pair (s, 7 - s) x one 8-column block
 
 // every row block of the warp is either dense or empty (act[a], warp-uniform): register-double-buffered, fully unrolled
 template <bool ALL>
@@ -306,16 +301,19 @@ __device__ __forceinline__ void sweep_mma_single(double (&acc)[SW_RBN][SW_CBN][2
 // ----------------------------------------------------------------------------------------------
 // K4 (narrow bands): one sweep of one chain over one slab per CTA
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SW_THREADS, 1)
+template <int NCB /* 8-column blocks of the slab owned by this CTA: 4, 2 or 1 */>
+__global__ void __launch_bounds__(sw_threads(NCB), 1)
 k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, double* __restrict__ X,
+        double* __restrict__ Z /* same shape as X: the forward sweep's intermediate, fragment order */,
         int n_items, int n_pad /* rows of the whole slab */, int row0 /* first row of this chain in the slab */,
         int pre_row /* first known tile row */, int npre /* known tile rows to preload into the ring */, int ktop,
         int pre_mode /* 0: backward, rows hold X row-major (second chain's separator solution), ring slot (ktop - row) % R;
                         1: forward continuation, rows hold Z in fragment order, ring slot row % R */,
         int xphase_bits /* bit s: ring slot s starts one mbarrier phase ahead (continuation of a program whose slot parities
                            count from its first row) */,
-        long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (JK_SWEEP_PROFILE) */,
+        long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (option profile_sweep) */,
         unsigned* __restrict__ started = nullptr /* nullable: every CTA adds 1 as soon as it is resident (gate of the early member post) */) {
+    constexpr int SW_CONSUMER_WARPS = 4 * NCB, SW_CONSUMERS = 32 * SW_CONSUMER_WARPS, CTAS_PER_SLAB = 4 / NCB;
     extern __shared__ __align__(128) unsigned char sw_smem[];
     if (started != nullptr && threadIdx.x == 0) { atomicAdd(started, 1u); __threadfence(); }
     double* As = reinterpret_cast<double*>(sw_smem);                 // [SW_STAGES][SW_TILE]   A tiles, fragment order
@@ -326,7 +324,9 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + SW_STAGES), bar_x = smem_u32(bars + 2 * SW_STAGES),
                    bar_bfull = smem_u32(bars + 2 * SW_STAGES + SW_RING), bar_bempty = smem_u32(bars + 2 * SW_STAGES + SW_RING + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* Xslab = X + ((size_t)blockIdx.x * (size_t)n_pad + (size_t)row0) * SLAB;
+    const int slab = blockIdx.x / CTAS_PER_SLAB, cbase = (blockIdx.x % CTAS_PER_SLAB) * NCB;
+    double* Xslab = X + ((size_t)slab * (size_t)n_pad + (size_t)row0) * SLAB;
+    double* Zslab = Z + ((size_t)slab * (size_t)n_pad + (size_t)row0) * SLAB;
 
     if (tid == 0) {
         for (int s = 0; s < SW_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, SW_CONSUMER_WARPS); }
@@ -360,7 +360,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
                 if (flags & SW_DIAG) {
                     mbar_wait(bar_bempty, ((unsigned)ndiag & 1u) ^ 1u);
                     mbar_arrive_expect_tx(bar_bfull, SW_XTILE * (unsigned)sizeof(double));
-                    bulk_g2s(smem_u32(Bs), Xslab + (size_t)row * SW_XTILE, SW_XTILE * (unsigned)sizeof(double), bar_bfull);
+                    bulk_g2s(smem_u32(Bs), Zslab + (size_t)row * SW_XTILE, SW_XTILE * (unsigned)sizeof(double), bar_bfull);
                     ++ndiag;
                 }
             }
@@ -373,22 +373,19 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     // scheduler (w, w + 4) cover all eight row blocks of one column block, so every scheduler has the same DMMA count
     // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
-    int rbs[SW_RBN], cb0;
-    if (SW_CONSUMER_WARPS == 16 && SW_RBN == 2) { cb0 = warp >> 2; rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
-    else if (SW_CONSUMER_WARPS == 16) { cb0 = 2 * (warp >> 3); rbs[0] = ((warp >> 2) & 1) ? 7 - (warp & 3) : (warp & 3); }   // scheduler s: row blocks s, 7 - s
-    else if (SW_RBN == 4) { cb0 = warp & 3; for (int a = 0; a < SW_RBN; ++a) rbs[a] = 2 * a + (warp >> 2); }
-    else { cb0 = 2 * (warp >> 2); rbs[0] = warp & 3; rbs[SW_RBN - 1] = 7 - (warp & 3); }
+    const int cb0 = cbase + (warp >> 2);
+    const int rbs[SW_RBN] = {warp & 3, 7 - (warp & 3)};
     // a program that continues another launch: bring the slots' mbarrier phases in step with the item parities
     if (xphase_bits) {
         if (lane == 0)
             for (int sl = 0; sl < SW_RING; ++sl) if ((xphase_bits >> sl) & 1) mbar_arrive(bar_x + 8 * sl);
-        consumer_bar_sync();
+        consumer_bar_sync<SW_CONSUMERS>();
     }
     // rows solved before this launch that its first rows need: the second chain's separator solution (backward,
     // row-major) or the rows just before a forward continuation (Z, already in fragment order) -> ring
     for (int q = 0; q < npre; ++q) {
         const int i = pre_row + q, slot = (pre_mode ? i : ktop - i) % SW_RING;
-        const double* g = Xslab + (size_t)i * SW_XTILE;
+        const double* g = (pre_mode ? Zslab : Xslab) + (size_t)i * SW_XTILE;
         double* dst = Xr + slot * SW_XTILE;
         if (pre_mode) { for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[e] = g[e]; }
         else { for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[sw_x_index(e / SLAB, e % SLAB)] = g[e]; }
@@ -413,7 +410,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         const uint4 f0 = prog[0];
         if (n_items > 0 && ((int)f0.z & SW_INIT_RHS)) load_rhs((int)f0.x);
     }
-    consumer_bar_sync();    // nobody stores a row before every consumer holds its first right-hand side
+    consumer_bar_sync<SW_CONSUMERS>();    // nobody stores a row before every consumer holds its first right-hand side
     int ndiag = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
@@ -483,7 +480,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         }
         if (flags & SW_DIAG) ++ndiag;
         if (flags & SW_ROW_END) {
-            double* g = Xslab + (size_t)row * SW_XTILE;
+            double* g = ((flags & SW_OUT_FRAG) ? Zslab : Xslab) + (size_t)row * SW_XTILE;
             const int oslot = (xinfo >> 16) & 0xff;
             double* xr = Xr + oslot * SW_XTILE;
 #pragma unroll
@@ -499,7 +496,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             if (profiling) { t0 = clock64(); pc[3] += t0 - t1; }
         }
     }
-    if (profiling && lane == 0 && warp < 8) {
+    if (profiling && lane == 0 && warp < min(8, SW_CONSUMER_WARPS)) {
         pc[6] = clock64() - t_begin;
         for (int i = 0; i < 8; ++i) prof[warp * 8 + i] = pc[i];
     }
