@@ -628,18 +628,15 @@ def run_ours(args):
 
     def step_resident():
         """inputs already in HBM: assemble + factor + scan + cross-rank reduction"""
-        eng.assemble(E, G)
-        eng.factor(overlap=True)      # side stream: runs concurrently with the Morison + load stage of the scan
+        # jk_step_dev: assemble + factorisation (side streams, concurrent with the Morison + load stage) + scan, one graph launch
         return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=(world > 1), t_dev=t_dev.data_ptr(),
-                                  host_results=False)    # critical pair and gathered table stay in HBM
+                                  host_results=False, moduli=(E, G))    # critical pair and gathered table stay in HBM
 
     def step_e2e():
         """host buffers in, host results out, through the public API: every rank gets the merged critical phase and its own
         shard of the table, rank 0 the whole table"""
         eng.set_static_load(F_static)
-        eng.assemble(E, G)
-        eng.factor(overlap=True)
-        return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=True, t_host=t_host)
+        return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=True, t_host=t_host, moduli=(E, G))
 
     sampler = ClockSampler(run.local_rank)
     if rank == 0:
@@ -665,6 +662,7 @@ def run_ours(args):
                "ms_per_step": ms_e2e, "critical_index": int(out_e["critical_index"]),
                "returns": "every rank: merged critical (value, index) + its own table shard on the host; rank 0: the full table"}
 
+    sst = eng.solver_stats()          # before the stage-timer steps switch the graph off
     stage = stage_timers(eng, step_resident)
     residual = eng.residual()
 
@@ -696,7 +694,6 @@ def run_ours(args):
                             "trace": traceback.format_exc()[-600:]}
 
     if rank == 0:
-        sst = eng.solver_stats()
         kernels, peak_src = kernel_table(stage, st, dims, sst, P, p)
         step_ms = ms_total / args.steps
         roofline = pick_roofline(kernels, stage, step_ms, args.workload, peak_src)
@@ -707,6 +704,7 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic", "config": cfg,
                 "solver_layout": {"solver": args.solver, "ordering": args.ordering, "tile": dims["tile"], "band_tiles": dims["band_tiles"],
                                   "n_tiles": dims["n_tiles"], "dof_half_bandwidth": dims["dof_half_bandwidth"], "factor_chains": dims["n_chains"],
+                                  "step_graph": sst["step_graph"], "graph_kernels": sst["graph_kernels"],
                                   "options": {eng.lib.jk_option_name(i).decode(): eng.get_option(eng.lib.jk_option_name(i).decode())
                                               for i in range(eng.lib.jk_option_count())}},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,

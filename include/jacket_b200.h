@@ -193,6 +193,15 @@ int jk_phase_scan(jk_handle_t h, int P, const double* t, double fy, double* tabl
 int jk_phase_scan_dev(jk_handle_t h, int P, const double* t_dev, double fy);
 int jk_read_table(jk_handle_t h, int P, double* table, int64_t* critical);
 
+/* One whole analysis step for a resident loop (design iterations, ensembles of structures): jk_assemble(E, G) +
+ * jk_factor_begin + the phase scan, as one call.  With option cuda_graph = 1 (default) the step's ~30 launches on three
+ * streams are captured once into a CUDA graph and replayed while nothing baked into it has changed (supports, wave, Morison
+ * set-up, moduli, fy, P, options, buffer sizes); results are bit-identical to the separate calls.
+ * jk_step_dev: t_dev[P] already in HBM, nothing is read back, no host synchronisation (results: jk_read_table, jk_table_dev,
+ * jk_critical_*_dev).  jk_step: host times in, host table + critical index out (NULL, NULL: queue only). */
+int jk_step_dev(jk_handle_t h, double E, double G, int P, const double* t_dev, double fy);
+int jk_step(jk_handle_t h, double E, double G, int P, const double* t, double fy, double* table, int64_t* critical);
+
 /* Sea-state ensemble (BASELINE configs[4]): n_states Airy sea states (amplitude a = H/2, wave number k from the
  * dispersion relation GUI.py:197-206, omega = 2 pi / T, math heading theta_wave) x n_phase phases each, evaluated as
  * ONE batch of n_states*n_phase load cases on the factor already computed.  Depth, current, dt come from
@@ -233,8 +242,10 @@ int jk_residual(jk_handle_t h, double* rel_residual);
  * or all tile products of the band on the legacy path), out[2] = sweep items per slab (0 on the legacy path),
  * out[3] = 1 if the TMA / mbarrier sweep pipeline is active, 0 for the cp.async slab sweep,
  * out[4] = non-zeros of L for the candidate ordering with the smallest envelope (symbolic count; the ordering in use
- * trades a larger envelope for fewer mask blocks), out[5] = right-hand sides per sweep CTA of the last solve. */
-int jk_solver_stats(jk_handle_t h, double* out /* [6] */);
+ * trades a larger envelope for fewer mask blocks), out[5] = right-hand sides per sweep CTA of the last solve,
+ * out[6] = state of the step graph (1: a captured CUDA graph is being replayed by jk_step*, 0: none, -1: capture failed on
+ * this driver and the steps are launched eagerly), out[7] = kernels inside that graph. */
+int jk_solver_stats(jk_handle_t h, double* out /* [8] */);
 /* Host-only introspection of the sweep item list (no device needed; used by the CPU tests): the program the TMA
  * sweep runs for a chain of n_tiles tile rows, tile half-bandwidth band_tiles, first partial / known tile row kx
  * (= n_tiles for a plain sweep), first_tile[n_tiles] (nullable) = first tile column of every tile row's envelope (tiles

@@ -75,6 +75,8 @@ def _sig(lib):
     lib.jk_morison_single.argtypes = [H, C.c_double, _dp, _dp, _dp]
     lib.jk_phase_scan.argtypes = [H, C.c_int, _dp, C.c_double, _dp, C.POINTER(C.c_int64)]
     lib.jk_phase_scan_dev.argtypes = [H, C.c_int, C.c_void_p, C.c_double]
+    lib.jk_step_dev.argtypes = [H, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_double]
+    lib.jk_step.argtypes = [H, C.c_double, C.c_double, C.c_int, _dp, C.c_double, _dp, C.POINTER(C.c_int64)]
     lib.jk_read_table.argtypes = [H, C.c_int, _dp, C.POINTER(C.c_int64)]
     lib.jk_solve.argtypes = [H, C.c_int, _dp, C.c_double]
     lib.jk_ensemble_scan.argtypes = [H, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.POINTER(C.c_int64)]
@@ -100,7 +102,7 @@ def _sig(lib):
                  "jk_set_wave_airy", "jk_set_wave_fourier", "jk_set_morison", "jk_morison_scan", "jk_morison_single",
                  "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_ensemble_scan", "jk_fetch_phase",
                  "jk_fetch_member_column", "jk_get_dims", "jk_get_order", "jk_get_K", "jk_get_elements",
-                 "jk_get_timings", "jk_residual", "jk_solver_stats", "jk_set_option", "jk_get_option", "jk_kinematics_points"):
+                 "jk_get_timings", "jk_residual", "jk_solver_stats", "jk_set_option", "jk_get_option", "jk_kinematics_points", "jk_step", "jk_step_dev"):
         getattr(lib, name).restype = C.c_int
 
 

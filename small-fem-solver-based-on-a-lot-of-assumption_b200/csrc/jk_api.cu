@@ -76,6 +76,7 @@ struct jk_handle_s {
     bool split_factor = false;
     cudaEvent_t ev_fork = nullptr, ev_factor = nullptr, ev_factor_bwd = nullptr;   // ev_factor: forward sweeps may start; ev_factor_bwd: backward tile streams built too
     bool factor_inflight = false;
+    bool ev_bwd_external = false;   // ev_factor_bwd was recorded outside a graph capture and has not been joined by the main stream yet
     std::string err;
     int64_t launches = 0;
 
@@ -143,6 +144,12 @@ struct jk_handle_s {
     int lastP = 0, last_ldP = 0;
     int sweep_slab_last = SLAB;   // right-hand sides per sweep CTA of the last solve
     bool last_morison = false, last_fem = false, last_fdir = false;
+    // captured CUDA graph of one resident step (jk_step_dev / jk_step): valid while nothing it bakes in has changed
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_epoch = 0, graph_epoch_built = -1, graph_launches = 0;      // epoch: bumped by every call that changes kernel arguments or buffers
+    int graph_P = 0; double graph_E = 0, graph_G = 0, graph_fy = 0;
+    unsigned graph_started_target = 0; bool graph_gate2_armed = false;
+    bool capturing = false, graph_unsupported = false;
     double last_fy = 355.0;
 
     cudaEvent_t ev0[JK_NTIMERS], ev1[JK_NTIMERS];
@@ -189,8 +196,9 @@ static unsigned char* pin_acquire(jk_handle_t h, size_t n) {
     }
     return h->h_pin;
 }
-static void tic(jk_handle_t h, int id, cudaStream_t s = nullptr) { cudaEventRecord(h->ev0[id], s ? s : h->stream); }
-static void toc(jk_handle_t h, int id, cudaStream_t s = nullptr) { cudaEventRecord(h->ev1[id], s ? s : h->stream); h->ev_set[id] = true; }
+// stage timers: CUDA events on the launching stream; not recorded into a captured graph (a replay cannot be timed by them)
+static void tic(jk_handle_t h, int id, cudaStream_t s = nullptr) { if (!h->capturing) cudaEventRecord(h->ev0[id], s ? s : h->stream); }
+static void toc(jk_handle_t h, int id, cudaStream_t s = nullptr) { if (!h->capturing) { cudaEventRecord(h->ev1[id], s ? s : h->stream); h->ev_set[id] = true; } }
 
 extern "C" int jk_version(void) { return 100; }
 
@@ -213,6 +221,7 @@ extern "C" int jk_set_option(jk_handle_t h, const char* key, int value) {
     if (value < g_opts[i].lo || value > g_opts[i].hi) JK_FAIL(h, JK_EINVAL, "jk_set_option: %s must be in %d..%d (got %d)", key, g_opts[i].lo, g_opts[i].hi, value);
     if (i == OPT_SWEEP_SLAB && value != 0 && value != 8 && value != 16 && value != 32) JK_FAIL(h, JK_EINVAL, "jk_set_option: sweep_slab must be 0 (auto), 8, 16 or 32");
     h->opt[i] = value;
+    h->graph_epoch++;
     return JK_OK;
 }
 extern "C" int jk_get_option(jk_handle_t h, const char* key, int* value) {
@@ -367,6 +376,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     dev_free(h->d_post_chunks);
     if (h->ev_post_fork) cudaEventDestroy(h->ev_post_fork);
     if (h->ev_post_join) cudaEventDestroy(h->ev_post_join);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JK_OK;
@@ -861,19 +871,26 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->graph_epoch++;
     h->have_supports = true; h->assembled = false; h->factored = false;
     // buffers sized by n_pad / n_fixed must be rebuilt; resident results no longer match the new row numbering
     h->cap_ldP = 0; h->lastP = 0; h->last_fem = false;
     return JK_OK;
 }
 
-extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
-    if (!h) return JK_EINVAL;
-    if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "jk_assemble: call jk_set_supports first");
-    if (!(E > 0) || !(G > 0)) JK_FAIL(h, JK_EINVAL, "jk_assemble: E and G must be positive");
-    cudaSetDevice(h->device);
+// the main stream joins a factorisation still running on the side streams (no host synchronisation).  After a scan the
+// side streams have already been joined (run_fem waits for the backward tile streams), inside a captured step as well.
+static int join_factor(jk_handle_t h, cudaStream_t s) {
+    if (h->factor_inflight && h->ev_bwd_external && !h->capturing) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0));
+    h->ev_bwd_external = false;
+    return JK_OK;
+}
+
+static int assemble_launch(jk_handle_t h, double E, double G) {
     cudaStream_t s = h->stream;
-    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0)); h->factor_inflight = false; }
+    int rcj = join_factor(h, s);
+    if (rcj != JK_OK) return rcj;
+    h->factor_inflight = false;
     h->E = E; h->G = G;
     tic(h, JK_T_ASSEMBLE);
     k_member_setup<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, h->d_xyz, h->d_conn, h->d_sec, h->d_secp, JK_SEC_NPROP, E, G, h->d_mc, h->d_Ke, h->d_Kl);
@@ -889,6 +906,14 @@ extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
     h->assembled = true; h->factored = false;
     h->lastP = 0; h->last_fem = false;        // resident rows belong to the previous stiffness
     return JK_OK;
+}
+
+extern "C" int jk_assemble(jk_handle_t h, double E, double G) {
+    if (!h) return JK_EINVAL;
+    if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "jk_assemble: call jk_set_supports first");
+    if (!(E > 0) || !(G > 0)) JK_FAIL(h, JK_EINVAL, "jk_assemble: E and G must be positive");
+    cudaSetDevice(h->device);
+    return assemble_launch(h, E, G);
 }
 
 // end of a factorisation: latch a non-positive pivot into the sticky flag (reported by the next call that talks to the host;
@@ -1062,6 +1087,7 @@ extern "C" int jk_factor(jk_handle_t h) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fwd1, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->ev_factor, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->ev_factor_bwd, h->stream));
+    h->ev_bwd_external = true;
     h->assembled = false;       // the tile storage now holds L
     h->factored = true;
     h->factor_inflight = true;
@@ -1072,10 +1098,10 @@ extern "C" int jk_factor(jk_handle_t h) {
 // Asynchronous variant: the factorisation is queued on the handle's side stream (after everything already queued on
 // the main stream) and the call returns at once.  The next scan runs its Morison + load stage concurrently and joins
 // before the triangular sweeps; a non-positive pivot is reported by that scan's jk_read_table / jk_phase_scan.
-extern "C" int jk_factor_begin(jk_handle_t h) {
-    if (!h) return JK_EINVAL;
-    if (!h->assembled) JK_FAIL(h, JK_ESTATE, "jk_factor_begin: call jk_assemble first");
-    cudaSetDevice(h->device);
+static int factor_begin_launch(jk_handle_t h) {
+    // the gate counter restarts with every asynchronous factorisation: targets are then the same constants in every step,
+    // which is what a captured graph replays
+    if (h->d_started) { CUDA_TRY(h, cudaMemsetAsync(h->d_started, 0, sizeof(unsigned), h->stream)); h->started_target = 0; }
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     const unsigned target0 = h->started_target;
@@ -1094,7 +1120,15 @@ extern "C" int jk_factor_begin(jk_handle_t h) {
     h->assembled = false;
     h->factored = true;
     h->factor_inflight = true;
+    h->ev_bwd_external = !h->capturing;
     return JK_OK;
+}
+
+extern "C" int jk_factor_begin(jk_handle_t h) {
+    if (!h) return JK_EINVAL;
+    if (!h->assembled) JK_FAIL(h, JK_ESTATE, "jk_factor_begin: call jk_assemble first");
+    cudaSetDevice(h->device);
+    return factor_begin_launch(h);
 }
 
 extern "C" int jk_set_static_load(jk_handle_t h, const double* F) {
@@ -1118,7 +1152,7 @@ extern "C" int jk_set_wave_airy(jk_handle_t h, double a, double k, double omega,
     if (!(k > 0) || !(omega > 0) || !(d > 0) || !(dt > 0)) JK_FAIL(h, JK_EINVAL, "jk_set_wave_airy: k, omega, d, dt must be positive");
     h->wv.a = a; h->wv.k = k; h->wv.omega = omega; h->wv.d = d; h->wv.Uc = U_c; h->wv.dt = dt; h->wv.inv_dt = 1.0 / dt;
     h->wave_kind = 0; h->n_harm = 0;
-    h->have_wave = true; h->gp_valid = false;
+    h->have_wave = true; h->gp_valid = false; h->graph_epoch++;
     return JK_OK;
 }
 
@@ -1135,7 +1169,7 @@ extern "C" int jk_set_wave_fourier(jk_handle_t h, double k, double omega, double
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->wv.a = E[0]; h->wv.k = k; h->wv.omega = omega; h->wv.d = d; h->wv.Uc = U_c; h->wv.dt = dt; h->wv.inv_dt = 1.0 / dt;
     h->wave_kind = 1; h->n_harm = n_harm;
-    h->have_wave = true; h->gp_valid = false;
+    h->have_wave = true; h->gp_valid = false; h->graph_epoch++;
     return JK_OK;
 }
 
@@ -1152,7 +1186,7 @@ extern "C" int jk_set_morison(jk_handle_t h, double theta_wave, double theta_cur
     CUDA_TRY(h, dev_alloc(&h->d_gsw, gsw.size()));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_gsw, gsw.data(), gsw.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->have_morison = true; h->gp_valid = false;
+    h->have_morison = true; h->gp_valid = false; h->graph_epoch++;
     return JK_OK;
 }
 
@@ -1163,6 +1197,7 @@ static int ensure_buffers(jk_handle_t h, int P, bool need_fem, bool need_details
     int ldP = ceil_div(P, SLAB) * SLAB;
     bool need = ldP > h->cap_ldP || (need_details && !h->cap_details) || (need_fem && !h->d_X);
     if (!need) return JK_OK;
+    h->graph_epoch++;                       // buffers move
     ldP = std::max(ldP, h->cap_ldP);
     size_t l = (size_t)ldP;
     int n_mchunk = ceil_div(h->M, MCHUNK), n_nchunk = ceil_div(h->Nn, NCHUNK);
@@ -1204,6 +1239,25 @@ static WaveAiry launch_wave(jk_handle_t h) {
     return w;
 }
 
+// Gauss-point tables of the current wave (once per wave / Morison set-up; allocation inside, so never during a capture)
+static int ensure_gauss_tables(jk_handle_t h) {
+    if (h->gp_valid) return JK_OK;
+    cudaStream_t s = h->stream;
+    WaveAiry w = launch_wave(h);
+    const int Nh = h->n_harm;
+    const size_t gstride = h->wave_kind == 1 ? (size_t)(3 + 2 * Nh) : (size_t)GP_STRIDE;
+    int n = h->M * h->ng;
+    size_t need = (size_t)n * gstride;
+    if (need > h->gp_elems) { CUDA_TRY(h, dev_alloc(&h->d_gp, need)); h->gp_elems = need; h->graph_epoch++; }
+    if (h->wave_kind == 1)
+        k_gauss_setup_fourier<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, Nh, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_four, h->d_gp);
+    else
+        k_gauss_setup_airy<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_gp);
+    LAUNCH_CHECK(h);
+    h->gp_valid = true;
+    return JK_OK;
+}
+
 // Morison stage for the phases already in d_t: trig tables, Gauss-point tables (once per wave), K1
 static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
     cudaStream_t s = h->stream;
@@ -1211,17 +1265,7 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
     tic(h, JK_T_WAVE_SETUP);
     const int Nh = h->n_harm;
     const size_t gstride = h->wave_kind == 1 ? (size_t)(3 + 2 * Nh) : (size_t)GP_STRIDE;
-    if (!h->gp_valid) {
-        int n = h->M * h->ng;
-        size_t need = (size_t)n * gstride;
-        if (need > h->gp_elems) { CUDA_TRY(h, dev_alloc(&h->d_gp, need)); h->gp_elems = need; }
-        if (h->wave_kind == 1)
-            k_gauss_setup_fourier<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, Nh, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_four, h->d_gp);
-        else
-            k_gauss_setup_airy<<<ceil_div(n, 128), 128, 0, s>>>(h->M, h->ng, h->d_xyz, h->d_conn, h->d_gsw, w, h->d_gp);
-        LAUNCH_CHECK(h);
-        h->gp_valid = true;
-    }
+    { int rcg = ensure_gauss_tables(h); if (rcg != JK_OK) return rcg; }
     k_phase_setup<<<ceil_div(ldP, 128), 128, 0, s>>>(P, ldP, h->d_t, w.omega, w.dt, h->d_trig);
     LAUNCH_CHECK(h);
     toc(h, JK_T_WAVE_SETUP);
@@ -1365,7 +1409,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         }
         sweep(0, 0, split ? 2 : 0); LAUNCH_CHECK(h);
         if (split) toc(h, JK_T_SOLVE_FWD2); else { toc(h, JK_T_SOLVE_FWD); h->ev_set[JK_T_SOLVE_FWD2] = false; }
-        if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0));
+        if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0)); h->ev_bwd_external = false; }
         tic(h, JK_T_SOLVE_BWD);
         sweep(0, 1); LAUNCH_CHECK(h);
         if (h->n_chains == 2) {
@@ -1497,7 +1541,7 @@ extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* criti
     const size_t tb = table ? (size_t)P * JK_TABLE_NCOL * sizeof(double) : 0;
     if (unsigned char* pin = pin_acquire(h, tb + 16)) {
         // table, critical index and the factorisation's pivot flag in one pinned buffer, one synchronisation
-        if (h->factor_inflight) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0));   // d_info is final behind this event
+        { int rcj = join_factor(h, s); if (rcj != JK_OK) return rcj; }   // the pivot flag is final behind the factorisation
         tic(h, JK_T_D2H);
         if (table) CUDA_TRY(h, cudaMemcpyAsync(pin, h->d_table, tb, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(h, cudaMemcpyAsync(pin + tb, h->d_argidx, sizeof(long long), cudaMemcpyDeviceToHost, s));
@@ -1528,13 +1572,8 @@ extern "C" int jk_read_table(jk_handle_t h, int P, double* table, int64_t* criti
     return finish_factor(h);
 }
 
-static int scan_host(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical, bool fem) {
-    if (!h) return JK_EINVAL;
-    int rc = check_scan_ready(h, P, t, fem);
-    if (rc != JK_OK) return rc;
-    cudaSetDevice(h->device);
-    if ((rc = ensure_buffers(h, P, fem, false)) != JK_OK) return rc;
-    tic(h, JK_T_SCAN_TOTAL);
+// phase times host -> d_t through the pinned staging buffer (asynchronous; the caller's array is free on return)
+static int upload_times(jk_handle_t h, int P, const double* t) {
     tic(h, JK_T_H2D);
     if (h->pin_t_busy) { cudaEventSynchronize(h->ev_pin_t); h->pin_t_busy = false; }
     if ((size_t)P > h->pin_t_elems) {
@@ -1550,6 +1589,17 @@ static int scan_host(jk_handle_t h, int P, const double* t, double fy, double* t
         CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     toc(h, JK_T_H2D);
+    return JK_OK;
+}
+
+static int scan_host(jk_handle_t h, int P, const double* t, double fy, double* table, int64_t* critical, bool fem) {
+    if (!h) return JK_EINVAL;
+    int rc = check_scan_ready(h, P, t, fem);
+    if (rc != JK_OK) return rc;
+    cudaSetDevice(h->device);
+    if ((rc = ensure_buffers(h, P, fem, false)) != JK_OK) return rc;
+    tic(h, JK_T_SCAN_TOTAL);
+    if ((rc = upload_times(h, P, t)) != JK_OK) return rc;
     if ((rc = scan_core(h, P, fy, fem)) != JK_OK) return rc;
     toc(h, JK_T_SCAN_TOTAL);
     if (!table && !critical) return JK_OK;      // asynchronous form: the results stay in HBM (jk_read_table / jk_table_dev)
@@ -1577,6 +1627,96 @@ extern "C" int jk_phase_scan_dev(jk_handle_t h, int P, const double* t_dev, doub
     if ((rc = scan_core(h, P, fy, true)) != JK_OK) return rc;
     toc(h, JK_T_SCAN_TOTAL);
     return JK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One whole analysis step of a resident loop: assemble + asynchronous factorisation + phase scan.  The ~30 launches on three
+// streams (with their event joins and start gates) are captured once into a CUDA graph and replayed while nothing the graph
+// bakes in has changed (geometry, supports, wave, Morison set-up, moduli, fy, phase count, options, buffers).
+// ------------------------------------------------------------------------------------------------
+static int step_launch(jk_handle_t h, int P, double fy, double E, double G) {
+    int rc;
+    if ((rc = assemble_launch(h, E, G)) != JK_OK) return rc;
+    if ((rc = factor_begin_launch(h)) != JK_OK) return rc;
+    return scan_core(h, P, fy, true);
+}
+
+static int step_core(jk_handle_t h, int P, double fy, double E, double G) {
+    int rc;
+    if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
+    if ((rc = ensure_gauss_tables(h)) != JK_OK) return rc;
+    if ((rc = join_factor(h, h->stream)) != JK_OK) return rc;                 // a factorisation queued by an earlier eager call
+    const bool want_graph = h->opt[OPT_CUDA_GRAPH] && !h->graph_unsupported && h->tma_sweep && h->wait_value32 != nullptr &&
+                            !h->opt[OPT_PROFILE_CHOL] && !h->opt[OPT_PROFILE_SWEEP] && h->wave_kind == 0;
+    if (!want_graph) return step_launch(h, P, fy, E, G);
+    const bool hit = h->graph_exec != nullptr && h->graph_epoch_built == h->graph_epoch && h->graph_P == P && h->graph_E == E &&
+                     h->graph_G == G && h->graph_fy == fy;
+    if (!hit) {
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        const long long launches0 = h->launches;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); h->graph_unsupported = true; return step_launch(h, P, fy, E, G); }
+        h->capturing = true;
+        rc = step_launch(h, P, fy, E, G);
+        h->capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != JK_OK || ce != cudaSuccess || graph == nullptr) {
+            // something in the step cannot be captured on this driver (e.g. the stream memory operations of the start gates):
+            // run the step the ordinary way from now on
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->graph_unsupported = true;
+            h->launches = launches0;
+            h->factor_inflight = false;
+            return step_launch(h, P, fy, E, G);
+        }
+        ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { cudaGetLastError(); h->graph_exec = nullptr; h->graph_unsupported = true; h->launches = launches0; h->factor_inflight = false; return step_launch(h, P, fy, E, G); }
+        h->graph_epoch_built = h->graph_epoch; h->graph_P = P; h->graph_E = E; h->graph_G = G; h->graph_fy = fy;
+        h->graph_launches = h->launches - launches0;
+        h->graph_started_target = h->started_target;
+        h->launches = launches0;
+    }
+    CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    // host-side state exactly as the eager step leaves it
+    h->launches += h->graph_launches;
+    h->E = E; h->G = G;
+    h->assembled = false; h->factored = true; h->factor_inflight = true; h->ev_bwd_external = false;
+    h->gate2_armed = false; h->started_target = h->graph_started_target;
+    const int ldP = ceil_div(P, SLAB) * SLAB;
+    h->lastP = P; h->last_ldP = ldP; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = false;
+    return JK_OK;
+}
+
+static int check_step_ready(jk_handle_t h, int P, const void* t, double fy, double E, double G) {
+    if (P <= 0 || !t) JK_FAIL(h, JK_EINVAL, "jk_step: P must be positive and t non-NULL (P=%d)", P);
+    if (!h->have_supports) JK_FAIL(h, JK_ESTATE, "jk_step: call jk_set_supports first");
+    if (!h->have_wave || !h->have_morison) JK_FAIL(h, JK_ESTATE, "jk_step: call jk_set_wave_* and jk_set_morison first");
+    if (!(E > 0) || !(G > 0) || !(fy > 0)) JK_FAIL(h, JK_EINVAL, "jk_step: E, G and fy must be positive");
+    return JK_OK;
+}
+
+extern "C" int jk_step_dev(jk_handle_t h, double E, double G, int P, const double* t_dev, double fy) {
+    if (!h) return JK_EINVAL;
+    int rc = check_step_ready(h, P, t_dev, fy, E, G);
+    if (rc != JK_OK) return rc;
+    cudaSetDevice(h->device);
+    if ((rc = ensure_buffers(h, P, true, false)) != JK_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t_dev, (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return step_core(h, P, fy, E, G);
+}
+
+extern "C" int jk_step(jk_handle_t h, double E, double G, int P, const double* t, double fy, double* table, int64_t* critical) {
+    if (!h) return JK_EINVAL;
+    int rc = check_step_ready(h, P, t, fy, E, G);
+    if (rc != JK_OK) return rc;
+    cudaSetDevice(h->device);
+    if ((rc = ensure_buffers(h, P, true, false)) != JK_OK) return rc;
+    if ((rc = upload_times(h, P, t)) != JK_OK) return rc;
+    if ((rc = step_core(h, P, fy, E, G)) != JK_OK) return rc;
+    if (!table && !critical) return JK_OK;
+    return jk_read_table(h, P, table, critical);
 }
 
 __global__ void k_nodal_single(int Nn, int ldP, int p, const double* __restrict__ Fm, const int* __restrict__ adj_ptr,
@@ -1859,7 +1999,7 @@ extern "C" int jk_solver_stats(jk_handle_t h, double* out) {
     if (!h->factored) JK_FAIL(h, JK_ESTATE, "jk_solver_stats: factor first");
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
-    if (h->factor_inflight) { CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_factor_bwd, 0)); }
+    { int rcj = join_factor(h, s); if (rcj != JK_OK) return rcj; }
     unsigned long long* d_cnt = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&d_cnt, sizeof(unsigned long long)));
     CUDA_TRY(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
@@ -1899,6 +2039,7 @@ extern "C" int jk_solver_stats(jk_handle_t h, double* out) {
     cudaFree(d_cnt);
     out[0] = (double)cnt; out[1] = exec; out[2] = (double)items; out[3] = h->tma_sweep ? 1.0 : 0.0;
     out[4] = (double)h->nnz_env_min; out[5] = (double)h->sweep_slab_last;
+    out[6] = h->graph_unsupported ? -1.0 : (h->graph_exec != nullptr ? 1.0 : 0.0); out[7] = (double)h->graph_launches;
     return JK_OK;
 }
 

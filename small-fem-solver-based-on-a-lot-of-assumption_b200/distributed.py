@@ -131,7 +131,7 @@ def _allgather_table(table, n_total, world_size, P, group=None):
 
 
 def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=None, gather_table=True,
-                       t_dev=None, t_host=None, host_results=True, table_rank=0):
+                       t_dev=None, t_host=None, host_results=True, table_rank=0, moduli=None):
     """One rank's part of an n_total-phase scan + the cross-rank critical-phase reduction.
 
     Returns dict(local_table, offset, critical_value, critical_index (global), table).
@@ -141,21 +141,29 @@ def sharded_phase_scan(engine, wave, n_total, fy, rank=0, world_size=1, group=No
                           0-d tensors, local_table = view of the library's table, table = all-gathered device tensor on
                           every rank if gather_table.
     With t_dev (device pointer to this rank's times) nothing crosses PCIe before the reduction either.
+    moduli=(E, G): the call is a whole step -- K is re-assembled and re-factored first (jk_step / jk_step_dev: one library
+    call, replayed as a CUDA graph); without it the engine's current factor is used.
     """
     import torch
     import torch.distributed as dist
     lo, hi = shard_bounds(n_total, world_size, rank)
     P = hi - lo
     if t_dev is not None:
-        engine.phase_scan_dev(P, t_dev, fy)
+        if moduli is None:
+            engine.phase_scan_dev(P, t_dev, fy)
+        else:
+            engine.step_dev(moduli[0], moduli[1], P, t_dev, fy)
     else:
         if t_host is None:
             t_host, _ = shard_times(wave.T, n_total, world_size, rank)
-        if world_size == 1 and host_results:
-            table, crit = engine.phase_scan(t_host, fy)         # one pinned copy of table + critical index, one synchronisation
+        if world_size == 1 and host_results:                    # one pinned copy of table + critical index, one synchronisation
+            table, crit = engine.phase_scan(t_host, fy) if moduli is None else engine.step(moduli[0], moduli[1], t_host, fy)
             return dict(local_table=table, offset=lo, critical_value=float(table[crit, 2]), critical_index=int(crit) + lo,
                         table=table if gather_table else None)
-        engine.phase_scan_begin(t_host, fy)                     # queue only: the table is needed on the device first
+        if moduli is None:
+            engine.phase_scan_begin(t_host, fy)                 # queue only: the table is needed on the device first
+        else:
+            engine.step(moduli[0], moduli[1], t_host, fy, read=False)
     table, val, idx = device_views(engine, P)
     # everything below is ordered behind the scan on the engine's own (non-blocking) stream
     stream = torch.cuda.ExternalStream(engine.stream(), device=f"cuda:{engine.device}")

@@ -191,6 +191,31 @@ class Engine:
         self._bump()
         self._ck(self.lib.jk_phase_scan_dev(self.h, int(P), C.c_void_p(t_dev_ptr), float(fy)))
 
+    # -- whole steps (assemble + asynchronous factor + scan as one call; replayed as a CUDA graph) ------------------
+    def _after_step(self, E, G):
+        self._moduli = (float(E), float(G))
+        self._factored = True
+
+    def step_dev(self, E, G, P, t_dev_ptr, fy):
+        """jk_step_dev: resident step, nothing crosses PCIe, no host synchronisation."""
+        self._bump()
+        self._ck(self.lib.jk_step_dev(self.h, float(E), float(G), int(P), C.c_void_p(t_dev_ptr), float(fy)))
+        self._after_step(E, G)
+
+    def step(self, E, G, t, fy, read=True):
+        """jk_step: host times in; with read=True the host table and the critical index come back (one synchronisation)."""
+        self._bump()
+        t = L.f64(t).reshape(-1)
+        if not read:
+            self._ck(self.lib.jk_step(self.h, float(E), float(G), t.shape[0], L.dptr(t), float(fy), None, None))
+            self._after_step(E, G)
+            return t.shape[0]
+        table = np.empty((t.shape[0], L.TABLE_NCOL))
+        crit = C.c_int64(-1)
+        self._ck(self.lib.jk_step(self.h, float(E), float(G), t.shape[0], L.dptr(t), float(fy), L.dptr(table), C.byref(crit)))
+        self._after_step(E, G)
+        return table, int(crit.value)
+
     def read_table(self, P):
         table = np.zeros((P, L.TABLE_NCOL))
         crit = C.c_int64(-1)
@@ -285,10 +310,11 @@ class Engine:
 
     def solver_stats(self):
         """nnz(L), executed sweep flops per load case, sweep items per slab, TMA-pipeline flag."""
-        out = np.zeros(6)
+        out = np.zeros(8)
         self._ck(self.lib.jk_solver_stats(self.h, L.dptr(out)))
         return {"nnz_L": int(out[0]), "sweep_flops_executed_per_case": float(out[1]), "sweep_items": int(out[2]),
-                "tma_sweep": bool(out[3]), "nnz_L_min_envelope": int(out[4]), "sweep_slab": int(out[5])}
+                "tma_sweep": bool(out[3]), "nnz_L_min_envelope": int(out[4]), "sweep_slab": int(out[5]),
+                "step_graph": {1: "replayed", 0: "none", -1: "capture unsupported (eager)"}[int(out[6])], "graph_kernels": int(out[7])}
 
     def launch_count(self):
         return int(self.lib.jk_launch_count(self.h))

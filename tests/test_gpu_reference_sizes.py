@@ -236,3 +236,59 @@ def test_options_api():
     names = [eng.lib.jk_option_name(i).decode() for i in range(eng.lib.jk_option_count())]
     assert "cuda_graph" in names and "fused_loads" in names and "sweep_slab" in names
     eng.close()
+
+
+def test_graph_step_is_bit_identical_to_separate_calls():
+    """jk_step / jk_step_dev (assemble + asynchronous factor + scan in one call, captured into a CUDA graph and replayed)
+    against the separate calls and against the same step launched without the graph: identical bits, also when the times
+    in HBM change between replays and after a re-capture (other phase count, other option)."""
+    import torch
+    import jacket_b200 as jb
+    ap = jb.AnalysisParams(wave_model="Airy")
+    G = ap.E / (2 * (1 + ap.nu))
+    nodes, members, fixed, top = jb.generate_jacket(8, 40)
+    out = {}
+    for mode, opts in (("graph", {}), ("eager", {"cuda_graph": 0})):
+        st = jb.build_structure(nodes, members, fixed, top, ap)
+        eng = jb.Engine(st, options=opts)
+        st._engine = eng
+        wave = jb.RaschiiWave(ap.H, ap.T, ap.d, ap.U_c, "Airy")
+        eng.set_supports(st.indices(fixed))
+        eng.set_static_load(jb.static_load(st, ap))
+        eng.set_wave(wave)
+        eng.set_morison(np.deg2rad(90 - ap.wave_dir), np.deg2rad(90 - ap.current_dir), ap.rho_water, ap.Cd, ap.Cm, 15)
+        t = jb.phase_times(wave.T, 200)
+        eng.assemble(ap.E, G); eng.factor(overlap=True)
+        ref_tab, ref_crit = eng.phase_scan(t, ap.fy)                             # separate calls
+        ref_u = eng.fetch_phase(77)["U"].copy()
+        res = []
+        for k in range(3):                                                       # first call captures, the others replay
+            tab, crit = eng.step(ap.E, G, t, ap.fy)
+            res.append((tab, crit, eng.fetch_phase(77)["U"].copy()))
+        for tab, crit, u in res:
+            assert crit == ref_crit and np.array_equal(tab, ref_tab) and np.array_equal(u, ref_u), mode
+        # resident form, times changed in HBM between replays
+        t2 = t + 0.219
+        want2, crit2 = eng.phase_scan(t2, ap.fy)
+        td = torch.as_tensor(t, device=f"cuda:{eng.device}")
+        eng.step_dev(ap.E, G, 200, td.data_ptr(), ap.fy)
+        a, ca = eng.read_table(200)
+        td.copy_(torch.as_tensor(t2))
+        torch.cuda.synchronize()
+        eng.step_dev(ap.E, G, 200, td.data_ptr(), ap.fy)
+        b, cb = eng.read_table(200)
+        assert ca == ref_crit and np.array_equal(a, ref_tab) and cb == crit2 and np.array_equal(b, want2), mode
+        # other phase count / other option -> new capture, same answers
+        tab3, crit3 = eng.step(ap.E, G, t[:96], ap.fy)
+        eng.set_option("early_totals", 0)
+        tab4, crit4 = eng.step(ap.E, G, t[:96], ap.fy)
+        assert crit3 == crit4 and np.array_equal(tab3, tab4) and np.array_equal(tab3[:, 2:10], ref_tab[:96, 2:10])
+        # other moduli: a stiffer structure deflects less, the Morison columns do not move
+        tab5, _ = eng.step(2 * ap.E, 2 * G, t[:96], ap.fy)
+        assert np.array_equal(tab5[:, :8], tab3[:, :8]) and relmax(tab5[:, 8], 0.5 * tab3[:, 8]) < 1e-9
+        assert eng.solver_stats()["step_graph"] == ("replayed" if mode == "graph" else "none")
+        out[mode] = (res[0][0], b, tab5, eng.launch_count())
+        assert eng.residual() < 1e-9
+    for i in range(3):
+        assert np.array_equal(out["graph"][i], out["eager"][i])
+    assert out["graph"][3] == out["eager"][3]                                    # the same kernels are counted either way
