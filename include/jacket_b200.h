@@ -113,8 +113,10 @@ const char* jk_last_error(jk_handle_t h);
  *   post_overlap [1]        member post of first-chain chunks beside the second chain's backward sweep
  *   early_totals [1]        Morison columns of the table reduced on a side stream behind the Morison kernel
  *   cuda_graph [1]          jk_phase_scan_dev replays the resident scan as a captured CUDA graph
- *   fused_loads [1]         the Morison kernel lumps member end forces into nodal loads itself (0: member forces are
- *                           written to HBM and gathered by a second kernel; same sums in the same order)
+ *   fused_loads [0]         1: the Morison kernel lumps member end forces into nodal loads itself (register runs + deposit
+ *                           rows, finalised in-kernel by a chained look-back; halves the load stage's HBM traffic but
+ *                           measured slower at c4, 1.81 vs 1.70 ms); 0: member forces are written to HBM and gathered by a
+ *                           second kernel in the reference's member order.  Same sums in another fixed order (1e-15)
  *   sweep_slab [0]          right-hand sides per triangular-sweep CTA: 0 = chosen so that the CTAs fill the SMs, 8, 16, 32
  * Ordering / storage switches, read by the next jk_set_supports (results agree to rounding, the reference's run_analysis
  * has no counterpart: GUI.py:481-490 is a dense LU):

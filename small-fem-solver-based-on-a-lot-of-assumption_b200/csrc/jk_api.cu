@@ -27,12 +27,13 @@ using namespace jk;
 static thread_local std::string g_err;
 
 // Run-time options (jk_set_option / jk_get_option).  The library never reads the environment.
-enum JkOpt { OPT_DEBUG_MORISON_SMEM_PAD, OPT_START_GATE, OPT_START_GATE2, OPT_POST_OVERLAP, OPT_EARLY_TOTALS, OPT_FACTOR_SPLIT, OPT_SPLIT_PCT, OPT_TWO_CHAINS,
+enum JkOpt { OPT_DEBUG_MORISON_SMEM_PAD, OPT_DEBUG_FUSE_MODE, OPT_START_GATE, OPT_START_GATE2, OPT_POST_OVERLAP, OPT_EARLY_TOTALS, OPT_FACTOR_SPLIT, OPT_SPLIT_PCT, OPT_TWO_CHAINS,
              OPT_LEVEL_REGROUP, OPT_SUPPORT_ROOTED_RCM, OPT_TMA_SWEEP, OPT_BLOCKED_INVERSE, OPT_PROFILE_CHOL, OPT_PROFILE_SWEEP,
              OPT_DEBUG_FACTOR_DELAY, OPT_SWEEP_SLAB, OPT_CUDA_GRAPH, OPT_FUSED_LOADS, OPT_COUNT };
 struct JkOptDesc { const char* key; int def, lo, hi; };
 static const JkOptDesc g_opts[OPT_COUNT] = {
-    {"debug_morison_smem_pad", 0, 0, 160},  // experiment: extra KB of dynamic shared memory per Morison block (occupancy probe)
+    {"debug_morison_smem_pad", 0, 0, 160},
+    {"debug_fuse_mode", 0, 0, 2},           // experiment: 1 = fused Morison kernel without finalisation, 2 = without waiting (wrong results; timing only)  // experiment: extra KB of dynamic shared memory per Morison block (occupancy probe)
     {"start_gate", 1, 0, 1},            // main stream waits until the factor clusters are resident (asynchronous factorisation)
     {"start_gate2", 1, 0, 1},           // first forward sweep parts wait until the second factor segment is resident
     {"post_overlap", 1, 0, 1},          // member post of first-chain chunks beside the second chain's backward sweep
@@ -49,7 +50,8 @@ static const JkOptDesc g_opts[OPT_COUNT] = {
     {"debug_factor_delay", 0, 0, 2000000000},   // test aid: spin this many clocks in front of the factorisation
     {"sweep_slab", 0, 0, 32},           // right-hand sides per sweep CTA: 0 = auto (fill the SMs), 8, 16 or 32
     {"cuda_graph", 1, 0, 1},            // replay the resident scan (jk_phase_scan_dev) as a captured CUDA graph
-    {"fused_loads", 1, 0, 1},           // Morison kernel lumps member end forces into nodal loads itself (no member-force round trip)
+    {"fused_loads", 0, 0, 1},           // Morison kernel lumps member end forces into nodal loads itself (no member-force round trip;
+                                        // measured slower than the two-kernel path at c4: 1.81 vs 1.70 ms, see jk_morison.cuh)
 };
 
 struct jk_handle_s {
@@ -118,6 +120,13 @@ struct jk_handle_s {
     bool assembled = false, factored = false;
     double E = 0, G = 0;
 
+    // fused load lumping (jk_morison.cuh, LoadFuse): member processing order, chunk-local nodes, finalisation lists
+    int fuse_n_pairs = 0, fuse_n_fin = 0, fuse_n_chunk = 0;
+    int *d_fuse_order = nullptr, *d_fuse_pair_base = nullptr, *d_fuse_fin_ptr = nullptr, *d_fuse_fin_node = nullptr,
+        *d_fuse_fin_rowptr = nullptr, *d_fuse_fin_rows = nullptr, *d_fuse_dep_lo = nullptr, *d_fuse_sync = nullptr, *d_fuse_fin_of_node = nullptr;
+    unsigned* d_fuse_ends = nullptr;
+    double* d_part = nullptr;          // [n_pairs][3][ldP] chunk-local nodal sums of the last fused scan
+    bool last_fused = false;
     // loads / wave / morison
     double* d_Fstatic = nullptr;
     bool have_wave = false, have_morison = false, gp_valid = false;
@@ -149,7 +158,7 @@ struct jk_handle_s {
     long long graph_epoch = 0, graph_epoch_built = -1, graph_launches = 0;      // epoch: bumped by every call that changes kernel arguments or buffers
     int graph_P = 0; double graph_E = 0, graph_G = 0, graph_fy = 0;
     unsigned graph_started_target = 0; bool graph_gate2_armed = false;
-    bool capturing = false, graph_unsupported = false;
+    bool capturing = false, graph_unsupported = false, graph_fused = false;
     double last_fy = 355.0;
 
     cudaEvent_t ev0[JK_NTIMERS], ev1[JK_NTIMERS];
@@ -351,6 +360,9 @@ extern "C" int jk_destroy(jk_handle_t h) {
     for (auto& c : h->ch) { dev_free(c.d_blocks); dev_free(c.d_contrib); dev_free(c.d_tiles); dev_free(c.d_Linv); dev_free(c.d_dinv);
                             for (auto& w : c.sw) { dev_free(w.d_prog); dev_free(w.d_stream); } }
     dev_free(h->d_info); dev_free(h->d_info_sticky);
+    dev_free(h->d_fuse_order); dev_free(h->d_fuse_pair_base); dev_free(h->d_fuse_fin_ptr); dev_free(h->d_fuse_fin_node);
+    dev_free(h->d_fuse_fin_rowptr); dev_free(h->d_fuse_fin_rows); dev_free(h->d_fuse_dep_lo); dev_free(h->d_fuse_sync);
+    dev_free(h->d_fuse_ends); dev_free(h->d_part); dev_free(h->d_fuse_fin_of_node);
     dev_free(h->d_Fstatic); dev_free(h->d_gsw); dev_free(h->d_gp); dev_free(h->d_four); dev_free(h->d_states); dev_free(h->d_state_crit);
     dev_free(h->d_t); dev_free(h->d_trig); dev_free(h->d_Fm); dev_free(h->d_X); dev_free(h->d_Z); dev_free(h->d_Ffix); dev_free(h->d_rows);
     dev_free(h->d_totpart); dev_free(h->d_part_util); dev_free(h->d_part_vm); dev_free(h->d_part_disp); dev_free(h->d_react);
@@ -598,6 +610,89 @@ static std::vector<int> chain_tile_reach(int NT, int n_nodes_chain, const std::v
         jmin[k] = reach / NB;
     }
     return jmin;
+}
+
+// Metadata of the fused load lumping (LoadFuse): members sorted by their upper node (the end later in the solver's linear
+// order; fixed nodes come first), chunks of MCHUNK consecutive members, one row per member (deposit of the lower end) and per
+// run of members sharing the upper node inside a chunk, and, for every node, the rows to add -- listed with the LAST chunk
+// that touches the node.
+static int build_load_fusion(jk_handle_t h, const std::vector<int>& pos /* position of free nodes, -1 for fixed */) {
+    const int M = h->M, Nn = h->Nn;
+    auto key = [&](int node) { return pos[node] < 0 ? -1 : pos[node]; };
+    // upper / lower end of every member: larger key wins, ties (two supports) go to end 2
+    std::vector<int> up_end(M), up_node(M), lo_node(M);
+    for (int m = 0; m < M; ++m) {
+        const int a = h->h_conn[2 * m], b = h->h_conn[2 * m + 1];
+        up_end[m] = key(b) >= key(a) ? 1 : 0;
+        up_node[m] = up_end[m] ? b : a; lo_node[m] = up_end[m] ? a : b;
+    }
+    std::vector<int> order(M);
+    for (int m = 0; m < M; ++m) order[m] = m;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        const int kx = key(up_node[x]), ky = key(up_node[y]);
+        if (kx != ky) return kx < ky;
+        if (up_node[x] != up_node[y]) return up_node[x] < up_node[y];
+        return key(lo_node[x]) < key(lo_node[y]);
+    });
+    const int n_chunk = ceil_div(M, MCHUNK);
+    std::vector<unsigned> ends(M);
+    std::vector<int> pair_base(n_chunk + 1, 0);
+    std::vector<std::vector<int>> rows_of_node(Nn);       // rows in a fixed order: ascending chunk, ascending position
+    std::vector<int> last_chunk(Nn, -1), first_chunk(Nn, -1);
+    int n_pairs = 0;
+    for (int c = 0; c < n_chunk; ++c) {
+        pair_base[c] = n_pairs;
+        const int q0 = c * MCHUNK, q1 = std::min(M, (c + 1) * MCHUNK);
+        int n_local = 0, run_row = -1;
+        auto touch = [&](int node) { if (first_chunk[node] < 0) first_chunk[node] = c; last_chunk[node] = c; };
+        for (int q = q0; q < q1; ++q) {
+            const int m = order[q];
+            const bool begin = q == q0 || up_node[order[q - 1]] != up_node[m];
+            const bool end = q + 1 == q1 || up_node[order[q + 1]] != up_node[m];
+            if (begin) run_row = n_local++;
+            const int lo_row = n_local++;
+            ends[q] = (unsigned)lo_row | ((unsigned)run_row << 8) | ((unsigned)up_end[m] << 16) | (begin ? 1u << 17 : 0u) | (end ? 1u << 18 : 0u);
+            rows_of_node[lo_node[m]].push_back(n_pairs + lo_row); touch(lo_node[m]);
+            if (end) { rows_of_node[up_node[m]].push_back(n_pairs + run_row); touch(up_node[m]); }
+        }
+        if (n_local > 255) JK_FAIL(h, JK_EINVAL, "internal: a member chunk needs more than 255 load rows");
+        n_pairs += n_local;
+    }
+    pair_base[n_chunk] = n_pairs;
+    // finalisation lists: node -> its last chunk (nodes without any member -- only supports can be -- go to chunk 0 with no rows)
+    std::vector<std::vector<int>> fin(n_chunk);
+    for (int node = 0; node < Nn; ++node) fin[last_chunk[node] < 0 ? 0 : last_chunk[node]].push_back(node);
+    std::vector<int> fin_ptr(n_chunk + 1, 0), fin_node, fin_rowptr(1, 0), fin_rows, dep_lo(n_chunk);
+    for (int c = 0; c < n_chunk; ++c) {
+        fin_ptr[c] = (int)fin_node.size();
+        int lo = c;
+        for (int node : fin[c]) {
+            fin_node.push_back(node);
+            for (int r : rows_of_node[node]) fin_rows.push_back(r);
+            fin_rowptr.push_back((int)fin_rows.size());
+            if (first_chunk[node] >= 0) lo = std::min(lo, first_chunk[node]);
+        }
+        dep_lo[c] = lo;
+    }
+    fin_ptr[n_chunk] = (int)fin_node.size();
+    h->fuse_n_pairs = n_pairs; h->fuse_n_fin = (int)fin_node.size(); h->fuse_n_chunk = n_chunk;
+    auto up_i = [&](int*& d, const std::vector<int>& v) -> cudaError_t {
+        cudaError_t e = dev_alloc(&d, v.size());
+        return e != cudaSuccess ? e : cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+    };
+    CUDA_TRY(h, up_i(h->d_fuse_order, order));
+    CUDA_TRY(h, up_i(h->d_fuse_pair_base, pair_base));
+    CUDA_TRY(h, up_i(h->d_fuse_fin_ptr, fin_ptr));
+    CUDA_TRY(h, up_i(h->d_fuse_fin_node, fin_node));
+    CUDA_TRY(h, up_i(h->d_fuse_fin_rowptr, fin_rowptr));
+    CUDA_TRY(h, up_i(h->d_fuse_fin_rows, fin_rows));
+    CUDA_TRY(h, up_i(h->d_fuse_dep_lo, dep_lo));
+    std::vector<int> fin_of_node(Nn, 0);
+    for (size_t e = 0; e < fin_node.size(); ++e) fin_of_node[fin_node[e]] = (int)e;
+    CUDA_TRY(h, up_i(h->d_fuse_fin_of_node, fin_of_node));
+    CUDA_TRY(h, dev_alloc(&h->d_fuse_ends, ends.size()));
+    CUDA_TRY(h, cudaMemcpy(h->d_fuse_ends, ends.data(), ends.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    return JK_OK;
 }
 
 extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_nodes, int ordering, int solver) {
@@ -871,6 +966,7 @@ extern "C" int jk_set_supports(jk_handle_t h, int n_fixed, const int32_t* fixed_
     CUDA_TRY(h, cudaMemcpyAsync(h->d_fixed_nodes, h->h_fixed.data(), (size_t)h->n_fixed * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_free_nodes, h->h_free_nodes.data(), (size_t)h->n_free_nodes * sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    { int rcf = build_load_fusion(h, pos); if (rcf != JK_OK) return rcf; }
     h->graph_epoch++;
     h->have_supports = true; h->assembled = false; h->factored = false;
     // buffers sized by n_pad / n_fixed must be rebuilt; resident results no longer match the new row numbering
@@ -1212,6 +1308,8 @@ static int ensure_buffers(jk_handle_t h, int P, bool need_fem, bool need_details
         CUDA_TRY(h, dev_alloc(&h->d_X, (size_t)h->n_pad * l));
         CUDA_TRY(h, cudaMemsetAsync(h->d_X, 0, (size_t)h->n_pad * l * sizeof(double), h->stream));
         if (h->tma_sweep) CUDA_TRY(h, dev_alloc(&h->d_Z, (size_t)h->n_pad * l));     // forward intermediate of the TMA sweeps (fragment order)
+        CUDA_TRY(h, dev_alloc(&h->d_part, (size_t)h->fuse_n_pairs * 3 * l));
+        CUDA_TRY(h, dev_alloc(&h->d_fuse_sync, 1 + (size_t)(h->fuse_n_chunk + FUSE_LAG) * ceil_div(ldP, PH_TPB)));
         CUDA_TRY(h, dev_alloc(&h->d_Ffix, (size_t)h->n_fixed * 6 * l));
         CUDA_TRY(h, dev_alloc(&h->d_react, (size_t)h->n_fixed * 6 * l));
         CUDA_TRY(h, dev_alloc(&h->d_rows, (size_t)h->M * JK_MEMBER_NCOL * l));
@@ -1259,7 +1357,7 @@ static int ensure_gauss_tables(jk_handle_t h) {
 }
 
 // Morison stage for the phases already in d_t: trig tables, Gauss-point tables (once per wave), K1
-static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
+static int run_morison(jk_handle_t h, int P, int ldP, bool details, bool fuse = false) {
     cudaStream_t s = h->stream;
     WaveAiry w = launch_wave(h);
     tic(h, JK_T_WAVE_SETUP);
@@ -1289,9 +1387,21 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details) {
             k_morison_airy<true, 0><<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, h->d_details, 0);
         } else {
             // the default 15-point rule may have its own instantiation with fully unrolled point loops (-DJK_MORISON_G15=1)
-            auto kern = (JK_MORISON_G15 && h->ng == 15) ? k_morison_airy<false, 15> : k_morison_airy<false, 0>;
-            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr, 0);
+            if (fuse) {
+                // load lumping inside the kernel (LoadFuse): ticket + flags start at zero
+                const int n_tiles = (int)grid.x;
+                CUDA_TRY(h, cudaMemsetAsync(h->d_fuse_sync, 0, (1 + (size_t)(h->fuse_n_chunk + FUSE_LAG) * n_tiles) * sizeof(int), s));
+                LoadFuse lf{h->d_fuse_order, h->d_fuse_ends, h->d_fuse_pair_base, h->d_part, h->d_fuse_fin_ptr, h->d_fuse_fin_node,
+                            h->d_fuse_fin_rowptr, h->d_fuse_fin_rows, h->d_fuse_dep_lo, h->d_fuse_sync, h->d_fuse_sync + 1,
+                            h->d_node2slot, h->d_Fstatic, h->d_X, h->d_Ffix, h->n_pad, n_tiles, h->opt[OPT_DEBUG_FUSE_MODE]};
+                auto kern = (JK_MORISON_G15 && h->ng == 15) ? k_morison_airy<false, 15, true> : k_morison_airy<false, 0, true>;
+                CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<dim3(grid.x, grid.y + FUSE_LAG), PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, nullptr, h->d_totpart, nullptr, 0, lf);
+            } else {
+                auto kern = (JK_MORISON_G15 && h->ng == 15) ? k_morison_airy<false, 15> : k_morison_airy<false, 0>;
+                CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr, 0, LoadFuse{});
+            }
         }
     }
     LAUNCH_CHECK(h);
@@ -1508,10 +1618,15 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
     int rc;
     if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
     const int nbx = ceil_div(ldP, PH_TPB);
-    if ((rc = run_morison(h, P, ldP, false)) != JK_OK) return rc;
+    const bool fuse = fem && h->opt[OPT_FUSED_LOADS] && h->wave_kind == 0 && h->fuse_n_pairs > 0;
+    if ((rc = run_morison(h, P, ldP, false, fuse)) != JK_OK) return rc;
     const bool totals_early = fem && h->opt[OPT_EARLY_TOTALS] && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
     if (totals_early && (rc = reduce_totals_early(h, P, ldP)) != JK_OK) return rc;
-    if (fem) {
+    h->last_fused = fuse;
+    if (fem && fuse) {
+        h->ev_set[JK_T_RHS] = false;                       // no separate load stage: the Morison kernel wrote the right-hand sides
+        if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
+    } else if (fem) {
         tic(h, JK_T_RHS);
         dim3 g(nbx, std::min(h->Nn, 65535));
         k_rhs_gather<<<g, PH_TPB, 0, s>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
@@ -1676,6 +1791,7 @@ static int step_core(jk_handle_t h, int P, double fy, double E, double G) {
         h->graph_epoch_built = h->graph_epoch; h->graph_P = P; h->graph_E = E; h->graph_G = G; h->graph_fy = fy;
         h->graph_launches = h->launches - launches0;
         h->graph_started_target = h->started_target;
+        h->graph_fused = h->last_fused;
         h->launches = launches0;
     }
     CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
@@ -1686,6 +1802,7 @@ static int step_core(jk_handle_t h, int P, double fy, double E, double G) {
     h->gate2_armed = false; h->started_target = h->graph_started_target;
     const int ldP = ceil_div(P, SLAB) * SLAB;
     h->lastP = P; h->last_ldP = ldP; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = false;
+    h->last_fused = h->graph_fused;
     return JK_OK;
 }
 
@@ -1863,7 +1980,7 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     k_argmax_per_state<<<ceil_div(n_states, 128), 128, 0, s>>>(n_states, n_phase, h->d_table, JK_TABLE_NCOL, JK_COL_TOTAL_KN, h->d_state_crit);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SCAN_TOTAL);
-    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = F_dir != nullptr;
+    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = F_dir != nullptr; h->last_fused = false;
     tic(h, JK_T_D2H);
     if (table) CUDA_TRY(h, cudaMemcpyAsync(table, h->d_table, (size_t)C * JK_TABLE_NCOL * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<long long> crit(n_states);
@@ -1900,7 +2017,7 @@ extern "C" int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy) {
     if ((rc = reduce_and_argmax(h, nrhs, ldP, false, true)) != JK_OK) return rc;
     toc(h, JK_T_SCAN_TOTAL);
     CUDA_TRY(h, cudaStreamSynchronize(s));
-    h->lastP = nrhs; h->last_ldP = ldP; h->last_morison = false; h->last_fem = true; h->last_fy = fy; h->last_fdir = false;
+    h->lastP = nrhs; h->last_ldP = ldP; h->last_morison = false; h->last_fem = true; h->last_fy = fy; h->last_fdir = false; h->last_fused = false;
     return finish_factor(h);
 }
 
@@ -1932,7 +2049,10 @@ extern "C" int jk_fetch_phase(jk_handle_t h, int phase, double* U, double* react
         if (end_forces) CUDA_TRY(h, cudaMemcpyAsync(end_forces, dE, nE * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     if (nodal_forces) {
-        if (h->last_morison) { k_nodal_single<<<ceil_div(h->Nn, 128), 128, 0, s>>>(h->Nn, ldP, phase, h->d_Fm, h->d_adj_ptr, h->d_adj, dN); LAUNCH_CHECK(h); }
+        if (h->last_morison && h->last_fused) {
+            k_nodal_from_partials<<<ceil_div(h->fuse_n_fin, 128), 128, 0, s>>>(h->fuse_n_fin, ldP, phase, h->d_fuse_fin_node, h->d_fuse_fin_rowptr, h->d_fuse_fin_rows, h->d_part, dN);
+            LAUNCH_CHECK(h);
+        } else if (h->last_morison) { k_nodal_single<<<ceil_div(h->Nn, 128), 128, 0, s>>>(h->Nn, ldP, phase, h->d_Fm, h->d_adj_ptr, h->d_adj, dN); LAUNCH_CHECK(h); }
         else CUDA_TRY(h, cudaMemsetAsync(dN, 0, nN * sizeof(double), s));
         CUDA_TRY(h, cudaMemcpyAsync(nodal_forces, dN, nN * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
@@ -2105,13 +2225,20 @@ k_free_residual(int n_free_nodes, const int* __restrict__ free_nodes, int P, int
                 const int* __restrict__ node2slot, const int* __restrict__ conn, const int* __restrict__ adj_ptr,
                 const int* __restrict__ adj, const double* __restrict__ Ke, const double* __restrict__ Fstatic,
                 const double* __restrict__ Fm /* null: loads from Fload */, const double* __restrict__ Fload, int Nn,
-                unsigned long long* __restrict__ out /* [2]: max |r|, max |F| as double bits */) {
+                unsigned long long* __restrict__ out /* [2]: max |r|, max |F| as double bits */,
+                const int* __restrict__ fin_of_node = nullptr /* fused scan: Morison loads = sum of the node's partial rows */,
+                const int* __restrict__ fin_rowptr = nullptr, const int* __restrict__ fin_rows = nullptr, const double* __restrict__ part = nullptr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     double rmax = 0.0, fmaxv = 0.0;
     for (int sidx = blockIdx.y; sidx < n_free_nodes && p < P; sidx += gridDim.y) {        // grid.y is capped at 65,535
         int node = free_nodes[sidx];
         double r[6] = {0, 0, 0, 0, 0, 0}, f[6];
-        for (int c = 0; c < 6; ++c) f[c] = Fm ? Fstatic[6 * node + c] : Fload[(size_t)p * 6 * Nn + 6 * node + c];
+        for (int c = 0; c < 6; ++c) f[c] = (Fm || part) ? Fstatic[6 * node + c] : Fload[(size_t)p * 6 * Nn + 6 * node + c];
+        if (part) {
+            const int e = fin_of_node[node];
+            for (int r = fin_rowptr[e]; r < fin_rowptr[e + 1]; ++r)
+                for (int c = 0; c < 3; ++c) f[c] += part[((size_t)fin_rows[r] * 3 + c) * ldP + p];
+        }
         for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
             int m = adj[q] >> 1, end = adj[q] & 1;
             double ue[12];
@@ -2145,7 +2272,8 @@ extern "C" int jk_residual(jk_handle_t h, double* rel) {
     dim3 g(ceil_div(h->lastP, PH_TPB), std::min(h->n_free_nodes, 65535));
     k_free_residual<<<g, PH_TPB, 0, s>>>(h->n_free_nodes, h->d_free_nodes, h->lastP, h->last_ldP, h->n_pad, h->d_X, h->d_node2slot,
                                          h->d_conn, h->d_adj_ptr, h->d_adj, h->d_Ke, h->d_Fstatic,
-                                         h->last_morison ? h->d_Fm : nullptr, h->d_Fload, h->Nn, (unsigned long long*)h->d_res);
+                                         (h->last_morison && !h->last_fused) ? h->d_Fm : nullptr, h->d_Fload, h->Nn, (unsigned long long*)h->d_res,
+                                         h->d_fuse_fin_of_node, h->d_fuse_fin_rowptr, h->d_fuse_fin_rows, (h->last_morison && h->last_fused) ? h->d_part : nullptr);
     LAUNCH_CHECK(h);
     double v[2];
     CUDA_TRY(h, cudaMemcpyAsync(v, h->d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));

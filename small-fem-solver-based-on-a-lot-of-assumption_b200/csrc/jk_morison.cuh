@@ -87,6 +87,9 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 #ifndef JK_MORISON_SUBFAST
 #define JK_MORISON_SUBFAST 1      // drag-only point loop + closed-form inertia sums for members below the lowest trough
 #endif
+#if !JK_MORISON_SSUM
+#error "the component form of the Airy Morison kernel was removed (scalar-sum form only); morison_point is kept for the Fourier / ensemble kernels"
+#endif
 #if JK_MORISON_SSUM
 // Scalar-sum form.  With w^ = wave heading, c = current vector, z^ = vertical and e = member axis, the velocity and
 // acceleration of GUI.py:573-588 are U = uw w^ + c + w z^ and A = du w^ + dw z^, so their components normal to the
@@ -95,12 +98,48 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 // GUI.py:648-659 then only need the SCALARS sum(kd), sum(kd uw), sum(kd w), sum(ci du), sum(ci dw) and their
 // s-weighted twins; the 3-vectors are formed once per member.  ~30 % fewer FP64 instructions per point than the
 // component form (morison_point), same results to rounding (1e-15 relative).
-template <bool DETAILS, int GT /* compile-time Gauss point count (fully unrolled point loops) or 0 */>
+// Load lumping fused into the Morison kernel (FUSED = true): instead of writing the six end forces of every member to HBM for a
+// second kernel to gather (4 GB of traffic at 10,000 members x 4,096 phases), the kernel forms the nodal sums itself.
+// Members are processed in an order sorted by their "upper" node (the end that comes later in the solver's ordering), so
+// all members that share an upper node are consecutive: that end is summed in three registers and leaves the thread as ONE
+// row per run; the other ("lower") end of each member is deposited as its own row.  Rows are plain coalesced stores
+// [3][ldP] per row -- no read-modify-write in the member loop -- and stay in L2 until the LAST chunk that touches a node adds
+// the node's rows (its run rows and the deposits of the neighbouring chunks, in a fixed order), the static load, and writes
+// the solver's right-hand side.  Blocks take their (chunk, phase tile) from a ticket counter, so a block only ever waits for
+// blocks that started before it (flags set after a __threadfence: the decoupled look-back pattern).  Every sum has a fixed
+// order -> results are bit-identical from run to run.
+// MEASURED (c4, 10,000 members x 4,096 phases, kernel alone): member forces + gather kernel 1.28 + 0.42 = 1.70 ms; fused 1.81 ms
+// (member loop with the sorted order and row stores 1.42, finalisation 0.25, waiting for neighbouring chunks 0.14) -- the
+// kernel is occupancy-limited by its shared-memory tables (5 blocks per SM), so a block that spends a fifth of its life
+// in a memory-bound epilogue takes FP64 issue slots away instead of hiding under the others.  The fused path halves the
+// HBM traffic of the load stage (rows 1.3 GB instead of member forces 2 x 2.0 GB) and is kept as option fused_loads = 1;
+// the default is the two-kernel path.
+constexpr int FUSE_LAG = 0;      // a chunk's nodes are finalised by the block that handles the chunk FUSE_LAG further on (0: by itself;
+                                 // 3 measured slower: 1.89 vs 1.81 ms at c4 -- the waits are not what costs)
+struct LoadFuse {
+    const int* order;           // [n_chunk * MCHUNK] member processed at each position (-1: padding)
+    const unsigned* ends;       // per position: deposit row of the lower end | run row of the upper end << 8 (both chunk-local) |
+                                // upper end is end 2 << 16 | run begins << 17 | run ends (store the run row) << 18
+    const int* pair_base;       // [n_chunk + 1] first row of each chunk
+    double* part;               // [n_rows][3][ldP] run sums and deposits
+    const int* fin_ptr;         // [n_chunk + 1] nodes whose last chunk this is
+    const int* fin_node;        // [n_fin] node index
+    const int* fin_rowptr;      // [n_fin + 1]
+    const int* fin_rows;        // partial rows of a node in ascending chunk order
+    const int* dep_lo;          // [n_chunk] lowest chunk whose rows this chunk's finalisation reads
+    int* ticket;                // [1] zeroed before the launch
+    int* flags;                 // [n_chunk * n_tiles] zeroed before the launch
+    const int* node2slot; const double* Fstatic; double* B; double* Ffix; int n_pad, n_tiles;
+    int debug_mode;             // timing experiments only: 1 = no finalisation, 2 = finalisation without waiting for the other chunks
+};
+
+template <bool DETAILS, int GT /* compile-time Gauss point count (fully unrolled point loops) or 0 */, bool FUSED = false>
 __global__ void __launch_bounds__(PH_TPB)
 k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
                const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
                WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
-               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details, int p_off /* first phase of this launch */) {
+               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details, int p_off /* first phase of this launch */,
+               LoadFuse lf = LoadFuse{}) {
     extern __shared__ __align__(16) double smem[];
     const int G = GT > 0 ? GT : G_rt;
     constexpr int MS = 16;                                  // per-member constants
@@ -111,11 +150,28 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
 #if JK_MORISON_SUBFAST
     double* s_i = s_c + MCHUNK * G * 4;                    // [MCHUNK][8]: inertia sums of an always-submerged member (below)
 #endif
-    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
-    int nm = min(MCHUNK, M - m0);
-    for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
+    __shared__ int s_ids[MCHUNK + 2];
+    __shared__ unsigned s_ends[MCHUNK];
+    int chunk = blockIdx.y, tile = blockIdx.x;
+    if (FUSED) {                                           // (chunk, phase tile) in the order the blocks actually start
+        if (threadIdx.x == 0) s_ids[MCHUNK] = atomicAdd(lf.ticket, 1);
+        __syncthreads();
+        chunk = s_ids[MCHUNK] / lf.n_tiles; tile = s_ids[MCHUNK] % lf.n_tiles;
+    }
+    const int m0 = chunk * MCHUNK;
+    int nm = max(0, min(MCHUNK, M - m0));                  // fused: the last FUSE_LAG "chunks" hold no members, they only finalise
+    if (FUSED) {
+        for (int i = threadIdx.x; i < nm; i += blockDim.x) { s_ids[i] = lf.order[m0 + i]; s_ends[i] = lf.ends[m0 + i]; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) {
+            const int mm = i / (G * GP_STRIDE);
+            s_gp[i] = gp[(size_t)s_ids[mm] * G * GP_STRIDE + (i - mm * G * GP_STRIDE)];
+        }
+    } else {
+        for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
+    }
     for (int i = threadIdx.x; i < nm; i += blockDim.x) {
-        const double* c = mc + (size_t)(m0 + i) * MC_STRIDE;
+        const double* c = mc + (size_t)(FUSED ? s_ids[i] : m0 + i) * MC_STRIDE;
         const double e0 = c[MC_E], e1 = c[MC_E + 1], e2 = c[MC_E + 2];
         const double we = fma(wv.sin_w, e1, wv.cos_w * e0), ce = fma(wv.uc_sin_c, e1, wv.uc_cos_c * e0);
         double* o = s_m + MS * i;
@@ -166,8 +222,10 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
     __syncthreads();
 #endif
 
-    int p = p_off + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= ldP) return;
+    int p = p_off + tile * blockDim.x + threadIdx.x;
+    if (!FUSED && p >= ldP) return;
+    const bool live = p < ldP;                             // a fused block stays together for its barriers
+    if (!live) { p = ldP - 1; nm = 0; }
     const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
 #if JK_MORISON_SUBFAST
     const double dcw = (cw1 - cw0) * wv.inv_dt, dsw = (sw1 - sw0) * wv.inv_dt;
@@ -175,6 +233,8 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
     const double wc2 = 2.0 * fma(wv.sin_w, wv.uc_sin_c, wv.cos_w * wv.uc_cos_c);       // 2 w^.c
     const double cc = fma(wv.uc_sin_c, wv.uc_sin_c, wv.uc_cos_c * wv.uc_cos_c);        // c.c
     double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
+    const int pbase = FUSED ? lf.pair_base[chunk] : 0;
+    double run[3] = {0.0, 0.0, 0.0};
 
     for (int mm = 0; mm < nm; ++mm) {
         const double* cmem = s_m + MS * mm;
@@ -251,6 +311,9 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
         const double T1 = Td1 + Ti1, T3 = Td3 + Ti3;
         double md[3], mi[3];
         size_t o = ((size_t)(m0 + mm) * 6) * ldP + p;
+        const unsigned ends = FUSED ? s_ends[mm] : 0u;     // block-uniform: no divergence
+        double* plo = FUSED ? lf.part + ((size_t)(pbase + (int)(ends & 255u)) * 3) * ldP + p : nullptr;
+        double* phi = FUSED ? lf.part + ((size_t)(pbase + (int)((ends >> 8) & 255u)) * 3) * ldP + p : nullptr;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const double p1 = cmem[4 + k], p0 = cmem[7 + k], p3 = cmem[10 + k];
@@ -258,8 +321,17 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
             mi[k] = fma(p3, Si3, p1 * Si1);
             const double F2 = fma(p3, T3, fma(p0, Td0, p1 * T1));
             const double mt = md[k] + mi[k];
-            Fm[o + (size_t)k * ldP] = mt - F2;                                 // F1 = sum (1-s) f   (GUI.py:658)
-            Fm[o + (size_t)(3 + k) * ldP] = F2;                                // F2 = sum s f       (GUI.py:659)
+            if (FUSED) {                                                       // nodal_forces[n1] += F1, [n2] += F2 (GUI.py:661-662)
+                const double F1 = mt - F2;
+                const bool up2 = (ends & 0x10000u) != 0;
+                const double up = up2 ? F2 : F1, lo = up2 ? F1 : F2;
+                run[k] = (ends & 0x20000u) ? up : run[k] + up;                 // the upper node's run lives in registers
+                plo[(size_t)k * ldP] = lo;                                     // the lower end: one deposit row per member
+                if (ends & 0x40000u) phi[(size_t)k * ldP] = run[k];
+            } else {
+                Fm[o + (size_t)k * ldP] = mt - F2;                             // F1 = sum (1-s) f   (GUI.py:658)
+                Fm[o + (size_t)(3 + k) * ldP] = F2;                            // F2 = sum s f       (GUI.py:659)
+            }
             td[k] += md[k]; ti[k] += mi[k]; tm[k] += mt;                        // GUI.py:664-666
         }
         if (DETAILS) {
@@ -272,103 +344,63 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
         }
     }
     size_t ot = ((size_t)chunk * 9) * ldP + p;
+    if (live && m0 < M) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        totpart[ot + (size_t)k * ldP] = td[k];
-        totpart[ot + (size_t)(3 + k) * ldP] = ti[k];
-        totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
+        for (int k = 0; k < 3; ++k) {
+            totpart[ot + (size_t)k * ldP] = td[k];
+            totpart[ot + (size_t)(3 + k) * ldP] = ti[k];
+            totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
+        }
+    }
+    if (FUSED) {
+        // publish this block's rows, then finish the nodes whose last chunk lies FUSE_LAG chunks back: those chunks' blocks took
+        // their tickets FUSE_LAG * n_tiles earlier and have (almost always) finished, so nobody waits in the common case
+        __threadfence();
+        __syncthreads();
+        volatile int* flags = lf.flags;
+        if (threadIdx.x == 0 && m0 < M) flags[chunk * lf.n_tiles + tile] = 1;
+        const int fc = chunk - FUSE_LAG;
+        const int f0 = fc >= 0 ? lf.fin_ptr[fc] : 0, f1 = (fc >= 0 && lf.debug_mode != 1) ? lf.fin_ptr[fc + 1] : f0;
+        if (f1 > f0) {
+            if (threadIdx.x == 0 && lf.debug_mode != 2) {
+                for (int c = lf.dep_lo[fc]; c <= fc; ++c) {             // blocks with earlier tickets: already running or done
+                    unsigned spins = 0;
+                    while (flags[c * lf.n_tiles + tile] == 0) { __nanosleep(64); if (++spins > (1u << 24)) __trap(); }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            if (live) {
+                for (int e = f0; e < f1; ++e) {
+                    const int node = lf.fin_node[e];
+                    const int r0 = lf.fin_rowptr[e], r1 = lf.fin_rowptr[e + 1];
+                    double v[3] = {0.0, 0.0, 0.0};
+                    for (int r = r0; r < r1; ++r) {
+                        const double* q = lf.part + ((size_t)lf.fin_rows[r] * 3) * ldP + p;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) v[k] += __ldcg(q + (size_t)k * ldP);
+                    }
+                    const int sl = lf.node2slot[node];
+                    if (sl >= 0) {
+                        const size_t ob = rhs_off(sl, p, lf.n_pad);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) lf.B[ob + (size_t)k * SLAB] = lf.Fstatic[6 * node + k] + v[k];
+#pragma unroll
+                        for (int k = 3; k < 6; ++k) lf.B[ob + (size_t)k * SLAB] = lf.Fstatic[6 * node + k];
+                    } else {
+                        const int fi = -1 - sl;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) lf.Ffix[(size_t)(6 * fi + k) * ldP + p] = lf.Fstatic[6 * node + k] + v[k];
+#pragma unroll
+                        for (int k = 3; k < 6; ++k) lf.Ffix[(size_t)(6 * fi + k) * ldP + p] = lf.Fstatic[6 * node + k];
+                    }
+                }
+            }
+        }
     }
 }
 constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 16 + 8 * JK_MORISON_SUBFAST;   // doubles per member beside the Gauss tables (s_m, s_i)
 constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 4;     // doubles per Gauss point beside GP_STRIDE (s_c)
-#else
-template <bool DETAILS, int GT /* unused in the component form */>
-__global__ void __launch_bounds__(PH_TPB)
-k_morison_airy(int M, int G, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
-               const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
-               WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
-               double* __restrict__ Fm, double* __restrict__ totpart, double* __restrict__ details, int p_off /* first phase of this launch */) {
-    extern __shared__ __align__(16) double smem[];
-    double* s_gp = smem;                                   // [MCHUNK][G][GP_STRIDE]
-    double* s_m = s_gp + MCHUNK * G * GP_STRIDE;           // [MCHUNK][8]: e0 e1 e2 cD cI L
-    double* s_g = s_m + MCHUNK * 8;                        // s[G], w[G]
-    double* s_c = s_g + 2 * G;                             // [MCHUNK][G][2]: cD L w_g, cI L w_g
-    int chunk = blockIdx.y, m0 = chunk * MCHUNK;
-    int nm = min(MCHUNK, M - m0);
-    for (int i = threadIdx.x; i < nm * G * GP_STRIDE; i += blockDim.x) s_gp[i] = gp[(size_t)m0 * G * GP_STRIDE + i];
-    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
-        const double* c = mc + (size_t)(m0 + i) * MC_STRIDE;
-        s_m[8 * i + 0] = c[MC_E]; s_m[8 * i + 1] = c[MC_E + 1]; s_m[8 * i + 2] = c[MC_E + 2];
-        s_m[8 * i + 3] = cD0 * c[MC_D];                    // 0.5*rho*Cd*D      (GUI.py:649)
-        s_m[8 * i + 4] = cI0 * c[MC_ACROSS];               // rho*Cm*A_cross    (GUI.py:652)
-        s_m[8 * i + 5] = c[MC_L];
-    }
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_g[i] = gsw[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < nm * G; i += blockDim.x) {
-        const int mm = i / G, g = i % G;
-        const double Lw = s_m[8 * mm + 5] * s_g[G + g];
-        s_c[2 * i] = s_m[8 * mm + 3] * Lw; s_c[2 * i + 1] = s_m[8 * mm + 4] * Lw;
-    }
-    __syncthreads();
-
-    int p = p_off + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= ldP) return;
-    const double cw0 = trig[p], sw0 = trig[ldP + p], cw1 = trig[2 * (size_t)ldP + p], sw1 = trig[3 * (size_t)ldP + p];
-    double td[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tm[3] = {0, 0, 0};
-
-    for (int mm = 0; mm < nm; ++mm) {
-        const double e0 = s_m[8 * mm], e1 = s_m[8 * mm + 1], e2 = s_m[8 * mm + 2];
-        MemberAcc A = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        double sub = 0.0;
-        const double* gpm = s_gp + mm * G * GP_STRIDE;
-        const double* cm = s_c + mm * G * 2;
-        for (int g = 0; g < G; ++g) {
-            const double ckx = gpm[g * GP_STRIDE], skx = gpm[g * GP_STRIDE + 1];
-            const double Cu = gpm[g * GP_STRIDE + 2], Cw = gpm[g * GP_STRIDE + 3], z = gpm[g * GP_STRIDE + 4];
-            // cos / sin of (k xw - omega t) at t and t + dt
-            const double c0 = fma(skx, sw0, ckx * cw0), s0 = fma(skx, cw0, -(ckx * sw0));
-            const double eta0 = wv.a * c0;                                     // GUI.py:265
-            if (z > eta0) continue;                                            // dry at t (GUI.py:292, 627)
-            const double c1 = fma(skx, sw1, ckx * cw1), s1 = fma(skx, cw1, -(ckx * sw1));
-            const double eta1 = wv.a * c1;
-            const bool wet1 = !(z > eta1);                                     // GUI.py:269 at t + dt
-            const double u0 = fma(Cu, c0, wv.Uc), w0 = Cw * s0;                // GUI.py:279-281
-            const double u1 = wet1 ? fma(Cu, c1, wv.Uc) : 0.0, w1 = wet1 ? Cw * s1 : 0.0;
-            const double du = (u1 - u0) * wv.inv_dt, dw = (w1 - w0) * wv.inv_dt;   // GUI.py:288
-            const double uwo = u0 - wv.Uc;                                     // GUI.py:573
-            morison_point(A, fma(uwo, wv.cos_w, wv.uc_cos_c), fma(uwo, wv.sin_w, wv.uc_sin_c), w0,
-                          du * wv.cos_w, du * wv.sin_w, dw, e0, e1, e2, cm[2 * g], cm[2 * g + 1], s_g[g]);
-            if (DETAILS) sub += s_m[8 * mm + 5] * s_g[G + g];
-        }
-        size_t o = ((size_t)(m0 + mm) * 6) * ldP + p;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double mt = A.md[k] + A.mi[k];
-            Fm[o + (size_t)k * ldP] = mt - A.F2[k];                            // F1 = sum (1-s) f   (GUI.py:658)
-            Fm[o + (size_t)(3 + k) * ldP] = A.F2[k];                           // F2 = sum s f       (GUI.py:659)
-            td[k] += A.md[k]; ti[k] += A.mi[k]; tm[k] += mt;                    // GUI.py:664-666
-        }
-        if (DETAILS) {
-            size_t od = ((size_t)(m0 + mm) * 4) * ldP + p;
-            double mt0 = A.md[0] + A.mi[0], mt1 = A.md[1] + A.mi[1], mt2 = A.md[2] + A.mi[2];
-            details[od] = sqrt(A.md[0] * A.md[0] + A.md[1] * A.md[1] + A.md[2] * A.md[2]) / 1000.0;
-            details[od + ldP] = sqrt(A.mi[0] * A.mi[0] + A.mi[1] * A.mi[1] + A.mi[2] * A.mi[2]) / 1000.0;
-            details[od + 2 * (size_t)ldP] = sqrt(mt0 * mt0 + mt1 * mt1 + mt2 * mt2) / 1000.0;
-            details[od + 3 * (size_t)ldP] = sub;
-        }
-    }
-    size_t ot = ((size_t)chunk * 9) * ldP + p;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        totpart[ot + (size_t)k * ldP] = td[k];
-        totpart[ot + (size_t)(3 + k) * ldP] = ti[k];
-        totpart[ot + (size_t)(6 + k) * ldP] = tm[k];
-    }
-}
-
-constexpr int MORISON_AIRY_SMEM_PER_MEMBER_EXTRA = 8;
-constexpr int MORISON_AIRY_SMEM_PER_POINT_EXTRA = 2;
 #endif
 
 // ----------------------------------------------------------------------------------------------
@@ -847,6 +879,20 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
         for (int c = 3; c < 6; ++c) Ffix[(size_t)(6 * fi + c) * ldP + p] = Fstatic[6 * node + c] + fdir[c];
     }
     }
+}
+
+// Morison nodal loads of one phase after a FUSED scan: the sum of the node's partial rows (same order as the kernel's own
+// finalisation).  e = position of the node in the finalisation lists.
+__global__ void k_nodal_from_partials(int n_fin, int ldP, int p, const int* __restrict__ fin_node, const int* __restrict__ fin_rowptr,
+                                      const int* __restrict__ fin_rows, const double* __restrict__ part, double* __restrict__ nodal) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_fin) return;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int r = fin_rowptr[e]; r < fin_rowptr[e + 1]; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] += part[((size_t)fin_rows[r] * 3 + k) * ldP + p];
+    const int node = fin_node[e];
+    nodal[3 * node] = v[0]; nodal[3 * node + 1] = v[1]; nodal[3 * node + 2] = v[2];
 }
 
 // caller-built load cases (jk_solve): F[p][6*Nn] host layout already on device -> B / Ffix
