@@ -88,15 +88,16 @@ def peaks():
 
 
 def measured_traffic(workload, kernel):
-    """dram read + write bytes per launch of `kernel` from the newest ncu --set full summary under profiles/ (written by
-    tools/ncu_summary.py --traffic-json); None when no capture of this workload is committed -- never a constant in this file."""
+    """dram read + write bytes of all launches of `kernel` in ONE step, from the newest ncu --set full summary under profiles/
+    (written by tools/ncu_summary.py --traffic-json from a capture of exactly one step); None when no capture of this workload
+    is committed -- never a constant in this file."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.isfile(path):
         return None, None
     with open(path) as f:
         data = json.load(f)
     entry = data.get(workload, {}).get(kernel)
-    return (entry.get("bytes_per_launch"), entry.get("source")) if entry else (None, None)
+    return (entry.get("bytes_per_step"), entry.get("source")) if entry else (None, None)
 
 
 def shard(args, world, rank):
@@ -563,6 +564,8 @@ def pick_roofline(kernels, stage, step_ms, workload, peak_src):
     dom = max((kk for kk in exposed if kk in kernels), key=lambda kk: exposed[kk])
     d = kernels[dom]
     traffic, traffic_src = measured_traffic(workload, dom)
+    if traffic is not None:
+        traffic /= d.get("launches_per_step", 1)        # the capture covers one step; the roofline entry is per "launch" as counted here
     return {"kernel": dom, "bound": "tensor" if d["bound"] in ("tensor", "fp64") else "hbm", "achieved": d["achieved"], "peak": d["peak"],
             "unit": d["unit"], "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src,
             "executed": d.get("executed"), "frac_executed": d.get("frac_executed"), "frac_min_envelope": d.get("frac_min_envelope"),

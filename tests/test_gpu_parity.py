@@ -268,6 +268,19 @@ def test_overlapped_factor_matches_blocking():
     e2.set_morison(0.3, 0.3, 1025.0, 0.7, 2.0, 15)
     with pytest.raises(jb.NotPositiveDefinite):
         e2.phase_scan(np.linspace(0.0, 9.0, 8), ap.fy)
+    assert not e2._factored                                  # the engine does not keep an unusable factor
+    # resident loop (nothing read back between steps): the pivot flag is sticky across re-assembly, the on-device critical pair
+    # is poisoned meanwhile, and the first call that talks to the host reports the failure
+    import torch
+    from jacket_b200.distributed import device_views
+    td = torch.linspace(0.0, 9.0, 8, dtype=torch.float64, device=f"cuda:{e2.device}")
+    for _ in range(3):
+        e2.step_dev(ap.E, G, 8, td.data_ptr(), ap.fy)
+    torch.cuda.synchronize()
+    _, val, idx = device_views(e2, 8)
+    assert int(idx.cpu()) == -1 and np.isnan(float(val.cpu()))
+    with pytest.raises(jb.NotPositiveDefinite):
+        e2.read_table(8)
 
 
 @pytest.mark.parametrize("model,N,H", [("Stokes", 5, 8.0), ("Fenton", 10, 17.038), ("Airy", 1, 6.0)])

@@ -5,7 +5,7 @@ tag=$1; shift
 for v in "$@"; do
   name=$(basename $v .so)
   if [ "$v" = "default" ]; then unset JK_LIB; else export JK_LIB=$PWD/$v; fi
-  timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
+  timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
   python - "$name" gpurun_out/${tag}_${name}.json <<'PY'
 import json, sys
 name, f = sys.argv[1], sys.argv[2]

@@ -44,7 +44,7 @@ ncu)
   $cmd > gpurun_out/${tag}_plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${tag}_launches.csv $cmd > gpurun_out/${tag}_ncu1.log 2>&1
   $cmd > gpurun_out/${tag}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"k_sweep$|k_sweep<|k_morison_airy|k_member_post|k_rhs_gather|k_band_chol_cluster|k_tile_inverse|k_load_assemble" -s ${NCU_SKIP:-57} -c ${NCU_COUNT:-19} \
+  ncu --set full --clock-control none --import-source on -k regex:"^k_sweep$|k_morison_airy|k_member_post|k_rhs_gather|k_band_chol_cluster|k_tile_inverse" -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-15} \
       -f -o gpurun_out/${tag}_prof $cmd > gpurun_out/${tag}_ncu2.log 2>&1
   ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
   tail -3 gpurun_out/${tag}_ncu2.log ;;

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Summarise ncu outputs for profiles/: a launch list (`--metrics gpu__time_duration.sum --csv --log-file`) and the raw
 page of one `--set full` capture (`ncu -i X.ncu-rep --page raw --csv`).  Usage:
-    python tools/ncu_summary.py launches.csv raw.csv bench.json > profiles/rNN_ncu.md"""
+    python tools/ncu_summary.py launches.csv raw.csv bench.json > profiles/rNN_ncu.md
+    python tools/ncu_summary.py --traffic-json raw.csv profiles/ncu_traffic.json c4_jacket10k profiles/rNN_raw.csv.gz"""
 import csv
 import json
 import re
@@ -82,7 +83,34 @@ def full_table(path):
     return "\n".join(out)
 
 
+def traffic_json(raw_path, out_path, workload, source):
+    """profiles/ncu_traffic.json: dram read + write bytes per launch of every captured kernel (mean over its launches) --
+    bench.py fills roofline.traffic from this file, never from a constant."""
+    import os
+    rows = list(csv.reader(open(raw_path, errors="replace")))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = {}
+    for r in rows[2:]:
+        name = re.sub(r"<.*", "", short(r[ki]))
+        try:
+            b = float(r[ri].replace(",", "")) * scale.get(units[ri], 1.0) + float(r[wi].replace(",", "")) * scale.get(units[wi], 1.0)
+        except ValueError:
+            continue
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += b
+    data = json.load(open(out_path)) if os.path.isfile(out_path) else {}
+    # the capture covers exactly one step: bytes_per_step = all launches of the kernel in that step
+    data[workload] = {k: {"bytes_per_launch": v[1] / v[0], "launches_in_step": v[0], "bytes_per_step": v[1], "source": source} for k, v in agg.items()}
+    json.dump(data, open(out_path, "w"), indent=1, sort_keys=True)
+
+
 def main():
+    if sys.argv[1] == "--traffic-json":       # tools/ncu_summary.py --traffic-json raw.csv profiles/ncu_traffic.json workload source
+        traffic_json(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+        return
     launches, raw = sys.argv[1], sys.argv[2]
     print("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)\n")
     print(launch_table(launches))
