@@ -86,7 +86,7 @@ struct jk_handle_s {
     int Nn = 0, M = 0, nsec = 0;
     std::vector<double> h_xyz;
     std::vector<int> h_conn, h_sec;
-    double *d_xyz = nullptr, *d_secp = nullptr, *d_mc = nullptr, *d_Ke = nullptr, *d_Kl = nullptr;
+    double *d_xyz = nullptr, *d_secp = nullptr, *d_mc = nullptr, *d_Ke = nullptr, *d_Kl = nullptr, *d_pk = nullptr;
     int *d_conn = nullptr, *d_sec = nullptr, *d_adj_ptr = nullptr, *d_adj = nullptr;
     std::vector<int> h_adj_ptr, h_adj;
 
@@ -315,6 +315,7 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, dev_alloc(&h->d_sec, (size_t)n_members));
     CUDA_TRY(h, dev_alloc(&h->d_secp, (size_t)n_sec * JK_SEC_NPROP));
     CUDA_TRY(h, dev_alloc(&h->d_mc, (size_t)n_members * MC_STRIDE));
+    CUDA_TRY(h, dev_alloc(&h->d_pk, (size_t)n_members * PK_STRIDE));
     CUDA_TRY(h, dev_alloc(&h->d_Ke, (size_t)n_members * 144));
     CUDA_TRY(h, dev_alloc(&h->d_Kl, (size_t)n_members * 144));
     CUDA_TRY(h, dev_alloc(&h->d_adj_ptr, (size_t)n_nodes + 1));
@@ -354,7 +355,7 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (!h) return JK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    dev_free(h->d_xyz); dev_free(h->d_secp); dev_free(h->d_mc); dev_free(h->d_Ke); dev_free(h->d_Kl);
+    dev_free(h->d_xyz); dev_free(h->d_secp); dev_free(h->d_mc); dev_free(h->d_Ke); dev_free(h->d_Kl); dev_free(h->d_pk);
     dev_free(h->d_conn); dev_free(h->d_sec); dev_free(h->d_adj_ptr); dev_free(h->d_adj);
     dev_free(h->d_node2slot); dev_free(h->d_fixed_nodes); dev_free(h->d_free_nodes);
     for (auto& c : h->ch) { dev_free(c.d_blocks); dev_free(c.d_contrib); dev_free(c.d_tiles); dev_free(c.d_Linv); dev_free(c.d_dinv);
@@ -991,6 +992,8 @@ static int assemble_launch(jk_handle_t h, double E, double G) {
     tic(h, JK_T_ASSEMBLE);
     k_member_setup<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, h->d_xyz, h->d_conn, h->d_sec, h->d_secp, JK_SEC_NPROP, E, G, h->d_mc, h->d_Ke, h->d_Kl);
     LAUNCH_CHECK(h);
+    k_pack_member_consts<<<ceil_div(h->M, 128), 128, 0, s>>>(h->M, h->d_mc, h->sp, h->d_pk);
+    LAUNCH_CHECK(h);
     for (int c = 0; c < h->n_chains; ++c) {
         auto& chn = h->ch[c];
         CUDA_TRY(h, cudaMemsetAsync(chn.d_tiles, 0, chn.tiles_elems * sizeof(double), s));
@@ -1535,7 +1538,7 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
                 if (h->wait_value32((CUstream)s3, (CUdeviceptr)h->d_started, (cuuint32_t)h->started_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
                     JK_FAIL(h, JK_ECUDA, "run_fem: cuStreamWaitValue32 failed");
                 k_member_post<<<dim3(h->n_post_early, gm_all.y), JK_POST_TPB, 0, s3>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
-                                                                                   h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, h->d_post_chunks);
+                                                                                   h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, h->d_post_chunks, h->d_pk);
                 LAUNCH_CHECK(h);
                 CUDA_TRY(h, cudaEventRecord(h->ev_post_early, s3));
                 post_early = true;
@@ -1598,13 +1601,13 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     if (post_early) {
         if (h->n_post_late > 0) {
             k_member_post<<<dim3(h->n_post_late, gm_all.y), JK_POST_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
-                                                                              h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, h->d_post_chunks + h->n_post_early);
+                                                                              h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, h->d_post_chunks + h->n_post_early, h->d_pk);
             LAUNCH_CHECK(h);
         }
         CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_post_early, 0));
     } else {
         k_member_post<<<gm_all, JK_POST_TPB, 0, s>>>(h->M, ldP, ldP, h->n_pad, h->d_X, h->d_node2slot, h->d_conn, h->d_mc, h->sp, fy,
-                                                 h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem);
+                                                 h->d_rows, h->d_part_util, h->d_part_vm, h->d_part_mem, nullptr, h->d_pk);
         LAUNCH_CHECK(h);
     }
     if (s2 != s) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_post_join, 0));

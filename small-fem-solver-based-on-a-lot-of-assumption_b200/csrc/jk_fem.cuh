@@ -281,6 +281,12 @@ __device__ __forceinline__ void member_row_pk(const double* pk, const double* Fl
     row[6] = vm * inv_fy;
 }
 
+// packed per-member constants of the member post, once per assembly: pk[M][PK_STRIDE]
+__global__ void k_pack_member_consts(int M, const double* __restrict__ mc, StressPts sp, double* __restrict__ pk) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) pack_member_consts(mc + (size_t)m * MC_STRIDE, sp, pk + (size_t)m * PK_STRIDE);
+}
+
 __device__ __forceinline__ double load_u(const double* __restrict__ X, const int* __restrict__ node2slot,
                                          int node, int comp, int p, int n_pad) {
     int s = node2slot[node];
@@ -294,24 +300,27 @@ __global__ void __launch_bounds__(JK_POST_TPB)
 k_member_post(int M, int P, int ldP, int n_pad, const double* __restrict__ X, const int* __restrict__ node2slot,
               const int* __restrict__ conn, const double* __restrict__ mc, StressPts sp, double fy,
               double* __restrict__ rows, double* __restrict__ part_util, double* __restrict__ part_vm,
-              int* __restrict__ part_mem, const int* __restrict__ chunk_list = nullptr /* nullable: member chunks of this launch */) {
-    __shared__ double s_mc[MCHUNK * MC_STRIDE];
+              int* __restrict__ part_mem, const int* __restrict__ chunk_list = nullptr /* nullable: member chunks of this launch */,
+              const double* __restrict__ pk_all = nullptr /* [M][PK_STRIDE] from k_pack_member_consts */) {
+    // 8.5 KB of shared memory per block (the packed rows come ready-made from k_pack_member_consts): two of these blocks fit
+    // beside a sweep CTA, so the early member post runs on the SMs the backward sweep occupies, not only on the idle ones
     __shared__ int s_slot[MCHUNK * 2];
 #if JK_POST_PACKED
     __shared__ __align__(16) double s_pk[MCHUNK * PK_STRIDE];
 #else
+    __shared__ double s_mc[MCHUNK * MC_STRIDE];
     __shared__ double s_pt[MCHUNK * 24];
 #endif
     // chunk index is the FAST grid dimension: the blocks in flight share one or two 128-phase tiles, whose slice of
     // the solution (n x 128 doubles = 20 MB at c4) stays L2-resident while every member chunk re-reads its nodes
     int chunk = chunk_list ? chunk_list[blockIdx.x] : (int)blockIdx.x, m0 = chunk * MCHUNK;
     int nm = min(MCHUNK, M - m0);
-    for (int i = threadIdx.x; i < nm * MC_STRIDE; i += blockDim.x) s_mc[i] = mc[(size_t)m0 * MC_STRIDE + i];
     for (int i = threadIdx.x; i < nm * 2; i += blockDim.x) s_slot[i] = node2slot[conn[2 * m0 + i]];
-    __syncthreads();
 #if JK_POST_PACKED
-    for (int i = threadIdx.x; i < nm; i += blockDim.x) pack_member_consts(s_mc + i * MC_STRIDE, sp, s_pk + i * PK_STRIDE);
+    for (int i = threadIdx.x; i < nm * PK_STRIDE; i += blockDim.x) s_pk[i] = pk_all[(size_t)m0 * PK_STRIDE + i];
 #else
+    for (int i = threadIdx.x; i < nm * MC_STRIDE; i += blockDim.x) s_mc[i] = mc[(size_t)m0 * MC_STRIDE + i];
+    __syncthreads();
     for (int i = threadIdx.x; i < nm * 8; i += blockDim.x) stress_point_coeffs(s_mc + (i / 8) * MC_STRIDE, sp, i % 8, s_pt + 3 * i);
 #endif
     __syncthreads();
