@@ -216,6 +216,15 @@ int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const double* a, 
                      const double* theta_wave, const double* t, const double* F_dir, double fy, double* table,
                      int64_t* critical_per_state);
 
+/* The same ensemble from the raw sea-state parameters: significant numbers as the GUI takes them (H [m], T [s], wave
+ * direction in compass degrees, GUI.py:1880-1900).  Amplitude, omega, the dispersion Newton iteration (GUI.py:197-206, one
+ * thread per sea state, the reference's start value and stopping test), the heading cos/sin (GUI.py:548) and the case times
+ * t = i*T/n_phase (GUI.py:696) are computed on the device; nothing but 3*n_states doubles crosses the bus.
+ * k_out[n_states] (nullable) receives the wave numbers. */
+int jk_ensemble_scan_sea_states(jk_handle_t h, int n_states, int n_phase, const double* H, const double* T,
+                                const double* wave_dir_deg, double gravity, const double* F_dir, double fy,
+                                double* table, int64_t* critical_per_state, double* k_out);
+
 /* FEMSolver.solve with caller-built right-hand sides (GUI.py:481-490):
  * F[nrhs*6*n_nodes] (row = load case) -> same pipeline as jk_phase_scan minus Morison. */
 int jk_solve(jk_handle_t h, int nrhs, const double* F, double fy);

@@ -80,6 +80,7 @@ def _sig(lib):
     lib.jk_read_table.argtypes = [H, C.c_int, _dp, C.POINTER(C.c_int64)]
     lib.jk_solve.argtypes = [H, C.c_int, _dp, C.c_double]
     lib.jk_ensemble_scan.argtypes = [H, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, C.POINTER(C.c_int64)]
+    lib.jk_ensemble_scan_sea_states.argtypes = [H, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp, C.c_double, _dp, C.POINTER(C.c_int64), _dp]
     lib.jk_fetch_phase.argtypes = [H, C.c_int, _dp, _dp, _dp, _dp, _dp]
     lib.jk_fetch_member_column.argtypes = [H, C.c_int, C.c_int, C.c_int, _dp]
     lib.jk_get_dims.argtypes = [H, _ip]
@@ -100,7 +101,7 @@ def _sig(lib):
         getattr(lib, name).restype = C.c_void_p
     for name in ("jk_create", "jk_destroy", "jk_set_supports", "jk_assemble", "jk_factor", "jk_factor_begin", "jk_set_static_load",
                  "jk_set_wave_airy", "jk_set_wave_fourier", "jk_set_morison", "jk_morison_scan", "jk_morison_single",
-                 "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_ensemble_scan", "jk_fetch_phase",
+                 "jk_phase_scan", "jk_phase_scan_dev", "jk_read_table", "jk_solve", "jk_ensemble_scan", "jk_ensemble_scan_sea_states", "jk_fetch_phase",
                  "jk_fetch_member_column", "jk_get_dims", "jk_get_order", "jk_get_K", "jk_get_elements",
                  "jk_get_timings", "jk_residual", "jk_solver_stats", "jk_set_option", "jk_get_option", "jk_kinematics_points", "jk_step", "jk_step_dev"):
         getattr(lib, name).restype = C.c_int

@@ -318,7 +318,7 @@ def dispersion_wavenumbers(T, d, gravity=g):
 
 def ensemble_scan(structure, H, T, wave_dir, n_phase=16, *, d=50.0, U_c=0.0, current_direction=0.0, Cd=0.7, Cm=2.0,
                   rho_water=1025.0, E=210000.0, nu=0.3, fy=355.0, params: AnalysisParams | None = None, n_gauss=15,
-                  dt=0.001, engine=None):
+                  dt=0.001, engine=None, host_dispersion=False):
     """Morison + FEM for n_phase phases of every sea state (H[i], T[i], wave_dir[i]) -- Airy kinematics (the pinned
     model), current and depth common to all states, one Cholesky factor for the whole ensemble.  With ``params`` the
     GUI's interface loads and self-weight are applied; the interface shear follows each state's wave direction as
@@ -340,11 +340,16 @@ def ensemble_scan(structure, H, T, wave_dir, n_phase=16, *, d=50.0, U_c=0.0, cur
             F_dir[1, 6 * i + 1] = params.F_shear * 1000.0 / len(top)
     else:
         eng.set_static_load(np.zeros(structure.n_dof))
-    k = dispersion_wavenumbers(T, d)
-    omega = 2.0 * np.pi / T
     wave0 = RaschiiWave(float(H[0]), float(T[0]), d, U_c, "Airy", 1, dt)          # carries depth / current / dt
     eng.set_wave(wave0)
     eng.set_morison(0.0, np.deg2rad(90.0 - current_direction), rho_water, Cd, Cm, n_gauss)
-    t = np.arange(n_phase)[None, :] * T[:, None] / n_phase                           # (i*T)/n_steps, GUI.py:696, per state
-    table, crit = eng.ensemble_scan(H / 2.0, k, omega, np.deg2rad(90.0 - wave_dir), t, fy, F_dir)
+    if host_dispersion:
+        # host set-up (vectorised NumPy Newton): the arrays jk_ensemble_scan takes
+        k = dispersion_wavenumbers(T, d)
+        omega = 2.0 * np.pi / T
+        t = np.arange(n_phase)[None, :] * T[:, None] / n_phase                       # (i*T)/n_steps, GUI.py:696, per state
+        table, crit = eng.ensemble_scan(H / 2.0, k, omega, np.deg2rad(90.0 - wave_dir), t, fy, F_dir)
+    else:
+        # default: raw sea-state numbers in, dispersion / headings / case times on the device
+        table, crit, k = eng.ensemble_scan_sea_states(H, T, wave_dir, n_phase, fy, F_dir, gravity=g)
     return EnsembleResult(structure, H, T, wave_dir, k, table, crit, fy, eng, generation=eng.generation)

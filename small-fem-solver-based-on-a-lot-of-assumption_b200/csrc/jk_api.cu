@@ -1917,46 +1917,98 @@ extern "C" int jk_kinematics_points(jk_handle_t h, int n, const double* xyz, dou
 }
 
 // Sea-state ensemble: n_states Airy sea states x n_phase phases each = one batch of load cases on one factor.
-extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const double* a, const double* k, const double* omega,
-                                const double* theta_wave, const double* t, const double* F_dir, double fy, double* table,
-                                int64_t* critical_per_state) {
-    if (!h) return JK_EINVAL;
-    if (n_states <= 0 || !a || !k || !omega || !theta_wave || !t) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: empty or NULL sea-state arrays");
-    if (n_phase < 8 || n_phase > 4096) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: n_phase must be in 8..4096 (got %d)", n_phase);
-    if ((long long)n_states * n_phase > (1LL << 30)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: too many load cases");
+// common front of the two ensemble entry points: argument checks, buffers, the optional direction loads
+static int ensemble_prepare(jk_handle_t h, const char* who, int n_states, int n_phase, const double* F_dir, double fy, double** d_Fdir) {
+    if (n_phase < 8 || n_phase > 4096) JK_FAIL(h, JK_EINVAL, "%s: n_phase must be in 8..4096 (got %d)", who, n_phase);
+    if ((long long)n_states * n_phase > (1LL << 30)) JK_FAIL(h, JK_EINVAL, "%s: too many load cases", who);
     if (!h->have_wave || !h->have_morison || h->wave_kind != 0)
-        JK_FAIL(h, JK_ESTATE, "jk_ensemble_scan: call jk_set_wave_airy (depth, current, dt) and jk_set_morison (current heading, coefficients) first");
-    if (!h->factored) JK_FAIL(h, JK_ESTATE, "jk_ensemble_scan: call jk_assemble and jk_factor first");
-    if (!(fy > 0)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: fy must be positive");
+        JK_FAIL(h, JK_ESTATE, "%s: call jk_set_wave_airy (depth, current, dt) and jk_set_morison (current heading, coefficients) first", who);
+    if (!h->factored) JK_FAIL(h, JK_ESTATE, "%s: call jk_assemble and jk_factor first", who);
+    if (!(fy > 0)) JK_FAIL(h, JK_EINVAL, "%s: fy must be positive", who);
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     const int C = n_states * n_phase;
     int rc;
     if ((rc = ensure_buffers(h, C, true, false)) != JK_OK) return rc;
-    const int ldC = ceil_div(C, SLAB) * SLAB;
     if (n_states > h->cap_states) {
         CUDA_TRY(h, dev_alloc(&h->d_states, 5 * (size_t)n_states));
         CUDA_TRY(h, dev_alloc(&h->d_state_crit, (size_t)n_states));
         h->cap_states = n_states;
     }
+    *d_Fdir = nullptr;
+    if (F_dir) {
+        size_t nF = 12 * (size_t)h->Nn;
+        if (nF > h->fload_elems) { CUDA_TRY(h, dev_alloc(&h->d_Fload, nF)); h->fload_elems = nF; }
+        *d_Fdir = h->d_Fload;
+        CUDA_TRY(h, cudaMemcpyAsync(*d_Fdir, F_dir, nF * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    return JK_OK;
+}
+
+static int ensemble_run(jk_handle_t h, int n_states, int n_phase, double* d_Fdir, bool have_fdir, double fy, double* table,
+                        int64_t* critical_per_state);
+
+extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const double* a, const double* k, const double* omega,
+                                const double* theta_wave, const double* t, const double* F_dir, double fy, double* table,
+                                int64_t* critical_per_state) {
+    if (!h) return JK_EINVAL;
+    if (n_states <= 0 || !a || !k || !omega || !theta_wave || !t) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: empty or NULL sea-state arrays");
+    int rc;
+    double* d_Fdir;
+    if ((rc = ensemble_prepare(h, "jk_ensemble_scan", n_states, n_phase, F_dir, fy, &d_Fdir)) != JK_OK) return rc;
+    cudaStream_t s = h->stream;
+    const int C = n_states * n_phase;
     std::vector<double> st(5 * (size_t)n_states);
     for (int i = 0; i < n_states; ++i) {
         if (!(k[i] > 0) || !(omega[i] > 0)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan: state %d has non-positive k or omega", i);
         st[i] = a[i]; st[(size_t)n_states + i] = k[i]; st[2 * (size_t)n_states + i] = omega[i];
         st[3 * (size_t)n_states + i] = cos(theta_wave[i]); st[4 * (size_t)n_states + i] = sin(theta_wave[i]);
     }
-    double* d_Fdir = nullptr;
-    if (F_dir) {
-        size_t nF = 12 * (size_t)h->Nn;
-        if (nF > h->fload_elems) { CUDA_TRY(h, dev_alloc(&h->d_Fload, nF)); h->fload_elems = nF; }
-        d_Fdir = h->d_Fload;
-        CUDA_TRY(h, cudaMemcpyAsync(d_Fdir, F_dir, nF * sizeof(double), cudaMemcpyHostToDevice, s));
-    }
     tic(h, JK_T_SCAN_TOTAL);
     tic(h, JK_T_H2D);
     CUDA_TRY(h, cudaMemcpyAsync(h->d_states, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_t, t, (size_t)C * sizeof(double), cudaMemcpyHostToDevice, s));
     toc(h, JK_T_H2D);
+    return ensemble_run(h, n_states, n_phase, d_Fdir, F_dir != nullptr, fy, table, critical_per_state);
+}
+
+extern "C" int jk_ensemble_scan_sea_states(jk_handle_t h, int n_states, int n_phase, const double* H, const double* T,
+                                           const double* wave_dir_deg, double gravity, const double* F_dir, double fy,
+                                           double* table, int64_t* critical_per_state, double* k_out) {
+    if (!h) return JK_EINVAL;
+    if (n_states <= 0 || !H || !T || !wave_dir_deg) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan_sea_states: empty or NULL sea-state arrays");
+    if (!(gravity > 0)) JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan_sea_states: gravity must be positive");
+    int rc;
+    double* d_Fdir;
+    if ((rc = ensemble_prepare(h, "jk_ensemble_scan_sea_states", n_states, n_phase, F_dir, fy, &d_Fdir)) != JK_OK) return rc;
+    cudaStream_t s = h->stream;
+    const size_t S = (size_t)n_states;
+    if ((rc = ensure_tmp(h, 3 * S + 1)) != JK_OK) return rc;
+    double *dH = h->d_tmp, *dT = dH + S, *dD = dT + S;
+    int* d_bad = reinterpret_cast<int*>(dD + S);
+    tic(h, JK_T_SCAN_TOTAL);
+    tic(h, JK_T_H2D);
+    CUDA_TRY(h, cudaMemcpyAsync(dH, H, S * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(dT, T, S * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(dD, wave_dir_deg, S * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+    toc(h, JK_T_H2D);
+    k_sea_state_setup<<<ceil_div(n_states, 128), 128, 0, s>>>(n_states, n_phase, dH, dT, dD, h->wv.d, gravity, h->d_states, h->d_t, d_bad);
+    LAUNCH_CHECK(h);
+    int bad = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (k_out) CUDA_TRY(h, cudaMemcpyAsync(k_out, h->d_states + S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    rc = ensemble_run(h, n_states, n_phase, d_Fdir, F_dir != nullptr, fy, table, critical_per_state);   // synchronises the stream
+    if (bad) { h->lastP = 0; JK_FAIL(h, JK_EINVAL, "jk_ensemble_scan_sea_states: state %d has a negative height or a non-positive period", bad - 1); }
+    return rc;
+}
+
+static int ensemble_run(jk_handle_t h, int n_states, int n_phase, double* d_Fdir, bool have_fdir, double fy, double* table,
+                        int64_t* critical_per_state) {
+    cudaStream_t s = h->stream;
+    const int C = n_states * n_phase;
+    const int ldC = ceil_div(C, SLAB) * SLAB;
+    int rc;
     if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
     WaveAiry w = launch_wave(h);
     tic(h, JK_T_MORISON);
@@ -1983,7 +2035,7 @@ extern "C" int jk_ensemble_scan(jk_handle_t h, int n_states, int n_phase, const 
     k_argmax_per_state<<<ceil_div(n_states, 128), 128, 0, s>>>(n_states, n_phase, h->d_table, JK_TABLE_NCOL, JK_COL_TOTAL_KN, h->d_state_crit);
     LAUNCH_CHECK(h);
     toc(h, JK_T_SCAN_TOTAL);
-    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = F_dir != nullptr; h->last_fused = false;
+    h->lastP = C; h->last_ldP = ldC; h->last_morison = true; h->last_fem = true; h->last_fy = fy; h->last_fdir = have_fdir; h->last_fused = false;
     tic(h, JK_T_D2H);
     if (table) CUDA_TRY(h, cudaMemcpyAsync(table, h->d_table, (size_t)C * JK_TABLE_NCOL * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<long long> crit(n_states);

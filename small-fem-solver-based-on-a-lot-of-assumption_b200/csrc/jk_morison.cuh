@@ -821,6 +821,34 @@ __global__ void k_kinematics_points(int n, const double* __restrict__ xyz, doubl
 }
 
 // first index (within each sea state) of the maximum of table[:, col]; one thread per state
+// Sea-state set-up of the ensemble on the device: per state a = H/2, omega = 2 pi / T, the wave number by the
+// reference's Newton iteration (GUI.py:197-206: deep-water start, the loop breaks BEFORE the last update is applied), the
+// heading cos/sin of the math angle 90 deg - wave_dir (GUI.py:548) and the case times t = i*T/n_phase (GUI.py:696).
+// st[5][S] = a, k, omega, cos, sin (the layout k_morison_ensemble reads); bad[0] = 1 + index of a state with a non-positive
+// H or T (0: none).
+__global__ void k_sea_state_setup(int S, int n_phase, const double* __restrict__ H, const double* __restrict__ T,
+                                  const double* __restrict__ wave_dir_deg, double d, double gravity,
+                                  double* __restrict__ st, double* __restrict__ t, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const double Ti = T[i];
+    if (!(Ti > 0.0) || !(H[i] >= 0.0)) { atomicMax(bad, i + 1); return; }
+    const double omega = 2.0 * 3.141592653589793 / Ti, w2 = omega * omega;
+    double k = w2 / gravity;
+    for (int it = 0; it < 50; ++it) {
+        const double th = tanh(k * d), ch = cosh(k * d);
+        const double resid = w2 - gravity * k * th;
+        const double slope = -gravity * (th + k * d / (ch * ch));
+        const double k_next = k - resid / slope;
+        if (fabs(k_next - k) < 1e-10) break;
+        k = k_next;
+    }
+    double sn, cs;
+    sincos((90.0 - wave_dir_deg[i]) * (3.141592653589793 / 180.0), &sn, &cs);
+    st[i] = 0.5 * H[i]; st[(size_t)S + i] = k; st[2 * (size_t)S + i] = omega; st[3 * (size_t)S + i] = cs; st[4 * (size_t)S + i] = sn;
+    for (int q = 0; q < n_phase; ++q) t[(size_t)i * n_phase + q] = __ddiv_rn(__dmul_rn((double)q, Ti), (double)n_phase);
+}
+
 __global__ void k_argmax_per_state(int S, int n_phase, const double* __restrict__ table, int ncol, int col, long long* __restrict__ out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;

@@ -47,7 +47,11 @@ constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1
 constexpr int SW_MAX_BW = SW_RING - 1;
 constexpr int SW_MAX_CONSUMER_WARPS = 16;
-__host__ __device__ constexpr int sw_threads(int ncb) { return 128 * ncb + 32; }   // 4 consumer warps per column block + the producer warp
+#ifndef JK_SW_CBN
+#define JK_SW_CBN 1         // 8-column blocks per consumer warp.  2 (2 x 2 register blocking: half the warps, 2/3 of the shared-memory loads; whole-slab
+                            // CTAs only) MEASURED SLOWER at c4: forward 1.25 vs 1.17 ms, backward 1.59 vs 1.47 ms -- the shared-memory pipe is not the bound
+#endif
+__host__ __device__ constexpr int sw_threads(int ncb) { return 32 * (4 * ncb / JK_SW_CBN) + 32; }   // consumer warps + the producer warp
 constexpr int SW_TILE = NB * NB;            // doubles per A tile
 constexpr int SW_XTILE = NB * SLAB;         // doubles per X tile
 
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(256) k_sweep_build(SweepBuildArgs a, SweepBuil
 
 // Inner products of one item for one consumer warp: acc[a][b] += A(row block a) * X(column block b) over the k-groups.
 // ap[a] / bp point at this lane's element of the first fragment; all further offsets are compile-time constants.
-constexpr int SW_RBN = 2, SW_CBN = 1;     // per consumer warp: the row-block pair (s, 7 - s) x one 8-column block
+constexpr int SW_RBN = 2, SW_CBN = JK_SW_CBN;     // per consumer warp: the row-block pair (s, 7 - s) x one 8-column block
 
 // every row block of the warp is either dense or empty (act[a], warp-uniform): register-double-buffered, fully unrolled
 template <bool ALL>
@@ -314,7 +318,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
                            count from its first row) */,
         long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (option profile_sweep) */,
         unsigned* __restrict__ started = nullptr /* nullable: every CTA adds 1 as soon as it is resident (gate of the early member post) */) {
-    constexpr int SW_CONSUMER_WARPS = 4 * NCB, SW_CONSUMERS = 32 * SW_CONSUMER_WARPS, CTAS_PER_SLAB = 4 / NCB;
+    constexpr int SW_CONSUMER_WARPS = 4 * NCB / SW_CBN, SW_CONSUMERS = 32 * SW_CONSUMER_WARPS, CTAS_PER_SLAB = 4 / NCB;
     extern __shared__ __align__(128) unsigned char sw_smem[];
     if (started != nullptr && threadIdx.x == 0) { atomicAdd(started, 1u); __threadfence(); }
     double* As = reinterpret_cast<double*>(sw_smem);                 // [SW_STAGES][SW_TILE]   A tiles, fragment order
@@ -374,7 +378,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     // scheduler (w, w + 4) cover all eight row blocks of one column block, so every scheduler has the same DMMA count
     // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
-    const int cb0 = cbase + (warp >> 2);
+    const int cb0 = cbase + (warp >> 2) * SW_CBN;
     const int rbs[SW_RBN] = {warp & 3, 7 - (warp & 3)};
     // a program that continues another launch: bring the slots' mbarrier phases in step with the item parities
     if (xphase_bits) {

@@ -235,6 +235,22 @@ class Engine:
                                            L.dptr(Fd), float(fy), L.dptr(table), crit.ctypes.data_as(C.POINTER(C.c_int64))))
         return table.reshape(S, n_phase, L.TABLE_NCOL), crit
 
+    def ensemble_scan_sea_states(self, H, T, wave_dir_deg, n_phase, fy, F_dir=None, gravity=9.81):
+        """Ensemble from the raw sea-state numbers: dispersion, headings and case times are computed on the device
+        (jk_ensemble_scan_sea_states).  Returns (table[S][n_phase][16], critical[S], k[S])."""
+        self._bump()
+        H, T, wave_dir_deg = (L.f64(v).reshape(-1) for v in (H, T, wave_dir_deg))
+        S = H.shape[0]
+        if T.shape[0] != S or wave_dir_deg.shape[0] != S:
+            raise ValueError("H, T and wave_dir must have one entry per sea state")
+        table = np.zeros((S * int(n_phase), L.TABLE_NCOL))
+        crit = np.zeros(S, dtype=np.int64)
+        k = np.zeros(S)
+        Fd = None if F_dir is None else L.f64(F_dir).reshape(2, 6 * self.n_nodes)
+        self._ck(self.lib.jk_ensemble_scan_sea_states(self.h, S, int(n_phase), L.dptr(H), L.dptr(T), L.dptr(wave_dir_deg), float(gravity),
+                                                      L.dptr(Fd), float(fy), L.dptr(table), crit.ctypes.data_as(C.POINTER(C.c_int64)), L.dptr(k)))
+        return table.reshape(S, int(n_phase), L.TABLE_NCOL), crit, k
+
     def solve(self, F, fy=355.0):
         self._bump()
         F = L.f64(F).reshape(-1, 6 * self.n_nodes)
