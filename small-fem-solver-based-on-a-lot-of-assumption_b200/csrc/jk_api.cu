@@ -46,7 +46,7 @@ static const JkOptDesc g_opts[OPT_COUNT] = {
     {"tma_sweep", 1, 0, 1},             // TMA / mbarrier sweep pipeline (0: cp.async slab sweep)        [next jk_set_supports]
     {"blocked_inverse", 1, 0, 1},       // diagonal-tile inverses from the factor's 8x8 block inverses
     {"profile_chol", 0, 0, 1},          // debug: clock stamps of the cluster factorisation to stderr
-    {"profile_sweep", 0, 0, 1},         // debug: clock sums of the sweep warps to stderr
+    {"profile_sweep", 0, 0, 2},         // debug: clock sums of the sweep warps to stderr (2: plus per-item clock stamps of two warps)
     {"debug_factor_delay", 0, 0, 2000000000},   // test aid: spin this many clocks in front of the factorisation
     {"sweep_slab", 0, 0, 32},           // right-hand sides per sweep CTA: 0 = auto (fill the SMs), 8, 16 or 32
     {"cuda_graph", 1, 0, 1},            // replay the resident scan (jk_phase_scan_dev) as a captured CUDA graph
@@ -1463,7 +1463,10 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
     dim3 gsep(ceil_div(ldP, 128), std::max(1, nS6));
     const bool sweep_prof = h->opt[OPT_PROFILE_SWEEP] != 0;
     long long* d_prof = nullptr;
-    if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, 4 * 64 * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, 4 * 64 * sizeof(long long), s)); }
+    constexpr int TRACE_ITEMS = 1024;
+    const size_t prof_elems = 4 * 64 + 4 * (size_t)TRACE_ITEMS * 8;
+    const bool sweep_trace = h->opt[OPT_PROFILE_SWEEP] >= 2;     // per-item clock stamps of two warps of CTA 0 (stderr)
+    if (sweep_prof && h->tma_sweep) { CUDA_TRY(h, cudaMalloc((void**)&d_prof, prof_elems * sizeof(long long))); CUDA_TRY(h, cudaMemsetAsync(d_prof, 0, prof_elems * sizeof(long long), s)); }
     // Right-hand sides per sweep CTA: a whole slab (32) when the slabs fill the GPU, otherwise half or a quarter of a slab per CTA
     // (option sweep_slab = 32 / 16 / 8 forces it).  Few phases make a sweep a latency chain per CTA; narrower CTAs shorten it.
     int ncb = 4;
@@ -1481,9 +1484,10 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         const double* strm = w.d_stream + (size_t)lo * SW_TILE;
         const int pre_row = cont ? w.k_split - w.npre2 : w.pre_row, npre = cont ? w.npre2 : w.npre, xph = cont ? w.xphase2 : 0;
         long long* pf = d_prof ? d_prof + (2 * c + d) * 64 : nullptr;
-        if (ncb == 4) k_sweep<4><<<sweep_ctas, sw_threads(4), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started);
-        else if (ncb == 2) k_sweep<2><<<sweep_ctas, sw_threads(2), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started);
-        else k_sweep<1><<<sweep_ctas, sw_threads(1), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started);
+        long long* tr = (d_prof && sweep_trace && part == 0 && hi - lo <= TRACE_ITEMS) ? d_prof + 4 * 64 + (size_t)(2 * c + d) * TRACE_ITEMS * 8 : nullptr;
+        if (ncb == 4) k_sweep<4><<<sweep_ctas, sw_threads(4), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
+        else if (ncb == 2) k_sweep<2><<<sweep_ctas, sw_threads(2), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
+        else k_sweep<1><<<sweep_ctas, sw_threads(1), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
         return true;
     };
     // Early member post (see d_post_chunks): only when the backward sweep of the second chain leaves SMs idle (one CTA per
@@ -1546,10 +1550,26 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         }
         toc(h, JK_T_SOLVE_BWD);
         if (d_prof) {   // debug aid: where the consumer warps of CTA 0 spend their clocks
-            long long hp[4 * 64];
-            CUDA_TRY(h, cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, s));
+            std::vector<long long> hpv(prof_elems);
+            long long* hp = hpv.data();
+            CUDA_TRY(h, cudaMemcpyAsync(hp, d_prof, prof_elems * sizeof(long long), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(h, cudaStreamSynchronize(s));
             cudaFree(d_prof);
+            if (sweep_trace)
+                for (int q = 0; q < 4; ++q) {
+                    auto& w = h->ch[q / 2].sw[q % 2];
+                    if (q / 2 >= h->n_chains || w.n_items == 0 || w.n_items > TRACE_ITEMS) continue;
+                    std::vector<uint4> hprog((size_t)w.n_items * SW_ITEM_U4);
+                    cudaMemcpy(hprog.data(), w.d_prog, hprog.size() * sizeof(uint4), cudaMemcpyDeviceToHost);
+                    const long long* tr = hp + 4 * 64 + (size_t)q * TRACE_ITEMS * 8;
+                    for (int n = 0; n < w.n_items; ++n) {
+                        const uint4 it = hprog[(size_t)n * SW_ITEM_U4], mk = hprog[(size_t)n * SW_ITEM_U4 + 2];
+                        const int cells = __builtin_popcount(mk.x) + __builtin_popcount(mk.y) + __builtin_popcount(mk.z) + __builtin_popcount(mk.w);
+                        fprintf(stderr, "[jk sweep trace] %d %d row %u src %u flags %u cells %d |", q, n, it.x, it.y, it.z, cells);
+                        for (int tw = 0; tw < 2; ++tw) fprintf(stderr, " %lld %lld %lld %lld", tr[(n * 2 + tw) * 4] - tr[0], tr[(n * 2 + tw) * 4 + 1] - tr[0], tr[(n * 2 + tw) * 4 + 2] - tr[0], tr[(n * 2 + tw) * 4 + 3] - tr[0]);
+                        fprintf(stderr, "\n");
+                    }
+                }
             for (int q = 0; q < 4; ++q) {
                 if (h->ch[q / 2].sw[q % 2].n_items == 0 || q / 2 >= h->n_chains) continue;
                 fprintf(stderr, "[jk sweep profile] chain %d %s: %d items\n", q / 2, q % 2 ? "backward" : "forward", h->ch[q / 2].sw[q % 2].n_items);

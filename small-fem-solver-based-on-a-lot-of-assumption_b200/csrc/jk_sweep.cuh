@@ -47,6 +47,11 @@ constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1
 constexpr int SW_MAX_BW = SW_RING - 1;
 constexpr int SW_MAX_CONSUMER_WARPS = 16;
+#ifndef JK_SW_PRED
+#define JK_SW_PRED 0        // sparse items: 1 = unconditional double-buffered fragment loads + predicated DMMAs, 2 = only the split chain for a
+                            // single active row block.  BOTH MEASURED SLOWER at c4 (forward sweeps 1.32 / 1.29 vs 1.20 ms): every extra
+                            // shared-memory fragment load costs more than the latency chain it removes.
+#endif
 #ifndef JK_SW_CBN
 #define JK_SW_CBN 1         // 8-column blocks per consumer warp.  2 (2 x 2 register blocking: half the warps, 2/3 of the shared-memory loads; whole-slab
                             // CTAs only) MEASURED SLOWER at c4: forward 1.25 vs 1.17 ms, backward 1.59 vs 1.47 ms -- the shared-memory pipe is not the bound
@@ -303,6 +308,65 @@ __device__ __forceinline__ void sweep_mma_single(double (&acc)[SW_RBN][SW_CBN][2
     }
 }
 
+// Sparse items (JK_SW_PRED = 1, measured and dropped -- see the switch).  The paths above put a shared-memory load in front of every DMMA inside a warp-uniform branch
+// and run the two row blocks of a warp one after the other when their masks differ: a sparse item then costs a chain of 16-32
+// load + DMMA latencies (~850 clocks measured, option profile_sweep = 2) for a handful of DMMAs, as much as a dense item.
+// Here the fragments of EVERY k-group are loaded (the tile is complete in shared memory, masked cells are zeros) in the
+// register-double-buffered pattern of the dense loop and only the DMMAs are predicated, so the two row blocks' chains
+// interleave and no load waits on a branch.
+__device__ __forceinline__ void sweep_mma_pred(double (&acc)[SW_RBN][SW_CBN][2], const double* const (&ap)[SW_RBN], const unsigned (&m)[SW_RBN],
+                                               const double* __restrict__ bp) {
+    double af[2][SW_RBN], bf[2][SW_CBN];
+#pragma unroll
+    for (int a = 0; a < SW_RBN; ++a) af[0][a] = ap[a][0];
+#pragma unroll
+    for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * 32];
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+        const int cur = k4 & 1, nxt = cur ^ 1;
+        if (k4 + 1 < 16) {
+#pragma unroll
+            for (int a = 0; a < SW_RBN; ++a) af[nxt][a] = ap[a][(k4 + 1) * 32];
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+        }
+#pragma unroll
+        for (int a = 0; a < SW_RBN; ++a)
+            if ((m[a] >> k4) & 1u) {
+#pragma unroll
+                for (int b = 0; b < SW_CBN; ++b) dmma(acc[a][b][0], acc[a][b][1], af[cur][a], bf[cur][b]);
+            }
+    }
+}
+// only row block A of the warp holds non-zeros: its k-groups alternate between the accumulator and a second partial sum, which
+// halves the dependent DMMA chain (the only chain this warp has in the item)
+template <int A>
+__device__ __forceinline__ void sweep_mma_one(double (&acc)[SW_RBN][SW_CBN][2], const double* __restrict__ ap, unsigned mask,
+                                              const double* __restrict__ bp) {
+    double af[2], bf[2][SW_CBN], part[SW_CBN][2];
+#pragma unroll
+    for (int b = 0; b < SW_CBN; ++b) { part[b][0] = 0.0; part[b][1] = 0.0; bf[0][b] = bp[b * 32]; }
+    af[0] = ap[0];
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+        const int cur = k4 & 1, nxt = cur ^ 1;
+        if (k4 + 1 < 16) {
+            af[nxt] = ap[(k4 + 1) * 32];
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+        }
+        if ((mask >> k4) & 1u) {
+#pragma unroll
+            for (int b = 0; b < SW_CBN; ++b) {
+                if (k4 & 1) dmma(part[b][0], part[b][1], af[cur], bf[cur][b]);
+                else dmma(acc[A][b][0], acc[A][b][1], af[cur], bf[cur][b]);
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < SW_CBN; ++b) { acc[A][b][0] += part[b][0]; acc[A][b][1] += part[b][1]; }
+}
+
 // ----------------------------------------------------------------------------------------------
 // K4 (narrow bands): one sweep of one chain over one slab per CTA
 // ----------------------------------------------------------------------------------------------
@@ -317,7 +381,8 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         int xphase_bits /* bit s: ring slot s starts one mbarrier phase ahead (continuation of a program whose slot parities
                            count from its first row) */,
         long long* __restrict__ prof /* nullable: [8 warps][8] clock sums of CTA 0 (option profile_sweep) */,
-        unsigned* __restrict__ started = nullptr /* nullable: every CTA adds 1 as soon as it is resident (gate of the early member post) */) {
+        unsigned* __restrict__ started = nullptr /* nullable: every CTA adds 1 as soon as it is resident (gate of the early member post) */,
+        long long* __restrict__ trace = nullptr /* nullable: [items][2 warps][4] clock stamps of CTA 0 (option profile_sweep = 2) */) {
     constexpr int SW_CONSUMER_WARPS = 4 * NCB / SW_CBN, SW_CONSUMERS = 32 * SW_CONSUMER_WARPS, CTAS_PER_SLAB = 4 / NCB;
     extern __shared__ __align__(128) unsigned char sw_smem[];
     if (started != nullptr && threadIdx.x == 0) { atomicAdd(started, 1u); __threadfence(); }
@@ -418,6 +483,8 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     consumer_bar_sync<SW_CONSUMERS>();    // nobody stores a row before every consumer holds its first right-hand side
     int ndiag = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0;
+    const int trace_w = (warp == 0) ? 0 : (warp == SW_CONSUMER_WARPS - 3 ? 1 : -1);
+    const bool tracing = trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_w >= 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
     const long long t_begin = profiling ? clock64() : 0;
     for (int n = 0; n < n_items; ++n) {
@@ -425,6 +492,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         if (profiling) t0 = clock64();
         mbar_wait(bar_full + 8 * s, (unsigned)(n / SW_STAGES) & 1u);
         if (profiling) { t1 = clock64(); pc[0] += t1 - t0; }
+        if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 0] = clock64();
         const uint4 d0 = Ds[s * SW_ITEM_U4], d1 = Ds[s * SW_ITEM_U4 + 1], mk = Ds[s * SW_ITEM_U4 + 2];
         const int row = (int)d0.x, flags = (int)d0.z, xinfo = (int)d0.w;
         if (flags & SW_ROW_BEGIN) {
@@ -449,6 +517,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             xb = Xr + slot * SW_XTILE;
         }
         if (profiling) { t0 = clock64(); pc[1] += t0 - t1; }
+        if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 1] = clock64();
         // masks of this warp's row blocks
         const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
         unsigned m[SW_RBN];
@@ -469,12 +538,18 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         const double* bp = xb + cb0 * 32 + lane;
         if (any && !(flags & SW_NO_OPERAND)) {
             if (all_dense) sweep_mma_dense<true>(acc, ap, act, bp);
+#if JK_SW_PRED
+            else if (SW_RBN == 2 && m[0] == 0u) sweep_mma_one<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp);
+            else if (SW_RBN == 2 && m[1] == 0u) sweep_mma_one<0>(acc, ap[0], m[0], bp);
+            else if (SW_RBN == 2 && JK_SW_PRED == 1) sweep_mma_pred(acc, ap, m, bp);
+#endif
             else if (all_equal) sweep_mma_uniform(acc, ap, m[0], bp);
             else if (SW_RBN <= 2) { sweep_mma_single<0>(acc, ap[0], m[0], bp); sweep_mma_single<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp); }
             else if (dense_or_empty) sweep_mma_dense<false>(acc, ap, act, bp);
             else sweep_mma_masked(acc, ap, m, bp);
         }
         __syncwarp();
+        if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 2] = clock64();
         if (profiling) {
             t1 = clock64(); pc[2] += t1 - t0; pc[5] += 1;
             for (int a = 0; a < SW_RBN; ++a) pc[4] += __popc(m[a]) * SW_CBN;
@@ -500,6 +575,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             if (!(flags & SW_NO_RING)) { __syncwarp(); if (lane == 0) mbar_arrive(bar_x + 8 * oslot); }
             if (profiling) { t0 = clock64(); pc[3] += t0 - t1; }
         }
+        if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 3] = clock64();
     }
     if (profiling && lane == 0 && warp < min(8, SW_CONSUMER_WARPS)) {
         pc[6] = clock64() - t_begin;
