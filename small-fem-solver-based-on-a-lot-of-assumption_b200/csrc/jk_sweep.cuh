@@ -47,6 +47,17 @@ constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1
 constexpr int SW_MAX_BW = SW_RING - 1;
 constexpr int SW_MAX_CONSUMER_WARPS = 16;
+#ifndef JK_SW_GROUP_BARS
+#define JK_SW_GROUP_BARS 1  // row barriers per column group (4 warps) instead of per CTA.  A/B at c4: 5.209 vs 5.224 ms per step (noise level); kept: groups never wait for each other's rows
+#endif
+#ifndef JK_SW_STAGGER
+#define JK_SW_STAGGER 0     // clocks between the starts of the column groups of a CTA.  MEASURED: 300 / 600 / 1200 change nothing at c4 (5.227 / 5.229 / 5.230 vs
+                            // 5.209 ms per step) -- the groups are not held in lockstep by their bookkeeping, so there is nothing to hide
+#endif
+#ifndef JK_SW_ZPREFETCH
+#define JK_SW_ZPREFETCH 0   // backward sweeps: L2 prefetch of the Z rows this many tile rows ahead of the diagonal item.  MEASURED with 3: no change at c4 (1.50 ms)
+                            // nor at c5 (2 GB of Z: 2.91 vs 2.93 ms) -- the Z stage is not what the backward sweeps wait for
+#endif
 #ifndef JK_SW_PRED
 #define JK_SW_PRED 0        // sparse items: 1 = unconditional double-buffered fragment loads + predicated DMMAs, 2 = only the split chain for a
                             // single active row block.  BOTH MEASURED SLOWER at c4 (forward sweeps 1.32 / 1.29 vs 1.20 ms): every extra
@@ -77,7 +88,7 @@ constexpr int SW_WAIT_X = 128;              // first use of the operand row by t
 constexpr int SW_ITEM_U4 = 3;
 
 constexpr size_t SW_SMEM = (size_t)(SW_STAGES * SW_TILE + SW_XTILE + SW_RING * SW_XTILE) * sizeof(double)
-                         + (size_t)SW_STAGES * SW_ITEM_U4 * sizeof(uint4) + 16 * sizeof(unsigned long long) + 128;
+                         + (size_t)SW_STAGES * SW_ITEM_U4 * sizeof(uint4) + 40 * sizeof(unsigned long long) + 128;
 
 __host__ __device__ __forceinline__ int sw_a_index(int r, int c) { return ((r >> 3) * 16 + (c >> 2)) * 32 + (r & 7) * 4 + (c & 3); }
 __host__ __device__ __forceinline__ int sw_x_index(int r, int c) { return ((r >> 2) * 4 + (c >> 3)) * 32 + (c & 7) * 4 + (r & 3); }
@@ -115,6 +126,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(src), "r"(bytes) : "memory");
 }
 template <int CONSUMERS>
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;\n" :: "n"(CONSUMERS) : "memory"); }
@@ -391,8 +405,13 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     double* Xr = Bs + SW_XTILE;                                      // [SW_RING][SW_XTILE]    newest solved tiles, fragment order
     uint4* Ds = reinterpret_cast<uint4*>(Xr + SW_RING * SW_XTILE);   // [SW_STAGES][SW_ITEM_U4] item descriptors, staged by the producer
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ds + SW_STAGES * SW_ITEM_U4);
-    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + SW_STAGES), bar_x = smem_u32(bars + 2 * SW_STAGES),
-                   bar_bfull = smem_u32(bars + 2 * SW_STAGES + SW_RING), bar_bempty = smem_u32(bars + 2 * SW_STAGES + SW_RING + 1);
+    // row barriers: one per ring slot and COLUMN GROUP (JK_SW_GROUP_BARS): a warp only ever reads its own 8-column block of a solved
+    // row, written by the warps of its group, so the groups need not wait for each other at a row end -- they stay coupled only
+    // through the tile stages, and can run out of phase (see the stagger below)
+    constexpr int XG = JK_SW_GROUP_BARS ? NCB : 1, X_ARRIVALS = JK_SW_GROUP_BARS ? SW_CONSUMER_WARPS / NCB : SW_CONSUMER_WARPS;
+    static_assert(2 * SW_STAGES + SW_RING * XG + 2 <= 40, "barrier area");
+    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + SW_STAGES), bar_x0 = smem_u32(bars + 2 * SW_STAGES),
+                   bar_bfull = smem_u32(bars + 2 * SW_STAGES + SW_RING * XG), bar_bempty = smem_u32(bars + 2 * SW_STAGES + SW_RING * XG + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slab = blockIdx.x / CTAS_PER_SLAB, cbase = (blockIdx.x % CTAS_PER_SLAB) * NCB;
     double* Xslab = X + ((size_t)slab * (size_t)n_pad + (size_t)row0) * SLAB;
@@ -400,7 +419,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
 
     if (tid == 0) {
         for (int s = 0; s < SW_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, SW_CONSUMER_WARPS); }
-        for (int s = 0; s < SW_RING; ++s) mbar_init(bar_x + 8 * s, SW_CONSUMER_WARPS);
+        for (int s = 0; s < SW_RING * XG; ++s) mbar_init(bar_x0 + 8 * s, X_ARRIVALS);
         mbar_init(bar_bfull, 1);
         mbar_init(bar_bempty, SW_CONSUMER_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -428,6 +447,16 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
                     d0 = q[0]; d1 = q[1]; d2 = q[2];
                 }
                 if (flags & SW_DIAG) {
+#if JK_SW_ZPREFETCH
+                    // Z_k is staged through ONE buffer, at most SW_STAGES items ahead of its use: with short tile rows and a slab set
+                    // larger than L2 (sea-state ensembles: 2 GB of Z) that is less than an HBM round trip.  Pull the rows the sweep
+                    // reaches next (backward: row - 1, row - 2, ...) into L2 now.
+                    if (cbase == 0) {
+                        const int first = ndiag == 0 ? 1 : JK_SW_ZPREFETCH;
+                        for (int q = first; q <= JK_SW_ZPREFETCH; ++q)
+                            if (row - q >= 0) bulk_prefetch_l2(Zslab + (size_t)(row - q) * SW_XTILE, SW_XTILE * (unsigned)sizeof(double));
+                    }
+#endif
                     mbar_wait(bar_bempty, ((unsigned)ndiag & 1u) ^ 1u);
                     mbar_arrive_expect_tx(bar_bfull, SW_XTILE * (unsigned)sizeof(double));
                     bulk_g2s(smem_u32(Bs), Zslab + (size_t)row * SW_XTILE, SW_XTILE * (unsigned)sizeof(double), bar_bfull);
@@ -444,6 +473,8 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
     const int cb0 = cbase + (warp >> 2) * SW_CBN;
+    const int xgroup = JK_SW_GROUP_BARS ? (warp >> 2) : 0;
+    const unsigned bar_x = bar_x0 + 8 * SW_RING * xgroup;      // this group's row barriers, [slot]
     const int rbs[SW_RBN] = {warp & 3, 7 - (warp & 3)};
     // a program that continues another launch: bring the slots' mbarrier phases in step with the item parities
     if (xphase_bits) {
@@ -459,8 +490,12 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         double* dst = Xr + slot * SW_XTILE;
         if (pre_mode) { for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[e] = g[e]; }
         else { for (int e = tid; e < SW_XTILE; e += SW_CONSUMERS) dst[sw_x_index(e / SLAB, e % SLAB)] = g[e]; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_x + 8 * slot);
+    }
+    if (npre > 0) {
+        // the rows were written by all consumer threads, whatever their column group
+        consumer_bar_sync<SW_CONSUMERS>();
+        if (lane == 0)
+            for (int q = 0; q < npre; ++q) mbar_arrive(bar_x + 8 * ((pre_mode ? pre_row + q : ktop - (pre_row + q)) % SW_RING));
     }
     // this lane's elements of a 64 x 32 tile: rows 8*mb + fr, columns 8*nt + 2*fk + {0, 1}
     auto rm_off = [&](int mb, int nt) { return (8 * mb + fr) * SLAB + 8 * nt + 2 * fk; };                       // row-major, double2
@@ -491,6 +526,13 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         const int s = n % SW_STAGES;
         if (profiling) t0 = clock64();
         mbar_wait(bar_full + 8 * s, (unsigned)(n / SW_STAGES) & 1u);
+#if JK_SW_STAGGER
+        // Identical column groups would run in lockstep: all sixteen warps in their DMMA loops (the FP64 pipe saturated, every loop
+        // stretched) and then all in the per-item bookkeeping (barrier round trips, descriptor and mask decode: the pipe idle).
+        // A one-off offset between the groups persists (the groups only meet at the tile stages), so one group's bookkeeping
+        // hides under the other groups' DMMAs.
+        if (n == 0 && xgroup > 0) { const long long t_go = clock64() + (long long)xgroup * JK_SW_STAGGER; while (clock64() < t_go) { } }
+#endif
         if (profiling) { t1 = clock64(); pc[0] += t1 - t0; }
         if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 0] = clock64();
         const uint4 d0 = Ds[s * SW_ITEM_U4], d1 = Ds[s * SW_ITEM_U4 + 1], mk = Ds[s * SW_ITEM_U4 + 2];

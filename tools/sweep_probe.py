@@ -8,6 +8,8 @@ opts = {"profile_sweep": 1}
 for a in sys.argv[1:]:
     k, v = a.split("=")
     if k == "P": P = int(v)
+    elif k == "legs": legs = int(v)
+    elif k == "bays": bays = int(v)
     else: opts[k] = int(v)
 p = jb.AnalysisParams(wave_model="Airy")
 nodes, members, fixed, top = jb.generate_jacket(legs, bays)
