@@ -47,6 +47,13 @@ constexpr int SW_STAGES = JK_SW_STAGES;
 constexpr int SW_RING = 5;                  // solved tiles kept in shared memory: tile half-bandwidth <= SW_RING - 1
 constexpr int SW_MAX_BW = SW_RING - 1;
 constexpr int SW_MAX_CONSUMER_WARPS = 16;
+#ifndef JK_SW_CTA_GROUPS
+#define JK_SW_CTA_GROUPS 1      // CTA groups (blockIdx % groups) whose producers start JK_SW_CTA_STAGGER clocks apart.  MEASURED at c4: 4 / 8 / 16 groups give
+                                // 5.199 / 5.212 / 5.254 ms per step against 5.198 -- the L2 slices holding the current tile are NOT what the sweeps wait for
+#endif
+#ifndef JK_SW_CTA_STAGGER
+#define JK_SW_CTA_STAGGER 2000
+#endif
 #ifndef JK_SW_GROUP_BARS
 #define JK_SW_GROUP_BARS 1  // row barriers per column group (4 warps) instead of per CTA.  A/B at c4: 5.209 vs 5.224 ms per step (noise level); kept: groups never wait for each other's rows
 #endif
@@ -431,6 +438,13 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         // ------------------------------- producer (one elected thread) -------------------------------
         // tiles are contiguous in the stream AND in shared memory (fragment order needs no padding): one bulk copy each
         if (lane == 0) {
+#if JK_SW_CTA_GROUPS > 1
+            // All CTAs of a sweep stream the SAME tiles in the same order.  Started together they ask the L2 for the same 32 KB at
+            // the same time: those few slices serve every SM while the others idle, and a tile takes as long to arrive as its
+            // products take to compute, whatever the masks skip.  CTA groups that start a tile-time apart read different tiles
+            // at any moment, which spreads the stream over all slices.
+            { const long long t_go = clock64() + (long long)(blockIdx.x % JK_SW_CTA_GROUPS) * JK_SW_CTA_STAGGER; while (clock64() < t_go) { } }
+#endif
             int ndiag = 0;
             uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, d2 = d0;
             if (n_items > 0) { d0 = prog[0]; d1 = prog[1]; d2 = prog[2]; }
