@@ -112,7 +112,7 @@ const char* jk_last_error(jk_handle_t h);
  *   start_gate2 [1]         the first forward sweep parts wait until the second factor segment is resident
  *   post_overlap [1]        member post of first-chain chunks beside the second chain's backward sweep
  *   early_totals [1]        Morison columns of the table reduced on a side stream behind the Morison kernel
- *   cuda_graph [1]          jk_phase_scan_dev replays the resident scan as a captured CUDA graph
+ *   cuda_graph [1]          jk_step / jk_step_dev replay the whole step (assemble + factor + scan) as a captured CUDA graph
  *   fused_loads [0]         1: the Morison kernel lumps member end forces into nodal loads itself (register runs + deposit
  *                           rows, finalised in-kernel by a chained look-back; halves the load stage's HBM traffic but
  *                           measured slower at c4, 1.81 vs 1.70 ms); 0: member forces are written to HBM and gathered by a
@@ -122,7 +122,9 @@ const char* jk_last_error(jk_handle_t h);
  * has no counterpart: GUI.py:481-490 is a dense LU):
  *   two_chains [1]  factor_split [1]  split_pct [70]  level_regroup [1]  support_rooted_rcm [1]  tma_sweep [1]
  *   blocked_inverse [1]
- * Debug aids: profile_chol [0], profile_sweep [0] (clock breakdowns on stderr), debug_factor_delay [0] (clocks).
+ * Debug aids: profile_chol [0], profile_sweep [0] (1: clock breakdown of the sweep warps on stderr, 2: plus per-item clock
+ * stamps), debug_factor_delay [0] (clocks), debug_morison_smem_pad [0] (KB, occupancy probe), debug_fuse_mode [0] (timing
+ * probes of the fused load path; 1 and 2 give WRONG results by design).
  * jk_option_count / jk_option_name enumerate the keys. */
 int         jk_set_option(jk_handle_t h, const char* key, int value);
 int         jk_get_option(jk_handle_t h, const char* key, int* value);

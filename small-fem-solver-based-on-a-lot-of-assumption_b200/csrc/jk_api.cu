@@ -32,8 +32,8 @@ enum JkOpt { OPT_DEBUG_MORISON_SMEM_PAD, OPT_DEBUG_FUSE_MODE, OPT_START_GATE, OP
              OPT_DEBUG_FACTOR_DELAY, OPT_SWEEP_SLAB, OPT_CUDA_GRAPH, OPT_FUSED_LOADS, OPT_COUNT };
 struct JkOptDesc { const char* key; int def, lo, hi; };
 static const JkOptDesc g_opts[OPT_COUNT] = {
-    {"debug_morison_smem_pad", 0, 0, 160},
-    {"debug_fuse_mode", 0, 0, 2},           // experiment: 1 = fused Morison kernel without finalisation, 2 = without waiting (wrong results; timing only)  // experiment: extra KB of dynamic shared memory per Morison block (occupancy probe)
+    {"debug_morison_smem_pad", 0, 0, 160},  // experiment: extra KB of dynamic shared memory per Morison block (occupancy probe)
+    {"debug_fuse_mode", 0, 0, 2},           // experiment: 1 = fused Morison kernel without finalisation, 2 = without waiting (wrong results; timing only)
     {"start_gate", 1, 0, 1},            // main stream waits until the factor clusters are resident (asynchronous factorisation)
     {"start_gate2", 1, 0, 1},           // first forward sweep parts wait until the second factor segment is resident
     {"post_overlap", 1, 0, 1},          // member post of first-chain chunks beside the second chain's backward sweep
