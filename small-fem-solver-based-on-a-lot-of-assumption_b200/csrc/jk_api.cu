@@ -343,9 +343,12 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     CUDA_TRY(h, cudaFuncSetAttribute(k_band_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_CLUSTER_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_slab_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
     CUDA_TRY(h, cudaFuncSetAttribute(k_sweep_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWB_SMEM));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     return JK_OK;
@@ -1485,9 +1488,11 @@ static int run_fem(jk_handle_t h, int ldP, double fy) {
         const int pre_row = cont ? w.k_split - w.npre2 : w.pre_row, npre = cont ? w.npre2 : w.npre, xph = cont ? w.xphase2 : 0;
         long long* pf = d_prof ? d_prof + (2 * c + d) * 64 : nullptr;
         long long* tr = (d_prof && sweep_trace && part == 0 && hi - lo <= TRACE_ITEMS) ? d_prof + 4 * 64 + (size_t)(2 * c + d) * TRACE_ITEMS * 8 : nullptr;
-        if (ncb == 4) k_sweep<4><<<sweep_ctas, sw_threads(4), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
-        else if (ncb == 2) k_sweep<2><<<sweep_ctas, sw_threads(2), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
-        else k_sweep<1><<<sweep_ctas, sw_threads(1), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
+        auto launch = [&](auto kern, int nc) {
+            kern<<<sweep_ctas, sw_threads(nc), SW_SMEM, s>>>(prog, strm, h->d_X, h->d_Z, hi - lo, h->n_pad, chn.row0, pre_row, npre, w.ktop, cont ? 1 : 0, xph, pf, started, tr);
+        };
+        if (pf) { if (ncb == 4) launch(k_sweep<4, true>, 4); else if (ncb == 2) launch(k_sweep<2, true>, 2); else launch(k_sweep<1, true>, 1); }
+        else { if (ncb == 4) launch(k_sweep<4, false>, 4); else if (ncb == 2) launch(k_sweep<2, false>, 2); else launch(k_sweep<1, false>, 1); }
         return true;
     };
     // Early member post (see d_post_chunks): only when the backward sweep of the second chain leaves SMs idle (one CTA per

@@ -391,7 +391,9 @@ __device__ __forceinline__ void sweep_mma_one(double (&acc)[SW_RBN][SW_CBN][2], 
 // ----------------------------------------------------------------------------------------------
 // K4 (narrow bands): one sweep of one chain over one slab per CTA
 // ----------------------------------------------------------------------------------------------
-template <int NCB /* 8-column blocks of the slab owned by this CTA: 4, 2 or 1 */>
+template <int NCB /* 8-column blocks of the slab owned by this CTA: 4, 2 or 1 */,
+          bool PROF = false /* clock counters / stamps of option profile_sweep compiled in (the production kernel carries none of them:
+                               every bookkeeping instruction between two items' DMMAs is warp latency the FP64 pipe sits out) */>
 __global__ void __launch_bounds__(sw_threads(NCB), 1)
 k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, double* __restrict__ X,
         double* __restrict__ Z /* same shape as X: the forward sweep's intermediate, fragment order */,
@@ -531,15 +533,15 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     }
     consumer_bar_sync<SW_CONSUMERS>();    // nobody stores a row before every consumer holds its first right-hand side
     int ndiag = 0;
-    const bool profiling = prof != nullptr && blockIdx.x == 0;
+    const bool profiling = PROF && prof != nullptr && blockIdx.x == 0;
     const int trace_w = (warp == 0) ? 0 : (warp == SW_CONSUMER_WARPS - 3 ? 1 : -1);
-    const bool tracing = trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_w >= 0;
+    const bool tracing = PROF && trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_w >= 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
     const long long t_begin = profiling ? clock64() : 0;
-    for (int n = 0; n < n_items; ++n) {
-        const int s = n % SW_STAGES;
+    int s = 0; unsigned sphase = 0u;                 // stage of item n and its mbarrier parity, carried instead of n % / n /
+    for (int n = 0; n < n_items; ++n, s = (s + 1 == SW_STAGES) ? 0 : s + 1, sphase ^= (s == 0) ? 1u : 0u) {
         if (profiling) t0 = clock64();
-        mbar_wait(bar_full + 8 * s, (unsigned)(n / SW_STAGES) & 1u);
+        mbar_wait(bar_full + 8 * s, sphase);
 #if JK_SW_STAGGER
         // Identical column groups would run in lockstep: all sixteen warps in their DMMA loops (the FP64 pipe saturated, every loop
         // stretched) and then all in the per-item bookkeeping (barrier round trips, descriptor and mask decode: the pipe idle).
