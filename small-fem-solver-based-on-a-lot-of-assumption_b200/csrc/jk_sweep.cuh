@@ -65,6 +65,12 @@ constexpr int SW_MAX_CONSUMER_WARPS = 16;
 #define JK_SW_ZPREFETCH 0   // backward sweeps: L2 prefetch of the Z rows this many tile rows ahead of the diagonal item.  MEASURED with 3: no change at c4 (1.50 ms)
                             // nor at c5 (2 GB of Z: 2.91 vs 2.93 ms) -- the Z stage is not what the backward sweeps wait for
 #endif
+#ifndef JK_SW_ROLE_MASKS
+#define JK_SW_ROLE_MASKS 1
+#endif
+#ifndef JK_SW_MASKED
+#define JK_SW_MASKED 0
+#endif
 #ifndef JK_SW_PRED
 #define JK_SW_PRED 0        // sparse items: 1 = unconditional double-buffered fragment loads + predicated DMMAs, 2 = only the split chain for a
                             // single active row block.  BOTH MEASURED SLOWER at c4 (forward sweeps 1.32 / 1.29 vs 1.20 ms): every extra
@@ -223,7 +229,12 @@ __global__ void __launch_bounds__(256) k_sweep_build(SweepBuildArgs a, SweepBuil
         }
     __syncthreads();
     if (tid == 0)
+#if JK_SW_ROLE_MASKS
+        // word s = masks of the row-block pair (s, 7 - s) a consumer warp owns: one 32-bit load, no selects
+        prog[(size_t)n * SW_ITEM_U4 + 2] = make_uint4(msk[0] | (msk[7] << 16), msk[1] | (msk[6] << 16), msk[2] | (msk[5] << 16), msk[3] | (msk[4] << 16));
+#else
         prog[(size_t)n * SW_ITEM_U4 + 2] = make_uint4(msk[0] | (msk[1] << 16), msk[2] | (msk[3] << 16), msk[4] | (msk[5] << 16), msk[6] | (msk[7] << 16));
+#endif
 }
 
 // Inner products of one item for one consumer warp: acc[a][b] += A(row block a) * X(column block b) over the k-groups.
@@ -577,10 +588,24 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
         if (profiling) { t0 = clock64(); pc[1] += t0 - t1; }
         if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 1] = clock64();
         // masks of this warp's row blocks
-        const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
         unsigned m[SW_RBN];
         bool act[SW_RBN], all_dense = true, dense_or_empty = true, any = false, all_equal = true;
         const double* ap[SW_RBN];
+#if JK_SW_ROLE_MASKS
+        static_assert(SW_RBN == 2, "role-packed masks assume the row-block pair (s, 7 - s)");
+        {
+            const unsigned w = reinterpret_cast<const unsigned*>(Ds + s * SW_ITEM_U4 + 2)[warp & 3];
+            m[0] = w & 0xffffu; m[1] = w >> 16;
+            act[0] = m[0] == 0xffffu; act[1] = m[1] == 0xffffu;
+            all_dense = w == 0xffffffffu;
+            any = w != 0u;
+            all_equal = m[0] == m[1];
+            dense_or_empty = (act[0] || m[0] == 0u) && (act[1] || m[1] == 0u);
+            const double* abase = As + s * SW_TILE + lane;
+            ap[0] = abase + rbs[0] * 512; ap[1] = abase + rbs[1] * 512;
+        }
+#else
+        const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
         for (int a = 0; a < SW_RBN; ++a) {
             const int rb = rbs[a];
@@ -593,6 +618,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             all_equal = all_equal && m[a] == m[0];
             ap[a] = As + s * SW_TILE + (rb * 16) * 32 + lane;
         }
+#endif
         const double* bp = xb + cb0 * 32 + lane;
         if (any && !(flags & SW_NO_OPERAND)) {
             if (all_dense) sweep_mma_dense<true>(acc, ap, act, bp);
@@ -602,6 +628,9 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             else if (SW_RBN == 2 && JK_SW_PRED == 1) sweep_mma_pred(acc, ap, m, bp);
 #endif
             else if (all_equal) sweep_mma_uniform(acc, ap, m[0], bp);
+#if JK_SW_MASKED
+            else if (m[0] != 0u && m[SW_RBN - 1] != 0u) sweep_mma_masked(acc, ap, m, bp);     // both row blocks active, different masks: one interleaved loop, B loaded once
+#endif
             else if (SW_RBN <= 2) { sweep_mma_single<0>(acc, ap[0], m[0], bp); sweep_mma_single<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp); }
             else if (dense_or_empty) sweep_mma_dense<false>(acc, ap, act, bp);
             else sweep_mma_masked(acc, ap, m, bp);
