@@ -117,6 +117,8 @@ const char* jk_last_error(jk_handle_t h);
  *                           rows, finalised in-kernel by a chained look-back; halves the load stage's HBM traffic but
  *                           measured slower at c4, 1.81 vs 1.70 ms); 0: member forces are written to HBM and gathered by a
  *                           second kernel in the reference's member order.  Same sums in another fixed order (1e-15)
+ *   gather_blocks [1]       phase blocks of the Morison stage: the load gather of block b (HBM-bound, side stream) runs beside
+ *                           the Morison kernel of block b + 1 (FP64-bound); gather_rows [0] = grid rows of those gather launches
  *   sweep_slab [0]          right-hand sides per triangular-sweep CTA: 0 = chosen so that the CTAs fill the SMs, 8, 16, 32
  * Ordering / storage switches, read by the next jk_set_supports (results agree to rounding, the reference's run_analysis
  * has no counterpart: GUI.py:481-490 is a dense LU):

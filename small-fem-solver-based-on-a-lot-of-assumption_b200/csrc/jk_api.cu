@@ -29,7 +29,7 @@ static thread_local std::string g_err;
 // Run-time options (jk_set_option / jk_get_option).  The library never reads the environment.
 enum JkOpt { OPT_DEBUG_MORISON_SMEM_PAD, OPT_DEBUG_FUSE_MODE, OPT_START_GATE, OPT_START_GATE2, OPT_POST_OVERLAP, OPT_EARLY_TOTALS, OPT_FACTOR_SPLIT, OPT_SPLIT_PCT, OPT_TWO_CHAINS,
              OPT_LEVEL_REGROUP, OPT_SUPPORT_ROOTED_RCM, OPT_TMA_SWEEP, OPT_BLOCKED_INVERSE, OPT_PROFILE_CHOL, OPT_PROFILE_SWEEP,
-             OPT_DEBUG_FACTOR_DELAY, OPT_SWEEP_SLAB, OPT_CUDA_GRAPH, OPT_FUSED_LOADS, OPT_COUNT };
+             OPT_DEBUG_FACTOR_DELAY, OPT_SWEEP_SLAB, OPT_CUDA_GRAPH, OPT_FUSED_LOADS, OPT_GATHER_BLOCKS, OPT_GATHER_ROWS, OPT_COUNT };
 struct JkOptDesc { const char* key; int def, lo, hi; };
 static const JkOptDesc g_opts[OPT_COUNT] = {
     {"debug_morison_smem_pad", 0, 0, 160},  // experiment: extra KB of dynamic shared memory per Morison block (occupancy probe)
@@ -52,6 +52,9 @@ static const JkOptDesc g_opts[OPT_COUNT] = {
     {"cuda_graph", 1, 0, 1},            // replay the resident scan (jk_phase_scan_dev) as a captured CUDA graph
     {"fused_loads", 0, 0, 1},           // Morison kernel lumps member end forces into nodal loads itself (no member-force round trip;
                                         // measured slower than the two-kernel path at c4: 1.81 vs 1.70 ms, see jk_morison.cuh)
+    {"gather_blocks", 1, 1, 16},        // phase blocks of the Morison stage: the load gather of block b (HBM-bound, side stream) runs beside the
+                                        // Morison kernel of block b + 1 (FP64-bound); 1 = one Morison launch, then one gather
+    {"gather_rows", 0, 0, 65535},       // grid.y of the overlapped gather launches (0: one block row per node)
 };
 
 struct jk_handle_s {
@@ -72,6 +75,7 @@ struct jk_handle_s {
     // while the second chain's backward sweep runs (HBM-bound work on the SMs the sweep leaves idle)
     int* d_post_chunks = nullptr; int n_post_early = 0, n_post_late = 0, n_sm = 0;
     cudaEvent_t ev_bwd0 = nullptr, ev_post_early = nullptr, ev_mor = nullptr, ev_tot = nullptr;
+    cudaEvent_t ev_blk[16] = {}, ev_gather = nullptr;      // Morison phase blocks -> overlapped load gathers (option gather_blocks)
     unsigned gate2_target = 0; bool gate2_armed = false;   // second factor segment resident (awaited before the first forward parts)
     CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     cudaEvent_t ev_seg1 = nullptr, ev_fwd1 = nullptr;   // first factor segment done / its forward tile streams built
@@ -292,6 +296,8 @@ extern "C" int jk_create(int device, void* stream, int n_nodes, const double* xy
     cudaEventCreateWithFlags(&h->ev_fwd1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_bwd0, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_mor, cudaEventDisableTiming);
+    for (auto& e : h->ev_blk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_tot, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_early, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_post_fork, cudaEventDisableTiming);
@@ -387,6 +393,8 @@ extern "C" int jk_destroy(jk_handle_t h) {
     if (h->ev_fwd1) cudaEventDestroy(h->ev_fwd1);
     if (h->ev_bwd0) cudaEventDestroy(h->ev_bwd0);
     if (h->ev_mor) cudaEventDestroy(h->ev_mor);
+    for (auto& e : h->ev_blk) if (e) cudaEventDestroy(e);
+    if (h->ev_gather) cudaEventDestroy(h->ev_gather);
     if (h->ev_tot) cudaEventDestroy(h->ev_tot);
     if (h->ev_post_early) cudaEventDestroy(h->ev_post_early);
     dev_free(h->d_post_chunks);
@@ -1363,18 +1371,25 @@ static int ensure_gauss_tables(jk_handle_t h) {
 }
 
 // Morison stage for the phases already in d_t: trig tables, Gauss-point tables (once per wave), K1
-static int run_morison(jk_handle_t h, int P, int ldP, bool details, bool fuse = false) {
+// tile0 / ntiles: phase tiles (PH_TPB phases each) of this launch; ntiles < 0 = all.  Tables are set up with the first tile.
+static int run_morison(jk_handle_t h, int P, int ldP, bool details, bool fuse = false, int tile0 = 0, int ntiles = -1) {
     cudaStream_t s = h->stream;
     WaveAiry w = launch_wave(h);
-    tic(h, JK_T_WAVE_SETUP);
     const int Nh = h->n_harm;
     const size_t gstride = h->wave_kind == 1 ? (size_t)(3 + 2 * Nh) : (size_t)GP_STRIDE;
-    { int rcg = ensure_gauss_tables(h); if (rcg != JK_OK) return rcg; }
-    k_phase_setup<<<ceil_div(ldP, 128), 128, 0, s>>>(P, ldP, h->d_t, w.omega, w.dt, h->d_trig);
-    LAUNCH_CHECK(h);
-    toc(h, JK_T_WAVE_SETUP);
-    tic(h, JK_T_MORISON);
-    dim3 grid(ceil_div(ldP, PH_TPB), ceil_div(h->M, MCHUNK));
+    const int all_tiles = ceil_div(ldP, PH_TPB);
+    const bool ranged = ntiles >= 0;
+    if (!ranged) ntiles = all_tiles;
+    if (tile0 == 0) {
+        tic(h, JK_T_WAVE_SETUP);
+        { int rcg = ensure_gauss_tables(h); if (rcg != JK_OK) return rcg; }
+        k_phase_setup<<<ceil_div(ldP, 128), 128, 0, s>>>(P, ldP, h->d_t, w.omega, w.dt, h->d_trig);
+        LAUNCH_CHECK(h);
+        toc(h, JK_T_WAVE_SETUP);
+        tic(h, JK_T_MORISON);
+    }
+    const int p_off = tile0 * PH_TPB;
+    dim3 grid(ntiles, ceil_div(h->M, MCHUNK));
     double cD0 = 0.5 * h->rho * h->Cd, cI0 = h->rho * h->Cm;
     if (h->wave_kind == 1) {
         size_t smem = ((size_t)FCHUNK * h->ng * gstride + MCHUNK * 8 + 2 * h->ng + 3 * Nh) * sizeof(double);
@@ -1406,12 +1421,12 @@ static int run_morison(jk_handle_t h, int P, int ldP, bool details, bool fuse = 
             } else {
                 auto kern = (JK_MORISON_G15 && h->ng == 15) ? k_morison_airy<false, 15> : k_morison_airy<false, 0>;
                 CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr, 0, LoadFuse{});
+                kern<<<grid, PH_TPB, smem, s>>>(h->M, h->ng, ldP, h->d_gp, h->d_mc, h->d_gsw, h->d_trig, w, cD0, cI0, h->d_Fm, h->d_totpart, nullptr, p_off, LoadFuse{});
             }
         }
     }
     LAUNCH_CHECK(h);
-    toc(h, JK_T_MORISON);
+    if (tile0 + ntiles >= all_tiles) toc(h, JK_T_MORISON);
     return JK_OK;
 }
 
@@ -1647,12 +1662,35 @@ static int scan_core(jk_handle_t h, int P, double fy, bool fem) {
     if ((rc = ensure_member_consts(h)) != JK_OK) return rc;
     const int nbx = ceil_div(ldP, PH_TPB);
     const bool fuse = fem && h->opt[OPT_FUSED_LOADS] && h->wave_kind == 0 && h->fuse_n_pairs > 0;
-    if ((rc = run_morison(h, P, ldP, false, fuse)) != JK_OK) return rc;
+    // Phase blocks: the Morison kernel is FP64-bound, the load gather HBM-bound -- the gather of block b runs on the
+    // high-priority side stream while the Morison kernel works on block b + 1.  Same kernels, same arithmetic per phase.
+    int nblk = (fem && !fuse && h->wave_kind == 0 && h->stream3 && h->ev_gather) ? std::min(h->opt[OPT_GATHER_BLOCKS], std::min(16, nbx)) : 1;
+    bool gathered = false;
+    if (nblk > 1) {
+        cudaStream_t s3 = h->stream3;
+        const int gy = h->opt[OPT_GATHER_ROWS] > 0 ? std::min(h->opt[OPT_GATHER_ROWS], h->Nn) : std::min(h->Nn, 65535);
+        for (int b = 0; b < nblk; ++b) {
+            const int t0 = (int)((long long)nbx * b / nblk), t1 = (int)((long long)nbx * (b + 1) / nblk);
+            if ((rc = run_morison(h, P, ldP, false, false, t0, t1 - t0)) != JK_OK) return rc;
+            CUDA_TRY(h, cudaEventRecord(h->ev_blk[b], s));
+            CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_blk[b], 0));
+            k_rhs_gather<<<dim3(t1 - t0, gy), PH_TPB, 0, s3>>>(h->Nn, ldP, h->n_pad, h->d_Fm, h->d_adj_ptr, h->d_adj, h->d_node2slot, h->d_Fstatic,
+                                                               h->d_X, h->d_Ffix, nullptr, nullptr, nullptr, 0, 1, 0, t0 * PH_TPB);
+            LAUNCH_CHECK(h);
+        }
+        CUDA_TRY(h, cudaEventRecord(h->ev_gather, s3));
+        gathered = true;
+    } else if ((rc = run_morison(h, P, ldP, false, fuse)) != JK_OK) return rc;
     const bool totals_early = fem && h->opt[OPT_EARLY_TOTALS] && h->stream3 != nullptr && h->ev_mor && h->ev_tot;
     if (totals_early && (rc = reduce_totals_early(h, P, ldP)) != JK_OK) return rc;
     h->last_fused = fuse;
     if (fem && fuse) {
         h->ev_set[JK_T_RHS] = false;                       // no separate load stage: the Morison kernel wrote the right-hand sides
+        if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
+    } else if (fem && gathered) {
+        tic(h, JK_T_RHS);                                  // what is left of the last block's gather
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_gather, 0));
+        toc(h, JK_T_RHS);
         if ((rc = run_fem(h, ldP, fy)) != JK_OK) return rc;
     } else if (fem) {
         tic(h, JK_T_RHS);

@@ -500,6 +500,7 @@ def test_overlap_switches_are_bit_identical():
     variants = (("default", {}), ("no_post_overlap", {"post_overlap": 0}), ("no_early_totals", {"early_totals": 0}),
                 ("no_gate2", {"start_gate2": 0}), ("slab16", {"sweep_slab": 16}), ("slab8", {"sweep_slab": 8}),
                 ("none", {"post_overlap": 0, "early_totals": 0, "start_gate2": 0, "cuda_graph": 0, "sweep_slab": 32}),
+                ("gather_blocks", {"gather_blocks": 2}), ("gather_blocks_rows", {"gather_blocks": 2, "gather_rows": 64, "cuda_graph": 0}),
                 ("fused_loads", {"fused_loads": 1}))
     for mode, opts in variants:
         if True:
