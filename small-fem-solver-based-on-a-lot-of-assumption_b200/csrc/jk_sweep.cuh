@@ -65,11 +65,16 @@ constexpr int SW_MAX_CONSUMER_WARPS = 16;
 #define JK_SW_ZPREFETCH 0   // backward sweeps: L2 prefetch of the Z rows this many tile rows ahead of the diagonal item.  MEASURED with 3: no change at c4 (1.50 ms)
                             // nor at c5 (2 GB of Z: 2.91 vs 2.93 ms) -- the Z stage is not what the backward sweeps wait for
 #endif
+#ifndef JK_SW_PAIR
+#define JK_SW_PAIR 0          // paired fragment order (two k-groups per 16-byte shared-memory load: half the load instructions of the DMMA loops).
+                            // MEASURED SLOWER at c4: forward 1.170 vs 1.118 ms, backward 1.48 vs 1.43 ms (parity suite green on both)
+#endif
 #ifndef JK_SW_ROLE_MASKS
-#define JK_SW_ROLE_MASKS 1
+#define JK_SW_ROLE_MASKS 1    // zero-block masks stored per row-block pair (s, 7 - s): one 32-bit load per warp and item (5.127 vs 5.144 ms per step at c4)
 #endif
 #ifndef JK_SW_MASKED
-#define JK_SW_MASKED 0
+#define JK_SW_MASKED 0        // row blocks with different non-empty masks in ONE interleaved loop (B fragment loaded once) instead of one after the
+                            // other: no measurable difference at c4 (5.133 vs 5.127 ms per step)
 #endif
 #ifndef JK_SW_PRED
 #define JK_SW_PRED 0        // sparse items: 1 = unconditional double-buffered fragment loads + predicated DMMAs, 2 = only the split chain for a
@@ -103,8 +108,22 @@ constexpr int SW_ITEM_U4 = 3;
 constexpr size_t SW_SMEM = (size_t)(SW_STAGES * SW_TILE + SW_XTILE + SW_RING * SW_XTILE) * sizeof(double)
                          + (size_t)SW_STAGES * SW_ITEM_U4 * sizeof(uint4) + 40 * sizeof(unsigned long long) + 128;
 
+#if JK_SW_PAIR
+// Paired fragment order: the fragments of two consecutive k-groups are interleaved, so that one 16-byte shared-memory load
+// brings a lane's elements of both (half the load instructions of the DMMA loops; same bytes, still conflict-free):
+//   A tile:  ((r/8)*8 + c/8)*64 + ((r%8)*4 + c%4)*2 + (c/4)%2        X tile:  ((r/8)*4 + c/8)*64 + ((c%8)*4 + r%4)*2 + (r/4)%2
+__host__ __device__ __forceinline__ int sw_a_index(int r, int c) { return ((((r >> 3) * 8 + (c >> 3)) * 32 + (r & 7) * 4 + (c & 3)) << 1) | ((c >> 2) & 1); }
+__host__ __device__ __forceinline__ int sw_x_index(int r, int c) { return ((((r >> 3) * 4 + (c >> 3)) * 32 + (c & 7) * 4 + (r & 3)) << 1) | ((r >> 2) & 1); }
+#define SW_A_OFF(k4) ((((k4) >> 1) * 64) + ((k4) & 1))      /* this lane's element of k-group k4, relative to its row block's pointer */
+#define SW_B_OFF(k4) ((((k4) >> 1) * 256) + ((k4) & 1))
+constexpr int SW_LANE_STRIDE = 2, SW_B_CB = 64;             // doubles per lane in a fragment pair / per 8-column block in a k-group pair
+#else
 __host__ __device__ __forceinline__ int sw_a_index(int r, int c) { return ((r >> 3) * 16 + (c >> 2)) * 32 + (r & 7) * 4 + (c & 3); }
 __host__ __device__ __forceinline__ int sw_x_index(int r, int c) { return ((r >> 2) * 4 + (c >> 3)) * 32 + (c & 7) * 4 + (r & 3); }
+#define SW_A_OFF(k4) ((k4) * 32)
+#define SW_B_OFF(k4) ((k4) * 128)
+constexpr int SW_LANE_STRIDE = 1, SW_B_CB = 32;
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+)
@@ -249,15 +268,15 @@ __device__ __forceinline__ void sweep_mma_dense(double (&acc)[SW_RBN][SW_CBN][2]
 #pragma unroll
     for (int a = 0; a < SW_RBN; ++a) { af[0][a] = 0.0; af[1][a] = 0.0; if (ALL || act[a]) af[0][a] = ap[a][0]; }
 #pragma unroll
-    for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * 32];
+    for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * SW_B_CB];
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {
         const int cur = k4 & 1, nxt = cur ^ 1;
         if (k4 + 1 < 16) {      // fragments of the next k-group before the DMMAs of this one
 #pragma unroll
-            for (int a = 0; a < SW_RBN; ++a) if (ALL || act[a]) af[nxt][a] = ap[a][(k4 + 1) * 32];
+            for (int a = 0; a < SW_RBN; ++a) if (ALL || act[a]) af[nxt][a] = ap[a][SW_A_OFF(k4 + 1)];
 #pragma unroll
-            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[SW_B_OFF(k4 + 1) + b * SW_B_CB];
         }
 #pragma unroll
         for (int a = 0; a < SW_RBN; ++a)
@@ -267,6 +286,40 @@ __device__ __forceinline__ void sweep_mma_dense(double (&acc)[SW_RBN][SW_CBN][2]
             }
     }
 }
+#if JK_SW_PAIR
+// paired layout, both row blocks dense: three 16-byte loads feed four DMMAs (k-groups 2q and 2q + 1 of both row blocks)
+__device__ __forceinline__ void sweep_mma_dense_pair(double (&acc)[SW_RBN][SW_CBN][2], const double* const (&ap)[SW_RBN], const double* __restrict__ bp) {
+    static_assert(SW_RBN == 2 && SW_CBN == 1, "paired dense loop");
+    double2 a0[2], a1[2], b[2];
+    a0[0] = *reinterpret_cast<const double2*>(ap[0]); a1[0] = *reinterpret_cast<const double2*>(ap[1]); b[0] = *reinterpret_cast<const double2*>(bp);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int cur = q & 1, nxt = cur ^ 1;
+        if (q + 1 < 8) {
+            a0[nxt] = *reinterpret_cast<const double2*>(ap[0] + (q + 1) * 64);
+            a1[nxt] = *reinterpret_cast<const double2*>(ap[1] + (q + 1) * 64);
+            b[nxt] = *reinterpret_cast<const double2*>(bp + (q + 1) * 256);
+        }
+        dmma(acc[0][0][0], acc[0][0][1], a0[cur].x, b[cur].x);
+        dmma(acc[1][0][0], acc[1][0][1], a1[cur].x, b[cur].x);
+        dmma(acc[0][0][0], acc[0][0][1], a0[cur].y, b[cur].y);
+        dmma(acc[1][0][0], acc[1][0][1], a1[cur].y, b[cur].y);
+    }
+}
+// one dense row block on its own: two 16-byte loads feed two DMMAs
+template <int A>
+__device__ __forceinline__ void sweep_mma_single_dense_pair(double (&acc)[SW_RBN][SW_CBN][2], const double* __restrict__ ap, const double* __restrict__ bp) {
+    double2 a[2], b[2];
+    a[0] = *reinterpret_cast<const double2*>(ap); b[0] = *reinterpret_cast<const double2*>(bp);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int cur = q & 1, nxt = cur ^ 1;
+        if (q + 1 < 8) { a[nxt] = *reinterpret_cast<const double2*>(ap + (q + 1) * 64); b[nxt] = *reinterpret_cast<const double2*>(bp + (q + 1) * 256); }
+        dmma(acc[A][0][0], acc[A][0][1], a[cur].x, b[cur].x);
+        dmma(acc[A][0][0], acc[A][0][1], a[cur].y, b[cur].y);
+    }
+}
+#endif
 // general masks: unrolled, one warp-uniform branch per k-group and row block
 __device__ __forceinline__ void sweep_mma_masked(double (&acc)[SW_RBN][SW_CBN][2], const double* const (&ap)[SW_RBN], const unsigned (&m)[SW_RBN],
                                                  const double* __restrict__ bp) {
@@ -278,11 +331,11 @@ __device__ __forceinline__ void sweep_mma_masked(double (&acc)[SW_RBN][SW_CBN][2
         if (mu & (1u << k4)) {
             double bf[SW_CBN];
 #pragma unroll
-            for (int b = 0; b < SW_CBN; ++b) bf[b] = bp[k4 * 128 + b * 32];
+            for (int b = 0; b < SW_CBN; ++b) bf[b] = bp[SW_B_OFF(k4) + b * SW_B_CB];
 #pragma unroll
             for (int a = 0; a < SW_RBN; ++a)
                 if (m[a] & (1u << k4)) {
-                    const double af = ap[a][k4 * 32];
+                    const double af = ap[a][SW_A_OFF(k4)];
 #pragma unroll
                     for (int b = 0; b < SW_CBN; ++b) dmma(acc[a][b][0], acc[a][b][1], af, bf[b]);
                 }
@@ -298,9 +351,9 @@ __device__ __forceinline__ void sweep_mma_uniform(double (&acc)[SW_RBN][SW_CBN][
         if (mask & (1u << k4)) {
             double af[SW_RBN], bf[SW_CBN];
 #pragma unroll
-            for (int a = 0; a < SW_RBN; ++a) af[a] = ap[a][k4 * 32];
+            for (int a = 0; a < SW_RBN; ++a) af[a] = ap[a][SW_A_OFF(k4)];
 #pragma unroll
-            for (int b = 0; b < SW_CBN; ++b) bf[b] = bp[k4 * 128 + b * 32];
+            for (int b = 0; b < SW_CBN; ++b) bf[b] = bp[SW_B_OFF(k4) + b * SW_B_CB];
 #pragma unroll
             for (int a = 0; a < SW_RBN; ++a)
 #pragma unroll
@@ -312,18 +365,21 @@ __device__ __forceinline__ void sweep_mma_uniform(double (&acc)[SW_RBN][SW_CBN][
 template <int A>
 __device__ __forceinline__ void sweep_mma_single(double (&acc)[SW_RBN][SW_CBN][2], const double* __restrict__ ap, unsigned mask,
                                                  const double* __restrict__ bp) {
+#if JK_SW_PAIR
+    if (mask == 0xffffu) { sweep_mma_single_dense_pair<A>(acc, ap, bp); return; }
+#endif
     if (mask == 0xffffu) {
         double af[2], bf[2][SW_CBN];
         af[0] = ap[0];
 #pragma unroll
-        for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * 32];
+        for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * SW_B_CB];
 #pragma unroll
         for (int k4 = 0; k4 < 16; ++k4) {
             const int cur = k4 & 1, nxt = cur ^ 1;
             if (k4 + 1 < 16) {
-                af[nxt] = ap[(k4 + 1) * 32];
+                af[nxt] = ap[SW_A_OFF(k4 + 1)];
 #pragma unroll
-                for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+                for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[SW_B_OFF(k4 + 1) + b * SW_B_CB];
             }
 #pragma unroll
             for (int b = 0; b < SW_CBN; ++b) dmma(acc[A][b][0], acc[A][b][1], af[cur], bf[cur][b]);
@@ -332,9 +388,9 @@ __device__ __forceinline__ void sweep_mma_single(double (&acc)[SW_RBN][SW_CBN][2
 #pragma unroll
         for (int k4 = 0; k4 < 16; ++k4) {
             if (mask & (1u << k4)) {
-                const double af = ap[k4 * 32];
+                const double af = ap[SW_A_OFF(k4)];
 #pragma unroll
-                for (int b = 0; b < SW_CBN; ++b) dmma(acc[A][b][0], acc[A][b][1], af, bp[k4 * 128 + b * 32]);
+                for (int b = 0; b < SW_CBN; ++b) dmma(acc[A][b][0], acc[A][b][1], af, bp[SW_B_OFF(k4) + b * SW_B_CB]);
             }
         }
     }
@@ -352,15 +408,15 @@ __device__ __forceinline__ void sweep_mma_pred(double (&acc)[SW_RBN][SW_CBN][2],
 #pragma unroll
     for (int a = 0; a < SW_RBN; ++a) af[0][a] = ap[a][0];
 #pragma unroll
-    for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * 32];
+    for (int b = 0; b < SW_CBN; ++b) bf[0][b] = bp[b * SW_B_CB];
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {
         const int cur = k4 & 1, nxt = cur ^ 1;
         if (k4 + 1 < 16) {
 #pragma unroll
-            for (int a = 0; a < SW_RBN; ++a) af[nxt][a] = ap[a][(k4 + 1) * 32];
+            for (int a = 0; a < SW_RBN; ++a) af[nxt][a] = ap[a][SW_A_OFF(k4 + 1)];
 #pragma unroll
-            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[SW_B_OFF(k4 + 1) + b * SW_B_CB];
         }
 #pragma unroll
         for (int a = 0; a < SW_RBN; ++a)
@@ -377,15 +433,15 @@ __device__ __forceinline__ void sweep_mma_one(double (&acc)[SW_RBN][SW_CBN][2], 
                                               const double* __restrict__ bp) {
     double af[2], bf[2][SW_CBN], part[SW_CBN][2];
 #pragma unroll
-    for (int b = 0; b < SW_CBN; ++b) { part[b][0] = 0.0; part[b][1] = 0.0; bf[0][b] = bp[b * 32]; }
+    for (int b = 0; b < SW_CBN; ++b) { part[b][0] = 0.0; part[b][1] = 0.0; bf[0][b] = bp[b * SW_B_CB]; }
     af[0] = ap[0];
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {
         const int cur = k4 & 1, nxt = cur ^ 1;
         if (k4 + 1 < 16) {
-            af[nxt] = ap[(k4 + 1) * 32];
+            af[nxt] = ap[SW_A_OFF(k4 + 1)];
 #pragma unroll
-            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[(k4 + 1) * 128 + b * 32];
+            for (int b = 0; b < SW_CBN; ++b) bf[nxt][b] = bp[SW_B_OFF(k4 + 1) + b * SW_B_CB];
         }
         if ((mask >> k4) & 1u) {
 #pragma unroll
@@ -526,7 +582,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     }
     // this lane's elements of a 64 x 32 tile: rows 8*mb + fr, columns 8*nt + 2*fk + {0, 1}
     auto rm_off = [&](int mb, int nt) { return (8 * mb + fr) * SLAB + 8 * nt + 2 * fk; };                       // row-major, double2
-    auto fx_off = [&](int mb, int nt, int e) { return ((2 * mb + (fr >> 2)) * 4 + nt) * 32 + (2 * fk + e) * 4 + (fr & 3); };   // fragment order
+    auto fx_off = [&](int mb, int nt, int e) { return sw_x_index(8 * mb + fr, 8 * nt + 2 * fk + e); };   // fragment order
     double acc[SW_RBN][SW_CBN][2], rhs[SW_RBN][SW_CBN][2];
     auto load_rhs = [&](int r) {
         const double* g = Xslab + (size_t)r * SW_XTILE;
@@ -601,7 +657,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             any = w != 0u;
             all_equal = m[0] == m[1];
             dense_or_empty = (act[0] || m[0] == 0u) && (act[1] || m[1] == 0u);
-            const double* abase = As + s * SW_TILE + lane;
+            const double* abase = As + s * SW_TILE + lane * SW_LANE_STRIDE;
             ap[0] = abase + rbs[0] * 512; ap[1] = abase + rbs[1] * 512;
         }
 #else
@@ -616,12 +672,16 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
             dense_or_empty = dense_or_empty && (act[a] || m[a] == 0u);
             any = any || m[a] != 0u;
             all_equal = all_equal && m[a] == m[0];
-            ap[a] = As + s * SW_TILE + (rb * 16) * 32 + lane;
+            ap[a] = As + s * SW_TILE + (rb * 16) * 32 + lane * SW_LANE_STRIDE;
         }
 #endif
-        const double* bp = xb + cb0 * 32 + lane;
+        const double* bp = xb + cb0 * SW_B_CB + lane * SW_LANE_STRIDE;
         if (any && !(flags & SW_NO_OPERAND)) {
+#if JK_SW_PAIR
+            if (all_dense) sweep_mma_dense_pair(acc, ap, bp);
+#else
             if (all_dense) sweep_mma_dense<true>(acc, ap, act, bp);
+#endif
 #if JK_SW_PRED
             else if (SW_RBN == 2 && m[0] == 0u) sweep_mma_one<SW_RBN - 1>(acc, ap[SW_RBN - 1], m[SW_RBN - 1], bp);
             else if (SW_RBN == 2 && m[1] == 0u) sweep_mma_one<0>(acc, ap[0], m[0], bp);
