@@ -65,6 +65,10 @@ constexpr int SW_MAX_CONSUMER_WARPS = 16;
 #define JK_SW_ZPREFETCH 0   // backward sweeps: L2 prefetch of the Z rows this many tile rows ahead of the diagonal item.  MEASURED with 3: no change at c4 (1.50 ms)
                             // nor at c5 (2 GB of Z: 2.91 vs 2.93 ms) -- the Z stage is not what the backward sweeps wait for
 #endif
+#ifndef JK_SW_CB_MINOR
+#define JK_SW_CB_MINOR 0      // column group as the minor index of the warp id (each scheduler hosts all four roles of one column group).
+                            // MEASURED SLOWER at c4: forward 1.17 vs 1.12 ms, backward equal -- see the comment at the mapping
+#endif
 #ifndef JK_SW_PAIR
 #define JK_SW_PAIR 0          // paired fragment order (two k-groups per 16-byte shared-memory load: half the load instructions of the DMMA loops).
                             // MEASURED SLOWER at c4: forward 1.170 vs 1.118 ms, backward 1.48 vs 1.43 ms (parity suite green on both)
@@ -555,10 +559,21 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
     // scheduler (w, w + 4) cover all eight row blocks of one column block, so every scheduler has the same DMMA count
     // in every tile row whatever the masks look like (rows end with an all-to-all exchange: imbalance is idle time).
     const int fr = lane >> 2, fk = lane & 3;
-    const int cb0 = cbase + (warp >> 2) * SW_CBN;
-    const int xgroup = JK_SW_GROUP_BARS ? (warp >> 2) : 0;
+    // Which warp does what.  A warp's role is the row-block pair (role, 7 - role); its column group is one of the CTA's 8-column
+    // blocks.  Consecutive warp ids sit on different schedulers (SM sub-partitions, each with its own share of the FP64 pipe), so
+    // with the column group as the MINOR index (JK_SW_CB_MINOR) a scheduler hosts all four roles of one column group and does
+    // a quarter of every item's DMMAs whatever the masks look like; with the role as the minor index a scheduler hosts ONE role
+    // for all column groups, and a row-sparse item (the far tiles of the envelope staircase touch only the last row blocks)
+    // lands on one scheduler while three idle.  That was the expectation; the measurement says otherwise (forward sweeps 1.17
+    // instead of 1.12 ms), so the role stays the minor index: the four warps of a scheduler then share their A fragments'
+    // addresses and run the same code path per item.
+    constexpr int GROUPS = SW_CONSUMER_WARPS / 4;      // column groups of this CTA (4 warps each)
+    const int cgroup = JK_SW_CB_MINOR ? (warp % GROUPS) : (warp >> 2);
+    const int role = JK_SW_CB_MINOR ? (warp / GROUPS) : (warp & 3);
+    const int cb0 = cbase + cgroup * SW_CBN;
+    const int xgroup = JK_SW_GROUP_BARS ? cgroup : 0;
     const unsigned bar_x = bar_x0 + 8 * SW_RING * xgroup;      // this group's row barriers, [slot]
-    const int rbs[SW_RBN] = {warp & 3, 7 - (warp & 3)};
+    const int rbs[SW_RBN] = {role, 7 - role};
     // a program that continues another launch: bring the slots' mbarrier phases in step with the item parities
     if (xphase_bits) {
         if (lane == 0)
@@ -650,7 +665,7 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
 #if JK_SW_ROLE_MASKS
         static_assert(SW_RBN == 2, "role-packed masks assume the row-block pair (s, 7 - s)");
         {
-            const unsigned w = reinterpret_cast<const unsigned*>(Ds + s * SW_ITEM_U4 + 2)[warp & 3];
+            const unsigned w = reinterpret_cast<const unsigned*>(Ds + s * SW_ITEM_U4 + 2)[role];
             m[0] = w & 0xffffu; m[1] = w >> 16;
             act[0] = m[0] == 0xffffu; act[1] = m[1] == 0xffffu;
             all_dense = w == 0xffffffffu;
