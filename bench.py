@@ -795,8 +795,8 @@ def run_ensemble(args):
         line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
-                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(8 * (5 * n_states + C + 18 * st.n_nodes)),
-                        "d2h_bytes_per_step": int(C * L.TABLE_NCOL * 8 + 8 * n_states), "ms_per_step": step_ms,
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": int(8 * (3 * n_states + 18 * st.n_nodes)),      # H, T, direction per sea state + static load + 2 direction loads
+                        "d2h_bytes_per_step": int(C * L.TABLE_NCOL * 8 + 16 * n_states),       # table + critical phase and wave number per sea state "ms_per_step": step_ms,
                         "note": "the timed step takes host arrays (H, T, direction per sea state) and returns the host table: value == e2e by construction"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
                 "stage_ms": {k: stage[k] for k in ("assemble", "factor", "morison", "rhs", "solve_fwd", "solve_bwd", "post", "reduce", "scan_total", "h2d", "d2h") if k in stage},
