@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="phases in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather-table", action="store_true", help="resident step at N > 1: also all-gather the per-phase table to every rank")
     ap.add_argument("--option", action="append", default=[], help="library option key=value (jk_set_option), repeatable")
     ap.add_argument("--per-step", action="store_true", help="debug: print every timed step's duration (ms) to stderr")
     return ap.parse_args()
@@ -632,8 +633,10 @@ def run_ours(args):
     def step_resident():
         """inputs already in HBM: assemble + factor + scan + cross-rank reduction"""
         # jk_step_dev: assemble + factorisation (side streams, concurrent with the Morison + load stage) + scan, one graph launch
-        return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=(world > 1), t_dev=t_dev.data_ptr(),
-                                  host_results=False, moduli=(E, G))    # critical pair and gathered table stay in HBM
+        # The cross-rank exchange is the critical-phase reduction (one value / index pair per rank); every rank keeps its own shard of
+        # the per-phase table in HBM.  --gather-table also all-gathers the table to every rank each step (round 1's resident step).
+        return sharded_phase_scan(eng, wave, n_total, p.fy, rank, world, gather_table=(world > 1 and args.gather_table), t_dev=t_dev.data_ptr(),
+                                  host_results=False, moduli=(E, G))
 
     def step_e2e():
         """host buffers in, host results out, through the public API: every rank gets the merged critical phase and its own
