@@ -78,6 +78,9 @@ __global__ void k_phase_setup(int P, int ldP, const double* __restrict__ t, doub
 //   totpart[chunk][9][ldP] chunk partial sums of drag / inertia / (drag+inertia) in member order
 //   details[m][4][ldP]     optional drag_kN, inertia_kN, total_kN, submerged_length (GUI.py:668-674)
 // ----------------------------------------------------------------------------------------------
+#ifndef JK_FM_STREAMING
+#define JK_FM_STREAMING 0      // streaming (evict-first) stores / loads for the member-force array: measured slower (5.36 vs 5.31 ms per step on the same box)
+#endif
 #ifndef JK_MORISON_SSUM
 #define JK_MORISON_SSUM 1
 #endif
@@ -333,8 +336,13 @@ k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const do
                 plo[(size_t)k * ldP] = lo;                                     // the lower end: one deposit row per member
                 if (ends & 0x40000u) phi[(size_t)k * ldP] = run[k];
             } else {
+#if JK_FM_STREAMING
+                __stcs(Fm + o + (size_t)k * ldP, mt - F2);                     // F1 = sum (1-s) f   (GUI.py:658); write-once stream, read once by the gather
+                __stcs(Fm + o + (size_t)(3 + k) * ldP, F2);                    // F2 = sum s f       (GUI.py:659)
+#else
                 Fm[o + (size_t)k * ldP] = mt - F2;                             // F1 = sum (1-s) f   (GUI.py:658)
                 Fm[o + (size_t)(3 + k) * ldP] = F2;                            // F2 = sum s f       (GUI.py:659)
+#endif
             }
             td[k] += md[k]; ti[k] += mi[k]; tm[k] += mt;                        // GUI.py:664-666
         }
@@ -891,7 +899,11 @@ k_rhs_gather(int Nn, int ldP, int n_pad, const double* __restrict__ Fm, const in
     for (int q = adj_ptr[node]; q < adj_ptr[node + 1]; ++q) {
         int m = adj[q] >> 1, end = adj[q] & 1;
         size_t o = ((size_t)m * 6 + 3 * end) * ldP + p;
+#if JK_FM_STREAMING
+        f[0] += __ldcs(Fm + o); f[1] += __ldcs(Fm + o + ldP); f[2] += __ldcs(Fm + o + 2 * (size_t)ldP);
+#else
         f[0] += Fm[o]; f[1] += Fm[o + ldP]; f[2] += Fm[o + 2 * (size_t)ldP];
+#endif
     }
     if (nodal && p == 0) { nodal[3 * node] = f[0]; nodal[3 * node + 1] = f[1]; nodal[3 * node + 2] = f[2]; }
     int s = node2slot[node];

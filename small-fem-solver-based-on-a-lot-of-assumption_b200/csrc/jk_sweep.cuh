@@ -633,7 +633,10 @@ k_sweep(const uint4* __restrict__ prog, const double* __restrict__ stream, doubl
 #endif
         if (profiling) { t1 = clock64(); pc[0] += t1 - t0; }
         if (tracing) trace[((size_t)n * 2 + trace_w) * 4 + 0] = clock64();
-        const uint4 d0 = Ds[s * SW_ITEM_U4], d1 = Ds[s * SW_ITEM_U4 + 1], mk = Ds[s * SW_ITEM_U4 + 2];
+        const uint4 d0 = Ds[s * SW_ITEM_U4], d1 = Ds[s * SW_ITEM_U4 + 1];
+#if !JK_SW_ROLE_MASKS
+        const uint4 mk = Ds[s * SW_ITEM_U4 + 2];
+#endif
         const int row = (int)d0.x, flags = (int)d0.z, xinfo = (int)d0.w;
         if (flags & SW_ROW_BEGIN) {
 #pragma unroll
