@@ -137,11 +137,15 @@ struct LoadFuse {
 };
 
 #ifndef JK_MORISON_MINBLOCKS
-#define JK_MORISON_MINBLOCKS 1   // A/B: resident blocks per SM the register allocation must allow.  MEASURED at c4: JK_MCHUNK=24 with 6 blocks per SM (80 registers,
+#define JK_MORISON_MINBLOCKS 0   // A/B: resident blocks per SM the register allocation must allow.  MEASURED at c4: JK_MCHUNK=24 with 6 blocks per SM (80 registers,
                                  // no spills) 1.43 ms, JK_MCHUNK=16 1.44 ms, against 1.35 ms with 32 members and 5 blocks -- staging per block costs more than occupancy gives
 #endif
 template <bool DETAILS, int GT /* compile-time Gauss point count (fully unrolled point loops) or 0 */, bool FUSED = false>
+#if JK_MORISON_MINBLOCKS > 0
 __global__ void __launch_bounds__(PH_TPB, JK_MORISON_MINBLOCKS)
+#else
+__global__ void __launch_bounds__(PH_TPB)          // no minimum: ptxas settles at 96 registers (5 blocks per SM); "(PH_TPB, 1)" lets it take 224 (2 blocks, 1.55 ms)
+#endif
 k_morison_airy(int M, int G_rt, int ldP, const double* __restrict__ gp, const double* __restrict__ mc,
                const double* __restrict__ gsw /* s[G], w[G] */, const double* __restrict__ trig,
                WaveAiry wv, double cD0 /* 0.5 rho Cd */, double cI0 /* rho Cm */,
