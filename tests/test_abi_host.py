@@ -120,3 +120,35 @@ def test_structure_pack_roundtrip():
     assert np.array_equal(xyz, g["xyz"]) and np.array_equal(conn, g["conn"])
     assert np.array_equal(sec_id == sec_id[0], g["is_leg"] == g["is_leg"][0]) and props.shape == (2, 8)
     assert st.n_dof == 6 * st.n_nodes and st.get_member_geometry(st.members[0])["L_mm"] > 0
+
+
+def test_occupancy_critical_kernels_keep_their_register_budget():
+    """The Morison kernel is occupancy-bound (5 blocks of 128 threads per SM need <= 102 registers; with 224 it runs 15 %
+    slower) and a sweep CTA of 544 threads needs <= 120: read the built library's resource usage so that a stray
+    __launch_bounds__ or a code change that blows the budget fails here, on the CPU, before any GPU time is spent."""
+    import re
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    import os
+    tool = shutil.which("cuobjdump")
+    lib = os.path.join(ROOT, "small-fem-solver-based-on-a-lot-of-assumption_b200", "libjacket_b200.so")
+    if tool is None or not os.path.isfile(lib):
+        import pytest
+        pytest.skip("cuobjdump or the built library is missing")
+    out = subprocess.run([tool, "-res-usage", lib], capture_output=True, text=True, timeout=300).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    morison = [v for k, v in regs.items() if "k_morison_airyILb0ELi15ELb0" in k]
+    sweep = [v for k, v in regs.items() if "k_sweepILi4ELb0" in k]
+    post = [v for k, v in regs.items() if "k_member_post" in k and "single" not in k]
+    assert morison and max(morison) <= 102, morison
+    assert sweep and max(sweep) <= 120, sweep
+    assert post and max(post) <= 64, post
